@@ -1,0 +1,68 @@
+"""ctypes binding of include/beluga_b200.h.  There is no CPU fallback: if the shared library is
+missing or no CUDA device is present, loading / blg_create raise."""
+import ctypes as C
+import os
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+SO = os.path.join(HERE, "libbeluga_b200.so")
+
+_lib = None
+
+# every symbol include/beluga_b200.h declares
+SYMBOLS = [
+    "blg_create", "blg_destroy", "blg_last_error", "blg_set_profiles", "blg_set_topology", "blg_set_params",
+    "blg_rebuild", "blg_logpdf_full", "blg_logpdf_from", "blg_logpdf_root", "blg_logpdf_full_async",
+    "blg_logpdf_from_async", "blg_logpdf_root_async", "blg_gradient", "blg_gradient_cr", "blg_gradient_async",
+    "blg_commit", "blg_revert", "blg_extend", "blg_shrink", "blg_get_column", "blg_get_family_logpdf",
+    "blg_get_eps", "blg_get_W", "blg_ncols", "blg_npatterns", "blg_last_algorithmic", "blg_sync",
+]
+
+
+class BelugaError(RuntimeError):
+    pass
+
+
+def lib():
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(SO):
+        raise BelugaError(
+            "libbeluga_b200.so is not built (%s). Run `python -c 'import __graft_entry__ as g; g.build()'`; "
+            "there is no CPU fallback." % SO
+        )
+    L = C.CDLL(SO)
+    vp, dp, ip = C.c_void_p, C.POINTER(C.c_double), C.POINTER(C.c_int)
+    i32p, i64p, u8p = C.POINTER(C.c_int32), C.POINTER(C.c_int64), C.POINTER(C.c_uint8)
+    L.blg_create.argtypes = [C.c_int, vp, C.POINTER(vp)]
+    L.blg_destroy.argtypes = [vp]
+    L.blg_last_error.argtypes = [vp]
+    L.blg_last_error.restype = C.c_char_p
+    L.blg_set_profiles.argtypes = [vp, i32p, i64p, C.c_int, C.c_int]
+    L.blg_set_topology.argtypes = [vp, C.c_int, i32p, u8p, i32p]
+    L.blg_set_params.argtypes = [vp, C.c_int, dp, dp, dp, dp, C.c_double]
+    L.blg_rebuild.argtypes = [vp, i32p, C.c_int]
+    L.blg_logpdf_full.argtypes = [vp, dp]
+    L.blg_logpdf_from.argtypes = [vp, C.c_int, dp]
+    L.blg_logpdf_root.argtypes = [vp, dp]
+    L.blg_logpdf_full_async.argtypes = [vp, vp]
+    L.blg_logpdf_from_async.argtypes = [vp, C.c_int, vp]
+    L.blg_logpdf_root_async.argtypes = [vp, vp]
+    L.blg_gradient.argtypes = [vp, dp, C.c_int, dp]
+    L.blg_gradient_cr.argtypes = [vp, dp, dp]
+    L.blg_gradient_async.argtypes = [vp, vp, C.c_int]
+    for f in ("blg_commit", "blg_revert", "blg_sync", "blg_npatterns"):
+        getattr(L, f).argtypes = [vp]
+    L.blg_extend.argtypes = [vp, C.c_int]
+    L.blg_shrink.argtypes = [vp, C.c_int]
+    L.blg_get_column.argtypes = [vp, C.c_int, C.c_int, C.c_int, dp, C.c_int, ip]
+    L.blg_get_family_logpdf.argtypes = [vp, dp, C.c_int]
+    L.blg_get_eps.argtypes = [vp, dp, dp, C.c_int]
+    L.blg_get_W.argtypes = [vp, C.c_int, dp, C.c_int, ip]
+    L.blg_ncols.argtypes = [vp, C.c_int]
+    L.blg_last_algorithmic.argtypes = [vp, dp, ip]
+    for s in SYMBOLS:
+        if s != "blg_last_error":
+            getattr(L, s).restype = C.c_int
+    _lib = L
+    return L

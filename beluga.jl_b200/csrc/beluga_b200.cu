@@ -1,0 +1,1067 @@
+// beluga_b200.cu — B200 (sm_100a) implementation of the DLWGD gene-family likelihood hot path.
+//
+// What this file replaces in arzwa/Beluga.jl (all Julia, file:line under the reference tree):
+//   per-branch numerics  setϵ!/setW!/wstar*!     src/node.jl:136-218, src/utils.jl:8-19
+//   pruning recursion    csuros_miklos!          src/model.jl:402-463
+//   root + conditioning  integrate_root, condition_oib   src/model.jl:465-501
+//   profile storage/DP   Profile/PArray, logpdf!, set!/rev!/extend!/shrink!   src/profile.jl:14-121
+//
+// Design: counts and partial likelihoods live on the device node-major and
+// family-contiguous; ℓ_u[n][f] is kept in LINEAR fp64 with one power-of-two exponent per
+// (family, node).  ε, W and the per-node merge tables are built on the device per parameter
+// update.  One pruning launch per internal node applies the edge contraction W·ℓ and the
+// conditional-survival merge to every family at once (one thread = one family, all global
+// accesses coalesced along the family axis).  No CPU fallback: every entry fails loudly when
+// CUDA is unavailable.
+#include <cuda_runtime.h>
+
+#include <algorithm>
+#include <cmath>
+#include <cstdint>
+#include <cstdio>
+#include <cstring>
+#include <map>
+#include <memory>
+#include <stdexcept>
+#include <string>
+#include <vector>
+
+#include "beluga_b200.h"
+
+#define BLG_MAXK 8          // max children of one node (polytomies)
+#define BLG_MAXCOUNT 1023   // largest extended count supported (binomials stay finite in fp64)
+
+namespace {
+
+struct CudaError : std::runtime_error { using std::runtime_error::runtime_error; };
+#define CK(call)                                                                                   \
+    do {                                                                                           \
+        cudaError_t e_ = (call);                                                                   \
+        if (e_ != cudaSuccess)                                                                     \
+            throw CudaError(std::string(#call) + ": " + cudaGetErrorString(e_) + " (" __FILE__ ":" + \
+                            std::to_string(__LINE__) + ")");                                       \
+    } while (0)
+
+thread_local std::string g_create_error;
+
+// ------------------------------------------------------------------------------------------------
+// device-side model description
+// ------------------------------------------------------------------------------------------------
+struct NodeTab {        // per node id, device-resident tables
+    double* W;          // wdim × wdim row-major [n][j], w*(n|j) for the branch above the node
+    int wdim;
+    double* ipow;       // (1-E_k)^(-n), n = 0..nrow-1  (NaN-poisoned when the reference would be)
+    int nrow;           // xmax_u + 1
+    double* coef[BLG_MAXK];   // coef[i][n*cstride[i]+s] = C(n,s)·E_{i-1}^s for child i >= 1
+    int cstride[BLG_MAXK];
+};
+
+struct ModelDev {
+    int n;                     // ncols (max id)
+    int model_kind;
+    const uint8_t* kind;
+    const int* parent;         // 0-based, -1 root/absent
+    const int* child_off;      // CSR over ordered children
+    const int* child_idx;
+    const double* t;
+    const double* lam;
+    const double* mu;
+    const double* q;
+    double eta;
+    double* eps0;              // ϵ[1]: extinction prob at the top of the branch above the node
+    double* eps1;              // ϵ[2]: at the node
+    NodeTab* tab;
+    const double* pascal;      // C(n,s), row stride pdim
+    int pdim;
+};
+
+__device__ __forceinline__ bool d_isapprox(double a, double b) {
+    if (a == b) return true;
+    if (!isfinite(a) || !isfinite(b)) return false;
+    return fabs(a - b) <= 1.4901161193847656e-8 * fmax(fabs(a), fabs(b));
+}
+__device__ __forceinline__ double d_approx1(double x) { return d_isapprox(x, 1.0) ? 1.0 : x; }   // utils.jl:19
+__device__ __forceinline__ double d_getphi(double t, double l, double m) {                       // utils.jl:8
+    if (d_isapprox(l, m)) return l * t / (1.0 + l * t);
+    double e = exp(t * (l - m));
+    return m * (e - 1.0) / (l * e - m);
+}
+__device__ __forceinline__ double d_getpsi(double t, double l, double m) {                       // utils.jl:9
+    if (d_isapprox(l, m)) return l * t / (1.0 + l * t);
+    return (l / m) * d_getphi(t, l, m);
+}
+__device__ __forceinline__ double d_ep(double l, double m, double t, double e) {                 // utils.jl:17-18
+    if (d_isapprox(l, m)) return 1.0 + (1.0 - e) / (m * (e - 1.0) * t - 1.0);
+    return d_approx1((m + (l - m) / (1.0 + exp((l - m) * t) * l * (e - 1.0) / (m - l * e))) / l);
+}
+__device__ __forceinline__ bool d_isawgd(const ModelDev& m, int i) {
+    uint8_t k = m.kind[i];
+    return k == BLG_WGD || k == BLG_WGT || k == BLG_WGDAFTER;
+}
+__device__ __forceinline__ int d_nonwgdparent(const ModelDev& m, int i) { while (d_isawgd(m, i)) i = m.parent[i]; return i; }
+__device__ __forceinline__ int d_nonwgdchild(const ModelDev& m, int i) { while (d_isawgd(m, i)) i = m.child_idx[m.child_off[i]]; return i; }
+// node.jl:220-230 getλμ(parent a, child b)
+__device__ __forceinline__ void d_getlm(const ModelDev& m, int a, int b, double& l, double& mu) {
+    b = d_isawgd(m, b) ? d_nonwgdchild(m, b) : b;
+    if (m.model_kind == BLG_NODE_MODEL) {
+        a = d_isawgd(m, a) ? d_nonwgdparent(m, a) : a;
+        l = (m.lam[a] + m.lam[b]) / 2.0;
+        mu = (m.mu[a] + m.mu[b]) / 2.0;
+    } else {
+        l = m.lam[b];
+        mu = m.mu[b];
+    }
+}
+__device__ __forceinline__ double d_powi(double b, int n) {   // b^n, n >= 0, by squaring
+    double r = 1.0;
+    while (n > 0) { if (n & 1) r *= b; b *= b; n >>= 1; }
+    return r;
+}
+
+// setϵ! (node.jl:136-162) for the listed nodes, in list order.  Sequential by construction (each
+// node needs its children's ϵ[2]); one thread, a few hundred flops per node.
+__global__ void eps_kernel(ModelDev m, const int* __restrict__ list, int nlist) {
+    if (blockIdx.x != 0 || threadIdx.x != 0) return;
+    for (int li = 0; li < nlist; ++li) {
+        int n = list[li];
+        int c0 = m.child_off[n], c1 = m.child_off[n + 1];
+        uint8_t kd = m.kind[n];
+        if (c0 == c1) {
+            m.eps1[n] = 0.0;
+        } else if (kd == BLG_WGD) {
+            double q = m.q[n];
+            int c = m.child_idx[c0];
+            double ec = m.eps1[c];
+            double v = q * (ec * ec) + (1.0 - q) * ec;
+            m.eps0[c] = v;
+            m.eps1[n] = v;
+        } else if (kd == BLG_WGT) {
+            double q = m.q[n];
+            int c = m.child_idx[c0];
+            double ec = m.eps1[c];
+            double v = q * (ec * ec * ec) + 2.0 * q * (1.0 - q) * (ec * ec) + (1.0 - q) * (1.0 - q) * ec;
+            m.eps0[c] = v;
+            m.eps1[n] = v;
+        } else {
+            double e = 1.0;
+            for (int ci = c0; ci < c1; ++ci) {
+                int c = m.child_idx[ci];
+                double l, mu;
+                d_getlm(m, n, c, l, mu);
+                double ec = d_approx1(d_ep(l, mu, m.t[c], m.eps1[c]));
+                m.eps0[c] = ec;
+                e *= ec;
+            }
+            m.eps1[n] = d_approx1(e);
+        }
+    }
+}
+
+// setW! (node.jl:164-218) and the per-node merge tables, one block per listed node.
+__global__ void __launch_bounds__(128) tables_kernel(ModelDev m, const int* __restrict__ list, int nlist) {
+    extern __shared__ double sm[];   // 2 * maxdim doubles
+    int n = list[blockIdx.x];
+    const NodeTab tb = m.tab[n];
+    const int tid = threadIdx.x, nt = blockDim.x;
+    uint8_t kd = m.kind[n];
+    // ---- W of the branch above n -------------------------------------------------------------
+    if (kd != BLG_ROOT && tb.W != nullptr) {
+        const int d = tb.wdim;
+        double* W = tb.W;
+        for (int i = tid; i < d * d; i += nt) W[i] = 0.0;
+        __syncthreads();
+        int par = m.parent[n];
+        double e = m.eps1[n];
+        if (kd == BLG_WGDAFTER && m.kind[par] == BLG_WGD) {                         // wstar_wgd!
+            double q = m.q[par];
+            double a = ((1.0 - q) + 2.0 * q * e) * (1.0 - e);
+            double b = q * ((1.0 - e) * (1.0 - e));
+            if (tid == 0) { W[0] = 1.0; if (d > 1) W[d + 1] = a; if (d > 2) W[d + 2] = b; }
+            __syncthreads();
+            for (int i = 1; i < d; ++i) {
+                for (int j = 2 + tid; j < d; j += nt)
+                    W[i * d + j] = a * W[(i - 1) * d + j - 1] + b * W[(i - 1) * d + j - 2];
+                __syncthreads();
+            }
+        } else if (kd == BLG_WGDAFTER && m.kind[par] == BLG_WGT) {                  // wstar_wgt! (literal, j from 3)
+            double q = m.q[par];
+            double q1 = q, q2 = 2.0 * q * (1.0 - q), q3 = (1.0 - q) * (1.0 - q), ome = 1.0 - e;
+            double a = q1 * ome + 2.0 * q2 * e * ome + 3.0 * q3 * (e * e) * ome;
+            double b = q2 * (ome * ome) + 3.0 * q3 * e * (ome * ome);
+            double c = q3 * (ome * ome * ome);
+            if (tid == 0) { W[0] = 1.0; if (d > 1) W[d + 1] = a; if (d > 2) W[d + 2] = b; if (d > 3) W[d + 3] = c; }
+            __syncthreads();
+            for (int i = 1; i < d; ++i) {
+                for (int j = 3 + tid; j < d; j += nt)
+                    W[i * d + j] = a * W[(i - 1) * d + j - 1] + b * W[(i - 1) * d + j - 2] + c * W[(i - 1) * d + j - 3];
+                __syncthreads();
+            }
+        } else {                                                                     // wstar!
+            double l, mu;
+            d_getlm(m, par, n, l, mu);
+            double t = m.t[n];
+            double phi = d_getphi(t, l, mu), psi = d_getpsi(t, l, mu);
+            double nn = 1.0 - psi * e;
+            double phip = d_approx1((phi * (1.0 - e) + (1.0 - psi) * e) / nn);
+            double psip = d_approx1(psi * (1.0 - e) / nn);
+            double cc = (1.0 - phip) * (1.0 - psip);
+            double* prev = sm;
+            double* cur = sm + d;
+            for (int i = tid; i < d; i += nt) prev[i] = (i == 0) ? 1.0 : 0.0;   // column 0
+            if (tid == 0) W[0] = 1.0;
+            __syncthreads();
+            for (int j = 1; j < d; ++j) {
+                for (int r = tid; r < d; r += nt) {
+                    double v = 0.0;
+                    if (r >= 1 && r <= j) v = psip * prev[r] + cc * prev[r - 1];
+                    cur[r] = v;
+                    if (r >= 1 && r <= j) W[r * d + j] = v;
+                }
+                __syncthreads();
+                double* tmp = prev; prev = cur; cur = tmp;
+            }
+        }
+    }
+    // ---- merge tables of n (internal nodes) -----------------------------------------------------
+    int c0 = m.child_off[n], c1 = m.child_off[n + 1];
+    int k = c1 - c0;
+    if (k > 0 && tb.ipow != nullptr) {
+        // _ϵ = cumprod([1; ϵ_c[1]...]) then clamp >1 to 1 (model.jl:415-419)
+        double E[BLG_MAXK + 1];
+        double raw = 1.0;
+        bool poison = false;
+        E[0] = 1.0;
+        for (int i = 0; i < k; ++i) {
+            raw *= m.eps0[m.child_idx[c0 + i]];
+            double v = raw > 1.0 ? 1.0 : raw;
+            E[i + 1] = v;
+            // the reference divides by (1-_ϵ)^n in log space: _ϵ == 1 gives 0·(-Inf) = NaN at n = 0
+            // (model.jl:433-435,453-455); a prefix outside [0,1) is treated the same way here.
+            if (!(v >= 0.0 && v < 1.0)) poison = true;
+        }
+        double inv = 1.0 / (1.0 - E[k]);
+        for (int r = tid; r < tb.nrow; r += nt) tb.ipow[r] = poison ? __longlong_as_double(0x7ff8000000000000LL) : d_powi(inv, r);
+        for (int i = 1; i < k; ++i) {
+            double* cf = tb.coef[i];
+            int cs = tb.cstride[i];
+            double p = E[i];
+            for (int idx = tid; idx < tb.nrow * cs; idx += nt) {
+                int r = idx / cs, s = idx - r * cs;
+                cf[idx] = (s <= r) ? m.pascal[(size_t)r * m.pdim + s] * d_powi(p, s) : 0.0;
+            }
+        }
+    }
+}
+
+// Pascal triangle C(n,s), n,s < dim, by the addition recurrence (exact while < 2^53).
+__global__ void pascal_kernel(double* P, int dim) {
+    extern __shared__ double sm[];
+    double* prev = sm;
+    double* cur = sm + dim;
+    int tid = threadIdx.x, nt = blockDim.x;
+    for (int s = tid; s < dim; s += nt) { prev[s] = (s == 0) ? 1.0 : 0.0; P[s] = prev[s]; }
+    __syncthreads();
+    for (int n = 1; n < dim; ++n) {
+        for (int s = tid; s < dim; s += nt) {
+            double v = (s == 0) ? 1.0 : (s <= n ? prev[s - 1] + prev[s] : 0.0);
+            cur[s] = v;
+            P[(size_t)n * dim + s] = v;
+        }
+        __syncthreads();
+        double* t = prev; prev = cur; cur = t;
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// pruning step at one internal node for every family (csuros_miklos!, model.jl:402-463)
+// ------------------------------------------------------------------------------------------------
+struct ChildRef {
+    const double* ell;     // child's slab [n][f] (nullptr: leaf, one-hot at its count)
+    const int* scl;        // child's per-family exponent (nullptr for leaves)
+    const uint16_t* cnt;   // child's extended counts
+    const double* W;       // child's W, row-major [s][j]
+    int wdim;
+    int id;                // child's node index (for ϵ[1])
+    const double* coef;    // merge coefficients for this child (i >= 1)
+    int cstride;
+};
+struct NodeStep {
+    int k;
+    ChildRef child[BLG_MAXK];
+    const double* ipow;
+    const double* eps0;
+    double* out;           // node slab [n][f]
+    int* out_scl;
+    const uint16_t* cnt;   // node's own extended counts
+};
+
+// Linear-space form of the recursion.  With ℓ_c the child's column, e_i = ϵ_{c_i}[1],
+// E_i = min(1, e_1⋯e_i):
+//   b_i[s]   = Σ_{j>=s} W_{c_i}[s,j] ℓ_{c_i}[j]                                   (model.jl:425-426)
+//   B_i[0,s] = b_i[s];  B_i[t,s] = B_i[t-1,s+1] + e_i B_i[t-1,s]                   (model.jl:428-431)
+//   Ã_1[n]   = b_1[n];  Ã_i[n] = Σ_{t+s=n} C(n,s) E_{i-1}^s Ã_{i-1}[t] B_i[t,s]   (model.jl:438-452)
+//   ℓ_u[n]   = Ã_k[n] / (1-E_k)^n                                                  (model.jl:453-461)
+// The reference normalises by (1-E_i)^n after every child and multiplies the next merge by the
+// Binomial(n, E_i) pmf; the (1-E_i) powers cancel exactly, so only the last division is kept.
+template <int CAP>
+__global__ void __launch_bounds__(128) prune_node_kernel(const NodeStep st, int N, size_t ld) {
+    int f = blockIdx.x * blockDim.x + threadIdx.x;
+    if (f >= N) return;
+    double A0[CAP], A1[CAP], Bc[CAP], lc[CAP];
+    double* Acur = A0;
+    double* Anew = A1;
+    int S = 0;
+    int sclsum = 0;
+    for (int i = 0; i < st.k; ++i) {
+        const ChildRef& c = st.child[i];
+        const int Mi = c.cnt[f];
+        const double* __restrict__ W = c.W;
+        const int wd = c.wdim;
+        if (c.ell == nullptr) {
+            for (int s = 0; s <= Mi; ++s) Bc[s] = W[s * wd + Mi];
+        } else {
+            for (int j = 0; j <= Mi; ++j) lc[j] = c.ell[(size_t)j * ld + f];
+            sclsum += c.scl[f];
+            for (int s = 0; s <= Mi; ++s) {
+                double acc = 0.0;
+                for (int j = s; j <= Mi; ++j) acc = fma(W[s * wd + j], lc[j], acc);
+                Bc[s] = acc;
+            }
+        }
+        if (i == 0) {
+            for (int n = 0; n <= Mi; ++n) Acur[n] = Bc[n];
+            S = Mi;
+        } else {
+            const double e = st.eps0[c.id];
+            const double* __restrict__ cf = c.coef;
+            const int cs = c.cstride;
+            for (int n = 0; n <= S + Mi; ++n) Anew[n] = 0.0;
+            for (int t = 0; t <= S; ++t) {
+                const double a = Acur[t];
+                for (int s = 0; s <= Mi; ++s) Anew[t + s] = fma(cf[(t + s) * cs + s], a * Bc[s], Anew[t + s]);
+                for (int s = 0; s < Mi; ++s) Bc[s] = fma(e, Bc[s], Bc[s + 1]);
+                Bc[Mi] = e * Bc[Mi];
+            }
+            double* tmp = Acur; Acur = Anew; Anew = tmp;
+            S += Mi;
+        }
+    }
+    const int X = st.cnt[f];   // == S for a consistent extended profile
+    double mxv = 0.0;
+    bool bad = false;
+    for (int n = 0; n <= X; ++n) {
+        double v = (n <= S ? Acur[n] : 0.0) * st.ipow[n];
+        Acur[n] = v;
+        if (!(v == v) || isinf(v)) bad = true;
+        mxv = fmax(mxv, v);
+    }
+    int ex = 0;
+    if (!bad && mxv > 0.0) ex = ilogb(mxv);
+    for (int n = 0; n <= X; ++n) st.out[(size_t)n * ld + f] = (ex != 0) ? scalbn(Acur[n], -ex) : Acur[n];
+    st.out_scl[f] = sclsum + ex;
+}
+
+// ------------------------------------------------------------------------------------------------
+// root: integrate_root (model.jl:465-475), condition_oib (model.jl:492-501), weighted reduction
+// ------------------------------------------------------------------------------------------------
+__device__ __forceinline__ double d_log1mexp(double x) { return x < -0.6931471805599453 ? log1p(-exp(x)) : log(-expm1(x)); }
+
+// rootw[n] = exp((n)·log1mexp(lε) + log η + (n-1)·log(1-η) - (n+1)·log1mexp(log(1-η)+lε)), n >= 1;
+// rootw[0] holds the conditioning constant log(1-r_1) + log(1-r_2) (+Inf marks "invalid").
+__global__ void root_tables_kernel(ModelDev m, double* rootw, int nrow) {
+    int root = 0;
+    double eta = m.eta;
+    double le = log(m.eps1[root]);
+    double a = d_log1mexp(le), b = log(eta), c = log(1.0 - eta), d = d_log1mexp(log(1.0 - eta) + le);
+    for (int n = 1 + threadIdx.x; n < nrow; n += blockDim.x) {
+        double f = (double)n * a + b + (double)(n - 1) * c;
+        f -= (double)(n + 1) * d;
+        rootw[n] = exp(f);
+    }
+    if (threadIdx.x == 0) {
+        int c0 = m.child_off[root], c1 = m.child_off[root + 1];
+        double cond = __longlong_as_double(0x7ff8000000000000LL);
+        if (c1 - c0 >= 2) {
+            double leta = log(eta);
+            double lr[2];
+            for (int i = 0; i < 2; ++i) {
+                double e = log(m.eps0[m.child_idx[c0 + i]]);
+                lr[i] = leta + e - d_log1mexp(d_log1mexp(leta) + e);           // utils.jl:22-23
+            }
+            if (lr[0] > 0.0 || lr[1] > 0.0) cond = -INFINITY;                   // model.jl:495-497
+            else cond = d_log1mexp(lr[0]) + d_log1mexp(lr[1]);
+        }
+        rootw[0] = cond;
+    }
+}
+
+__global__ void __launch_bounds__(256) root_kernel(const double* __restrict__ ell, const int* __restrict__ scl,
+                                                   const uint16_t* __restrict__ cnt, const double* __restrict__ rootw,
+                                                   const double* __restrict__ weight, double* __restrict__ fam_ll,
+                                                   double* __restrict__ partial, int N, size_t ld) {
+    __shared__ double red[256];
+    int f = blockIdx.x * blockDim.x + threadIdx.x;
+    double contrib = 0.0;
+    if (f < N) {
+        int X = cnt[f];
+        double p = 0.0;
+        for (int n = 1; n <= X; ++n) p = fma(ell[(size_t)n * ld + f], rootw[n], p);
+        double l = log(p) + (double)scl[f] * 0.6931471805599453 - rootw[0];
+        if (!isfinite(l)) l = -INFINITY;                                        // model.jl:366
+        fam_ll[f] = l;
+        contrib = weight[f] * l;
+    }
+    red[threadIdx.x] = contrib;
+    __syncthreads();
+    for (int s = 128; s > 0; s >>= 1) {                                         // fixed-order tree: deterministic
+        if ((int)threadIdx.x < s) red[threadIdx.x] += red[threadIdx.x + s];
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) partial[blockIdx.x] = red[0];
+}
+
+__global__ void __launch_bounds__(256) final_reduce_kernel(const double* __restrict__ partial, int nparts, double* __restrict__ out) {
+    __shared__ double red[256];
+    double s = 0.0;
+    for (int i = threadIdx.x; i < nparts; i += 256) s += partial[i];
+    red[threadIdx.x] = s;
+    __syncthreads();
+    for (int k = 128; k > 0; k >>= 1) {
+        if ((int)threadIdx.x < k) red[threadIdx.x] += red[threadIdx.x + k];
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) out[0] = red[0];
+}
+
+__global__ void zero_slab_kernel(double* ell, int* scl, size_t nell, int N) {
+    size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    size_t stride = (size_t)gridDim.x * blockDim.x;
+    for (size_t k = i; k < nell; k += stride) ell[k] = 0.0;
+    for (size_t k = i; k < (size_t)N; k += stride) scl[k] = 0;
+}
+
+// ------------------------------------------------------------------------------------------------
+// host-side state
+// ------------------------------------------------------------------------------------------------
+struct Slab {
+    double* ell = nullptr;
+    int* scl = nullptr;
+    int rows = 0;
+};
+struct Col {
+    const uint16_t* cnt = nullptr;   // device counts of this column (shared between aliases)
+    int xmax = 0;
+    double colsum = 0.0;             // Σ_f (x_f + 1), for the algorithmic byte count
+    std::shared_ptr<Slab> slab;      // null: never computed ("-Inf")
+};
+struct HostTab {                     // host mirror of NodeTab allocations
+    int wdim = 0, nrow = 0, k = 0;
+    int cstride[BLG_MAXK] = {0};
+    double* W = nullptr;
+    double* ipow = nullptr;
+    double* coef[BLG_MAXK] = {nullptr};
+    bool built = false;
+};
+
+template <class T> struct DevBuf {
+    T* p = nullptr;
+    size_t cap = 0;
+    void ensure(size_t n) {
+        if (n <= cap) return;
+        if (p) cudaFree(p);
+        p = nullptr;
+        cap = 0;
+        size_t want = std::max<size_t>(n, 16);
+        cudaError_t e = cudaMalloc(&p, want * sizeof(T));
+        if (e != cudaSuccess) throw CudaError(std::string("cudaMalloc: ") + cudaGetErrorString(e));
+        cap = want;
+    }
+    void free_() { if (p) cudaFree(p); p = nullptr; cap = 0; }
+};
+
+}  // namespace
+
+struct blg_handle {
+    int device = 0;
+    cudaStream_t stream = nullptr;
+    bool own_stream = false;
+    std::string err;
+
+    // profiles
+    int N = 0;           // patterns in this shard
+    size_t ld = 0;       // padded family stride
+    std::vector<Col> Tc, Tp;                 // committed / proposal column tables (by id-1)
+    std::vector<uint16_t*> count_allocs;
+    DevBuf<double> weight, fam_ll, partial, result, rootw;
+    std::map<int, std::vector<Slab*>> pool;  // free slabs by row count
+    std::vector<Slab*> all_slabs;
+    int maxcount = 0;
+    DevBuf<double> pascal;
+    int pdim = 0;
+
+    // topology (host)
+    int ncols_model = 0;
+    std::vector<int> parent, child_pos;
+    std::vector<uint8_t> kind;
+    std::vector<double> t;
+    std::vector<std::vector<int>> children;
+    std::vector<int> postorder;
+    bool have_topology = false;
+    // params (host staging)
+    int model_kind = BLG_BRANCH_MODEL;
+    std::vector<double> lam, mu, q;
+    double eta = 0.9;
+    bool have_params = false;
+    // device model arrays
+    DevBuf<uint8_t> d_kind;
+    DevBuf<int> d_parent, d_child_off, d_child_idx, d_list;
+    DevBuf<double> d_t, d_lam, d_mu, d_q, d_eps0, d_eps1;
+    DevBuf<NodeTab> d_tab;
+    std::vector<HostTab> tabs;
+    std::vector<NodeTab> tab_stage;
+    bool tabs_valid = false;
+
+    // accounting of the last likelihood call
+    double last_bytes = 0.0;
+    int last_launches = 0;
+
+    ~blg_handle() {
+        cudaSetDevice(device);
+        if (stream) cudaStreamSynchronize(stream);
+        for (auto* s : all_slabs) { cudaFree(s->ell); cudaFree(s->scl); delete s; }
+        for (auto* c : count_allocs) cudaFree(c);
+        for (auto& tb : tabs) free_tab(tb);
+        weight.free_(); fam_ll.free_(); partial.free_(); result.free_(); rootw.free_(); pascal.free_();
+        d_kind.free_(); d_parent.free_(); d_child_off.free_(); d_child_idx.free_(); d_list.free_();
+        d_t.free_(); d_lam.free_(); d_mu.free_(); d_q.free_(); d_eps0.free_(); d_eps1.free_(); d_tab.free_();
+        if (own_stream && stream) cudaStreamDestroy(stream);
+    }
+    static void free_tab(HostTab& tb) {
+        if (tb.W) cudaFree(tb.W);
+        if (tb.ipow) cudaFree(tb.ipow);
+        for (int i = 0; i < BLG_MAXK; ++i) if (tb.coef[i]) cudaFree(tb.coef[i]);
+        tb = HostTab();
+    }
+
+    // ---- slabs ---------------------------------------------------------------------------------
+    std::shared_ptr<Slab> new_slab(int rows) {
+        Slab* s = nullptr;
+        auto it = pool.find(rows);
+        if (it != pool.end() && !it->second.empty()) { s = it->second.back(); it->second.pop_back(); }
+        else {
+            s = new Slab();
+            s->rows = rows;
+            CK(cudaMalloc(&s->ell, (size_t)rows * ld * sizeof(double)));
+            cudaError_t e = cudaMalloc(&s->scl, ld * sizeof(int));
+            if (e != cudaSuccess) { cudaFree(s->ell); delete s; throw CudaError(std::string("cudaMalloc: ") + cudaGetErrorString(e)); }
+            all_slabs.push_back(s);
+        }
+        blg_handle* self = this;
+        return std::shared_ptr<Slab>(s, [self](Slab* p) { self->pool[p->rows].push_back(p); });
+    }
+    // slab the proposal may overwrite for column c (copy-on-write without the copy: a pruning step
+    // rewrites the whole column for every family)
+    Slab* writable(int c) {
+        Col& col = Tp[c];
+        if (!col.slab || col.slab.use_count() > 1) col.slab = new_slab(col.xmax + 1);
+        return col.slab.get();
+    }
+    Slab* readable(int c) {
+        Col& col = Tp[c];
+        if (!col.slab) {   // never computed: the reference holds -Inf there, i.e. ℓ = 0
+            col.slab = new_slab(col.xmax + 1);
+            zero_slab_kernel<<<296, 256, 0, stream>>>(col.slab->ell, col.slab->scl, (size_t)(col.xmax + 1) * ld, (int)ld);
+            CK(cudaGetLastError());
+        }
+        return col.slab.get();
+    }
+
+    void require(bool c, const char* msg) { if (!c) throw std::runtime_error(msg); }
+
+    // ---- topology helpers ------------------------------------------------------------------------
+    bool present(int i) const { return i >= 0 && i < ncols_model && kind[i] != BLG_ABSENT; }
+    void build_children() {
+        children.assign(ncols_model, {});
+        std::vector<std::vector<std::pair<int, int>>> tmp(ncols_model);
+        for (int i = 0; i < ncols_model; ++i) {
+            if (!present(i) || parent[i] < 0) continue;
+            require(present(parent[i]), "set_topology: parent id is absent");
+            tmp[parent[i]].push_back({child_pos[i], i});
+        }
+        for (int i = 0; i < ncols_model; ++i) {
+            std::sort(tmp[i].begin(), tmp[i].end());
+            for (auto& pr : tmp[i]) children[i].push_back(pr.second);
+            require((int)children[i].size() <= BLG_MAXK, "set_topology: more than 8 children at one node");
+        }
+        postorder.clear();
+        require(present(0) && kind[0] == BLG_ROOT, "set_topology: id 1 must be the root");
+        // iterative post-order from the root
+        std::vector<std::pair<int, size_t>> st;
+        st.push_back({0, 0});
+        while (!st.empty()) {
+            auto& top = st.back();
+            if (top.second < children[top.first].size()) { int c = children[top.first][top.second++]; st.push_back({c, 0}); }
+            else { postorder.push_back(top.first); st.pop_back(); }
+        }
+        int np = 0;
+        for (int i = 0; i < ncols_model; ++i) np += present(i) ? 1 : 0;
+        require((int)postorder.size() == np, "set_topology: graph is not a tree rooted at id 1");
+    }
+
+    ModelDev model_dev() {
+        ModelDev m;
+        m.n = ncols_model; m.model_kind = model_kind;
+        m.kind = d_kind.p; m.parent = d_parent.p; m.child_off = d_child_off.p; m.child_idx = d_child_idx.p;
+        m.t = d_t.p; m.lam = d_lam.p; m.mu = d_mu.p; m.q = d_q.p; m.eta = eta;
+        m.eps0 = d_eps0.p; m.eps1 = d_eps1.p; m.tab = d_tab.p; m.pascal = pascal.p; m.pdim = pdim;
+        return m;
+    }
+
+    // (re)allocate the tables of node i for the current proposal column dims
+    void ensure_tab(int i) {
+        HostTab& tb = tabs[i];
+        int k = (int)children[i].size();
+        int xm = (i < (int)Tp.size()) ? Tp[i].xmax : 0;
+        int wdim = (kind[i] == BLG_ROOT) ? 0 : xm + 1;
+        int nrow = k > 0 ? xm + 1 : 0;
+        bool same = tb.wdim == wdim && tb.nrow == nrow && tb.k == k;
+        for (int c = 1; c < k && same; ++c) {
+            int ci = children[i][c];
+            int cx = (ci < (int)Tp.size()) ? Tp[ci].xmax : 0;
+            if (tb.cstride[c] != cx + 1) same = false;
+        }
+        if (same && (tb.W || wdim == 0) && (tb.ipow || nrow == 0)) return;
+        free_tab(tb);
+        tb.wdim = wdim; tb.nrow = nrow; tb.k = k;
+        if (wdim > 0) CK(cudaMalloc(&tb.W, (size_t)wdim * wdim * sizeof(double)));
+        if (nrow > 0) {
+            CK(cudaMalloc(&tb.ipow, (size_t)nrow * sizeof(double)));
+            for (int c = 1; c < k; ++c) {
+                int ci = children[i][c];
+                int cx = (ci < (int)Tp.size()) ? Tp[ci].xmax : 0;
+                tb.cstride[c] = cx + 1;
+                CK(cudaMalloc(&tb.coef[c], (size_t)nrow * (cx + 1) * sizeof(double)));
+            }
+        }
+    }
+
+    void upload_params() {
+        require(have_topology, "set_params/rebuild: call blg_set_topology first");
+        require(have_params, "rebuild: call blg_set_params first");
+        size_t n = (size_t)ncols_model;
+        d_lam.ensure(n); d_mu.ensure(n); d_q.ensure(n); d_t.ensure(n); d_eps0.ensure(n); d_eps1.ensure(n);
+        CK(cudaMemcpyAsync(d_t.p, t.data(), n * sizeof(double), cudaMemcpyHostToDevice, stream));
+        CK(cudaMemcpyAsync(d_lam.p, lam.data(), n * sizeof(double), cudaMemcpyHostToDevice, stream));
+        CK(cudaMemcpyAsync(d_mu.p, mu.data(), n * sizeof(double), cudaMemcpyHostToDevice, stream));
+        CK(cudaMemcpyAsync(d_q.p, q.data(), n * sizeof(double), cudaMemcpyHostToDevice, stream));
+        // pageable sources: the copies are staged before the call returns
+    }
+
+    void rebuild(const int32_t* nodes, int n) {
+        require(have_topology && have_params, "rebuild: topology and params must be set first");
+        std::vector<int> list;
+        if (nodes == nullptr || n <= 0) list = postorder;
+        else {
+            for (int k = 0; k < n; ++k) {
+                int i = nodes[k] - 1;
+                require(present(i), "rebuild: node id not in the model");
+                list.push_back(i);
+            }
+        }
+        if (!tabs_valid) {
+            require(list.size() == postorder.size(), "rebuild: the topology changed; a full rebuild (nodes = NULL) is required");
+        }
+        if ((int)tabs.size() < ncols_model) tabs.resize(ncols_model);
+        if ((int)tab_stage.size() < ncols_model) tab_stage.resize(ncols_model);
+        int maxdim = 1;
+        for (int i : list) {
+            ensure_tab(i);
+            HostTab& tb = tabs[i];
+            NodeTab nt;
+            memset(&nt, 0, sizeof(nt));
+            nt.W = tb.W; nt.wdim = tb.wdim; nt.ipow = tb.ipow; nt.nrow = tb.nrow;
+            for (int c = 0; c < BLG_MAXK; ++c) { nt.coef[c] = tb.coef[c]; nt.cstride[c] = tb.cstride[c]; }
+            tab_stage[i] = nt;
+            tb.built = true;
+            maxdim = std::max(maxdim, tb.wdim);
+        }
+        d_tab.ensure((size_t)ncols_model);
+        CK(cudaMemcpyAsync(d_tab.p, tab_stage.data(), (size_t)ncols_model * sizeof(NodeTab), cudaMemcpyHostToDevice, stream));
+        d_list.ensure(list.size());
+        CK(cudaMemcpyAsync(d_list.p, list.data(), list.size() * sizeof(int), cudaMemcpyHostToDevice, stream));
+        ModelDev m = model_dev();
+        eps_kernel<<<1, 32, 0, stream>>>(m, d_list.p, (int)list.size());
+        CK(cudaGetLastError());
+        tables_kernel<<<(unsigned)list.size(), 128, 2 * (size_t)maxdim * sizeof(double), stream>>>(m, d_list.p, (int)list.size());
+        CK(cudaGetLastError());
+        // list/tab_stage are host vectors reused by later calls: make sure the copies are done
+        CK(cudaStreamSynchronize(stream));
+        if (list.size() == postorder.size()) tabs_valid = true;
+    }
+
+    // ---- pruning -----------------------------------------------------------------------------------
+    template <int CAP> void launch_prune(const NodeStep& st) {
+        int blocks = (N + 127) / 128;
+        prune_node_kernel<CAP><<<blocks, 128, 0, stream>>>(st, N, ld);
+    }
+    void prune_node(int u) {
+        int k = (int)children[u].size();
+        require(k >= 1, "prune_node: leaf");
+        require(u < (int)Tp.size(), "logpdf: model has more node ids than the profile has columns (call blg_extend)");
+        require(tabs_valid && tabs[u].built, "logpdf: ε/W tables are stale (call blg_rebuild)");
+        NodeStep st;
+        memset(&st, 0, sizeof(st));
+        st.k = k;
+        // children first: reading may allocate zero slabs
+        for (int i = 0; i < k; ++i) {
+            int c = children[u][i];
+            require(c < (int)Tp.size(), "logpdf: child id beyond the profile columns");
+            require(tabs[c].built && tabs[c].wdim == Tp[c].xmax + 1, "logpdf: W table of a child does not match the profile (call blg_rebuild)");
+            ChildRef& cr = st.child[i];
+            if (children[c].empty()) { cr.ell = nullptr; cr.scl = nullptr; }
+            else { Slab* s = readable(c); cr.ell = s->ell; cr.scl = s->scl; last_bytes += 8.0 * Tp[c].colsum + 4.0 * N; }
+            if (children[c].empty()) last_bytes += 2.0 * N;
+            cr.cnt = Tp[c].cnt;
+            cr.W = tabs[c].W;
+            cr.wdim = tabs[c].wdim;
+            cr.id = c;
+            cr.coef = tabs[u].coef[i];
+            cr.cstride = tabs[u].cstride[i];
+            if (i >= 1) require(tabs[u].cstride[i] == Tp[c].xmax + 1, "logpdf: merge table does not match the profile (call blg_rebuild)");
+        }
+        require(tabs[u].nrow == Tp[u].xmax + 1, "logpdf: node table does not match the profile (call blg_rebuild)");
+        Slab* o = writable(u);
+        st.out = o->ell; st.out_scl = o->scl; st.cnt = Tp[u].cnt;
+        st.ipow = tabs[u].ipow; st.eps0 = d_eps0.p;
+        last_bytes += 8.0 * Tp[u].colsum + 4.0 * N;
+        int need = Tp[u].xmax + 1;
+        if (need <= 16) launch_prune<16>(st);
+        else if (need <= 32) launch_prune<32>(st);
+        else if (need <= 64) launch_prune<64>(st);
+        else if (need <= 128) launch_prune<128>(st);
+        else if (need <= 256) launch_prune<256>(st);
+        else if (need <= 512) launch_prune<512>(st);
+        else launch_prune<1024>(st);
+        CK(cudaGetLastError());
+        last_launches++;
+    }
+    void root_reduce(double* d_out) {
+        require(tabs_valid, "logpdf: ε/W tables are stale (call blg_rebuild)");
+        require(!children[0].empty(), "logpdf: the root is a leaf");
+        Slab* s = readable(0);
+        int nrow = Tp[0].xmax + 1;
+        rootw.ensure((size_t)nrow + 1);
+        ModelDev m = model_dev();
+        root_tables_kernel<<<1, 128, 0, stream>>>(m, rootw.p, nrow);
+        CK(cudaGetLastError());
+        int blocks = (N + 255) / 256;
+        partial.ensure((size_t)blocks);
+        root_kernel<<<blocks, 256, 0, stream>>>(s->ell, s->scl, Tp[0].cnt, rootw.p, weight.p, fam_ll.p, partial.p, N, ld);
+        CK(cudaGetLastError());
+        final_reduce_kernel<<<1, 256, 0, stream>>>(partial.p, blocks, d_out);
+        CK(cudaGetLastError());
+        last_bytes += 8.0 * Tp[0].colsum + 4.0 * N + 8.0 * N;
+        last_launches += 3;
+    }
+    void logpdf(int mode, int node, double* d_out) {
+        // mode 0 full, 1 from node, 2 root only
+        require(have_topology, "logpdf: no topology");
+        last_bytes = 0.0;
+        last_launches = 0;
+        if (N == 0) { CK(cudaMemsetAsync(d_out, 0, sizeof(double), stream)); return; }   // profile.jl:56
+        require((int)Tp.size() >= 1, "logpdf: no profile columns");
+        if (mode == 0) {
+            for (int u : postorder) if (!children[u].empty()) prune_node(u);
+        } else if (mode == 1) {
+            int u = node - 1;
+            require(present(u), "logpdf_from: node id not in the model");
+            while (u >= 0) { if (!children[u].empty()) prune_node(u); u = parent[u]; }
+        }
+        root_reduce(d_out);
+    }
+};
+
+// ------------------------------------------------------------------------------------------------
+// C ABI
+// ------------------------------------------------------------------------------------------------
+#define BLG_ENTER(h)                                                    \
+    if (!(h)) return 1;                                                 \
+    try {                                                               \
+        CK(cudaSetDevice((h)->device));
+#define BLG_LEAVE(h)                                                    \
+    }                                                                   \
+    catch (const std::exception& e) { (h)->err = e.what(); return 2; }  \
+    return 0;
+
+extern "C" {
+
+int blg_create(int device, void* stream, blg_handle** out) {
+    if (!out) return 1;
+    *out = nullptr;
+    try {
+        int ndev = 0;
+        cudaError_t e = cudaGetDeviceCount(&ndev);
+        if (e != cudaSuccess || ndev == 0)
+            throw CudaError(std::string("no CUDA device available (") + cudaGetErrorString(e) + "); this library has no CPU path");
+        if (device < 0 || device >= ndev) throw std::runtime_error("blg_create: bad device index");
+        CK(cudaSetDevice(device));
+        auto* h = new blg_handle();
+        h->device = device;
+        if (stream) h->stream = (cudaStream_t)stream;
+        else { CK(cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking)); h->own_stream = true; }
+        h->result.ensure(16);
+        *out = h;
+    } catch (const std::exception& e) { g_create_error = e.what(); return 2; }
+    return 0;
+}
+int blg_destroy(blg_handle* h) { delete h; return 0; }
+const char* blg_last_error(blg_handle* h) { return h ? h->err.c_str() : g_create_error.c_str(); }
+
+int blg_set_profiles(blg_handle* h, const int32_t* X, const int64_t* weight, int ncols, int npatterns) {
+    BLG_ENTER(h)
+    h->require(ncols >= 0 && npatterns >= 0, "set_profiles: negative size");
+    CK(cudaStreamSynchronize(h->stream));
+    h->Tc.clear(); h->Tp.clear();
+    h->pool.clear();
+    for (auto* s : h->all_slabs) { cudaFree(s->ell); cudaFree(s->scl); delete s; }
+    h->all_slabs.clear();
+    for (auto* c : h->count_allocs) cudaFree(c);
+    h->count_allocs.clear();
+    h->N = npatterns;
+    h->ld = ((size_t)npatterns + 127) / 128 * 128;
+    h->tabs_valid = false;
+    for (auto& tb : h->tabs) blg_handle::free_tab(tb);
+    if (npatterns == 0) { h->Tc.clear(); h->Tp.clear(); return 0; }
+    h->require(X && weight, "set_profiles: null pointer");
+    size_t ld = h->ld;
+    std::vector<uint16_t> stage((size_t)ncols * ld, 0);
+    std::vector<Col> cols(ncols);
+    int gmax = 0;
+    for (int c = 0; c < ncols; ++c) {
+        int mx = 0;
+        double cs = 0.0;
+        uint16_t* dst = stage.data() + (size_t)c * ld;
+        for (int f = 0; f < npatterns; ++f) {
+            int32_t v = X[(size_t)f * ncols + c];
+            if (v < 0 || v > BLG_MAXCOUNT) throw std::runtime_error("set_profiles: count outside [0, 1023]");
+            dst[f] = (uint16_t)v;
+            mx = std::max(mx, (int)v);
+            cs += (double)v + 1.0;
+        }
+        cols[c].xmax = mx;
+        cols[c].colsum = cs;
+        gmax = std::max(gmax, mx);
+    }
+    uint16_t* dcnt = nullptr;
+    CK(cudaMalloc(&dcnt, stage.size() * sizeof(uint16_t)));
+    h->count_allocs.push_back(dcnt);
+    CK(cudaMemcpyAsync(dcnt, stage.data(), stage.size() * sizeof(uint16_t), cudaMemcpyHostToDevice, h->stream));
+    for (int c = 0; c < ncols; ++c) cols[c].cnt = dcnt + (size_t)c * ld;
+    std::vector<double> w(ld, 0.0);
+    for (int f = 0; f < npatterns; ++f) w[f] = (double)weight[f];
+    h->weight.ensure(ld);
+    h->fam_ll.ensure(ld);
+    CK(cudaMemcpyAsync(h->weight.p, w.data(), ld * sizeof(double), cudaMemcpyHostToDevice, h->stream));
+    CK(cudaMemsetAsync(h->fam_ll.p, 0, ld * sizeof(double), h->stream));
+    h->maxcount = gmax;
+    int pd = gmax + 1;
+    if (pd > h->pdim) {
+        h->pascal.ensure((size_t)pd * pd);
+        h->pdim = pd;
+        pascal_kernel<<<1, 256, 2 * (size_t)pd * sizeof(double), h->stream>>>(h->pascal.p, pd);
+        CK(cudaGetLastError());
+    }
+    CK(cudaStreamSynchronize(h->stream));
+    h->Tc = cols;
+    h->Tp = cols;
+    BLG_LEAVE(h)
+}
+
+int blg_set_topology(blg_handle* h, int ncols, const int32_t* parent, const uint8_t* kind, const int32_t* child_pos) {
+    BLG_ENTER(h)
+    h->require(ncols >= 1 && parent && kind && child_pos, "set_topology: bad arguments");
+    h->ncols_model = ncols;
+    h->parent.assign(ncols, -1);
+    h->kind.assign(kind, kind + ncols);
+    h->child_pos.assign(child_pos, child_pos + ncols);
+    for (int i = 0; i < ncols; ++i) {
+        if (kind[i] == BLG_ABSENT) continue;
+        h->require(kind[i] <= BLG_WGDAFTER, "set_topology: unknown node kind");
+        h->require(parent[i] >= 0 && parent[i] <= ncols, "set_topology: parent id out of range");
+        h->parent[i] = parent[i] - 1;
+    }
+    h->build_children();
+    for (int i = 0; i < ncols; ++i) {
+        if (!h->present(i)) continue;
+        uint8_t kd = h->kind[i];
+        if (kd == BLG_WGD || kd == BLG_WGT || kd == BLG_WGDAFTER) h->require(h->children[i].size() == 1, "set_topology: wgd/wgt/wgdafter nodes have exactly one child");
+        if (kd == BLG_WGDAFTER) h->require(h->kind[h->parent[i]] == BLG_WGD || h->kind[h->parent[i]] == BLG_WGT, "set_topology: wgdafter must sit below a wgd/wgt node");
+    }
+    size_t n = (size_t)ncols;
+    std::vector<int> off(n + 1, 0), idx;
+    for (int i = 0; i < ncols; ++i) { off[i + 1] = off[i] + (int)h->children[i].size(); for (int c : h->children[i]) idx.push_back(c); }
+    h->d_kind.ensure(n); h->d_parent.ensure(n); h->d_child_off.ensure(n + 1); h->d_child_idx.ensure(std::max<size_t>(idx.size(), 1));
+    CK(cudaMemcpyAsync(h->d_kind.p, h->kind.data(), n, cudaMemcpyHostToDevice, h->stream));
+    CK(cudaMemcpyAsync(h->d_parent.p, h->parent.data(), n * sizeof(int), cudaMemcpyHostToDevice, h->stream));
+    CK(cudaMemcpyAsync(h->d_child_off.p, off.data(), (n + 1) * sizeof(int), cudaMemcpyHostToDevice, h->stream));
+    if (!idx.empty()) CK(cudaMemcpyAsync(h->d_child_idx.p, idx.data(), idx.size() * sizeof(int), cudaMemcpyHostToDevice, h->stream));
+    CK(cudaStreamSynchronize(h->stream));
+    h->have_topology = true;
+    h->have_params = false;
+    h->tabs_valid = false;
+    for (auto& tb : h->tabs) tb.built = false;
+    BLG_LEAVE(h)
+}
+
+int blg_set_params(blg_handle* h, int model_kind, const double* lambda, const double* mu, const double* q, const double* t, double eta) {
+    BLG_ENTER(h)
+    h->require(h->have_topology, "set_params: call blg_set_topology first");
+    h->require(model_kind == BLG_NODE_MODEL || model_kind == BLG_BRANCH_MODEL, "set_params: bad model kind");
+    h->require(lambda && mu && q && t, "set_params: null pointer");
+    int n = h->ncols_model;
+    h->model_kind = model_kind;
+    h->lam.assign(lambda, lambda + n);
+    h->mu.assign(mu, mu + n);
+    h->q.assign(q, q + n);
+    h->t.assign(t, t + n);
+    h->eta = eta;
+    h->have_params = true;
+    h->upload_params();
+    BLG_LEAVE(h)
+}
+
+int blg_rebuild(blg_handle* h, const int32_t* nodes, int n) {
+    BLG_ENTER(h)
+    h->rebuild(nodes, n);
+    BLG_LEAVE(h)
+}
+
+static int logpdf_sync(blg_handle* h, int mode, int node, double* out) {
+    BLG_ENTER(h)
+    h->require(out != nullptr, "logpdf: null output");
+    h->logpdf(mode, node, h->result.p);
+    CK(cudaMemcpyAsync(out, h->result.p, sizeof(double), cudaMemcpyDeviceToHost, h->stream));
+    CK(cudaStreamSynchronize(h->stream));
+    BLG_LEAVE(h)
+}
+static int logpdf_async(blg_handle* h, int mode, int node, double* d_out) {
+    BLG_ENTER(h)
+    h->require(d_out != nullptr, "logpdf: null output");
+    h->logpdf(mode, node, d_out);
+    BLG_LEAVE(h)
+}
+int blg_logpdf_full(blg_handle* h, double* out) { return logpdf_sync(h, 0, 1, out); }
+int blg_logpdf_from(blg_handle* h, int node, double* out) { return logpdf_sync(h, 1, node, out); }
+int blg_logpdf_root(blg_handle* h, double* out) { return logpdf_sync(h, 2, 1, out); }
+int blg_logpdf_full_async(blg_handle* h, double* d_out) { return logpdf_async(h, 0, 1, d_out); }
+int blg_logpdf_from_async(blg_handle* h, int node, double* d_out) { return logpdf_async(h, 1, node, d_out); }
+int blg_logpdf_root_async(blg_handle* h, double* d_out) { return logpdf_async(h, 2, 1, d_out); }
+
+int blg_gradient(blg_handle* h, double*, int, double*) {
+    if (!h) return 1;
+    h->err = "blg_gradient: not built yet in this revision";
+    return 3;
+}
+int blg_gradient_cr(blg_handle* h, double*, double*) {
+    if (!h) return 1;
+    h->err = "blg_gradient_cr: not built yet in this revision";
+    return 3;
+}
+int blg_gradient_async(blg_handle* h, double*, int) {
+    if (!h) return 1;
+    h->err = "blg_gradient_async: not built yet in this revision";
+    return 3;
+}
+
+int blg_commit(blg_handle* h) {
+    BLG_ENTER(h)
+    h->Tc = h->Tp;
+    BLG_LEAVE(h)
+}
+int blg_revert(blg_handle* h) {
+    BLG_ENTER(h)
+    h->Tp = h->Tc;
+    BLG_LEAVE(h)
+}
+int blg_extend(blg_handle* h, int i) {
+    BLG_ENTER(h)
+    if (h->N == 0) return 0;
+    h->require(i >= 1 && i <= (int)h->Tp.size(), "extend: column out of range");
+    Col c = h->Tp[i - 1];
+    c.slab.reset();
+    h->Tp.push_back(c);
+    h->Tp.push_back(c);
+    BLG_LEAVE(h)
+}
+int blg_shrink(blg_handle* h, int i) {
+    BLG_ENTER(h)
+    if (h->N == 0) return 0;
+    h->require(i >= 1 && i + 1 <= (int)h->Tp.size(), "shrink: column out of range");
+    h->Tp.erase(h->Tp.begin() + (i - 1), h->Tp.begin() + (i + 1));
+    BLG_LEAVE(h)
+}
+
+int blg_get_column(blg_handle* h, int pattern, int node, int which, double* out, int cap, int* rows) {
+    BLG_ENTER(h)
+    std::vector<Col>& T = which ? h->Tp : h->Tc;
+    h->require(pattern >= 0 && pattern < h->N, "get_column: pattern out of range");
+    h->require(node >= 1 && node <= (int)T.size(), "get_column: node out of range");
+    Col& c = T[node - 1];
+    CK(cudaStreamSynchronize(h->stream));
+    uint16_t x;
+    CK(cudaMemcpy(&x, c.cnt + pattern, sizeof(uint16_t), cudaMemcpyDeviceToHost));
+    if (rows) *rows = c.xmax + 1;
+    for (int n = 0; n < cap; ++n) out[n] = -INFINITY;
+    bool leaf = h->have_topology && node - 1 < h->ncols_model && h->present(node - 1) && h->children[node - 1].empty();
+    if (leaf) { if (x < cap) out[x] = 0.0; return 0; }     // model.jl:409-410
+    if (!c.slab) return 0;
+    int sc;
+    CK(cudaMemcpy(&sc, c.slab->scl + pattern, sizeof(int), cudaMemcpyDeviceToHost));
+    for (int n = 0; n <= (int)x && n < cap; ++n) {
+        double v;
+        CK(cudaMemcpy(&v, c.slab->ell + (size_t)n * h->ld + pattern, sizeof(double), cudaMemcpyDeviceToHost));
+        out[n] = std::log(v) + (double)sc * 0.6931471805599453;
+    }
+    BLG_LEAVE(h)
+}
+int blg_get_family_logpdf(blg_handle* h, double* out, int n) {
+    BLG_ENTER(h)
+    h->require(n <= h->N, "get_family_logpdf: n exceeds the pattern count");
+    CK(cudaStreamSynchronize(h->stream));
+    if (n > 0) CK(cudaMemcpy(out, h->fam_ll.p, (size_t)n * sizeof(double), cudaMemcpyDeviceToHost));
+    BLG_LEAVE(h)
+}
+int blg_get_eps(blg_handle* h, double* eps_top, double* eps_node, int ncols) {
+    BLG_ENTER(h)
+    h->require(ncols <= h->ncols_model && h->d_eps0.p, "get_eps: nothing built");
+    CK(cudaStreamSynchronize(h->stream));
+    CK(cudaMemcpy(eps_top, h->d_eps0.p, (size_t)ncols * sizeof(double), cudaMemcpyDeviceToHost));
+    CK(cudaMemcpy(eps_node, h->d_eps1.p, (size_t)ncols * sizeof(double), cudaMemcpyDeviceToHost));
+    BLG_LEAVE(h)
+}
+int blg_get_W(blg_handle* h, int node, double* out, int cap, int* dim) {
+    BLG_ENTER(h)
+    h->require(node >= 1 && node <= (int)h->tabs.size(), "get_W: node out of range");
+    HostTab& tb = h->tabs[node - 1];
+    if (dim) *dim = tb.wdim;
+    h->require(tb.W != nullptr && tb.built, "get_W: no table");
+    h->require(cap >= tb.wdim * tb.wdim, "get_W: buffer too small");
+    CK(cudaStreamSynchronize(h->stream));
+    CK(cudaMemcpy(out, tb.W, (size_t)tb.wdim * tb.wdim * sizeof(double), cudaMemcpyDeviceToHost));
+    BLG_LEAVE(h)
+}
+int blg_ncols(blg_handle* h, int which) { return h ? (int)(which ? h->Tp.size() : h->Tc.size()) : -1; }
+int blg_npatterns(blg_handle* h) { return h ? h->N : -1; }
+int blg_last_algorithmic(blg_handle* h, double* bytes, int* launches) {
+    if (!h) return 1;
+    if (bytes) *bytes = h->last_bytes;
+    if (launches) *launches = h->last_launches;
+    return 0;
+}
+int blg_sync(blg_handle* h) {
+    BLG_ENTER(h)
+    CK(cudaStreamSynchronize(h->stream));
+    BLG_LEAVE(h)
+}
+
+}  // extern "C"

@@ -1,0 +1,299 @@
+"""Device-resident replacement of ``Profile``/``PArray`` (src/profile.jl).
+
+The reference keeps, per family, the extended counts ``x``/``xp`` and the log-space DP matrices
+``L``/``Lp`` in a DArray of heap objects and evaluates them with ``mapreduce``.  Here the same state
+lives in one CUDA library handle (include/beluga_b200.h): counts and partial likelihoods are
+node-major, family-contiguous device arrays, ``set!``/``rev!`` are pointer edits, and the likelihood
+entries launch the sm_100a kernels.  Method-for-method:
+
+    logpdf!(d, p), logpdf!(n, p)   profile.jl:56-60   -> logpdf_(d_or_n, p)
+    logpdfroot(n, p)               profile.jl:62-63   -> logpdfroot(n, p)
+    gradient, gradient_cr          profile.jl:71-75   -> gradient(d, p), gradient_cr(d, p)
+    set!, rev!                     profile.jl:79-80   -> set_(p), rev_(p)
+    extend!, shrink!               profile.jl:108-109 -> extend_(p, i), shrink_(p, i)
+"""
+import ctypes as C
+
+import numpy as np
+
+from . import _lib
+from .model import BRANCH, NODE, DLWGD, ModelNode, build_model, postwalk
+from .parallel import allreduce_sum_, dist_info, shard_range
+
+_MK = {NODE: 0, BRANCH: 1}
+
+
+def _dp(a):
+    return a.ctypes.data_as(C.POINTER(C.c_double))
+
+
+class PArray:
+    """PArray{Float64}: the phylogenetic profile matrix of one process / one GPU.
+
+    X: (npatterns, ncols) extended counts (``permutedims(M)`` of model.jl:48, one row per site
+    pattern), weights: pattern multiplicities.  ``X is None`` is the mock profile ``PArray()``
+    (profile.jl:28,31) and needs no GPU.  With ``distributed=True`` the patterns passed in are this
+    rank's shard and every likelihood/gradient is all-reduced over torch.distributed."""
+
+    def __init__(self, X=None, weights=None, device=0, distributed=False):
+        self.h = None
+        self.L = None
+        self.distributed = bool(distributed)
+        self._model = None
+        self._topo_seen = self._param_seen = self._seq_seen = -1
+        self._torch_out = None
+        if X is None:
+            self.N = 0
+            self.ncols0 = 0
+            return
+        X = np.ascontiguousarray(X, dtype=np.int32)
+        weights = np.ascontiguousarray(weights, dtype=np.int64)
+        assert X.ndim == 2 and weights.shape == (X.shape[0],)
+        self.N = X.shape[0]
+        self.ncols0 = X.shape[1]
+        self.L = _lib.lib()
+        stream = None
+        if self.distributed:
+            import torch
+            torch.cuda.set_device(device)
+            stream = C.c_void_p(torch.cuda.current_stream().cuda_stream)
+        h = C.c_void_p()
+        rc = self.L.blg_create(int(device), stream, C.byref(h))
+        if rc != 0:
+            raise _lib.BelugaError(self.L.blg_last_error(None).decode())
+        self.h = h
+        self.device = int(device)
+        self._ck(self.L.blg_set_profiles(self.h, X.ctypes.data_as(C.POINTER(C.c_int32)),
+                                         weights.ctypes.data_as(C.POINTER(C.c_int64)), X.shape[1], X.shape[0]))
+
+    def __del__(self):
+        try:
+            if self.h is not None:
+                self.L.blg_destroy(self.h)
+                self.h = None
+        except Exception:
+            pass
+
+    def __len__(self):
+        return self.N
+
+    def __repr__(self):
+        return "PArray{Float64}(%d)" % self.N
+
+    def _ck(self, rc):
+        if rc != 0:
+            raise _lib.BelugaError(self.L.blg_last_error(self.h).decode())
+
+    # ---- model → device mirroring -----------------------------------------------------------------
+    def sync(self, model):
+        """Replay on the device what the reference did eagerly on the host since the last call:
+        topology edits, θ changes and the set!(n) requests recorded by update!/set!."""
+        if self.h is None:
+            return
+        full = False
+        if self._model is not model or self._topo_seen != model._topo_version:
+            n, parent, kind, cpos = model.flat_topology()
+            self._ck(self.L.blg_set_topology(self.h, n, parent.ctypes.data_as(C.POINTER(C.c_int32)),
+                                             kind.ctypes.data_as(C.POINTER(C.c_uint8)),
+                                             cpos.ctypes.data_as(C.POINTER(C.c_int32))))
+            full = True
+            self._param_seen = -1
+        if self._param_seen != model._param_version or full:
+            lam, mu, q, t, eta = model.flat_params()
+            self._ck(self.L.blg_set_params(self.h, _MK[model.nt], _dp(lam), _dp(mu), _dp(q), _dp(t), eta))
+        if self._model is not model or self._seq_seen < model._log_start:
+            full = True
+        ids = []
+        for seq, req in model._log:
+            if seq <= self._seq_seen:
+                continue
+            if req is None:
+                full = True
+            else:
+                ids.extend(req)
+        if full:
+            self._ck(self.L.blg_rebuild(self.h, None, 0))
+        elif ids:
+            arr = np.asarray(ids, dtype=np.int32)
+            self._ck(self.L.blg_rebuild(self.h, arr.ctypes.data_as(C.POINTER(C.c_int32)), len(arr)))
+        self._model = model
+        self._topo_seen = model._topo_version
+        self._param_seen = model._param_version
+        self._seq_seen = model._seq
+
+    # ---- likelihood -----------------------------------------------------------------------------------
+    def _run(self, mode, node):
+        if self.distributed:
+            import torch
+            if self._torch_out is None:
+                self._torch_out = torch.zeros(1, dtype=torch.float64, device="cuda:%d" % self.device)
+            ptr = C.c_void_p(self._torch_out.data_ptr())
+            if mode == 0:
+                self._ck(self.L.blg_logpdf_full_async(self.h, ptr))
+            elif mode == 1:
+                self._ck(self.L.blg_logpdf_from_async(self.h, node, ptr))
+            else:
+                self._ck(self.L.blg_logpdf_root_async(self.h, ptr))
+            allreduce_sum_(self._torch_out)
+            return float(self._torch_out.item())
+        out = C.c_double()
+        if mode == 0:
+            self._ck(self.L.blg_logpdf_full(self.h, C.byref(out)))
+        elif mode == 1:
+            self._ck(self.L.blg_logpdf_from(self.h, node, C.byref(out)))
+        else:
+            self._ck(self.L.blg_logpdf_root(self.h, C.byref(out)))
+        return out.value
+
+    def logpdf_(self, x):
+        if self.N == 0 and not self.distributed:
+            return 0.0                                                   # profile.jl:56
+        if isinstance(x, DLWGD):
+            self.sync(x)
+            return self._run(0, 1)
+        self.sync(x.model)
+        return self._run(1, x.i)
+
+    def logpdfroot(self, n):
+        if self.N == 0 and not self.distributed:
+            return 0.0
+        self.sync(n.model)
+        return self._run(2, 1)
+
+    # ---- accept / reject / reversible jump ---------------------------------------------------------------
+    def set_(self):
+        if self.h is not None:
+            self._ck(self.L.blg_commit(self.h))
+
+    def rev_(self):
+        if self.h is not None:
+            self._ck(self.L.blg_revert(self.h))
+
+    def extend_(self, i):
+        if self.h is not None:
+            self._ck(self.L.blg_extend(self.h, int(i)))
+
+    def shrink_(self, i):
+        if self.h is not None:
+            self._ck(self.L.blg_shrink(self.h, int(i)))
+
+    # ---- inspection ---------------------------------------------------------------------------------------
+    def column(self, pattern, node, proposal=True):
+        cap = 1024
+        out = np.full(cap, np.nan)
+        rows = C.c_int()
+        self._ck(self.L.blg_get_column(self.h, int(pattern), int(node), 1 if proposal else 0, _dp(out), cap, C.byref(rows)))
+        return out[: rows.value]
+
+    def family_logpdf(self):
+        out = np.zeros(self.N)
+        self._ck(self.L.blg_get_family_logpdf(self.h, _dp(out), self.N))
+        return out
+
+    def eps(self):
+        n = self.L.blg_ncols(self.h, 1) if self._model is None else max(self._model.nodes)
+        e0, e1 = np.zeros(n), np.zeros(n)
+        self._ck(self.L.blg_get_eps(self.h, _dp(e0), _dp(e1), n))
+        return e0, e1
+
+    def W(self, node):
+        dim = C.c_int()
+        cap = 1024 * 1024
+        out = np.zeros(cap)
+        self._ck(self.L.blg_get_W(self.h, int(node), _dp(out), cap, C.byref(dim)))
+        d = dim.value
+        return out[: d * d].reshape(d, d).copy()
+
+    def ncols(self, proposal=True):
+        return self.L.blg_ncols(self.h, 1 if proposal else 0)
+
+    def last_algorithmic(self):
+        b, l = C.c_double(), C.c_int()
+        self.L.blg_last_algorithmic(self.h, C.byref(b), C.byref(l))
+        return b.value, l.value
+
+    def synchronize(self):
+        if self.h is not None:
+            self._ck(self.L.blg_sync(self.h))
+
+
+# ---- profile construction, src/model.jl:40-49 ---------------------------------------------------------
+def _as_table(df):
+    """Accept a pandas DataFrame, a (names, counts) pair or a dict name -> column."""
+    if hasattr(df, "columns") and hasattr(df, "to_numpy"):
+        return [str(c) for c in df.columns], np.asarray(df.to_numpy(), dtype=np.int64)
+    if isinstance(df, dict):
+        names = list(df.keys())
+        return names, np.stack([np.asarray(df[k], dtype=np.int64) for k in names], axis=1)
+    names, counts = df
+    return list(names), np.asarray(counts, dtype=np.int64)
+
+
+def profile(t, leaves, df):
+    """profile(t, l, df): site-pattern compression (unique rows + multiplicity, first-appearance
+    order) and extended counts (leaf = observed count, internal = Σ children).
+    -> (X [npatterns × nnodes], weights, m)."""
+    names, counts = _as_table(df)
+    col = {nm: j for j, nm in enumerate(names)}
+    if counts.shape[0] == 0:
+        raise ValueError("empty count table")
+    uniq, first, mult = np.unique(counts, axis=0, return_index=True, return_counts=True)
+    order = np.argsort(first, kind="stable")
+    uniq, mult = uniq[order], mult[order]
+    nn = max(leaves) if leaves else 1
+    nodes = []
+    stack = [t]
+    while stack:
+        n = stack.pop()
+        nodes.append(n)
+        stack.extend(n.c)
+    nn = len(nodes)
+    M = np.zeros((uniq.shape[0], nn), dtype=np.int64)
+    for n in reversed(nodes):          # reversed pre-order visits children before parents
+        if not n.c:
+            M[:, n.i - 1] = uniq[:, col[leaves[n.i]]]
+        else:
+            M[:, n.i - 1] = sum(M[:, c.i - 1] for c in n.c)
+    return M, mult.astype(np.int64), int(M.max()) + 1
+
+
+def DLWGD_(nw, df=None, lam=1.0, mu=1.0, eta=0.9, nt=BRANCH, device=0, distributed=False):
+    """(model, data) = DLWGD(nw, df, λ, μ, η, nt)   (src/model.jl:22-36).
+
+    With ``distributed=True`` every rank passes the SAME table; patterns are compressed globally and
+    each rank keeps a contiguous block of them (families shard across GPUs)."""
+    model, t, l = build_model(nw, lam, mu, eta, nt)
+    if df is None:
+        return model, PArray()
+    X, w, _m = profile(t, l, df)
+    if distributed:
+        rank, world = dist_info()
+        lo, hi = shard_range(X.shape[0], rank, world)
+        X, w = X[lo:hi], w[lo:hi]
+    return model, PArray(X, w, device=device, distributed=distributed)
+
+
+# ---- free functions with the reference's names ------------------------------------------------------------
+def logpdf_(x, p):
+    return p.logpdf_(x)
+
+
+def logpdfroot(n, p):
+    return p.logpdfroot(n)
+
+
+def set_(x):
+    """set!(p::PArray) (profile.jl:79) or set!(d::DLWGD) (model.jl:56-60)."""
+    x.set_()
+
+
+def rev_(p):
+    p.rev_()
+
+
+def extend_(p, i):
+    p.extend_(i)
+
+
+def shrink_(p, i):
+    p.shrink_(i)

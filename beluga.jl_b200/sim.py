@@ -1,0 +1,137 @@
+"""Synthetic inputs for tests and benchmarks.
+
+``rand_profiles`` is a COUNT-LEVEL sampler of the DLWGD model, equal in distribution to what
+``rand(model, N)`` (src/sim.jl:17-49) is meant to draw: root lineages ~ Geometric(η)+1
+(sim.jl:78), each lineage evolving along each branch under the linear birth–death process with the
+branch's (λ, μ) (sim.jl:124-145, here through its closed-form transition law: extinct w.p. ϕ(t),
+otherwise 1 + Geometric(1-ψ(t)) descendants, utils.jl:8-9), each lineage doubling w.p. q at a WGD
+node (sim.jl:112-115).  One deliberate difference: the reference's gene-tree simulator skips the
+branch segment between a WGD and the next speciation (sim.jl:94-96 jumps over the wgdafter node
+without simulating the child's remaining branch); this sampler simulates that segment, i.e. it
+draws from the model whose likelihood the hot path evaluates.  Benchmark-input generation is not on
+the hot path."""
+import numpy as np
+
+from .model import isawgd, isleaf, iswgd, iswgdafter, iswgt, nonwgdchild, nonwgdparent, prewalk
+
+
+def random_tree_newick(ntaxa, seed=20261019, height=1.0, prefix="t"):
+    """Kingman-coalescent topology and times, rescaled to the given root height (ultrametric)."""
+    rng = np.random.default_rng(seed)
+    nodes = [("%s%03d" % (prefix, i), 0.0) for i in range(ntaxa)]   # (newick string without length, height)
+    k = ntaxa
+    tnow = 0.0
+    events = []
+    live = list(range(ntaxa))
+    sub = {i: (nodes[i][0], 0.0) for i in live}
+    nxt = ntaxa
+    while k > 1:
+        tnow += rng.exponential(1.0 / (k * (k - 1) / 2.0))
+        a, b = rng.choice(len(live), size=2, replace=False)
+        ia, ib = live[a], live[b]
+        events.append((ia, ib, tnow))
+        sub[nxt] = (None, tnow, ia, ib)
+        live = [x for j, x in enumerate(live) if j not in (a, b)] + [nxt]
+        nxt += 1
+        k -= 1
+    scale = height / tnow
+
+    def render(i, parent_h):
+        rec = sub[i]
+        if rec[0] is not None:
+            return "%s:%.10f" % (rec[0], (parent_h - 0.0) * scale)
+        _, h, a, b = rec
+        inner = "(%s,%s)" % (render(a, h), render(b, h))
+        if parent_h is None:
+            return inner + ";"
+        return "%s:%.10f" % (inner, (parent_h - h) * scale)
+
+    return render(nxt - 1, None)
+
+
+def _phi_psi(t, lam, mu):
+    if abs(lam - mu) <= 1.4901161193847656e-8 * max(abs(lam), abs(mu)):
+        v = lam * t / (1.0 + lam * t)
+        return v, v
+    e = np.exp(t * (lam - mu))
+    phi = mu * (e - 1.0) / (lam * e - mu)
+    return phi, (lam / mu) * phi
+
+
+def _branch_rates(model, parent, child):
+    """getλμ(nonwgdparent(node), nonwgdchild(c)) as src/sim.jl:108 calls it (src/node.jl:220-230)."""
+    a, b = nonwgdparent(parent), nonwgdchild(child)
+    if model.nt == "Node":
+        return 0.5 * (a["λ"] + b["λ"]), 0.5 * (a["μ"] + b["μ"])
+    return b["λ"], b["μ"]
+
+
+def _evolve(rng, n, t, lam, mu):
+    """n lineages through a branch of length t under the linear BDP: vector in, vector out."""
+    if t <= 0.0:
+        return n
+    phi, psi = _phi_psi(t, lam, mu)
+    surv = rng.binomial(n, 1.0 - phi)
+    extra = np.zeros_like(n)
+    pos = surv > 0
+    if psi > 0.0 and pos.any():
+        extra[pos] = rng.negative_binomial(surv[pos], 1.0 - psi)
+    return surv + extra
+
+
+def rand_counts(model, N, rng):
+    """N unconditioned draws; returns (leaf_ids, counts[N × nleaves])."""
+    root = model.nodes[1]
+    at = {1: rng.geometric(root["η"], size=N).astype(np.int64)}
+    for n in prewalk(root):
+        x = at[n.i]
+        for c in n.c:
+            if iswgt(n):
+                raise NotImplementedError("sampling through WGT nodes is not supported")
+            y = x
+            if iswgd(n):
+                y = x + rng.binomial(x, n["q"])          # retention of the duplicate w.p. q
+            lam, mu = _branch_rates(model, n, c)
+            at[c.i] = _evolve(rng, y, c["t"], lam, mu)
+    leaf_ids = sorted(i for i, nd in model.nodes.items() if isleaf(nd))
+    return leaf_ids, np.stack([at[i] for i in leaf_ids], axis=1)
+
+
+def rootclades(model):
+    """Beluga.rootclades(d) (src/sim.jl:51): leaf ids below each child of the root."""
+    out = []
+    for c in model.nodes[1].c:
+        out.append(sorted(n.i for n in prewalk(c) if isleaf(n)))
+    return out
+
+
+def rand_profiles(model, N, seed=20261019, condition="rootclades", max_leaf=None, max_rootsum=None):
+    """rand(model, N, condition=…): rejection-sample N profiles.  ``condition``: "rootclades" (at least one
+    gene in each clade stemming from the root), "nonextinct" (the reference's default) or None.
+    max_leaf / max_rootsum additionally reject families with a leaf count / total count above the bound.
+    -> (names sorted alphabetically like DataFrame(sort(profile)), counts[N × ntaxa])."""
+    rng = np.random.default_rng(seed)
+    out = []
+    have = 0
+    leaf_ids = None
+    clades = rootclades(model) if condition == "rootclades" else None
+    while have < N:
+        leaf_ids, c = rand_counts(model, max(1024, int((N - have) * 1.5)), rng)
+        keep = np.ones(c.shape[0], dtype=bool)
+        if condition == "rootclades":
+            pos = {i: k for k, i in enumerate(leaf_ids)}
+            for cl in clades:
+                keep &= c[:, [pos[i] for i in cl]].sum(axis=1) > 0
+        elif condition == "nonextinct":
+            keep &= c.sum(axis=1) > 0
+        if max_leaf is not None:
+            keep &= c.max(axis=1) <= max_leaf
+        if max_rootsum is not None:
+            keep &= c.sum(axis=1) <= max_rootsum
+        c = c[keep]
+        out.append(c)
+        have += c.shape[0]
+    counts = np.concatenate(out, axis=0)[:N]
+    names = [model.leaves[i] for i in leaf_ids]
+    order = np.argsort(names)
+    return [names[k] for k in order], counts[:, order]

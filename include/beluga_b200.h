@@ -1,0 +1,128 @@
+/*
+ * beluga_b200.h — C ABI of the B200-native gene-family likelihood library.
+ *
+ * Drop-in boundary for ONE hot path of arzwa/Beluga.jl: the Csűrös–Miklós conditional-survival
+ * pruning likelihood behind logpdf!(model, profile) for the DLWGD model.  The reference has no
+ * FFI boundary of its own (pure Julia); each entry below names the Julia method it backs
+ * (file:line under the reference tree).  The Julia-side `ccall` stubs are in INTEGRATION.md and
+ * julia/BelugaB200.jl; the Python mirror used by the tests is beluga.jl_b200/.
+ *
+ * Conventions
+ *   - plain C: opaque handle, pointers and sizes only; no exceptions or aborts cross the ABI.
+ *   - every entry returns int: 0 = ok, non-zero = error (message via blg_last_error).
+ *   - numerical failures are VALUES, not errors: a family whose likelihood is not finite
+ *     contributes -Inf (model.jl:351,366,384,391).
+ *   - node ids are the reference's: 1-based, pre-order over the Newick tree (root = 1), WGD
+ *     pairs appended (wgd = max+1, wgdafter = max+2, model.jl:106-138).  Arrays "by id" are
+ *     indexed id-1 and have `ncols` entries (ncols = largest id in use).
+ *   - one handle drives ONE GPU on ONE stream.  Families shard across GPUs by giving each
+ *     process/handle a contiguous block of patterns (profile.jl:27,34-37 is the same DP); the
+ *     only cross-GPU step is the sum of the returned scalars / gradient vectors.
+ *   - host pointers are borrowed for the duration of the call only.  `d_*` pointers are device
+ *     pointers on the handle's device.
+ *   - not re-entrant per handle; independent handles are independent.
+ */
+#ifndef BELUGA_B200_H
+#define BELUGA_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct blg_handle blg_handle;
+
+/* node kinds: node.jl:38-66 (:root, :sp, :wgd, :wgt, :wgdafter); BLG_ABSENT marks an id that is
+ * not in model.nodes (possible between removewgd!(…, reindex=false) and reindex!, rjmcmc.jl:602) */
+enum { BLG_ROOT = 0, BLG_SP = 1, BLG_WGD = 2, BLG_WGT = 3, BLG_WGDAFTER = 4, BLG_ABSENT = 255 };
+/* node.jl:12-26: rates on nodes (branch rate = mean of flanking nodes) or on branches */
+enum { BLG_NODE_MODEL = 0, BLG_BRANCH_MODEL = 1 };
+
+/* --- lifetime ------------------------------------------------------------------------------
+ * backs DLWGD(nw, df, …) (model.jl:22-28) / the finalizer of the PArray replacement.
+ * `stream`: a cudaStream_t to run on (e.g. torch's current stream), or NULL to create one. */
+int blg_create(int device, void* stream, blg_handle** out);
+int blg_destroy(blg_handle* h);
+/* h may be NULL: message of the last failed blg_create on this thread */
+const char* blg_last_error(blg_handle* h);
+
+/* --- profiles: Profile(X, n) (profile.jl:36-37) -----------------------------------------------
+ * X is permutedims(M) of model.jl:48: ncols × npatterns, node (id-1) fastest; `weight` the
+ * site-pattern multiplicities (x1 of model.jl:41).  The library re-lays the counts out
+ * node-major / family-contiguous on the device and owns all partial-likelihood storage
+ * (committed L and proposal Lp, profile.jl:14-20).  npatterns == 0 is the mock profile
+ * (profile.jl:28,31): every likelihood entry then returns 0. */
+int blg_set_profiles(blg_handle* h, const int32_t* X, const int64_t* weight, int ncols, int npatterns);
+
+/* --- model graph: initmodel (model.jl:227-244), addwgd!/addwgt!/removewgd!/reindex!
+ * (model.jl:106-183) -----------------------------------------------------------------------------
+ * parent[i]: id of the parent (0 for the root); kind[i]: BLG_*; child_pos[i]: position of node
+ * i+1 in its parent's child vector (the iteration order of n.c).  A topology change invalidates
+ * every ε/W table: follow with blg_set_params and blg_rebuild(h, NULL, 0). */
+int blg_set_topology(blg_handle* h, int ncols, const int32_t* parent, const uint8_t* kind,
+                     const int32_t* child_pos);
+
+/* --- parameters: set!(d) (model.jl:56-60), update!(n, …) (node.jl:99-116), setrates!
+ * (model.jl:69-76) -------------------------------------------------------------------------------
+ * blg_set_params uploads θ (arrays by id: λ/μ are read at non-WGD ids, q at wgd/wgt ids, t — the
+ * branch length above the node, θ[:t] — at every id).
+ * blg_rebuild runs the on-device ε/W build — set!(n) = setϵ!(n); setW!(n) (node.jl:118-179) —
+ * for the listed ids in the listed order; nodes == NULL or n == 0 means all nodes in post-order
+ * (set!(d)).  update!(n) on a Branch model is the path n→root (setabove!, node.jl:123-128); on a
+ * Node model the children of n first (setbelow!, node.jl:130-134). */
+int blg_set_params(blg_handle* h, int model_kind, const double* lambda, const double* mu,
+                   const double* q, const double* t, double eta);
+int blg_rebuild(blg_handle* h, const int32_t* nodes, int n);
+
+/* --- likelihood ----------------------------------------------------------------------------------
+ * All three write the proposal state (Lp) and return Σ weight·logL over this handle's patterns;
+ * -Inf if any family is not finite.  The *_async forms leave the scalar in device memory
+ * (d_out, 8 bytes) on the handle's stream without synchronising, so an NCCL all-reduce can be
+ * issued behind it on the same stream. */
+int blg_logpdf_full(blg_handle* h, double* out);            /* logpdf!(d, p)      profile.jl:56-57 */
+int blg_logpdf_from(blg_handle* h, int node, double* out);  /* logpdf!(d[i], p)   profile.jl:59-60 */
+int blg_logpdf_root(blg_handle* h, double* out);            /* logpdfroot(n, p)   profile.jl:62-63 */
+int blg_logpdf_full_async(blg_handle* h, double* d_out);
+int blg_logpdf_from_async(blg_handle* h, int node, double* d_out);
+int blg_logpdf_root_async(blg_handle* h, double* d_out);
+
+/* --- gradient: gradient(d, p) / gradient_cr(d, p) (profile.jl:71-75, model.jl:517-533) -----------
+ * g has 2n+k+1 entries laid out as asvector (model.jl:541-546): [λ_1..λ_n, μ_1..μ_n, q…, η] with
+ * n = number of non-WGD nodes; the q block is ordered by ASCENDING wgd id (the order model(θ),
+ * model.jl:320-322, reads it; asvector itself lists them descending — see INTEGRATION.md).
+ * Does not disturb the committed or proposal state (the reference uses a fresh L, model.jl:395). */
+int blg_gradient(blg_handle* h, double* g, int len, double* logpdf_out);
+int blg_gradient_cr(blg_handle* h, double* g2, double* logpdf_out);
+int blg_gradient_async(blg_handle* h, double* d_g, int len);   /* d_g[0] = logL, d_g[1..] = ∇ */
+
+/* --- accept / reject / reversible jump: set!, rev!, extend!, shrink! (profile.jl:79-121) --------
+ * commit: proposal becomes committed (Lp→L, xp→x); revert: the reverse.  Both are O(#nodes)
+ * pointer edits, no bulk copies.  extend appends two columns (ids ncols+1, ncols+2) whose counts
+ * equal column i's and whose partial likelihoods are "-Inf"; shrink deletes columns i and i+1 and
+ * renumbers — in the proposal state only. */
+int blg_commit(blg_handle* h);
+int blg_revert(blg_handle* h);
+int blg_extend(blg_handle* h, int i);
+int blg_shrink(blg_handle* h, int i);
+
+/* --- inspection (tests; test/tests.jl:9-12 compares L[:,1]) --------------------------------------
+ * blg_get_column: log-space column of one pattern/node as the reference would hold it in Lp
+ * (which = 1) or L (which = 0); entries above the pattern's count are -Inf.  Returns the count
+ * bound+1 of that column in *rows. */
+int blg_get_column(blg_handle* h, int pattern, int node, int which, double* out, int cap, int* rows);
+int blg_get_family_logpdf(blg_handle* h, double* out, int n);      /* per-pattern logL of the last call */
+int blg_get_eps(blg_handle* h, double* eps_top, double* eps_node, int ncols);  /* ϵ[1], ϵ[2] by id */
+int blg_get_W(blg_handle* h, int node, double* out, int cap, int* dim);        /* row-major [n][j] */
+int blg_ncols(blg_handle* h, int which);
+int blg_npatterns(blg_handle* h);
+/* algorithmic bytes (definition of SURVEY.md §8(d): each internal column written once and read once by
+ * its parent, 2 B per leaf count, 4 B per stored scale exponent, 8 B per family result) and the number
+ * of kernels the last likelihood call launched */
+int blg_last_algorithmic(blg_handle* h, double* bytes, int* launches);
+int blg_sync(blg_handle* h);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

@@ -1,0 +1,150 @@
+"""Host-side logic (model graph mirror, profile construction, ABI surface, sharding) against the
+oracle.  CPU only — no compute call goes through the CUDA library here."""
+import ctypes
+import os
+import re
+
+import numpy as np
+import pytest
+
+import beluga_b200 as B
+from beluga_b200 import _lib
+from beluga_b200.model import KIND_CODE, build_model
+from conftest import DF1, ROOT, S1, read_csv, read_nw
+from oracle.oracle import BRANCH as OBRANCH, NODE as ONODE, OracleDLWGD
+
+
+def assert_same_graph(model, orc):
+    n, parent, kind, cpos = model.flat_topology()
+    e = orc.export()
+    assert n == orc.maxid
+    okind = np.where(e["kind"] < 0, 255, e["kind"]).astype(np.uint8)
+    np.testing.assert_array_equal(kind, okind)
+    present = kind != 255
+    np.testing.assert_array_equal(parent[present], e["parent"][present])
+    np.testing.assert_array_equal(cpos[present], e["child_pos"][present])
+    lam, mu, q, t, eta = model.flat_params()
+    np.testing.assert_array_equal(t[present], e["t"][present])
+    sp = present & (kind <= 1)
+    np.testing.assert_array_equal(lam[sp], e["lam"][sp])
+    np.testing.assert_array_equal(mu[sp], e["mu"][sp])
+    wg = present & ((kind == 2) | (kind == 3))
+    np.testing.assert_array_equal(q[wg], e["q"][wg])
+    assert eta == e["eta"]
+
+
+@pytest.mark.parametrize("tree,csv", [("plants1.nw", "plants1-100.csv"), ("9dicots.nw", "9dicots-f01-100.csv"),
+                                      ("12monocots.nw", "12monocots-f01-250.csv")])
+def test_newick_ids_and_profile_match_oracle(tree, csv):
+    nw = read_nw(tree)
+    names, counts = read_csv(csv)
+    model, t, l = build_model(nw, 0.3, 0.4, 0.8, B.NODE)
+    orc = OracleDLWGD(nw, names, counts, 0.3, 0.4, 0.8, ONODE)
+    assert_same_graph(model, orc)
+    X, w, m = B.profile(t, l, (names, counts))
+    ow, ox = orc.profile()
+    np.testing.assert_array_equal(w, ow)
+    np.testing.assert_array_equal(X, ox)
+    assert max(3, m) == orc.m
+    assert w.sum() == counts.shape[0]
+
+
+def test_wgd_insert_remove_reindex_bookkeeping():      # test/tests.jl:95-110 on the host mirror
+    model, _, _ = build_model(S1, 0.2, 0.3, 1 / 1.5, B.NODE)
+    orc = OracleDLWGD(S1, *DF1, 0.2, 0.3, 1 / 1.5, ONODE)
+    for (i, t, q) in [(3, 2.0, 0.2), (3, 1.0, 0.3), (2, 1.0, 0.4)]:
+        w = B.addwgd_(model, model[i], t, q)
+        assert w.i == orc.addwgd(i, t, q)
+        assert_same_graph(model, orc)
+    B.removewgd_(model, model[8])
+    orc.removewgd(8)
+    assert model[8]["q"] == 0.3 and model[10]["q"] == 0.4
+    assert_same_graph(model, orc)
+    B.removewgd_(model, model[10])
+    orc.removewgd(10)
+    assert model[8]["q"] == 0.3
+    assert "q" not in model[9].theta
+    assert 10 not in model.nodes and 11 not in model.nodes
+    assert_same_graph(model, orc)
+    assert model.getwgds() == orc.getwgds()
+    np.testing.assert_array_equal(model.asvector(), orc.asvector())
+    assert model.ne() == orc.ne and model.nwgd() == orc.nwgd
+
+
+def test_remove_without_reindex_leaves_gap_then_reinsert():   # rjmcmc.jl:591-620 flow
+    model, _, _ = build_model(read_nw("plants1.nw"), 0.5, 0.6, 0.7, B.BRANCH)
+    orc = OracleDLWGD(read_nw("plants1.nw"), None, None, 0.5, 0.6, 0.7, OBRANCH)
+    w1 = B.addwgd_(model, model[6], 0.3, 0.2); orc.addwgd(6, 0.3, 0.2)
+    w2 = B.addwgd_(model, model[9], 0.1, 0.6); orc.addwgd(9, 0.1, 0.6)
+    after = w1.c[0]
+    child = B.removewgd_(model, w1, False, True)
+    assert child.i == orc.removewgd(w1.i, False, True)
+    assert_same_graph(model, orc)                 # ids 20, 21 absent, 22, 23 present
+    n, parent, kind, cpos = model.flat_topology()
+    assert kind[w1.i - 1] == 255 and kind[w1.i] == 255
+    model.insertwgd_(child, w1, after)            # the rejected-move path puts the pair back
+    assert model[w1.i] is w1 and w1.c[0] is after and after.c[0] is child
+
+
+def test_model_functor_matches_oracle(plants1c):
+    nw, (names, counts) = plants1c
+    model, _, _ = build_model(nw, 2.0, 1.0, 0.9, B.BRANCH)
+    orc = OracleDLWGD(nw, names, counts, 2.0, 1.0, 0.9, OBRANCH)
+    B.addwgd_(model, model[6], 0.01, 0.25); orc.addwgd(6, 0.01, 0.25)
+    v = model.asvector()
+    np.testing.assert_array_equal(v, orc.asvector())
+    rng = np.random.default_rng(1)
+    th = rng.random(len(v))
+    m2 = model(th)
+    orc.set_from_vector(th)
+    assert_same_graph(m2, orc)
+    np.testing.assert_array_equal(m2.asvector(), th)
+
+
+def test_update_records_reference_refresh_order():
+    for nt, want in ((B.BRANCH, [5, 4, 2, 1]), (B.NODE, [6, 7, 5, 4, 2, 1])):
+        model, _, _ = build_model(read_nw("plants1.nw"), 0.5, 0.6, 0.7, nt)
+        B.update_(model[5], λ=1.5, μ=1.2)          # README.md:50
+        assert model._log[-1][1] == want
+        assert model[5]["λ"] == 1.5 and model[5]["μ"] == 1.2
+        B.update_(model[1], "η", 0.91)
+        assert model[1]["η"] == 0.91
+
+
+def test_mock_profile_returns_zero():             # profile.jl:28,31,56; test/rjmcmc.jl:3-24 relies on it
+    model, data = B.DLWGD(read_nw("plants1.nw"), None, 1.0, 1.0, 0.9)
+    assert len(data) == 0
+    assert B.logpdf_(model, data) == 0.0
+    assert B.logpdf_(model[5], data) == 0.0
+    assert B.logpdfroot(model[1], data) == 0.0
+    B.extend_(data, 3); B.set_(data); B.rev_(data)
+
+
+def test_shared_library_exports_every_declared_symbol():
+    import __graft_entry__
+    __graft_entry__.build()
+    header = open(os.path.join(ROOT, "include", "beluga_b200.h")).read()
+    declared = set(re.findall(r"\b(blg_[a-z_A-Z0-9]+)\s*\(", header))
+    assert declared == set(_lib.SYMBOLS)
+    L = ctypes.CDLL(_lib.SO)
+    for s in declared:
+        assert hasattr(L, s), s
+
+
+def test_no_cpu_fallback_without_gpu():
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip("GPU present")
+    with pytest.raises(_lib.BelugaError):
+        B.DLWGD(S1, DF1, 0.2, 0.3, 0.6, B.NODE)
+
+
+def test_shard_range_partitions():
+    for n in (0, 1, 7, 85, 1000003):
+        for world in (1, 2, 3, 8):
+            cuts = [B.shard_range(n, r, world) for r in range(world)]
+            assert cuts[0][0] == 0 and cuts[-1][1] == n
+            for a, b in zip(cuts, cuts[1:]):
+                assert a[1] == b[0]
+            sizes = [hi - lo for lo, hi in cuts]
+            assert max(sizes) - min(sizes) <= 1
