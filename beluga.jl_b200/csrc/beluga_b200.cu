@@ -528,6 +528,9 @@ struct blg_handle {
     ~blg_handle() {
         cudaSetDevice(device);
         if (stream) cudaStreamSynchronize(stream);
+        Tc.clear();      // the slab deleters push into `pool`: run them while it is still alive
+        Tp.clear();
+        pool.clear();
         for (auto* s : all_slabs) { cudaFree(s->ell); cudaFree(s->scl); delete s; }
         for (auto* c : count_allocs) cudaFree(c);
         for (auto& tb : tabs) free_tab(tb);

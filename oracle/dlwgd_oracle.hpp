@@ -112,17 +112,18 @@ template <class T> inline T log1mexp(const T& x) {
 }
 
 // log n! in extended precision (exact products summed in long double), used for the
-// binomial coefficient of the Binomial log-pmf.
-inline double lfact(int n) {
-    static std::vector<long double> tab(1, 0.0L);
-    while ((int)tab.size() <= n) tab.push_back(tab.back() + std::log((long double)tab.size()));
-    return (double)tab[n];
+// binomial coefficient of the Binomial log-pmf.  The table is filled once (thread-safe static
+// init) so OpenMP workers only ever read it.
+struct LFactTable {
+    std::vector<long double> tab;
+    LFactTable() : tab(1, 0.0L) { for (int k = 1; k <= 65536; ++k) tab.push_back(tab.back() + std::log((long double)k)); }
+};
+inline long double lfact(int n) {
+    static const LFactTable T;
+    if (n < (int)T.tab.size()) return T.tab[n];
+    return std::lgamma((long double)n + 1.0L);
 }
-inline double lchoose(int n, int s) {
-    static std::vector<long double> tab(1, 0.0L);
-    while ((int)tab.size() <= n) tab.push_back(tab.back() + std::log((long double)tab.size()));
-    return (double)(tab[n] - tab[s] - tab[n - s]);
-}
+inline double lchoose(int n, int s) { return (double)(lfact(n) - lfact(s) - lfact(n - s)); }
 // logpdf(Binomial(n, p), s)  (model.jl:448) -> Rmath dbinom(s, n, p, log=true).
 // Rmath's special cases (p == 0, q == 0, n == 0) are kept; the general case uses the exact
 // log binomial coefficient instead of Loader's saddle-point form (agrees to ~1 ulp).
