@@ -522,8 +522,15 @@ struct blg_handle {
     bool tabs_valid = false;
 
     // accounting of the last likelihood call
-    double last_bytes = 0.0;
+    double last_bytes = 0.0, last_prune_bytes = 0.0;
     int last_launches = 0;
+    bool timing = false;
+    cudaEvent_t ev[3] = {nullptr, nullptr, nullptr};
+    bool ev_valid = false;
+
+    // family order on the device (sorted by count profile so that the 32 families of a warp have
+    // similar loop bounds); perm[device index] = caller's pattern index
+    std::vector<int> perm, inv;
 
     ~blg_handle() {
         cudaSetDevice(device);
@@ -537,6 +544,7 @@ struct blg_handle {
         weight.free_(); fam_ll.free_(); partial.free_(); result.free_(); rootw.free_(); pascal.free_();
         d_kind.free_(); d_parent.free_(); d_child_off.free_(); d_child_idx.free_(); d_list.free_();
         d_t.free_(); d_lam.free_(); d_mu.free_(); d_q.free_(); d_eps0.free_(); d_eps1.free_(); d_tab.free_();
+        for (auto& e : ev) if (e) cudaEventDestroy(e);
         if (own_stream && stream) cudaStreamDestroy(stream);
     }
     static void free_tab(HostTab& tb) {
@@ -773,6 +781,7 @@ struct blg_handle {
         last_launches = 0;
         if (N == 0) { CK(cudaMemsetAsync(d_out, 0, sizeof(double), stream)); return; }   // profile.jl:56
         require((int)Tp.size() >= 1, "logpdf: no profile columns");
+        if (timing) { for (auto& e : ev) if (!e) CK(cudaEventCreate(&e)); CK(cudaEventRecord(ev[0], stream)); }
         if (mode == 0) {
             for (int u : postorder) if (!children[u].empty()) prune_node(u);
         } else if (mode == 1) {
@@ -780,7 +789,10 @@ struct blg_handle {
             require(present(u), "logpdf_from: node id not in the model");
             while (u >= 0) { if (!children[u].empty()) prune_node(u); u = parent[u]; }
         }
+        if (timing) CK(cudaEventRecord(ev[1], stream));
+        last_prune_bytes = last_bytes;
         root_reduce(d_out);
+        if (timing) { CK(cudaEventRecord(ev[2], stream)); ev_valid = true; }
     }
 };
 
@@ -837,6 +849,21 @@ int blg_set_profiles(blg_handle* h, const int32_t* X, const int64_t* weight, int
     if (npatterns == 0) { h->Tc.clear(); h->Tp.clear(); return 0; }
     h->require(X && weight, "set_profiles: null pointer");
     size_t ld = h->ld;
+    // device order: lexicographic on the first columns (ids are pre-order, so these are the root
+    // and the nodes next to it — where the large counts and most of the work are), descending
+    h->perm.resize(npatterns);
+    for (int f = 0; f < npatterns; ++f) h->perm[f] = f;
+    {
+        const int nk = std::min(ncols, 12);
+        std::stable_sort(h->perm.begin(), h->perm.end(), [&](int a, int b) {
+            const int32_t* xa = X + (size_t)a * ncols;
+            const int32_t* xb = X + (size_t)b * ncols;
+            for (int k = 0; k < nk; ++k) if (xa[k] != xb[k]) return xa[k] > xb[k];
+            return false;
+        });
+    }
+    h->inv.resize(npatterns);
+    for (int f = 0; f < npatterns; ++f) h->inv[h->perm[f]] = f;
     std::vector<uint16_t> stage((size_t)ncols * ld, 0);
     std::vector<Col> cols(ncols);
     int gmax = 0;
@@ -845,7 +872,7 @@ int blg_set_profiles(blg_handle* h, const int32_t* X, const int64_t* weight, int
         double cs = 0.0;
         uint16_t* dst = stage.data() + (size_t)c * ld;
         for (int f = 0; f < npatterns; ++f) {
-            int32_t v = X[(size_t)f * ncols + c];
+            int32_t v = X[(size_t)h->perm[f] * ncols + c];
             if (v < 0 || v > BLG_MAXCOUNT) throw std::runtime_error("set_profiles: count outside [0, 1023]");
             dst[f] = (uint16_t)v;
             mx = std::max(mx, (int)v);
@@ -861,7 +888,7 @@ int blg_set_profiles(blg_handle* h, const int32_t* X, const int64_t* weight, int
     CK(cudaMemcpyAsync(dcnt, stage.data(), stage.size() * sizeof(uint16_t), cudaMemcpyHostToDevice, h->stream));
     for (int c = 0; c < ncols; ++c) cols[c].cnt = dcnt + (size_t)c * ld;
     std::vector<double> w(ld, 0.0);
-    for (int f = 0; f < npatterns; ++f) w[f] = (double)weight[f];
+    for (int f = 0; f < npatterns; ++f) w[f] = (double)weight[h->perm[f]];
     h->weight.ensure(ld);
     h->fam_ll.ensure(ld);
     CK(cudaMemcpyAsync(h->weight.p, w.data(), ld * sizeof(double), cudaMemcpyHostToDevice, h->stream));
@@ -1011,6 +1038,7 @@ int blg_get_column(blg_handle* h, int pattern, int node, int which, double* out,
     h->require(node >= 1 && node <= (int)T.size(), "get_column: node out of range");
     Col& c = T[node - 1];
     CK(cudaStreamSynchronize(h->stream));
+    pattern = h->inv[pattern];
     uint16_t x;
     CK(cudaMemcpy(&x, c.cnt + pattern, sizeof(uint16_t), cudaMemcpyDeviceToHost));
     if (rows) *rows = c.xmax + 1;
@@ -1031,7 +1059,11 @@ int blg_get_family_logpdf(blg_handle* h, double* out, int n) {
     BLG_ENTER(h)
     h->require(n <= h->N, "get_family_logpdf: n exceeds the pattern count");
     CK(cudaStreamSynchronize(h->stream));
-    if (n > 0) CK(cudaMemcpy(out, h->fam_ll.p, (size_t)n * sizeof(double), cudaMemcpyDeviceToHost));
+    if (n > 0) {
+        std::vector<double> tmp(h->N);
+        CK(cudaMemcpy(tmp.data(), h->fam_ll.p, (size_t)h->N * sizeof(double), cudaMemcpyDeviceToHost));
+        for (int f = 0; f < n; ++f) out[f] = tmp[h->inv[f]];
+    }
     BLG_LEAVE(h)
 }
 int blg_get_eps(blg_handle* h, double* eps_top, double* eps_node, int ncols) {
@@ -1055,11 +1087,26 @@ int blg_get_W(blg_handle* h, int node, double* out, int cap, int* dim) {
 }
 int blg_ncols(blg_handle* h, int which) { return h ? (int)(which ? h->Tp.size() : h->Tc.size()) : -1; }
 int blg_npatterns(blg_handle* h) { return h ? h->N : -1; }
-int blg_last_algorithmic(blg_handle* h, double* bytes, int* launches) {
+int blg_last_algorithmic(blg_handle* h, double* bytes_total, double* bytes_prune, int* launches) {
     if (!h) return 1;
-    if (bytes) *bytes = h->last_bytes;
+    if (bytes_total) *bytes_total = h->last_bytes;
+    if (bytes_prune) *bytes_prune = h->last_prune_bytes;
     if (launches) *launches = h->last_launches;
     return 0;
+}
+int blg_set_timing(blg_handle* h, int on) {
+    if (!h) return 1;
+    h->timing = on != 0;
+    h->ev_valid = false;
+    return 0;
+}
+int blg_last_timing(blg_handle* h, float* prune_ms, float* root_ms) {
+    BLG_ENTER(h)
+    h->require(h->ev_valid, "last_timing: no timed likelihood call yet (blg_set_timing)");
+    CK(cudaEventSynchronize(h->ev[2]));
+    if (prune_ms) CK(cudaEventElapsedTime(prune_ms, h->ev[0], h->ev[1]));
+    if (root_ms) CK(cudaEventElapsedTime(root_ms, h->ev[1], h->ev[2]));
+    BLG_LEAVE(h)
 }
 int blg_sync(blg_handle* h) {
     BLG_ENTER(h)

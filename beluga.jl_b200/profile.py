@@ -53,10 +53,14 @@ class PArray:
         self.ncols0 = X.shape[1]
         self.L = _lib.lib()
         stream = None
+        self.torch_stream = None
         if self.distributed:
+            # a dedicated torch stream: the library's kernels, the NCCL all-reduce behind them and
+            # the caller's CUDA events all go on it
             import torch
             torch.cuda.set_device(device)
-            stream = C.c_void_p(torch.cuda.current_stream().cuda_stream)
+            self.torch_stream = torch.cuda.Stream(device=device)
+            stream = C.c_void_p(self.torch_stream.cuda_stream)
         h = C.c_void_p()
         rc = self.L.blg_create(int(device), stream, C.byref(h))
         if rc != 0:
@@ -125,17 +129,18 @@ class PArray:
     def _run(self, mode, node):
         if self.distributed:
             import torch
-            if self._torch_out is None:
-                self._torch_out = torch.zeros(1, dtype=torch.float64, device="cuda:%d" % self.device)
-            ptr = C.c_void_p(self._torch_out.data_ptr())
-            if mode == 0:
-                self._ck(self.L.blg_logpdf_full_async(self.h, ptr))
-            elif mode == 1:
-                self._ck(self.L.blg_logpdf_from_async(self.h, node, ptr))
-            else:
-                self._ck(self.L.blg_logpdf_root_async(self.h, ptr))
-            allreduce_sum_(self._torch_out)
-            return float(self._torch_out.item())
+            with torch.cuda.stream(self.torch_stream):
+                if self._torch_out is None:
+                    self._torch_out = torch.zeros(1, dtype=torch.float64, device="cuda:%d" % self.device)
+                ptr = C.c_void_p(self._torch_out.data_ptr())
+                if mode == 0:
+                    self._ck(self.L.blg_logpdf_full_async(self.h, ptr))
+                elif mode == 1:
+                    self._ck(self.L.blg_logpdf_from_async(self.h, node, ptr))
+                else:
+                    self._ck(self.L.blg_logpdf_root_async(self.h, ptr))
+                allreduce_sum_(self._torch_out)
+                return float(self._torch_out.item())
         out = C.c_double()
         if mode == 0:
             self._ck(self.L.blg_logpdf_full(self.h, C.byref(out)))
@@ -208,9 +213,17 @@ class PArray:
         return self.L.blg_ncols(self.h, 1 if proposal else 0)
 
     def last_algorithmic(self):
-        b, l = C.c_double(), C.c_int()
-        self.L.blg_last_algorithmic(self.h, C.byref(b), C.byref(l))
-        return b.value, l.value
+        b, bp, l = C.c_double(), C.c_double(), C.c_int()
+        self.L.blg_last_algorithmic(self.h, C.byref(b), C.byref(bp), C.byref(l))
+        return b.value, bp.value, l.value
+
+    def set_timing(self, on=True):
+        self._ck(self.L.blg_set_timing(self.h, 1 if on else 0))
+
+    def last_timing(self):
+        a, b = C.c_float(), C.c_float()
+        self._ck(self.L.blg_last_timing(self.h, C.byref(a), C.byref(b)))
+        return a.value, b.value
 
     def synchronize(self):
         if self.h is not None:

@@ -135,3 +135,83 @@ def rand_profiles(model, N, seed=20261019, condition="rootclades", max_leaf=None
     names = [model.leaves[i] for i in leaf_ids]
     order = np.argsort(names)
     return [names[k] for k in order], counts[:, order]
+
+
+# ---- benchmark-scale input generation on the GPU (same law as rand_counts, torch RNG) ------------------
+def rand_profiles_torch(model, N, seed=20261019, device="cuda", condition="rootclades", max_leaf=None,
+                        max_rootsum=None, chunk=1 << 21):
+    """Rejection sampler equal in distribution to ``rand_profiles`` that draws on the device with
+    torch's generators (input generation only; not part of the likelihood path).  Returns
+    (names, counts[N × ntaxa] int16 ndarray)."""
+    import torch
+
+    gen = torch.Generator(device=device)
+    gen.manual_seed(int(seed))
+    root = model.nodes[1]
+    order = prewalk(root)
+    leaf_ids = sorted(i for i, nd in model.nodes.items() if isleaf(nd))
+    pos = {i: k for k, i in enumerate(leaf_ids)}
+    clades = rootclades(model) if condition == "rootclades" else None
+    out, have = [], 0
+    while have < N:
+        at = {1: torch.empty(chunk, dtype=torch.float64, device=device).geometric_(float(root["η"]), generator=gen)}
+        leaves = torch.empty((chunk, len(leaf_ids)), dtype=torch.int16, device=device)
+        for n in order:
+            x = at.pop(n.i)
+            if isleaf(n):
+                leaves[:, pos[n.i]] = x.to(torch.int16)
+                continue
+            for c in n.c:
+                if iswgt(n):
+                    raise NotImplementedError("sampling through WGT nodes is not supported")
+                y = x
+                if iswgd(n):
+                    y = x + torch.binomial(x, torch.full_like(x, float(n["q"])), generator=gen)
+                lam, mu = _branch_rates(model, n, c)
+                t = c["t"]
+                if t > 0.0:
+                    phi, psi = _phi_psi(t, lam, mu)
+                    surv = torch.binomial(y, torch.full_like(y, 1.0 - float(phi)), generator=gen)
+                    if psi > 0.0:
+                        g = torch._standard_gamma(surv.clamp_min(1e-30), generator=gen) * (float(psi) / (1.0 - float(psi)))
+                        y = surv + torch.poisson(g, generator=gen)
+                    else:
+                        y = surv
+                at[c.i] = y
+        keep = torch.ones(chunk, dtype=torch.bool, device=device)
+        wide = leaves.to(torch.int32)
+        if condition == "rootclades":
+            for cl in clades:
+                keep &= wide[:, [pos[i] for i in cl]].sum(dim=1) > 0
+        elif condition == "nonextinct":
+            keep &= wide.sum(dim=1) > 0
+        if max_leaf is not None:
+            keep &= wide.max(dim=1).values <= max_leaf
+        if max_rootsum is not None:
+            keep &= wide.sum(dim=1) <= max_rootsum
+        sel = leaves[keep].cpu().numpy()
+        out.append(sel)
+        have += sel.shape[0]
+    counts = np.concatenate(out, axis=0)[:N]
+    names = [model.leaves[i] for i in leaf_ids]
+    order_ = np.argsort(names)
+    return [names[k] for k in order_], np.ascontiguousarray(counts[:, order_])
+
+
+def add_random_wgds(model, k, seed=20261019, qa=1.0, qb=3.0):
+    """k WGDs placed with the reference's randpos semantics (src/model.jl:197-206: branch ∝ length,
+    uniform position along it), retention q ~ Beta(qa, qb).  Returns the ids extend! must be
+    called with, in insertion order."""
+    rng = np.random.default_rng(seed)
+    ext = []
+    for _ in range(k):
+        ids = sorted(model.nodes)
+        w = np.array([model.nodes[i]["t"] for i in ids], dtype=np.float64)
+        i = int(rng.choice(ids, p=w / w.sum()))
+        n = model.nodes[i]
+        t = rng.random() * n["t"]
+        if not (n["t"] - t > 0.0):
+            t = 0.5 * n["t"]
+        model.addwgd_(n, t, float(rng.beta(qa, qb)))
+        ext.append(i)
+    return ext

@@ -1,0 +1,319 @@
+#!/usr/bin/env python
+"""Headline benchmark: family-likelihood evaluations per second of `logpdf!(model, profile)`.
+
+Workload (BASELINE.json configs[4] / SURVEY.md §8d C5): synthetic ultrametric 100-taxon tree
+(Kingman coalescent, height 1, seed 20261019) with 10 WGDs, Branch model λ=1.0 μ=1.2 η=0.8,
+10^6 families drawn from the model (conditioned on both root clades, max count 50 = the reference's
+m-1, i.e. Σ leaves ≤ 50), site-pattern compressed like profile() does.  A "step" is one full
+leaves-to-root sweep over every pattern of the rank's shard.  One process per GPU; each rank draws
+its own 10^6 families (weak scaling); the only cross-rank step is the all-reduce of the scalar.
+
+  python bench.py [--gpus N] [--steps K] [--warmup W]            # the CUDA path
+  python bench.py --impl reference [...]                         # the reference algorithm on host cores
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+METRIC = "family-likelihood evals/sec (logpdf!)"
+UNIT = "families/s"
+SEED = 20261019
+
+
+def parse():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--families", type=int, default=1_000_000, help="families drawn per GPU")
+    ap.add_argument("--taxa", type=int, default=100)
+    ap.add_argument("--wgds", type=int, default=10)
+    ap.add_argument("--max-count", type=int, default=50)
+    ap.add_argument("--cpu-seconds", type=float, default=15.0, help="target CPU time of the cpu_baseline sample")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    return ap.parse_args()
+
+
+def peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        return float(json.load(open(p))["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
+    return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+def build_workload(args, rank, device=None, families=None):
+    """-> (newick, model with WGDs, ext ids, names, counts) for this rank."""
+    import beluga_b200 as B
+    from beluga_b200.model import build_model
+    from beluga_b200.sim import add_random_wgds, rand_profiles, rand_profiles_torch, random_tree_newick
+
+    nw = random_tree_newick(args.taxa, seed=SEED)
+    model, t, l = build_model(nw, 1.0, 1.2, 0.8, B.BRANCH)
+    ext = add_random_wgds(model, args.wgds, seed=SEED)
+    nfam = families if families is not None else args.families
+    if device is not None:
+        names, counts = rand_profiles_torch(model, nfam, seed=SEED + rank, device=device, max_rootsum=args.max_count)
+    else:
+        names, counts = rand_profiles(model, nfam, seed=SEED + rank, max_rootsum=args.max_count)
+    return nw, model, ext, t, l, names, counts
+
+
+class ClockSampler(threading.Thread):
+    """nvidia-smi clocks / throttle reasons sampled while the timed region runs."""
+
+    Q = "clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
+
+    def __init__(self, index):
+        super().__init__(daemon=True)
+        self.index = index
+        self.stop_ = threading.Event()
+        self.rows = []
+
+    def run(self):
+        while not self.stop_.is_set():
+            try:
+                o = subprocess.run(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.Q, "--format=csv,noheader,nounits"],
+                                   capture_output=True, text=True, timeout=5).stdout.strip()
+                if o:
+                    self.rows.append([x.strip() for x in o.split(",")])
+            except Exception:
+                pass
+            self.stop_.wait(0.2)
+
+    def summary(self):
+        if not self.rows:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["unavailable"]}
+        sm = [float(r[0]) for r in self.rows if r[0].replace(".", "").isdigit()]
+        mx = [float(r[1]) for r in self.rows if r[1].replace(".", "").isdigit()]
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        reasons = [n for k, n in enumerate(names) if any(len(r) > 2 + k and r[2 + k].lower().startswith("active") for r in self.rows)]
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": reasons, "samples": len(self.rows)}
+
+
+def cpu_baseline(args, threads, target_seconds, steps=None, warmup=1):
+    """The reference algorithm (oracle/, literal log-space restatement) on host cores, on a bounded
+    sample of the same workload.  Test infrastructure used as a yard-stick, never as the product."""
+    from oracle.oracle import BRANCH as OBRANCH, OracleDLWGD, max_threads
+
+    threads = threads or max_threads()
+    nw, model, ext, t, l, names, counts = build_workload(args, 0, device=None, families=4000)
+
+    # the oracle API inserts a WGD at distance t above a node; replay in insertion order
+    def replay(o):
+        import beluga_b200 as B
+        from beluga_b200.model import build_model
+        from beluga_b200.sim import add_random_wgds
+        m2, _, _ = build_model(nw, 1.0, 1.2, 0.8, B.BRANCH)
+        rng = np.random.default_rng(SEED)
+        for _ in range(args.wgds):
+            ids = sorted(m2.nodes)
+            w = np.array([m2.nodes[i]["t"] for i in ids], dtype=np.float64)
+            i = int(rng.choice(ids, p=w / w.sum()))
+            n = m2.nodes[i]
+            tt = rng.random() * n["t"]
+            if not (n["t"] - tt > 0.0):
+                tt = 0.5 * n["t"]
+            q = float(rng.beta(1.0, 3.0))
+            m2.addwgd_(n, tt, q)
+            o.addwgd(i, tt, q)
+            o.extend(i)
+
+    n = 64
+    o = OracleDLWGD(nw, names, counts[:n], 1.0, 1.2, 0.8, OBRANCH, threads=threads)
+    replay(o)
+    t0 = time.perf_counter()
+    o.logpdf()
+    dt = time.perf_counter() - t0
+    per = dt / max(o.npatterns, 1)
+    reps = steps if steps else 5
+    n = int(min(len(counts), max(64, target_seconds / max(per, 1e-9) / (reps + warmup))))
+    o = OracleDLWGD(nw, names, counts[:n], 1.0, 1.2, 0.8, OBRANCH, threads=threads)
+    replay(o)
+    for _ in range(warmup):
+        o.logpdf()
+    t0 = time.perf_counter()
+    for _ in range(reps):
+        val = o.logpdf()
+    dt = (time.perf_counter() - t0) / reps
+    return {"value": o.npatterns / dt, "unit": UNIT, "cores": threads, "kind": "port",
+            "sample": "%d patterns (%d families) of the same workload, %d full sweeps, literal log-space C++ restatement of "
+                      "src/model.jl:402-463 with OpenMP over families; Julia is not installed in this image" % (o.npatterns, n, reps),
+            "ms_per_step": dt * 1e3, "logpdf": val}
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    from oracle.oracle import max_threads
+    threads = max_threads()
+    cb = cpu_baseline(args, threads, target_seconds=max(30.0, args.cpu_seconds), steps=args.steps, warmup=args.warmup)
+    line = {
+        "impl": "reference", "metric": METRIC, "value": cb["value"], "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
+        "warmup": args.warmup, "ms_per_step": cb["ms_per_step"], "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+        "config": workload_config(args, None, None),
+        "cpu_baseline": {k: cb[k] for k in ("value", "unit", "cores", "kind", "sample")},
+        "e2e": {"value": cb["value"], "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+    }
+    print(json.dumps(line))
+
+
+def workload_config(args, npat, nfam):
+    return {"workload": "C5: %d-taxon coalescent tree + %d WGDs, %s families/GPU drawn from the model (max count %d), pattern-compressed; "
+                        "full logpdf! sweep" % (args.taxa, args.wgds, args.families, args.max_count),
+            "patterns_per_gpu": npat, "families_per_gpu": nfam, "tree_seed": SEED, "lambda": 1.0, "mu": 1.2, "eta": 0.8,
+            "model": "Branch", "l2": "inputs larger than L2 (partial-likelihood slabs of one sweep exceed 126 MB)"}
+
+
+def main():
+    args = parse()
+    if args.impl == "reference":
+        return run_reference(args)
+
+    import torch
+    import torch.distributed as dist
+
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device; the product has no CPU path (use --impl reference for the CPU algorithm)")
+    torch.cuda.set_device(local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    import __graft_entry__
+    if rank == 0:
+        __graft_entry__.build()
+    if world > 1:
+        dist.barrier()
+
+    import beluga_b200 as B
+
+    nw, model, ext, t, l, names, counts = build_workload(args, rank, device="cuda:%d" % local)
+    torch.cuda.empty_cache()
+    X, w, m = B.profile(t, l, (names, counts))
+    X = np.ascontiguousarray(X, dtype=np.int32)
+    npat, nfam = X.shape[0], int(w.sum())
+    data = B.PArray(X, w, device=local, distributed=True)
+    for i in ext:                 # extend!(data, i) for every inserted WGD (src/profile.jl:108), then set!(data)
+        B.extend_(data, i)
+    B.set_(data)
+    del X, counts
+
+    stream = data.torch_stream
+    torch.cuda.set_stream(stream)          # everything below (kernels, all-reduce, events) on the handle's stream
+    out = torch.zeros(1, dtype=torch.float64, device="cuda")
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    # ---- kernel-only: inputs resident, parameters fixed ------------------------------------------------
+    data.sync(model)
+    import ctypes as C
+    ptr = C.c_void_p(out.data_ptr())
+
+    def step_resident():
+        data._ck(data.L.blg_logpdf_full_async(data.h, ptr))
+        B.allreduce_sum_(out)
+
+    for _ in range(args.warmup):
+        step_resident()
+    data.set_timing(True)
+    barrier()
+    sampler = ClockSampler(local)
+    sampler.start()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    prune_ms = []
+    e0.record(stream)
+    for _ in range(args.steps):
+        step_resident()
+    e1.record(stream)
+    barrier()
+    ms = e0.elapsed_time(e1) / args.steps
+    total_ll = float(out.item())
+    # per-launch-group durations of the LAST step (events recorded inside the timed region)
+    pm, rm = data.last_timing()
+    alg_bytes, prune_bytes, launches = data.last_algorithmic()
+    data.set_timing(False)
+
+    # ---- end to end through the public API: host θ in, host scalar out, every step -------------------------
+    rates = model.getrates()
+    rng = np.random.default_rng(SEED)
+    for _ in range(max(1, args.warmup // 2)):
+        model.setrates_(rates * np.exp(rng.normal(0, 1e-3, size=rates.shape)))
+        B.logpdf_(model, data)
+    barrier()
+    e2, e3 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    t0 = time.perf_counter()
+    e2.record(stream)
+    esteps = max(3, args.steps // 2)
+    for _ in range(esteps):
+        model.setrates_(rates * np.exp(rng.normal(0, 1e-3, size=rates.shape)))   # host-side parameter update
+        ll = B.logpdf_(model, data)                                             # H2D θ, ε/W build, sweep, all-reduce, D2H scalar
+    e3.record(stream)
+    barrier()
+    e2e_ms = max(e2.elapsed_time(e3), (time.perf_counter() - t0) * 1e3) / esteps
+    sampler.stop_.set()
+    sampler.join(2)
+    ncols = max(model.nodes)
+    h2d = 4 * ncols * 8 + ncols * 176 + ncols * 4
+    model.setrates_(rates)
+
+    # ---- max over ranks ----------------------------------------------------------------------------------
+    tt = torch.tensor([ms, e2e_ms, pm, rm], dtype=torch.float64, device="cuda")
+    cnt = torch.tensor([float(npat), float(nfam), alg_bytes], dtype=torch.float64, device="cuda")
+    # (roofline numbers below are rank 0's own kernel; counts are summed over ranks)
+    if world > 1:
+        dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+        dist.all_reduce(cnt, op=dist.ReduceOp.SUM)
+    ms, e2e_ms, pm, rm = [float(x) for x in tt.tolist()]
+    tot_pat, tot_fam, tot_bytes = [float(x) for x in cnt.tolist()]
+
+    if rank == 0:
+        peak, peak_src = peaks()
+        # dominant kernel: prune_node_kernel (one launch per internal node).  Its algorithmic bytes are the
+        # sweep's minus the root/reduction share; its duration is the event-bracketed pruning phase.
+        achieved = (prune_bytes / 1e9) / (pm / 1e3)
+        line = {
+            "metric": METRIC, "value": tot_pat / (ms / 1e3), "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+            "ms_per_step": ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+            "config": workload_config(args, npat, nfam),
+            "weighted_families_per_s": tot_fam / (ms / 1e3),
+            "logpdf": total_ll,
+            "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+                         "traffic": None, "kernel": "prune_node_kernel (%d launches/step, event-bracketed)" % (launches - 3),
+                         "algorithmic_bytes_per_launch_group": prune_bytes, "algorithmic_bytes_per_step": alg_bytes, "phase_ms": {"prune": pm, "root+reduce": rm},
+                         "peak_source": peak_src},
+            "e2e": {"value": tot_pat / (e2e_ms / 1e3), "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": 8,
+                    "ms_per_step": e2e_ms, "what": "setrates!(model, X) on host + logpdf!(model, profile): θ upload, on-device ε/W build, full sweep, scalar back"},
+            "gpu_launches": int(launches * args.steps),
+            "clocks": sampler.summary(),
+        }
+        if not args.no_cpu_baseline:
+            try:
+                line["cpu_baseline"] = {k: v for k, v in cpu_baseline(args, None, args.cpu_seconds).items()
+                                        if k in ("value", "unit", "cores", "kind", "sample")}
+            except Exception as e:  # the baseline must not take the measurement down with it
+                line["cpu_baseline"] = {"value": None, "unit": UNIT, "cores": 0, "kind": "port", "sample": "failed: %r" % (e,)}
+        print(json.dumps(line))
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

@@ -117,10 +117,15 @@ int blg_get_W(blg_handle* h, int node, double* out, int cap, int* dim);        /
 int blg_ncols(blg_handle* h, int which);
 int blg_npatterns(blg_handle* h);
 /* algorithmic bytes (definition of SURVEY.md §8(d): each internal column written once and read once by
- * its parent, 2 B per leaf count, 4 B per stored scale exponent, 8 B per family result) and the number
- * of kernels the last likelihood call launched */
-int blg_last_algorithmic(blg_handle* h, double* bytes, int* launches);
+ * its parent, 2 B per leaf count, 4 B per stored scale exponent, 8 B per family result) — in total and
+ * for the pruning launches alone — and the number of kernels the last likelihood call launched */
+int blg_last_algorithmic(blg_handle* h, double* bytes_total, double* bytes_prune, int* launches);
 int blg_sync(blg_handle* h);
+/* measurement: when on, every likelihood call records CUDA events on the handle's stream around its
+ * pruning launches and around its root/reduction launches; blg_last_timing waits for them and returns
+ * the two device durations of the last call in milliseconds. */
+int blg_set_timing(blg_handle* h, int on);
+int blg_last_timing(blg_handle* h, float* prune_ms, float* root_ms);
 
 #ifdef __cplusplus
 }
