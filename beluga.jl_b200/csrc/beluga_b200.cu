@@ -47,13 +47,18 @@ thread_local std::string g_create_error;
 // ------------------------------------------------------------------------------------------------
 // device-side model description
 // ------------------------------------------------------------------------------------------------
+#define BLG_TS 8            // register tile (counts per thread) of the contraction and the merge
 struct NodeTab {        // per node id, device-resident tables
-    double* W;          // wdim × wdim row-major [n][j], w*(n|j) for the branch above the node
-    int wdim;
+    double* Wt;         // TRANSPOSED w*: Wt[j*wdp + n] = w*(n|j) for the branch above the node, n <= j < wdim
+    int wdim;           // xmax + 1
+    int wdp;            // row stride, wdim rounded up to BLG_TS (padding is zero)
     double* ipow;       // (1-E_k)^(-n), n = 0..nrow-1  (NaN-poisoned when the reference would be)
     int nrow;           // xmax_u + 1
-    double* coef[BLG_MAXK];   // coef[i][n*cstride[i]+s] = C(n,s)·E_{i-1}^s for child i >= 1
-    int cstride[BLG_MAXK];
+    // merge coefficients for the child in merge position i >= 1, diagonal-major:
+    // coefD[i][t*cdp[i] + s] = C(t+s, s)·E_{i-1}^s  (0 where t+s > xmax_u or s > xmax of that child)
+    double* coefD[BLG_MAXK];
+    int cdp[BLG_MAXK];
+    int mo[BLG_MAXK];   // merge order: node indices of the children in the order they are merged
 };
 
 struct ModelDev {
@@ -165,10 +170,12 @@ __global__ void __launch_bounds__(128) tables_kernel(ModelDev m, const int* __re
     const int tid = threadIdx.x, nt = blockDim.x;
     uint8_t kd = m.kind[n];
     // ---- W of the branch above n -------------------------------------------------------------
-    if (kd != BLG_ROOT && tb.W != nullptr) {
+    if (kd != BLG_ROOT && tb.Wt != nullptr) {
         const int d = tb.wdim;
-        double* W = tb.W;
-        for (int i = tid; i < d * d; i += nt) W[i] = 0.0;
+        const int dp = tb.wdp;
+        double* W = tb.Wt;            // element (row n, column j) of w* lives at W[j*dp + n]
+#define WT(n_, j_) W[(size_t)(j_) * dp + (n_)]
+        for (int i = tid; i < d * dp; i += nt) W[i] = 0.0;
         __syncthreads();
         int par = m.parent[n];
         double e = m.eps1[n];
@@ -176,11 +183,11 @@ __global__ void __launch_bounds__(128) tables_kernel(ModelDev m, const int* __re
             double q = m.q[par];
             double a = ((1.0 - q) + 2.0 * q * e) * (1.0 - e);
             double b = q * ((1.0 - e) * (1.0 - e));
-            if (tid == 0) { W[0] = 1.0; if (d > 1) W[d + 1] = a; if (d > 2) W[d + 2] = b; }
+            if (tid == 0) { WT(0, 0) = 1.0; if (d > 1) WT(1, 1) = a; if (d > 2) WT(1, 2) = b; }
             __syncthreads();
             for (int i = 1; i < d; ++i) {
                 for (int j = 2 + tid; j < d; j += nt)
-                    W[i * d + j] = a * W[(i - 1) * d + j - 1] + b * W[(i - 1) * d + j - 2];
+                    WT(i, j) = a * WT(i - 1, j - 1) + b * WT(i - 1, j - 2);
                 __syncthreads();
             }
         } else if (kd == BLG_WGDAFTER && m.kind[par] == BLG_WGT) {                  // wstar_wgt! (literal, j from 3)
@@ -189,11 +196,11 @@ __global__ void __launch_bounds__(128) tables_kernel(ModelDev m, const int* __re
             double a = q1 * ome + 2.0 * q2 * e * ome + 3.0 * q3 * (e * e) * ome;
             double b = q2 * (ome * ome) + 3.0 * q3 * e * (ome * ome);
             double c = q3 * (ome * ome * ome);
-            if (tid == 0) { W[0] = 1.0; if (d > 1) W[d + 1] = a; if (d > 2) W[d + 2] = b; if (d > 3) W[d + 3] = c; }
+            if (tid == 0) { WT(0, 0) = 1.0; if (d > 1) WT(1, 1) = a; if (d > 2) WT(1, 2) = b; if (d > 3) WT(1, 3) = c; }
             __syncthreads();
             for (int i = 1; i < d; ++i) {
                 for (int j = 3 + tid; j < d; j += nt)
-                    W[i * d + j] = a * W[(i - 1) * d + j - 1] + b * W[(i - 1) * d + j - 2] + c * W[(i - 1) * d + j - 3];
+                    WT(i, j) = a * WT(i - 1, j - 1) + b * WT(i - 1, j - 2) + c * WT(i - 1, j - 3);
                 __syncthreads();
             }
         } else {                                                                     // wstar!
@@ -208,19 +215,20 @@ __global__ void __launch_bounds__(128) tables_kernel(ModelDev m, const int* __re
             double* prev = sm;
             double* cur = sm + d;
             for (int i = tid; i < d; i += nt) prev[i] = (i == 0) ? 1.0 : 0.0;   // column 0
-            if (tid == 0) W[0] = 1.0;
+            if (tid == 0) WT(0, 0) = 1.0;
             __syncthreads();
             for (int j = 1; j < d; ++j) {
                 for (int r = tid; r < d; r += nt) {
                     double v = 0.0;
                     if (r >= 1 && r <= j) v = psip * prev[r] + cc * prev[r - 1];
                     cur[r] = v;
-                    if (r >= 1 && r <= j) W[r * d + j] = v;
+                    if (r >= 1 && r <= j) WT(r, j) = v;
                 }
                 __syncthreads();
                 double* tmp = prev; prev = cur; cur = tmp;
             }
         }
+#undef WT
     }
     // ---- merge tables of n (internal nodes) -----------------------------------------------------
     int c0 = m.child_off[n], c1 = m.child_off[n + 1];
@@ -232,7 +240,7 @@ __global__ void __launch_bounds__(128) tables_kernel(ModelDev m, const int* __re
         bool poison = false;
         E[0] = 1.0;
         for (int i = 0; i < k; ++i) {
-            raw *= m.eps0[m.child_idx[c0 + i]];
+            raw *= m.eps0[tb.mo[i]];
             double v = raw > 1.0 ? 1.0 : raw;
             E[i + 1] = v;
             // the reference divides by (1-_ϵ)^n in log space: _ϵ == 1 gives 0·(-Inf) = NaN at n = 0
@@ -242,12 +250,14 @@ __global__ void __launch_bounds__(128) tables_kernel(ModelDev m, const int* __re
         double inv = 1.0 / (1.0 - E[k]);
         for (int r = tid; r < tb.nrow; r += nt) tb.ipow[r] = poison ? __longlong_as_double(0x7ff8000000000000LL) : d_powi(inv, r);
         for (int i = 1; i < k; ++i) {
-            double* cf = tb.coef[i];
-            int cs = tb.cstride[i];
+            double* cf = tb.coefD[i];
+            int cs = tb.cdp[i];
+            int smax = m.tab[tb.mo[i]].wdim - 1;      // xmax of that child
             double p = E[i];
             for (int idx = tid; idx < tb.nrow * cs; idx += nt) {
-                int r = idx / cs, s = idx - r * cs;
-                cf[idx] = (s <= r) ? m.pascal[(size_t)r * m.pdim + s] * d_powi(p, s) : 0.0;
+                int t = idx / cs, s = idx - t * cs;
+                int r = t + s;
+                cf[idx] = (r < tb.nrow && s <= smax) ? m.pascal[(size_t)r * m.pdim + s] * d_powi(p, s) : 0.0;
             }
         }
     }
@@ -279,17 +289,17 @@ struct ChildRef {
     const double* ell;     // child's slab [n][f] (nullptr: leaf, one-hot at its count)
     const int* scl;        // child's per-family exponent (nullptr for leaves)
     const uint16_t* cnt;   // child's extended counts
-    const double* W;       // child's W, row-major [s][j]
-    int wdim;
+    const double* Wt;      // child's transposed w*: Wt[j*wdp + s]
+    int wdp;
     int id;                // child's node index (for ϵ[1])
-    const double* coef;    // merge coefficients for this child (i >= 1)
-    int cstride;
+    const double* coefD;   // merge coefficients for this merge position (i >= 1), [t*cdp + s]
+    int cdp;
 };
 struct NodeStep {
     int k;
-    ChildRef child[BLG_MAXK];
+    int nrow;              // xmax_u + 1
+    ChildRef child[BLG_MAXK];   // in MERGE order
     const double* ipow;
-    const double* eps0;
     double* out;           // node slab [n][f]
     int* out_scl;
     const uint16_t* cnt;   // node's own extended counts
@@ -303,8 +313,13 @@ struct NodeStep {
 //   ℓ_u[n]   = Ã_k[n] / (1-E_k)^n                                                  (model.jl:453-461)
 // The reference normalises by (1-E_i)^n after every child and multiplies the next merge by the
 // Binomial(n, E_i) pmf; the (1-E_i) powers cancel exactly, so only the last division is kept.
+// The children of a node may be merged in any order (ℓ_u does not depend on it); the host puts
+// the child with the smaller counts first.
+
+// ---- v1: one launch per node, per-thread arrays in local memory.  Kept as the general fallback
+// (any count up to BLG_MAXCOUNT) and as an A/B reference for the sweep kernel below. ---------------
 template <int CAP>
-__global__ void __launch_bounds__(128) prune_node_kernel(const NodeStep st, int N, size_t ld) {
+__global__ void __launch_bounds__(128) prune_node_kernel(const NodeStep st, const double* __restrict__ eps0, int N, size_t ld) {
     int f = blockIdx.x * blockDim.x + threadIdx.x;
     if (f >= N) return;
     double A0[CAP], A1[CAP], Bc[CAP], lc[CAP];
@@ -315,16 +330,16 @@ __global__ void __launch_bounds__(128) prune_node_kernel(const NodeStep st, int 
     for (int i = 0; i < st.k; ++i) {
         const ChildRef& c = st.child[i];
         const int Mi = c.cnt[f];
-        const double* __restrict__ W = c.W;
-        const int wd = c.wdim;
+        const double* __restrict__ Wt = c.Wt;
+        const int wd = c.wdp;
         if (c.ell == nullptr) {
-            for (int s = 0; s <= Mi; ++s) Bc[s] = W[s * wd + Mi];
+            for (int s = 0; s <= Mi; ++s) Bc[s] = Wt[(size_t)Mi * wd + s];
         } else {
             for (int j = 0; j <= Mi; ++j) lc[j] = c.ell[(size_t)j * ld + f];
             sclsum += c.scl[f];
             for (int s = 0; s <= Mi; ++s) {
                 double acc = 0.0;
-                for (int j = s; j <= Mi; ++j) acc = fma(W[s * wd + j], lc[j], acc);
+                for (int j = s; j <= Mi; ++j) acc = fma(Wt[(size_t)j * wd + s], lc[j], acc);
                 Bc[s] = acc;
             }
         }
@@ -332,13 +347,13 @@ __global__ void __launch_bounds__(128) prune_node_kernel(const NodeStep st, int 
             for (int n = 0; n <= Mi; ++n) Acur[n] = Bc[n];
             S = Mi;
         } else {
-            const double e = st.eps0[c.id];
-            const double* __restrict__ cf = c.coef;
-            const int cs = c.cstride;
+            const double e = eps0[c.id];
+            const double* __restrict__ cf = c.coefD;
+            const int cs = c.cdp;
             for (int n = 0; n <= S + Mi; ++n) Anew[n] = 0.0;
             for (int t = 0; t <= S; ++t) {
                 const double a = Acur[t];
-                for (int s = 0; s <= Mi; ++s) Anew[t + s] = fma(cf[(t + s) * cs + s], a * Bc[s], Anew[t + s]);
+                for (int s = 0; s <= Mi; ++s) Anew[t + s] = fma(cf[(size_t)t * cs + s], a * Bc[s], Anew[t + s]);
                 for (int s = 0; s < Mi; ++s) Bc[s] = fma(e, Bc[s], Bc[s + 1]);
                 Bc[Mi] = e * Bc[Mi];
             }
@@ -359,6 +374,160 @@ __global__ void __launch_bounds__(128) prune_node_kernel(const NodeStep st, int 
     if (!bad && mxv > 0.0) ex = ilogb(mxv);
     for (int n = 0; n <= X; ++n) st.out[(size_t)n * ld + f] = (ex != 0) ? scalbn(Acur[n], -ex) : Acur[n];
     st.out_scl[f] = sclsum + ex;
+}
+
+// ---- v2: the sweep kernel.  ONE launch walks a list of nodes (a full post-order sweep, or the
+// path node→root of a partial recompute).  A warp owns 32 consecutive families for the whole list
+// and never synchronises with another warp: a parent only reads what the same thread wrote.
+// Per-family working columns live in a per-warp shared-memory slice laid out [index][lane]
+// (conflict-free); W and the merge coefficients are warp-uniform loads served by L1.  Both inner
+// loops keep BLG_TS counts per thread in registers:
+//   contraction: acc[s0..s0+7] += Wt[j][s0..s0+7]·ℓ[j]         (1 per-thread load per 8 FMA)
+//   merge:       tile [s0, s0+8) of the B row and of the anti-diagonal accumulators stays in
+//                registers while t runs; tiles are processed from high s to low s and hand their
+//                first column to the next tile through a per-family history column.
+__device__ __forceinline__ int warp_max(int v) { return __reduce_max_sync(0xffffffffu, v); }
+
+// b[s] = Σ_{j>=s} Wt[j][s]·ℓ[j], s = 0..Mw, into dst[s*32]  (leaf child: the column x_c of w*)
+__device__ __forceinline__ void sweep_contract(const ChildRef& c, int f, size_t ld, int M, int Mw, double* dst, int& sclsum) {
+    if (c.ell == nullptr) {
+        const double* row = c.Wt + (size_t)M * c.wdp;
+        for (int s = 0; s <= Mw; ++s) dst[s * 32] = (s <= M) ? row[s] : 0.0;
+        return;
+    }
+    sclsum += c.scl[f];
+    const double* col = c.ell + f;
+    for (int s0 = 0; s0 <= Mw; s0 += BLG_TS) {
+        double acc[BLG_TS];
+#pragma unroll
+        for (int k = 0; k < BLG_TS; ++k) acc[k] = 0.0;
+#pragma unroll 2
+        for (int j = s0; j <= Mw; ++j) {
+            const double x = (j <= M) ? col[(size_t)j * ld] : 0.0;
+            const double* __restrict__ w = c.Wt + (size_t)j * c.wdp + s0;
+#pragma unroll
+            for (int k = 0; k < BLG_TS; ++k) acc[k] = fma(w[k], x, acc[k]);
+        }
+#pragma unroll
+        for (int k = 0; k < BLG_TS; ++k)
+            if (s0 + k <= Mw) dst[(s0 + k) * 32] = acc[k];
+    }
+}
+
+// O[n] (n = 0..Sw+M2w) ← Σ_{t+s=n} coefD[t][s]·A[t]·B[t,s].  On entry O[0..M2w] holds B[0,·] and
+// O[M2w+1..Sw+M2w] is zero; H is scratch of Sw+1 entries.
+__device__ __forceinline__ void sweep_merge(const double* A, int Sw, double* O, int M2w, double* H,
+                                            const double* __restrict__ coefD, int cdp, double e) {
+    const int ntile = M2w / BLG_TS + 1;
+    const int nmax = Sw + M2w;
+    for (int tile = ntile - 1; tile >= 0; --tile) {
+        const int s0 = tile * BLG_TS;
+        const bool top = (tile == ntile - 1);
+        double B[BLG_TS], acc[BLG_TS];
+#pragma unroll
+        for (int k = 0; k < BLG_TS; ++k) {
+            B[k] = (s0 + k <= M2w) ? O[(s0 + k) * 32] : 0.0;
+            acc[k] = 0.0;
+        }
+#pragma unroll
+        for (int k = 0; k < BLG_TS; ++k)
+            if (s0 + k <= M2w) O[(s0 + k) * 32] = 0.0;
+        // t runs over Sw+1 real steps plus BLG_TS-1 draining steps (a = 0) that flush the accumulators;
+        // the accumulator of n = t+s0+k lives in slot (k+t) mod BLG_TS, a compile-time index below
+        for (int tb = 0; tb <= Sw + BLG_TS - 1; tb += BLG_TS) {
+#pragma unroll
+            for (int u = 0; u < BLG_TS; ++u) {
+                const int t = tb + u;
+                if (t <= Sw) {
+                    const double a = A[t * 32];
+                    const double halo = top ? 0.0 : H[t * 32];
+                    H[t * 32] = B[0];
+                    const double* __restrict__ cf = coefD + (size_t)t * cdp + s0;
+#pragma unroll
+                    for (int k = 0; k < BLG_TS; ++k) acc[(k + u) % BLG_TS] = fma(cf[k] * a, B[k], acc[(k + u) % BLG_TS]);
+#pragma unroll
+                    for (int k = 0; k < BLG_TS - 1; ++k) B[k] = fma(e, B[k], B[k + 1]);
+                    B[BLG_TS - 1] = fma(e, B[BLG_TS - 1], halo);
+                }
+                const int n = t + s0;
+                if (n <= nmax) O[n * 32] += acc[u % BLG_TS];
+                acc[u % BLG_TS] = 0.0;
+            }
+        }
+    }
+}
+
+__device__ __forceinline__ void sweep_node(const NodeStep& st, const double* __restrict__ eps0, int f, bool live,
+                                           size_t ld, double* sl, int slice_cap, double* gs, unsigned lane) {
+    const int k = st.k;
+    int M[BLG_MAXK], Mw[BLG_MAXK];
+    int capA = 1, capO = 0;
+    {
+        int sum = 0;
+#pragma unroll
+        for (int i = 0; i < BLG_MAXK; ++i) {
+            if (i < k) {
+                M[i] = live ? (int)st.child[i].cnt[f] : 0;
+                Mw[i] = warp_max(M[i]);
+                sum += Mw[i];
+                if (i == 0 || i < k - 1) capA = sum + 1;
+            }
+        }
+        if (k >= 2) capO = sum + 1;
+    }
+    const int need = (k >= 2) ? 2 * capA + capO : capA;
+    double* base = (need <= slice_cap) ? sl : gs;     // warp-uniform choice: shared slice or global scratch
+    double* rA = base;
+    double* rH = base + (size_t)capA * 32;
+    double* rO = base + (size_t)2 * capA * 32;
+    int sclsum = 0;
+    sweep_contract(st.child[0], f, ld, M[0], Mw[0], rA, sclsum);
+    int Sw = Mw[0];
+    for (int i = 1; i < k; ++i) {
+        sweep_contract(st.child[i], f, ld, M[i], Mw[i], rO, sclsum);
+        for (int n = Mw[i] + 1; n <= Sw + Mw[i]; ++n) rO[n * 32] = 0.0;
+        sweep_merge(rA, Sw, rO, Mw[i], rH, st.child[i].coefD, st.child[i].cdp, eps0[st.child[i].id]);
+        Sw += Mw[i];
+        if (i < k - 1)
+            for (int n = 0; n <= Sw; ++n) rA[n * 32] = rO[n * 32];
+    }
+    double* src = (k >= 2) ? rO : rA;
+    const int X = live ? (int)st.cnt[f] : 0;
+    const int Xw = warp_max(X);
+    double mxv = 0.0;
+    bool bad = false;
+    for (int n = 0; n <= Xw; ++n) {
+        double v = 0.0;
+        if (n <= X) {
+            v = (n <= Sw ? src[n * 32] : 0.0) * st.ipow[n];
+            src[n * 32] = v;
+            if (!(v == v) || isinf(v)) bad = true;
+            mxv = fmax(mxv, v);
+        }
+    }
+    int ex = 0;
+    if (!bad && mxv > 0.0) ex = ilogb(mxv);
+    if (live) {
+        double* o = st.out + f;
+        for (int n = 0; n <= X; ++n) o[(size_t)n * ld] = (ex != 0) ? scalbn(src[n * 32], -ex) : src[n * 32];
+        st.out_scl[f] = sclsum + ex;
+    }
+    __syncwarp();
+}
+
+__global__ void __launch_bounds__(128) sweep_kernel(const NodeStep* __restrict__ steps, int nsteps, const double* __restrict__ eps0,
+                                                    int N, size_t ld, int slice_cap, double* gscratch, size_t gs_stride) {
+    extern __shared__ double smem[];
+    const unsigned lane = threadIdx.x & 31u;
+    const int warp = threadIdx.x >> 5;
+    const int wg = blockIdx.x * (blockDim.x >> 5) + warp;
+    if ((long long)wg * 32 >= N) return;
+    int f = wg * 32 + (int)lane;
+    const bool live = f < N;
+    if (!live) f = N - 1;
+    double* sl = smem + (size_t)warp * slice_cap * 32 + lane;
+    double* gs = gscratch ? gscratch + (size_t)wg * gs_stride + lane : nullptr;
+    for (int s = 0; s < nsteps; ++s) sweep_node(steps[s], eps0, f, live, ld, sl, slice_cap, gs, lane);
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -455,13 +624,15 @@ struct Col {
     std::shared_ptr<Slab> slab;      // null: never computed ("-Inf")
 };
 struct HostTab {                     // host mirror of NodeTab allocations
-    int wdim = 0, nrow = 0, k = 0;
-    int cstride[BLG_MAXK] = {0};
-    double* W = nullptr;
+    int wdim = 0, wdp = 0, nrow = 0, k = 0;
+    int cdp[BLG_MAXK] = {0};
+    int mo[BLG_MAXK] = {0};          // merge order (node indices)
+    double* Wt = nullptr;
     double* ipow = nullptr;
-    double* coef[BLG_MAXK] = {nullptr};
+    double* coefD[BLG_MAXK] = {nullptr};
     bool built = false;
 };
+inline int round_up(int v, int m) { return (v + m - 1) / m * m; }
 
 template <class T> struct DevBuf {
     T* p = nullptr;
@@ -521,6 +692,17 @@ struct blg_handle {
     std::vector<NodeTab> tab_stage;
     bool tabs_valid = false;
 
+    // sweep-kernel plumbing
+    int kernel_version = 2;
+    int slice_cap = 80;                       // doubles per lane of the per-warp shared-memory slice
+    NodeStep* step_stage = nullptr;           // pinned
+    size_t step_stage_cap = 512;
+    cudaEvent_t stage_done = nullptr;
+    bool stage_busy = false;
+    DevBuf<NodeStep> d_steps;
+    DevBuf<double> gscratch;
+    size_t sweep_smem_set = 0;
+
     // accounting of the last likelihood call
     double last_bytes = 0.0, last_prune_bytes = 0.0;
     int last_launches = 0;
@@ -545,12 +727,15 @@ struct blg_handle {
         d_kind.free_(); d_parent.free_(); d_child_off.free_(); d_child_idx.free_(); d_list.free_();
         d_t.free_(); d_lam.free_(); d_mu.free_(); d_q.free_(); d_eps0.free_(); d_eps1.free_(); d_tab.free_();
         for (auto& e : ev) if (e) cudaEventDestroy(e);
+        if (stage_done) cudaEventDestroy(stage_done);
+        if (step_stage) cudaFreeHost(step_stage);
+        d_steps.free_(); gscratch.free_();
         if (own_stream && stream) cudaStreamDestroy(stream);
     }
     static void free_tab(HostTab& tb) {
-        if (tb.W) cudaFree(tb.W);
+        if (tb.Wt) cudaFree(tb.Wt);
         if (tb.ipow) cudaFree(tb.ipow);
-        for (int i = 0; i < BLG_MAXK; ++i) if (tb.coef[i]) cudaFree(tb.coef[i]);
+        for (int i = 0; i < BLG_MAXK; ++i) if (tb.coefD[i]) cudaFree(tb.coefD[i]);
         tb = HostTab();
     }
 
@@ -628,6 +813,17 @@ struct blg_handle {
         return m;
     }
 
+    // merge order of node i's children: the child with the smaller counts first (it becomes the
+    // "t" side of the merge, whose columns live in shared memory; the larger one is register-tiled)
+    std::vector<int> merge_order(int i) {
+        std::vector<int> mo = children[i];
+        if (mo.size() == 2) {
+            double a = mo[0] < (int)Tp.size() ? Tp[mo[0]].colsum : 0.0;
+            double b = mo[1] < (int)Tp.size() ? Tp[mo[1]].colsum : 0.0;
+            if (b < a) std::swap(mo[0], mo[1]);
+        }
+        return mo;
+    }
     // (re)allocate the tables of node i for the current proposal column dims
     void ensure_tab(int i) {
         HostTab& tb = tabs[i];
@@ -635,23 +831,26 @@ struct blg_handle {
         int xm = (i < (int)Tp.size()) ? Tp[i].xmax : 0;
         int wdim = (kind[i] == BLG_ROOT) ? 0 : xm + 1;
         int nrow = k > 0 ? xm + 1 : 0;
+        std::vector<int> mo = merge_order(i);
         bool same = tb.wdim == wdim && tb.nrow == nrow && tb.k == k;
-        for (int c = 1; c < k && same; ++c) {
-            int ci = children[i][c];
+        for (int c = 0; c < k && same; ++c) {
+            int ci = mo[c];
             int cx = (ci < (int)Tp.size()) ? Tp[ci].xmax : 0;
-            if (tb.cstride[c] != cx + 1) same = false;
+            if (tb.mo[c] != ci) same = false;
+            if (c >= 1 && tb.cdp[c] != round_up(cx + 1, BLG_TS)) same = false;
         }
-        if (same && (tb.W || wdim == 0) && (tb.ipow || nrow == 0)) return;
+        if (same && (tb.Wt || wdim == 0) && (tb.ipow || nrow == 0)) return;
         free_tab(tb);
-        tb.wdim = wdim; tb.nrow = nrow; tb.k = k;
-        if (wdim > 0) CK(cudaMalloc(&tb.W, (size_t)wdim * wdim * sizeof(double)));
+        tb.wdim = wdim; tb.wdp = round_up(std::max(wdim, 1), BLG_TS); tb.nrow = nrow; tb.k = k;
+        for (int c = 0; c < k; ++c) tb.mo[c] = mo[c];
+        if (wdim > 0) CK(cudaMalloc(&tb.Wt, (size_t)wdim * tb.wdp * sizeof(double)));
         if (nrow > 0) {
             CK(cudaMalloc(&tb.ipow, (size_t)nrow * sizeof(double)));
             for (int c = 1; c < k; ++c) {
-                int ci = children[i][c];
+                int ci = mo[c];
                 int cx = (ci < (int)Tp.size()) ? Tp[ci].xmax : 0;
-                tb.cstride[c] = cx + 1;
-                CK(cudaMalloc(&tb.coef[c], (size_t)nrow * (cx + 1) * sizeof(double)));
+                tb.cdp[c] = round_up(cx + 1, BLG_TS);
+                CK(cudaMalloc(&tb.coefD[c], (size_t)nrow * tb.cdp[c] * sizeof(double)));
             }
         }
     }
@@ -690,8 +889,8 @@ struct blg_handle {
             HostTab& tb = tabs[i];
             NodeTab nt;
             memset(&nt, 0, sizeof(nt));
-            nt.W = tb.W; nt.wdim = tb.wdim; nt.ipow = tb.ipow; nt.nrow = tb.nrow;
-            for (int c = 0; c < BLG_MAXK; ++c) { nt.coef[c] = tb.coef[c]; nt.cstride[c] = tb.cstride[c]; }
+            nt.Wt = tb.Wt; nt.wdim = tb.wdim; nt.wdp = tb.wdp; nt.ipow = tb.ipow; nt.nrow = tb.nrow;
+            for (int c = 0; c < BLG_MAXK; ++c) { nt.coefD[c] = tb.coefD[c]; nt.cdp[c] = tb.cdp[c]; nt.mo[c] = tb.mo[c]; }
             tab_stage[i] = nt;
             tb.built = true;
             maxdim = std::max(maxdim, tb.wdim);
@@ -713,38 +912,43 @@ struct blg_handle {
     // ---- pruning -----------------------------------------------------------------------------------
     template <int CAP> void launch_prune(const NodeStep& st) {
         int blocks = (N + 127) / 128;
-        prune_node_kernel<CAP><<<blocks, 128, 0, stream>>>(st, N, ld);
+        prune_node_kernel<CAP><<<blocks, 128, 0, stream>>>(st, d_eps0.p, N, ld);
     }
-    void prune_node(int u) {
+    // describe the pruning step at node u against the current proposal tables (allocates the output slab)
+    NodeStep make_step(int u) {
         int k = (int)children[u].size();
         require(k >= 1, "prune_node: leaf");
         require(u < (int)Tp.size(), "logpdf: model has more node ids than the profile has columns (call blg_extend)");
         require(tabs_valid && tabs[u].built, "logpdf: ε/W tables are stale (call blg_rebuild)");
+        require(tabs[u].k == k, "logpdf: node table does not match the topology (call blg_rebuild)");
         NodeStep st;
         memset(&st, 0, sizeof(st));
         st.k = k;
-        // children first: reading may allocate zero slabs
         for (int i = 0; i < k; ++i) {
-            int c = children[u][i];
-            require(c < (int)Tp.size(), "logpdf: child id beyond the profile columns");
+            int c = tabs[u].mo[i];
+            require(c >= 0 && c < (int)Tp.size(), "logpdf: child id beyond the profile columns");
             require(tabs[c].built && tabs[c].wdim == Tp[c].xmax + 1, "logpdf: W table of a child does not match the profile (call blg_rebuild)");
             ChildRef& cr = st.child[i];
-            if (children[c].empty()) { cr.ell = nullptr; cr.scl = nullptr; }
+            if (children[c].empty()) { cr.ell = nullptr; cr.scl = nullptr; last_bytes += 2.0 * N; }
             else { Slab* s = readable(c); cr.ell = s->ell; cr.scl = s->scl; last_bytes += 8.0 * Tp[c].colsum + 4.0 * N; }
-            if (children[c].empty()) last_bytes += 2.0 * N;
             cr.cnt = Tp[c].cnt;
-            cr.W = tabs[c].W;
-            cr.wdim = tabs[c].wdim;
+            cr.Wt = tabs[c].Wt;
+            cr.wdp = tabs[c].wdp;
             cr.id = c;
-            cr.coef = tabs[u].coef[i];
-            cr.cstride = tabs[u].cstride[i];
-            if (i >= 1) require(tabs[u].cstride[i] == Tp[c].xmax + 1, "logpdf: merge table does not match the profile (call blg_rebuild)");
+            cr.coefD = tabs[u].coefD[i];
+            cr.cdp = tabs[u].cdp[i];
+            if (i >= 1) require(tabs[u].cdp[i] == round_up(Tp[c].xmax + 1, BLG_TS), "logpdf: merge table does not match the profile (call blg_rebuild)");
         }
         require(tabs[u].nrow == Tp[u].xmax + 1, "logpdf: node table does not match the profile (call blg_rebuild)");
         Slab* o = writable(u);
+        st.nrow = tabs[u].nrow;
         st.out = o->ell; st.out_scl = o->scl; st.cnt = Tp[u].cnt;
-        st.ipow = tabs[u].ipow; st.eps0 = d_eps0.p;
+        st.ipow = tabs[u].ipow;
         last_bytes += 8.0 * Tp[u].colsum + 4.0 * N;
+        return st;
+    }
+    void prune_node_v1(int u) {
+        NodeStep st = make_step(u);
         int need = Tp[u].xmax + 1;
         if (need <= 16) launch_prune<16>(st);
         else if (need <= 32) launch_prune<32>(st);
@@ -753,6 +957,55 @@ struct blg_handle {
         else if (need <= 256) launch_prune<256>(st);
         else if (need <= 512) launch_prune<512>(st);
         else launch_prune<1024>(st);
+        CK(cudaGetLastError());
+        last_launches++;
+    }
+    // v2: one launch for a whole list of nodes
+    void sweep(const std::vector<int>& nodes) {
+        if (nodes.empty()) return;
+        if (!step_stage) CK(cudaMallocHost(&step_stage, sizeof(NodeStep) * step_stage_cap));
+        if (nodes.size() > step_stage_cap) {
+            CK(cudaStreamSynchronize(stream));
+            cudaFreeHost(step_stage);
+            step_stage = nullptr;
+            step_stage_cap = nodes.size() * 2;
+            CK(cudaMallocHost(&step_stage, sizeof(NodeStep) * step_stage_cap));
+        }
+        // the pinned staging buffer is reused by every call: wait until the previous upload left it
+        if (stage_busy) { CK(cudaEventSynchronize(stage_done)); stage_busy = false; }
+        int worst = 1;
+        for (size_t i = 0; i < nodes.size(); ++i) {
+            int u = nodes[i];
+            step_stage[i] = make_step(u);
+            // worst-case per-family working set (doubles) of this node, from the column bounds
+            int k = (int)children[u].size();
+            int sum = 0, capA = 1;
+            for (int c = 0; c < k; ++c) { sum += Tp[tabs[u].mo[c]].xmax; if (c == 0 || c < k - 1) capA = sum + 1; }
+            int need = k >= 2 ? 2 * capA + sum + 1 : capA;
+            worst = std::max(worst, need);
+        }
+        d_steps.ensure(nodes.size());
+        CK(cudaMemcpyAsync(d_steps.p, step_stage, nodes.size() * sizeof(NodeStep), cudaMemcpyHostToDevice, stream));
+        if (!stage_done) CK(cudaEventCreateWithFlags(&stage_done, cudaEventDisableTiming));
+        CK(cudaEventRecord(stage_done, stream));
+        stage_busy = true;
+        const int warps_per_block = 4;
+        int nwarps = (N + 31) / 32;
+        int blocks = (nwarps + warps_per_block - 1) / warps_per_block;
+        int cap = std::min(slice_cap, worst);            // doubles per lane in the shared slice
+        double* gs = nullptr;
+        size_t gstride = 0;
+        if (worst > cap) {                                // some warp may need more than its slice: global scratch
+            gstride = (size_t)worst * 32;
+            gscratch.ensure(gstride * (size_t)nwarps);
+            gs = gscratch.p;
+        }
+        size_t smem = (size_t)cap * 32 * warps_per_block * sizeof(double);
+        if (smem > sweep_smem_set) {
+            CK(cudaFuncSetAttribute(sweep_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+            sweep_smem_set = smem;
+        }
+        sweep_kernel<<<blocks, 32 * warps_per_block, smem, stream>>>(d_steps.p, (int)nodes.size(), d_eps0.p, N, ld, cap, gs, gstride);
         CK(cudaGetLastError());
         last_launches++;
     }
@@ -782,13 +1035,18 @@ struct blg_handle {
         if (N == 0) { CK(cudaMemsetAsync(d_out, 0, sizeof(double), stream)); return; }   // profile.jl:56
         require((int)Tp.size() >= 1, "logpdf: no profile columns");
         if (timing) { for (auto& e : ev) if (!e) CK(cudaEventCreate(&e)); CK(cudaEventRecord(ev[0], stream)); }
+        std::vector<int> nodes;
         if (mode == 0) {
-            for (int u : postorder) if (!children[u].empty()) prune_node(u);
+            for (int u : postorder) if (!children[u].empty()) nodes.push_back(u);
         } else if (mode == 1) {
             int u = node - 1;
             require(present(u), "logpdf_from: node id not in the model");
-            while (u >= 0) { if (!children[u].empty()) prune_node(u); u = parent[u]; }
+            while (u >= 0) { if (!children[u].empty()) nodes.push_back(u); u = parent[u]; }
         }
+        bool v1 = kernel_version == 1;
+        for (int u : nodes) if (Tp[u].xmax > 255) v1 = true;    // very large counts: the general kernel
+        if (v1) { for (int u : nodes) prune_node_v1(u); }
+        else sweep(nodes);
         if (timing) CK(cudaEventRecord(ev[1], stream));
         last_prune_bytes = last_bytes;
         root_reduce(d_out);
@@ -825,6 +1083,8 @@ int blg_create(int device, void* stream, blg_handle** out) {
         if (stream) h->stream = (cudaStream_t)stream;
         else { CK(cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking)); h->own_stream = true; }
         h->result.ensure(16);
+        if (const char* kv = getenv("BLG_KERNEL")) h->kernel_version = atoi(kv) == 1 ? 1 : 2;
+        if (const char* sc = getenv("BLG_SLICE")) h->slice_cap = std::max(8, std::min(224, atoi(sc)));
         *out = h;
     } catch (const std::exception& e) { g_create_error = e.what(); return 2; }
     return 0;
@@ -1079,10 +1339,13 @@ int blg_get_W(blg_handle* h, int node, double* out, int cap, int* dim) {
     h->require(node >= 1 && node <= (int)h->tabs.size(), "get_W: node out of range");
     HostTab& tb = h->tabs[node - 1];
     if (dim) *dim = tb.wdim;
-    h->require(tb.W != nullptr && tb.built, "get_W: no table");
+    h->require(tb.Wt != nullptr && tb.built, "get_W: no table");
     h->require(cap >= tb.wdim * tb.wdim, "get_W: buffer too small");
     CK(cudaStreamSynchronize(h->stream));
-    CK(cudaMemcpy(out, tb.W, (size_t)tb.wdim * tb.wdim * sizeof(double), cudaMemcpyDeviceToHost));
+    std::vector<double> wt((size_t)tb.wdim * tb.wdp);
+    CK(cudaMemcpy(wt.data(), tb.Wt, wt.size() * sizeof(double), cudaMemcpyDeviceToHost));
+    for (int n = 0; n < tb.wdim; ++n)
+        for (int j = 0; j < tb.wdim; ++j) out[(size_t)n * tb.wdim + j] = wt[(size_t)j * tb.wdp + n];
     BLG_LEAVE(h)
 }
 int blg_ncols(blg_handle* h, int which) { return h ? (int)(which ? h->Tp.size() : h->Tc.size()) : -1; }
