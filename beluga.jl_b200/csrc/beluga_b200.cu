@@ -30,6 +30,7 @@
 
 #define BLG_MAXK 8          // max children of one node (polytomies)
 #define BLG_MAXCOUNT 1023   // largest extended count supported (binomials stay finite in fp64)
+#define BLG_FAST_MAXCOUNT 100   // largest count bound the table-free sweep kernel handles
 
 namespace {
 
@@ -61,6 +62,11 @@ struct NodeTab {        // per node id, device-resident tables
     int mo[BLG_MAXK];   // merge order: node indices of the children in the order they are merged
 };
 
+struct SweepNodeConst {       // per node id, written by tables_kernel, read by sweep_kernel
+    double psi, cc;           // ψ', (1-ϕ')(1-ψ') of the (ordinary) branch above the node
+    double E[BLG_MAXK];       // clamped prefix products of the children's ϵ[1] in merge order (E[0] = 1)
+};
+
 struct ModelDev {
     int n;                     // ncols (max id)
     int model_kind;
@@ -78,6 +84,8 @@ struct ModelDev {
     NodeTab* tab;
     const double* pascal;      // C(n,s), row stride pdim
     int pdim;
+    SweepNodeConst* nc;        // per-node scalars of the table-free sweep kernel
+    int* fast_ok;              // per node: 1 if the factorial-scaled forms stay inside fp64 here
 };
 
 __device__ __forceinline__ bool d_isapprox(double a, double b) {
@@ -169,6 +177,8 @@ __global__ void __launch_bounds__(128) tables_kernel(ModelDev m, const int* __re
     const NodeTab tb = m.tab[n];
     const int tid = threadIdx.x, nt = blockDim.x;
     uint8_t kd = m.kind[n];
+    bool ok = true;                 // may the table-free sweep kernel be used at this node?
+    if (tid == 0) { m.nc[n].psi = 0.0; m.nc[n].cc = 0.0; }
     // ---- W of the branch above n -------------------------------------------------------------
     if (kd != BLG_ROOT && tb.Wt != nullptr) {
         const int d = tb.wdim;
@@ -212,6 +222,14 @@ __global__ void __launch_bounds__(128) tables_kernel(ModelDev m, const int* __re
             double phip = d_approx1((phi * (1.0 - e) + (1.0 - psi) * e) / nn);
             double psip = d_approx1(psi * (1.0 - e) / nn);
             double cc = (1.0 - phip) * (1.0 - psip);
+            if (tid == 0) { m.nc[n].psi = psip; m.nc[n].cc = cc; }
+            {   // range of ψ'^d/d! and c^n/(n-1)! over the count bound of this column
+                const int xm = d - 1;
+                if (xm > BLG_FAST_MAXCOUNT) ok = false;
+                if (!(psip >= 0.0 && psip <= 1.0 && cc >= 0.0 && cc <= 1.0)) ok = false;
+                if (psip > 0.0 && xm * log(psip) - lgamma(xm + 1.0) < -640.0) ok = false;
+                if (cc > 0.0 && xm * log(cc) - lgamma((double)(xm > 0 ? xm : 1)) < -640.0) ok = false;
+            }
             double* prev = sm;
             double* cur = sm + d;
             for (int i = tid; i < d; i += nt) prev[i] = (i == 0) ? 1.0 : 0.0;   // column 0
@@ -248,6 +266,10 @@ __global__ void __launch_bounds__(128) tables_kernel(ModelDev m, const int* __re
             if (!(v >= 0.0 && v < 1.0)) poison = true;
         }
         double inv = 1.0 / (1.0 - E[k]);
+        if (tid == 0) for (int i = 0; i < k; ++i) m.nc[n].E[i] = E[i];
+        if (tb.nrow - 1 > BLG_FAST_MAXCOUNT) ok = false;
+        for (int i = 1; i < k; ++i)
+            if (!poison && !(E[i] > 0.0 && -(double)tb.nrow * log(E[i]) < 600.0)) ok = false;
         for (int r = tid; r < tb.nrow; r += nt) tb.ipow[r] = poison ? __longlong_as_double(0x7ff8000000000000LL) : d_powi(inv, r);
         for (int i = 1; i < k; ++i) {
             double* cf = tb.coefD[i];
@@ -261,6 +283,7 @@ __global__ void __launch_bounds__(128) tables_kernel(ModelDev m, const int* __re
             }
         }
     }
+    if (tid == 0) m.fast_ok[n] = ok ? 1 : 0;
 }
 
 // Pascal triangle C(n,s), n,s < dim, by the addition recurrence (exact while < 2^53).
@@ -376,147 +399,207 @@ __global__ void __launch_bounds__(128) prune_node_kernel(const NodeStep st, cons
     st.out_scl[f] = sclsum + ex;
 }
 
-// ---- v2: the sweep kernel.  ONE launch walks a list of nodes (a full post-order sweep, or the
-// path node→root of a partial recompute).  A warp owns 32 consecutive families for the whole list
-// and never synchronises with another warp: a parent only reads what the same thread wrote.
-// Per-family working columns live in a per-warp shared-memory slice laid out [index][lane]
-// (conflict-free); W and the merge coefficients are warp-uniform loads served by L1.  Both inner
-// loops keep BLG_TS counts per thread in registers:
-//   contraction: acc[s0..s0+7] += Wt[j][s0..s0+7]·ℓ[j]         (1 per-thread load per 8 FMA)
-//   merge:       tile [s0, s0+8) of the B row and of the anti-diagonal accumulators stays in
-//                registers while t runs; tiles are processed from high s to low s and hand their
-//                first column to the next tile through a per-family history column.
+// ---- the sweep kernel.  ONE launch walks a list of nodes (a full post-order sweep, or the path
+// node→root of a partial recompute).  A warp owns 32 consecutive families for the whole list and never
+// synchronises with another warp: a parent only reads what the same thread wrote.
+//   * step descriptors travel as a __grid_constant__ kernel parameter (constant bank: uniform,
+//     cache-resident reads that streaming data cannot evict);
+//   * the per-family working column lives in a per-warp shared-memory slice laid out [index][lane]
+//     (conflict-free 64-bit accesses); a node needs S+2 doubles per family because both inner loops
+//     run IN PLACE;
+//   * NO coefficient tables are read in the inner loops.  They are generated in registers:
+//       contraction over an ordinary branch: w*(n|j) = C(j-1,n-1)·ψ'^(j-n)·c^n, c = (1-ϕ')(1-ψ')
+//         (closed form of the recurrence in wstar!, node.jl:181-192), hence for n >= 1
+//           b[n] = c^n/(n-1)! · Σ_{d>=0} [ψ'^d/d!] · [(n+d-1)!·ℓ[n+d]]
+//         — a sliding-window correlation: TS outputs and a TS-wide window stay in registers, one
+//         shared-memory load and TS FMAs per step;
+//       merge: C(n,s)·E^s = n!·E^n · 1/(t!·E^t) · 1/s!  (t+s = n), hence with a'[t] = A[t]/(t!E^t) and
+//         B†[t,s] = B[t,s]/s!:   B†[t,s] = (s+1)·B†[t-1,s+1] + e·B†[t-1,s]
+//                                 Ã[n]   = n!E^n · Σ_{t+s=n} a'[t]·B†[t,s]
+//         with the B† row and the anti-diagonal accumulators of the smaller child in registers;
+//     the branch below a WGD/WGT keeps its (banded) table, read from global memory;
+//   * the factorial scalings limit this kernel to count bounds <= BLG_FAST_MAXCOUNT and to parameter
+//     ranges where they stay inside fp64 (checked per node on the device when ε/W are built);
+//     otherwise the per-node general kernels above are used.
+__constant__ double c_fact[BLG_FAST_MAXCOUNT + 72];      // n!
+__constant__ double c_invfact[BLG_FAST_MAXCOUNT + 72];   // 1/n!
+__constant__ double c_inv[BLG_FAST_MAXCOUNT + 72];       // 1/n (c_inv[0] = 0)
+
+struct SweepChild {
+    const double* ell;     // nullptr: leaf
+    const int* scl;
+    const uint16_t* cnt;
+    const double* Wt;      // transposed w* of the child's branch (leaf gather, WGD/WGT-after contraction)
+    int wdp, id, table, pad_;   // table != 0: contract with Wt (branch below a WGD/WGT)
+};
+struct SweepStep {
+    int k, node, first, pad_;
+    const double* ipow;
+    double* out;
+    int* out_scl;
+    const uint16_t* cnt;
+};
+#define BLG_SWEEP_MAXSTEPS 192
+#define BLG_SWEEP_MAXCHILD 384
+struct SweepList {
+    int nsteps;
+    int pad_[3];
+    SweepStep step[BLG_SWEEP_MAXSTEPS];
+    SweepChild child[BLG_SWEEP_MAXCHILD];
+};
+static_assert(sizeof(SweepList) <= 32000, "kernel parameter space");
 __device__ __forceinline__ int warp_max(int v) { return __reduce_max_sync(0xffffffffu, v); }
 
-// b[s] = Σ_{j>=s} Wt[j][s]·ℓ[j], s = 0..Mw, into dst[s*32]  (leaf child: the column x_c of w*)
-__device__ __forceinline__ void sweep_contract(const ChildRef& c, int f, size_t ld, int M, int Mw, double* dst, int& sclsum) {
-    if (c.ell == nullptr) {
-        const double* row = c.Wt + (size_t)M * c.wdp;
-        for (int s = 0; s <= Mw; ++s) dst[s * 32] = (s <= M) ? row[s] : 0.0;
-        return;
-    }
-    sclsum += c.scl[f];
-    const double* col = c.ell + f;
-    for (int s0 = 0; s0 <= Mw; s0 += BLG_TS) {
-        double acc[BLG_TS];
+// in-place table contraction (branch below a WGD/WGT): col[s] ← Σ_{j=s..Mw} Wt[j*wdp+s]·col[j]
+template <int TS>
+__device__ __noinline__ void sweep_contract_table(double* col, int Mw, const double* __restrict__ Wt, int wdp) {
+    for (int s0 = 0; s0 <= Mw; s0 += TS) {
+        double acc[TS];
 #pragma unroll
-        for (int k = 0; k < BLG_TS; ++k) acc[k] = 0.0;
-#pragma unroll 2
+        for (int k = 0; k < TS; ++k) acc[k] = 0.0;
         for (int j = s0; j <= Mw; ++j) {
-            const double x = (j <= M) ? col[(size_t)j * ld] : 0.0;
-            const double* __restrict__ w = c.Wt + (size_t)j * c.wdp + s0;
+            const double x = col[j * 32];
+            const double* __restrict__ w = Wt + (size_t)j * wdp + s0;
 #pragma unroll
-            for (int k = 0; k < BLG_TS; ++k) acc[k] = fma(w[k], x, acc[k]);
+            for (int k = 0; k < TS; ++k) acc[k] = fma(w[k], x, acc[k]);
         }
 #pragma unroll
-        for (int k = 0; k < BLG_TS; ++k)
-            if (s0 + k <= Mw) dst[(s0 + k) * 32] = acc[k];
+        for (int k = 0; k < TS; ++k)
+            if (s0 + k <= Mw) col[(s0 + k) * 32] = acc[k];
     }
 }
-
-// O[n] (n = 0..Sw+M2w) ← Σ_{t+s=n} coefD[t][s]·A[t]·B[t,s].  On entry O[0..M2w] holds B[0,·] and
-// O[M2w+1..Sw+M2w] is zero; H is scratch of Sw+1 entries.
-__device__ __forceinline__ void sweep_merge(const double* A, int Sw, double* O, int M2w, double* H,
-                                            const double* __restrict__ coefD, int cdp, double e) {
-    const int ntile = M2w / BLG_TS + 1;
-    const int nmax = Sw + M2w;
-    for (int tile = ntile - 1; tile >= 0; --tile) {
-        const int s0 = tile * BLG_TS;
-        const bool top = (tile == ntile - 1);
-        double B[BLG_TS], acc[BLG_TS];
+// in-place closed-form contraction over an ordinary branch.  On entry col[j] = ℓ[j] (j = 0..Mw).
+template <int TS>
+__device__ __noinline__ void sweep_contract_fast(double* col, int Mw, double psi, double cc) {
+    // u[j] = (j-1)!·ℓ[j]
+    for (int j = 2; j <= Mw; ++j) col[j * 32] *= c_fact[j - 1];
+    double post = cc;                                  // c^n/(n-1)! at n = 1
+    for (int n0 = 1; n0 <= Mw; n0 += TS) {
+        double acc[TS], win[TS];
 #pragma unroll
-        for (int k = 0; k < BLG_TS; ++k) {
-            B[k] = (s0 + k <= M2w) ? O[(s0 + k) * 32] : 0.0;
+        for (int k = 0; k < TS; ++k) {
+            acc[k] = 0.0;
+            win[k] = (n0 + k <= Mw) ? col[(n0 + k) * 32] : 0.0;
+        }
+        double g = 1.0;                                // ψ'^d/d!
+        const int dmax = Mw - n0;
+        for (int d = 0; d <= dmax; ++d) {
+#pragma unroll
+            for (int k = 0; k < TS; ++k) acc[k] = fma(g, win[k], acc[k]);
+#pragma unroll
+            for (int k = 0; k < TS - 1; ++k) win[k] = win[k + 1];
+            const int j = n0 + TS + d;
+            win[TS - 1] = (j <= Mw) ? col[j * 32] : 0.0;
+            g *= psi * c_inv[d + 1];
+        }
+#pragma unroll
+        for (int k = 0; k < TS; ++k) {
+            const int n = n0 + k;
+            if (n <= Mw) col[n * 32] = acc[k] * post;
+            post *= cc * c_inv[n];                     // → c^(n+1)/n!
+        }
+    }
+}
+// single-tile in-place merge (M2w < TS).  R[0..Sw] = A, R[Sw+1..Sw+1+M2w] = B[0,·];
+// on exit R[0..Sw+M2w] = Σ_{t+s=n} C(n,s)·E^s·A[t]·B[t,s].
+template <int TS>
+__device__ __noinline__ void sweep_merge_fast(double* R, int Sw, int M2w, double E, double e) {
+    double B[TS], acc[TS];
+#pragma unroll
+    for (int k = 0; k < TS; ++k) {
+        B[k] = (k <= M2w) ? R[(Sw + 1 + k) * 32] * c_invfact[k] : 0.0;
+        acc[k] = 0.0;
+    }
+    const int nmax = Sw + M2w;
+    const double invE = 1.0 / E;
+    double tf = 1.0;       // 1/(t!·E^t)
+    double em = 1.0;       // n!·E^n
+    for (int t = 0; t <= nmax; ++t) {
+        if (t <= Sw) {
+            const double a = R[t * 32] * tf;
+#pragma unroll
+            for (int k = 0; k < TS; ++k) acc[k] = fma(a, B[k], acc[k]);
+#pragma unroll
+            for (int k = 0; k < TS - 1; ++k) B[k] = fma(e, B[k], (double)(k + 1) * B[k + 1]);
+            B[TS - 1] = e * B[TS - 1];
+            tf *= invE * c_inv[t + 1];
+        }
+        R[t * 32] = acc[0] * em;
+#pragma unroll
+        for (int k = 0; k < TS - 1; ++k) acc[k] = acc[k + 1];
+        acc[TS - 1] = 0.0;
+        em *= E * (double)(t + 1);
+    }
+}
+// general merge for a smaller child with >= 24 counts: 16-wide tiles from high s to low s chained
+// through the history column H.  A[0..Sw]; O[0..M2w] = B[0,·], O[M2w+1..Sw+M2w] = 0 on entry; result in O.
+__device__ __noinline__ void sweep_merge_tiled(const double* A, int Sw, double* O, int M2w, double* H, double E, double e) {
+    constexpr int TS = 16;
+    const int ntile = M2w / TS + 1;
+    const int nmax = Sw + M2w;
+    const double invE = 1.0 / E;
+    for (int tile = ntile - 1; tile >= 0; --tile) {
+        const int s0 = tile * TS;
+        const bool top = (tile == ntile - 1);
+        double B[TS], acc[TS];
+#pragma unroll
+        for (int k = 0; k < TS; ++k) {
+            B[k] = (s0 + k <= M2w) ? O[(s0 + k) * 32] * c_invfact[s0 + k] : 0.0;
             acc[k] = 0.0;
         }
 #pragma unroll
-        for (int k = 0; k < BLG_TS; ++k)
+        for (int k = 0; k < TS; ++k)
             if (s0 + k <= M2w) O[(s0 + k) * 32] = 0.0;
-        // t runs over Sw+1 real steps plus BLG_TS-1 draining steps (a = 0) that flush the accumulators;
-        // the accumulator of n = t+s0+k lives in slot (k+t) mod BLG_TS, a compile-time index below
-        for (int tb = 0; tb <= Sw + BLG_TS - 1; tb += BLG_TS) {
+        double tf = 1.0;
+        for (int t = 0; t <= Sw + TS - 1; ++t) {
+            if (t <= Sw) {
+                const double a = A[t * 32] * tf;
+                const double halo = top ? 0.0 : H[t * 32];
+                H[t * 32] = B[0];
 #pragma unroll
-            for (int u = 0; u < BLG_TS; ++u) {
-                const int t = tb + u;
-                if (t <= Sw) {
-                    const double a = A[t * 32];
-                    const double halo = top ? 0.0 : H[t * 32];
-                    H[t * 32] = B[0];
-                    const double* __restrict__ cf = coefD + (size_t)t * cdp + s0;
+                for (int k = 0; k < TS; ++k) acc[k] = fma(a, B[k], acc[k]);
 #pragma unroll
-                    for (int k = 0; k < BLG_TS; ++k) acc[(k + u) % BLG_TS] = fma(cf[k] * a, B[k], acc[(k + u) % BLG_TS]);
-#pragma unroll
-                    for (int k = 0; k < BLG_TS - 1; ++k) B[k] = fma(e, B[k], B[k + 1]);
-                    B[BLG_TS - 1] = fma(e, B[BLG_TS - 1], halo);
-                }
-                const int n = t + s0;
-                if (n <= nmax) O[n * 32] += acc[u % BLG_TS];
-                acc[u % BLG_TS] = 0.0;
+                for (int k = 0; k < TS - 1; ++k) B[k] = fma(e, B[k], (double)(s0 + k + 1) * B[k + 1]);
+                B[TS - 1] = fma(e, B[TS - 1], (double)(s0 + TS) * halo);
+                tf *= invE * c_inv[t + 1];
             }
+            const int n = t + s0;
+            if (n <= nmax) O[n * 32] += acc[0];
+#pragma unroll
+            for (int k = 0; k < TS - 1; ++k) acc[k] = acc[k + 1];
+            acc[TS - 1] = 0.0;
         }
+    }
+    double em = 1.0;
+    for (int n = 0; n <= nmax; ++n) { O[n * 32] *= em; em *= E * (double)(n + 1); }
+}
+
+// stage + contract one child into col[0..Mw]
+__device__ __noinline__ void sweep_child(const SweepChild& c, const SweepNodeConst* __restrict__ nc, int f, size_t ld,
+                                            int M, int Mw, double* col) {
+    if (c.ell == nullptr) {                        // leaf: column x_c of w* (one-hot likelihood)
+        const double* __restrict__ row = c.Wt + (size_t)M * c.wdp;
+#pragma unroll 4
+        for (int s = 0; s <= Mw; ++s) col[s * 32] = (s <= M) ? row[s] : 0.0;
+        return;
+    }
+    const double* __restrict__ src = c.ell + f;
+#pragma unroll 8
+    for (int j = 0; j <= Mw; ++j) col[j * 32] = (j <= M) ? src[(size_t)j * ld] : 0.0;
+    if (c.table) {
+        if (Mw < 8) sweep_contract_table<8>(col, Mw, c.Wt, c.wdp);
+        else sweep_contract_table<16>(col, Mw, c.Wt, c.wdp);
+    } else {
+        const double psi = nc[c.id].psi, cc = nc[c.id].cc;
+        if (Mw <= 4) sweep_contract_fast<4>(col, Mw, psi, cc);
+        else if (Mw <= 12) sweep_contract_fast<12>(col, Mw, psi, cc);
+        else sweep_contract_fast<24>(col, Mw, psi, cc);
     }
 }
 
-__device__ __forceinline__ void sweep_node(const NodeStep& st, const double* __restrict__ eps0, int f, bool live,
-                                           size_t ld, double* sl, int slice_cap, double* gs, unsigned lane) {
-    const int k = st.k;
-    int M[BLG_MAXK], Mw[BLG_MAXK];
-    int capA = 1, capO = 0;
-    {
-        int sum = 0;
-#pragma unroll
-        for (int i = 0; i < BLG_MAXK; ++i) {
-            if (i < k) {
-                M[i] = live ? (int)st.child[i].cnt[f] : 0;
-                Mw[i] = warp_max(M[i]);
-                sum += Mw[i];
-                if (i == 0 || i < k - 1) capA = sum + 1;
-            }
-        }
-        if (k >= 2) capO = sum + 1;
-    }
-    const int need = (k >= 2) ? 2 * capA + capO : capA;
-    double* base = (need <= slice_cap) ? sl : gs;     // warp-uniform choice: shared slice or global scratch
-    double* rA = base;
-    double* rH = base + (size_t)capA * 32;
-    double* rO = base + (size_t)2 * capA * 32;
-    int sclsum = 0;
-    sweep_contract(st.child[0], f, ld, M[0], Mw[0], rA, sclsum);
-    int Sw = Mw[0];
-    for (int i = 1; i < k; ++i) {
-        sweep_contract(st.child[i], f, ld, M[i], Mw[i], rO, sclsum);
-        for (int n = Mw[i] + 1; n <= Sw + Mw[i]; ++n) rO[n * 32] = 0.0;
-        sweep_merge(rA, Sw, rO, Mw[i], rH, st.child[i].coefD, st.child[i].cdp, eps0[st.child[i].id]);
-        Sw += Mw[i];
-        if (i < k - 1)
-            for (int n = 0; n <= Sw; ++n) rA[n * 32] = rO[n * 32];
-    }
-    double* src = (k >= 2) ? rO : rA;
-    const int X = live ? (int)st.cnt[f] : 0;
-    const int Xw = warp_max(X);
-    double mxv = 0.0;
-    bool bad = false;
-    for (int n = 0; n <= Xw; ++n) {
-        double v = 0.0;
-        if (n <= X) {
-            v = (n <= Sw ? src[n * 32] : 0.0) * st.ipow[n];
-            src[n * 32] = v;
-            if (!(v == v) || isinf(v)) bad = true;
-            mxv = fmax(mxv, v);
-        }
-    }
-    int ex = 0;
-    if (!bad && mxv > 0.0) ex = ilogb(mxv);
-    if (live) {
-        double* o = st.out + f;
-        for (int n = 0; n <= X; ++n) o[(size_t)n * ld] = (ex != 0) ? scalbn(src[n * 32], -ex) : src[n * 32];
-        st.out_scl[f] = sclsum + ex;
-    }
-    __syncwarp();
-}
-
-__global__ void __launch_bounds__(128) sweep_kernel(const NodeStep* __restrict__ steps, int nsteps, const double* __restrict__ eps0,
-                                                    int N, size_t ld, int slice_cap, double* gscratch, size_t gs_stride) {
+__global__ void __launch_bounds__(128, 4) sweep_kernel(const __grid_constant__ SweepList L, const double* __restrict__ eps0,
+                                                       const SweepNodeConst* __restrict__ nc,
+                                                       int N, size_t ld, int slice_cap, double* gscratch, size_t gs_stride) {
     extern __shared__ double smem[];
     const unsigned lane = threadIdx.x & 31u;
     const int warp = threadIdx.x >> 5;
@@ -527,7 +610,81 @@ __global__ void __launch_bounds__(128) sweep_kernel(const NodeStep* __restrict__
     if (!live) f = N - 1;
     double* sl = smem + (size_t)warp * slice_cap * 32 + lane;
     double* gs = gscratch ? gscratch + (size_t)wg * gs_stride + lane : nullptr;
-    for (int s = 0; s < nsteps; ++s) sweep_node(steps[s], eps0, f, live, ld, sl, slice_cap, gs, lane);
+
+    for (int si = 0; si < L.nsteps; ++si) {
+        const SweepStep& st = L.step[si];
+        const int k = st.k;
+        const SweepChild* ch = &L.child[st.first];
+        const int X = live ? (int)st.cnt[f] : 0;
+        int sclsum = 0, sumw = 0;
+        bool tiled = false;
+        for (int i = 0; i < k; ++i) {
+            const int Mi = warp_max(live ? (int)ch[i].cnt[f] : 0);
+            sumw += Mi;
+            if (i >= 1 && Mi >= 24) tiled = true;
+            if (ch[i].scl) sclsum += ch[i].scl[f];
+        }
+        const int Xw = warp_max(X);
+        const int need = tiled ? 3 * (sumw + 1) : sumw + k + 1;
+        double* R = (need <= slice_cap) ? sl : gs;
+
+        const int M0 = live ? (int)ch[0].cnt[f] : 0;
+        const int M0w = warp_max(M0);
+        sweep_child(ch[0], nc, f, ld, M0, M0w, R);
+        int Sw = M0w;
+        double* res = R;
+        if (!tiled) {
+            for (int i = 1; i < k; ++i) {
+                const int Mi = live ? (int)ch[i].cnt[f] : 0;
+                const int Miw = warp_max(Mi);
+                sweep_child(ch[i], nc, f, ld, Mi, Miw, R + (size_t)(Sw + 1) * 32);
+                const double e = eps0[ch[i].id];
+                const double E = nc[st.node].E[i];
+                if (Miw < 4) sweep_merge_fast<4>(R, Sw, Miw, E, e);
+                else if (Miw < 12) sweep_merge_fast<12>(R, Sw, Miw, E, e);
+                else sweep_merge_fast<24>(R, Sw, Miw, E, e);
+                Sw += Miw;
+            }
+        } else {
+            const int cap = sumw + 1;
+            double* rA = R;
+            double* rH = R + (size_t)cap * 32;
+            double* rO = R + (size_t)2 * cap * 32;
+            for (int i = 1; i < k; ++i) {
+                const int Mi = live ? (int)ch[i].cnt[f] : 0;
+                const int Miw = warp_max(Mi);
+                sweep_child(ch[i], nc, f, ld, Mi, Miw, rO);
+                for (int n = Miw + 1; n <= Sw + Miw; ++n) rO[n * 32] = 0.0;
+                sweep_merge_tiled(rA, Sw, rO, Miw, rH, nc[st.node].E[i], eps0[ch[i].id]);
+                Sw += Miw;
+                if (i < k - 1)
+                    for (int n = 0; n <= Sw; ++n) rA[n * 32] = rO[n * 32];
+            }
+            res = (k >= 2) ? rO : rA;
+        }
+        // ℓ_u[n] = Ã[n]·(1-E_k)^(-n), rescale to a power-of-two exponent, store
+        double mxv = 0.0;
+        bool bad = false;
+        const double* __restrict__ ipow = st.ipow;
+        for (int n = 0; n <= Xw; ++n) {
+            if (n <= X) {
+                double v = (n <= Sw ? res[n * 32] : 0.0) * ipow[n];
+                res[n * 32] = v;
+                if (!(v == v) || isinf(v)) bad = true;
+                mxv = fmax(mxv, v);
+            }
+        }
+        int ex = 0;
+        if (!bad && mxv > 0.0) ex = ilogb(mxv);
+        if (live) {
+            double* o = st.out + f;
+            const bool exact = (ex > -1000 && ex < 1000);
+            const double sc = exact ? scalbn(1.0, -ex) : 1.0;          // exact power of two
+            for (int n = 0; n <= X; ++n) o[(size_t)n * ld] = exact ? res[n * 32] * sc : scalbn(res[n * 32], -ex);
+            st.out_scl[f] = sclsum + ex;
+        }
+        __syncwarp();
+    }
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -688,18 +845,18 @@ struct blg_handle {
     DevBuf<int> d_parent, d_child_off, d_child_idx, d_list;
     DevBuf<double> d_t, d_lam, d_mu, d_q, d_eps0, d_eps1;
     DevBuf<NodeTab> d_tab;
+    DevBuf<SweepNodeConst> d_nc;
+    DevBuf<int> d_fast_ok;
+    std::vector<int> fast_ok;            // host copy, refreshed by every rebuild
     std::vector<HostTab> tabs;
     std::vector<NodeTab> tab_stage;
     bool tabs_valid = false;
 
     // sweep-kernel plumbing
     int kernel_version = 2;
-    int slice_cap = 80;                       // doubles per lane of the per-warp shared-memory slice
-    NodeStep* step_stage = nullptr;           // pinned
-    size_t step_stage_cap = 512;
-    cudaEvent_t stage_done = nullptr;
-    bool stage_busy = false;
-    DevBuf<NodeStep> d_steps;
+    int last_kernel = 0;
+    int slice_cap = 52;                       // doubles per lane of the per-warp shared-memory slice
+    std::unique_ptr<SweepList> sweep_list{new SweepList()};
     DevBuf<double> gscratch;
     size_t sweep_smem_set = 0;
 
@@ -726,10 +883,9 @@ struct blg_handle {
         weight.free_(); fam_ll.free_(); partial.free_(); result.free_(); rootw.free_(); pascal.free_();
         d_kind.free_(); d_parent.free_(); d_child_off.free_(); d_child_idx.free_(); d_list.free_();
         d_t.free_(); d_lam.free_(); d_mu.free_(); d_q.free_(); d_eps0.free_(); d_eps1.free_(); d_tab.free_();
+        d_nc.free_(); d_fast_ok.free_();
         for (auto& e : ev) if (e) cudaEventDestroy(e);
-        if (stage_done) cudaEventDestroy(stage_done);
-        if (step_stage) cudaFreeHost(step_stage);
-        d_steps.free_(); gscratch.free_();
+        gscratch.free_();
         if (own_stream && stream) cudaStreamDestroy(stream);
     }
     static void free_tab(HostTab& tb) {
@@ -810,17 +966,18 @@ struct blg_handle {
         m.kind = d_kind.p; m.parent = d_parent.p; m.child_off = d_child_off.p; m.child_idx = d_child_idx.p;
         m.t = d_t.p; m.lam = d_lam.p; m.mu = d_mu.p; m.q = d_q.p; m.eta = eta;
         m.eps0 = d_eps0.p; m.eps1 = d_eps1.p; m.tab = d_tab.p; m.pascal = pascal.p; m.pdim = pdim;
+        m.nc = d_nc.p; m.fast_ok = d_fast_ok.p;
         return m;
     }
 
-    // merge order of node i's children: the child with the smaller counts first (it becomes the
-    // "t" side of the merge, whose columns live in shared memory; the larger one is register-tiled)
+    // merge order of node i's children: the child with the larger counts first (the "t" side of the
+    // merge, whose column lives in shared memory); the smaller one is the register-tiled "s" side
     std::vector<int> merge_order(int i) {
         std::vector<int> mo = children[i];
         if (mo.size() == 2) {
             double a = mo[0] < (int)Tp.size() ? Tp[mo[0]].colsum : 0.0;
             double b = mo[1] < (int)Tp.size() ? Tp[mo[1]].colsum : 0.0;
-            if (b < a) std::swap(mo[0], mo[1]);
+            if (b > a) std::swap(mo[0], mo[1]);
         }
         return mo;
     }
@@ -896,6 +1053,8 @@ struct blg_handle {
             maxdim = std::max(maxdim, tb.wdim);
         }
         d_tab.ensure((size_t)ncols_model);
+        d_nc.ensure((size_t)ncols_model);
+        d_fast_ok.ensure((size_t)ncols_model);
         CK(cudaMemcpyAsync(d_tab.p, tab_stage.data(), (size_t)ncols_model * sizeof(NodeTab), cudaMemcpyHostToDevice, stream));
         d_list.ensure(list.size());
         CK(cudaMemcpyAsync(d_list.p, list.data(), list.size() * sizeof(int), cudaMemcpyHostToDevice, stream));
@@ -904,7 +1063,10 @@ struct blg_handle {
         CK(cudaGetLastError());
         tables_kernel<<<(unsigned)list.size(), 128, 2 * (size_t)maxdim * sizeof(double), stream>>>(m, d_list.p, (int)list.size());
         CK(cudaGetLastError());
-        // list/tab_stage are host vectors reused by later calls: make sure the copies are done
+        // list/tab_stage are host vectors reused by later calls: make sure the copies are done; the
+        // per-node "table-free kernel allowed" flags come back with the same synchronisation
+        fast_ok.resize(ncols_model, 0);
+        CK(cudaMemcpyAsync(fast_ok.data(), d_fast_ok.p, (size_t)ncols_model * sizeof(int), cudaMemcpyDeviceToHost, stream));
         CK(cudaStreamSynchronize(stream));
         if (list.size() == postorder.size()) tabs_valid = true;
     }
@@ -960,54 +1122,56 @@ struct blg_handle {
         CK(cudaGetLastError());
         last_launches++;
     }
-    // v2: one launch for a whole list of nodes
+    // one launch for a whole list of nodes (chunked only if the list exceeds the parameter space)
     void sweep(const std::vector<int>& nodes) {
-        if (nodes.empty()) return;
-        if (!step_stage) CK(cudaMallocHost(&step_stage, sizeof(NodeStep) * step_stage_cap));
-        if (nodes.size() > step_stage_cap) {
-            CK(cudaStreamSynchronize(stream));
-            cudaFreeHost(step_stage);
-            step_stage = nullptr;
-            step_stage_cap = nodes.size() * 2;
-            CK(cudaMallocHost(&step_stage, sizeof(NodeStep) * step_stage_cap));
+        size_t pos = 0;
+        while (pos < nodes.size()) {
+            SweepList& L = *sweep_list;
+            memset(&L, 0, sizeof(int) * 4);
+            int nch = 0, worst = 1;
+            while (pos < nodes.size() && L.nsteps < BLG_SWEEP_MAXSTEPS) {
+                int u = nodes[pos];
+                int k = (int)children[u].size();
+                if (nch + k > BLG_SWEEP_MAXCHILD) break;
+                NodeStep st = make_step(u);
+                SweepStep& ss = L.step[L.nsteps++];
+                ss.k = k; ss.node = u; ss.first = nch; ss.pad_ = 0;
+                ss.ipow = st.ipow; ss.out = st.out; ss.out_scl = st.out_scl; ss.cnt = st.cnt;
+                int sum = 0;
+                bool tiled = false;
+                for (int c = 0; c < k; ++c) {
+                    SweepChild& sc = L.child[nch++];
+                    const ChildRef& cr = st.child[c];
+                    sc.ell = cr.ell; sc.scl = cr.scl; sc.cnt = cr.cnt; sc.Wt = cr.Wt;
+                    sc.wdp = cr.wdp; sc.id = cr.id; sc.table = (kind[cr.id] == BLG_WGDAFTER) ? 1 : 0; sc.pad_ = 0;
+                    int xm = Tp[cr.id].xmax;
+                    sum += xm;
+                    if (c >= 1 && xm >= 24) tiled = true;
+                }
+                worst = std::max(worst, tiled ? 3 * (sum + 1) : sum + k + 1);
+                ++pos;
+            }
+            require(L.nsteps > 0, "sweep: a node has more children than one launch can describe");
+            const int warps_per_block = 4;
+            int nwarps = (N + 31) / 32;
+            int blocks = (nwarps + warps_per_block - 1) / warps_per_block;
+            int cap = std::min(slice_cap, worst);            // doubles per lane in the shared slice
+            double* gs = nullptr;
+            size_t gstride = 0;
+            if (worst > cap) {                                // some warp may need more than its slice: global scratch
+                gstride = (size_t)worst * 32;
+                gscratch.ensure(gstride * (size_t)nwarps);
+                gs = gscratch.p;
+            }
+            size_t smem = (size_t)cap * 32 * warps_per_block * sizeof(double);
+            if (smem > sweep_smem_set) {
+                CK(cudaFuncSetAttribute(sweep_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+                sweep_smem_set = smem;
+            }
+            sweep_kernel<<<blocks, 32 * warps_per_block, smem, stream>>>(L, d_eps0.p, d_nc.p, N, ld, cap, gs, gstride);
+            CK(cudaGetLastError());
+            last_launches++;
         }
-        // the pinned staging buffer is reused by every call: wait until the previous upload left it
-        if (stage_busy) { CK(cudaEventSynchronize(stage_done)); stage_busy = false; }
-        int worst = 1;
-        for (size_t i = 0; i < nodes.size(); ++i) {
-            int u = nodes[i];
-            step_stage[i] = make_step(u);
-            // worst-case per-family working set (doubles) of this node, from the column bounds
-            int k = (int)children[u].size();
-            int sum = 0, capA = 1;
-            for (int c = 0; c < k; ++c) { sum += Tp[tabs[u].mo[c]].xmax; if (c == 0 || c < k - 1) capA = sum + 1; }
-            int need = k >= 2 ? 2 * capA + sum + 1 : capA;
-            worst = std::max(worst, need);
-        }
-        d_steps.ensure(nodes.size());
-        CK(cudaMemcpyAsync(d_steps.p, step_stage, nodes.size() * sizeof(NodeStep), cudaMemcpyHostToDevice, stream));
-        if (!stage_done) CK(cudaEventCreateWithFlags(&stage_done, cudaEventDisableTiming));
-        CK(cudaEventRecord(stage_done, stream));
-        stage_busy = true;
-        const int warps_per_block = 4;
-        int nwarps = (N + 31) / 32;
-        int blocks = (nwarps + warps_per_block - 1) / warps_per_block;
-        int cap = std::min(slice_cap, worst);            // doubles per lane in the shared slice
-        double* gs = nullptr;
-        size_t gstride = 0;
-        if (worst > cap) {                                // some warp may need more than its slice: global scratch
-            gstride = (size_t)worst * 32;
-            gscratch.ensure(gstride * (size_t)nwarps);
-            gs = gscratch.p;
-        }
-        size_t smem = (size_t)cap * 32 * warps_per_block * sizeof(double);
-        if (smem > sweep_smem_set) {
-            CK(cudaFuncSetAttribute(sweep_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-            sweep_smem_set = smem;
-        }
-        sweep_kernel<<<blocks, 32 * warps_per_block, smem, stream>>>(d_steps.p, (int)nodes.size(), d_eps0.p, N, ld, cap, gs, gstride);
-        CK(cudaGetLastError());
-        last_launches++;
     }
     void root_reduce(double* d_out) {
         require(tabs_valid, "logpdf: ε/W tables are stale (call blg_rebuild)");
@@ -1044,7 +1208,11 @@ struct blg_handle {
             while (u >= 0) { if (!children[u].empty()) nodes.push_back(u); u = parent[u]; }
         }
         bool v1 = kernel_version == 1;
-        for (int u : nodes) if (Tp[u].xmax > 255) v1 = true;    // very large counts: the general kernel
+        for (int u : nodes) {          // outside the table-free kernel's range: the general per-node kernels
+            if (!fast_ok[u]) v1 = true;
+            for (int c : children[u]) if (!fast_ok[c]) v1 = true;
+        }
+        last_kernel = v1 ? 1 : 2;
         if (v1) { for (int u : nodes) prune_node_v1(u); }
         else sweep(nodes);
         if (timing) CK(cudaEventRecord(ev[1], stream));
@@ -1083,6 +1251,20 @@ int blg_create(int device, void* stream, blg_handle** out) {
         if (stream) h->stream = (cudaStream_t)stream;
         else { CK(cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking)); h->own_stream = true; }
         h->result.ensure(16);
+        {   // factorial tables of the table-free kernel (per device, idempotent)
+            const int n = BLG_FAST_MAXCOUNT + 72;
+            std::vector<double> f(n), fi(n), iv(n);
+            long double acc = 1.0L;
+            for (int i = 0; i < n; ++i) {
+                if (i > 0) acc *= (long double)i;
+                f[i] = (double)acc;
+                fi[i] = (double)(1.0L / acc);
+                iv[i] = i > 0 ? 1.0 / (double)i : 0.0;
+            }
+            CK(cudaMemcpyToSymbol(c_fact, f.data(), n * sizeof(double)));
+            CK(cudaMemcpyToSymbol(c_invfact, fi.data(), n * sizeof(double)));
+            CK(cudaMemcpyToSymbol(c_inv, iv.data(), n * sizeof(double)));
+        }
         if (const char* kv = getenv("BLG_KERNEL")) h->kernel_version = atoi(kv) == 1 ? 1 : 2;
         if (const char* sc = getenv("BLG_SLICE")) h->slice_cap = std::max(8, std::min(224, atoi(sc)));
         *out = h;
