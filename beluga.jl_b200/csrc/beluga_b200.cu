@@ -65,6 +65,7 @@ struct NodeTab {        // per node id, device-resident tables
 struct SweepNodeConst {       // per node id, written by tables_kernel, read by sweep_kernel
     double psi, cc;           // ψ', (1-ϕ')(1-ψ') of the (ordinary) branch above the node
     double E[BLG_MAXK];       // clamped prefix products of the children's ϵ[1] in merge order (E[0] = 1)
+    double inv, ip0;          // 1/(1-E_k) and (1-E_k)^0 — ip0 is NaN when the reference's column would be NaN
 };
 
 struct ModelDev {
@@ -257,16 +258,24 @@ __global__ void __launch_bounds__(128) tables_kernel(ModelDev m, const int* __re
         double raw = 1.0;
         bool poison = false;
         E[0] = 1.0;
-        for (int i = 0; i < k; ++i) {
+        for (int i = 0; i < k; ++i) {          // prefixes in MERGE order: what the merge coefficients use
             raw *= m.eps0[tb.mo[i]];
+            E[i + 1] = raw > 1.0 ? 1.0 : raw;
+        }
+        raw = 1.0;
+        for (int i = 0; i < k; ++i) {          // prefixes in the REFERENCE's child order decide the NaN rule:
+            raw *= m.eps0[m.child_idx[c0 + i]];
             double v = raw > 1.0 ? 1.0 : raw;
-            E[i + 1] = v;
-            // the reference divides by (1-_ϵ)^n in log space: _ϵ == 1 gives 0·(-Inf) = NaN at n = 0
-            // (model.jl:433-435,453-455); a prefix outside [0,1) is treated the same way here.
+            // the reference divides by (1-_ϵ)^n in log space after every child: _ϵ == 1 gives 0·(-Inf) = NaN
+            // at n = 0 (model.jl:433-435,453-455); a prefix outside [0,1) is treated the same way here.
             if (!(v >= 0.0 && v < 1.0)) poison = true;
         }
         double inv = 1.0 / (1.0 - E[k]);
-        if (tid == 0) for (int i = 0; i < k; ++i) m.nc[n].E[i] = E[i];
+        if (tid == 0) {
+            for (int i = 0; i < k; ++i) m.nc[n].E[i] = E[i];
+            m.nc[n].inv = inv;
+            m.nc[n].ip0 = poison ? __longlong_as_double(0x7ff8000000000000LL) : 1.0;
+        }
         if (tb.nrow - 1 > BLG_FAST_MAXCOUNT) ok = false;
         for (int i = 1; i < k; ++i)
             if (!poison && !(E[i] > 0.0 && -(double)tb.nrow * log(E[i]) < 600.0)) ok = false;
@@ -430,17 +439,20 @@ struct SweepChild {
     const int* scl;
     const uint16_t* cnt;
     const double* Wt;      // transposed w* of the child's branch (leaf gather, WGD/WGT-after contraction)
-    int wdp, id, table, pad_;   // table != 0: contract with Wt (branch below a WGD/WGT)
+    int wdp, table, pad0_, pad1_;   // table != 0: contract with Wt (branch below a WGD/WGT)
+    double e;              // ϵ[1] of the child (extinction probability at the top of its branch)
+    double Epre;           // clamped product of the e's of the children merged before this one (1 for the first)
+    double psi, cc;        // ψ', (1-ϕ')(1-ψ') of the child's branch
 };
 struct SweepStep {
-    int k, node, first, pad_;
-    const double* ipow;
+    int k, first, resident, pad_;   // resident != 0: child[0] is the node of the previous step (its column is still in shared memory)
+    double inv, ip0;                // 1/(1-E_k); (1-E_k)^0, NaN where the reference's column would be NaN
     double* out;
     int* out_scl;
     const uint16_t* cnt;
 };
-#define BLG_SWEEP_MAXSTEPS 192
-#define BLG_SWEEP_MAXCHILD 384
+#define BLG_SWEEP_MAXSTEPS 160
+#define BLG_SWEEP_MAXCHILD 280
 struct SweepList {
     int nsteps;
     int pad_[3];
@@ -448,6 +460,7 @@ struct SweepList {
     SweepChild child[BLG_SWEEP_MAXCHILD];
 };
 static_assert(sizeof(SweepList) <= 32000, "kernel parameter space");
+
 __device__ __forceinline__ int warp_max(int v) { return __reduce_max_sync(0xffffffffu, v); }
 
 // in-place table contraction (branch below a WGD/WGT): col[s] ← Σ_{j=s..Mw} Wt[j*wdp+s]·col[j]
@@ -500,14 +513,15 @@ __device__ __noinline__ void sweep_contract_fast(double* col, int Mw, double psi
         }
     }
 }
-// single-tile in-place merge (M2w < TS).  R[0..Sw] = A, R[Sw+1..Sw+1+M2w] = B[0,·];
-// on exit R[0..Sw+M2w] = Σ_{t+s=n} C(n,s)·E^s·A[t]·B[t,s].
+// single-tile in-place merge (M2w < TS).  A[0..Sw] is the "t" side, B0[0..M2w] the "s" side (both inside the
+// warp's slice); the result Σ_{t+s=n} C(n,s)·E^s·A[t]·B[t,s], n = 0..Sw+M2w, is written to O[n] at step n.
+// O may alias the slice as long as O+n never passes an unread A[t] (O == A, or O below A).
 template <int TS>
-__device__ __noinline__ void sweep_merge_fast(double* R, int Sw, int M2w, double E, double e) {
+__device__ __noinline__ void sweep_merge_fast(double* O, const double* A, int Sw, const double* B0, int M2w, double E, double e) {
     double B[TS], acc[TS];
 #pragma unroll
     for (int k = 0; k < TS; ++k) {
-        B[k] = (k <= M2w) ? R[(Sw + 1 + k) * 32] * c_invfact[k] : 0.0;
+        B[k] = (k <= M2w) ? B0[k * 32] * c_invfact[k] : 0.0;
         acc[k] = 0.0;
     }
     const int nmax = Sw + M2w;
@@ -516,7 +530,7 @@ __device__ __noinline__ void sweep_merge_fast(double* R, int Sw, int M2w, double
     double em = 1.0;       // n!·E^n
     for (int t = 0; t <= nmax; ++t) {
         if (t <= Sw) {
-            const double a = R[t * 32] * tf;
+            const double a = A[t * 32] * tf;
 #pragma unroll
             for (int k = 0; k < TS; ++k) acc[k] = fma(a, B[k], acc[k]);
 #pragma unroll
@@ -524,7 +538,7 @@ __device__ __noinline__ void sweep_merge_fast(double* R, int Sw, int M2w, double
             B[TS - 1] = e * B[TS - 1];
             tf *= invE * c_inv[t + 1];
         }
-        R[t * 32] = acc[0] * em;
+        O[t * 32] = acc[0] * em;
 #pragma unroll
         for (int k = 0; k < TS - 1; ++k) acc[k] = acc[k + 1];
         acc[TS - 1] = 0.0;
@@ -574,32 +588,35 @@ __device__ __noinline__ void sweep_merge_tiled(const double* A, int Sw, double* 
     for (int n = 0; n <= nmax; ++n) { O[n * 32] *= em; em *= E * (double)(n + 1); }
 }
 
-// stage + contract one child into col[0..Mw]
-__device__ __noinline__ void sweep_child(const SweepChild& c, const SweepNodeConst* __restrict__ nc, int f, size_t ld,
-                                            int M, int Mw, double* col) {
+// stage (unless the column is already resident in col) + contract one child into col[0..Mw]
+__device__ __noinline__ void sweep_child(const SweepChild& c, int f, size_t ld, int M, int Mw, double* col, bool resident) {
     if (c.ell == nullptr) {                        // leaf: column x_c of w* (one-hot likelihood)
         const double* __restrict__ row = c.Wt + (size_t)M * c.wdp;
 #pragma unroll 4
         for (int s = 0; s <= Mw; ++s) col[s * 32] = (s <= M) ? row[s] : 0.0;
         return;
     }
-    const double* __restrict__ src = c.ell + f;
+    if (!resident) {
+        const double* __restrict__ src = c.ell + f;
 #pragma unroll 8
-    for (int j = 0; j <= Mw; ++j) col[j * 32] = (j <= M) ? src[(size_t)j * ld] : 0.0;
+        for (int j = 0; j <= Mw; ++j) col[j * 32] = (j <= M) ? src[(size_t)j * ld] : 0.0;
+    }
     if (c.table) {
         if (Mw < 8) sweep_contract_table<8>(col, Mw, c.Wt, c.wdp);
         else sweep_contract_table<16>(col, Mw, c.Wt, c.wdp);
     } else {
-        const double psi = nc[c.id].psi, cc = nc[c.id].cc;
+        const double psi = c.psi, cc = c.cc;
         if (Mw <= 4) sweep_contract_fast<4>(col, Mw, psi, cc);
         else if (Mw <= 12) sweep_contract_fast<12>(col, Mw, psi, cc);
         else sweep_contract_fast<24>(col, Mw, psi, cc);
     }
 }
 
-__global__ void __launch_bounds__(128, 4) sweep_kernel(const __grid_constant__ SweepList L, const double* __restrict__ eps0,
-                                                       const SweepNodeConst* __restrict__ nc,
-                                                       int N, size_t ld, int slice_cap, double* gscratch, size_t gs_stride) {
+// PROF: per-(step, phase) warp-cycle totals into prof[step*8 + phase] (diagnostic build of the same kernel)
+#define BLG_TICK(ph) do { if (PROF) { long long t1_ = clock64(); if (lane == 0) atomicAdd(&prof[si * 8 + (ph)], (unsigned long long)(t1_ - t0_)); t0_ = t1_; } } while (0)
+template <bool PROF>
+__global__ void __launch_bounds__(128, 4) sweep_kernel(const __grid_constant__ SweepList L, int N, size_t ld, int slice_cap,
+                                                       double* gscratch, size_t gs_stride, unsigned long long* prof) {
     extern __shared__ double smem[];
     const unsigned lane = threadIdx.x & 31u;
     const int warp = threadIdx.x >> 5;
@@ -607,43 +624,81 @@ __global__ void __launch_bounds__(128, 4) sweep_kernel(const __grid_constant__ S
     if ((long long)wg * 32 >= N) return;
     int f = wg * 32 + (int)lane;
     const bool live = f < N;
-    if (!live) f = N - 1;
+    if (!live) f = N - 1;            // idle lanes shadow the last family (loads stay in bounds; they never store)
     double* sl = smem + (size_t)warp * slice_cap * 32 + lane;
     double* gs = gscratch ? gscratch + (size_t)wg * gs_stride + lane : nullptr;
 
+    int prevX = 0, prevScl = 0;      // count and exponent of the column left in the slice by the previous step
+    double* prevR = sl;
+    long long t0_ = PROF ? clock64() : 0;
+    // counts / exponents of the first two children and the node's own count are loaded one step ahead
+    int nX = 0, nM0 = 0, nM1 = 0, nS0 = 0, nS1 = 0;
+    {
+        const SweepStep& st = L.step[0];
+        const SweepChild* ch = &L.child[st.first];
+        nX = st.cnt[f];
+        nM0 = ch[0].cnt[f];
+        nS0 = ch[0].scl ? ch[0].scl[f] : 0;
+        if (st.k >= 2) { nM1 = ch[1].cnt[f]; nS1 = ch[1].scl ? ch[1].scl[f] : 0; }
+    }
     for (int si = 0; si < L.nsteps; ++si) {
         const SweepStep& st = L.step[si];
         const int k = st.k;
         const SweepChild* ch = &L.child[st.first];
-        const int X = live ? (int)st.cnt[f] : 0;
-        int sclsum = 0, sumw = 0;
-        bool tiled = false;
-        for (int i = 0; i < k; ++i) {
-            const int Mi = warp_max(live ? (int)ch[i].cnt[f] : 0);
-            sumw += Mi;
-            if (i >= 1 && Mi >= 24) tiled = true;
+        const bool res0 = st.resident != 0;
+        const int X = nX;
+        const int M0 = res0 ? prevX : nM0;
+        const int M1 = (k >= 2) ? nM1 : 0;
+        int sclsum = (res0 ? prevScl : nS0) + ((k >= 2) ? nS1 : 0);
+        if (si + 1 < L.nsteps) {                       // prefetch the next step's counts
+            const SweepStep& sn = L.step[si + 1];
+            const SweepChild* cn = &L.child[sn.first];
+            nX = sn.cnt[f];
+            if (!sn.resident) { nM0 = cn[0].cnt[f]; nS0 = cn[0].scl ? cn[0].scl[f] : 0; }
+            if (sn.k >= 2) { nM1 = cn[1].cnt[f]; nS1 = cn[1].scl ? cn[1].scl[f] : 0; }
+        }
+        const int M0w = warp_max(M0);
+        const int M1w = warp_max(M1);
+        const int Xw = warp_max(X);
+        int sumw = M0w + M1w;
+        // which side of a binary merge is register-tiled: the child with the smaller bound in THIS warp
+        const bool swap = (k == 2) && (M0w < M1w);
+        bool tiled = (k == 2) ? (min(M0w, M1w) >= 24) : (M1w >= 24);
+        for (int i = 2; i < k; ++i) {
+            const int Miw = warp_max((int)ch[i].cnt[f]);
+            sumw += Miw;
+            if (Miw >= 24) tiled = true;
             if (ch[i].scl) sclsum += ch[i].scl[f];
         }
-        const int Xw = warp_max(X);
         const int need = tiled ? 3 * (sumw + 1) : sumw + k + 1;
         double* R = (need <= slice_cap) ? sl : gs;
+        if (res0 && R != prevR)
+            for (int n = 0; n <= M0w; ++n) R[n * 32] = prevR[n * 32];
+        BLG_TICK(0);
 
-        const int M0 = live ? (int)ch[0].cnt[f] : 0;
-        const int M0w = warp_max(M0);
-        sweep_child(ch[0], nc, f, ld, M0, M0w, R);
+        sweep_child(ch[0], f, ld, M0, M0w, R, res0);
+        BLG_TICK(1);
         int Sw = M0w;
-        double* res = R;
         if (!tiled) {
             for (int i = 1; i < k; ++i) {
-                const int Mi = live ? (int)ch[i].cnt[f] : 0;
-                const int Miw = warp_max(Mi);
-                sweep_child(ch[i], nc, f, ld, Mi, Miw, R + (size_t)(Sw + 1) * 32);
-                const double e = eps0[ch[i].id];
-                const double E = nc[st.node].E[i];
-                if (Miw < 4) sweep_merge_fast<4>(R, Sw, Miw, E, e);
-                else if (Miw < 12) sweep_merge_fast<12>(R, Sw, Miw, E, e);
-                else sweep_merge_fast<24>(R, Sw, Miw, E, e);
+                const int Mi = (i == 1) ? M1 : (int)ch[i].cnt[f];
+                const int Miw = (i == 1) ? M1w : warp_max(Mi);
+                double* colB = R + (size_t)(Sw + 1) * 32;
+                sweep_child(ch[i], f, ld, Mi, Miw, colB, false);
+                BLG_TICK(2);
+                if (!swap) {
+                    const double E = ch[i].Epre, e = ch[i].e;
+                    if (Miw < 4) sweep_merge_fast<4>(R, R, Sw, colB, Miw, E, e);
+                    else if (Miw < 12) sweep_merge_fast<12>(R, R, Sw, colB, Miw, E, e);
+                    else sweep_merge_fast<24>(R, R, Sw, colB, Miw, E, e);
+                } else {       // k == 2: child 1 is the "t" side, child 0 (at the front) the register-tiled "s" side
+                    const double E = fmin(ch[1].e, 1.0), e = ch[0].e;
+                    if (Sw < 4) sweep_merge_fast<4>(R, colB, Miw, R, Sw, E, e);
+                    else if (Sw < 12) sweep_merge_fast<12>(R, colB, Miw, R, Sw, E, e);
+                    else sweep_merge_fast<24>(R, colB, Miw, R, Sw, E, e);
+                }
                 Sw += Miw;
+                BLG_TICK(3);
             }
         } else {
             const int cap = sumw + 1;
@@ -651,39 +706,57 @@ __global__ void __launch_bounds__(128, 4) sweep_kernel(const __grid_constant__ S
             double* rH = R + (size_t)cap * 32;
             double* rO = R + (size_t)2 * cap * 32;
             for (int i = 1; i < k; ++i) {
-                const int Mi = live ? (int)ch[i].cnt[f] : 0;
-                const int Miw = warp_max(Mi);
-                sweep_child(ch[i], nc, f, ld, Mi, Miw, rO);
+                const int Mi = (i == 1) ? M1 : (int)ch[i].cnt[f];
+                const int Miw = (i == 1) ? M1w : warp_max(Mi);
+                sweep_child(ch[i], f, ld, Mi, Miw, rO, false);
                 for (int n = Miw + 1; n <= Sw + Miw; ++n) rO[n * 32] = 0.0;
-                sweep_merge_tiled(rA, Sw, rO, Miw, rH, nc[st.node].E[i], eps0[ch[i].id]);
+                sweep_merge_tiled(rA, Sw, rO, Miw, rH, ch[i].Epre, ch[i].e);
                 Sw += Miw;
-                if (i < k - 1)
-                    for (int n = 0; n <= Sw; ++n) rA[n * 32] = rO[n * 32];
+                for (int n = 0; n <= Sw; ++n) rA[n * 32] = rO[n * 32];     // result back to the front of R
+                BLG_TICK(4);
             }
-            res = (k >= 2) ? rO : rA;
         }
-        // ℓ_u[n] = Ã[n]·(1-E_k)^(-n), rescale to a power-of-two exponent, store
+        // ℓ_u[n] = Ã[n]·(1-E_k)^(-n), rescale to a power-of-two exponent, store; the column also stays
+        // in R[0..Xw] (zero above the family's own count) for a parent that follows immediately
         double mxv = 0.0;
         bool bad = false;
-        const double* __restrict__ ipow = st.ipow;
-        for (int n = 0; n <= Xw; ++n) {
-            if (n <= X) {
-                double v = (n <= Sw ? res[n * 32] : 0.0) * ipow[n];
-                res[n * 32] = v;
-                if (!(v == v) || isinf(v)) bad = true;
-                mxv = fmax(mxv, v);
+        {
+            double ip = st.ip0;
+            const double inv = st.inv;
+            for (int n = 0; n <= Xw; ++n) {
+                double v = 0.0;
+                if (n <= X) {
+                    v = (n <= Sw ? R[n * 32] : 0.0) * ip;
+                    if (!(v == v) || isinf(v)) bad = true;
+                    mxv = fmax(mxv, v);
+                }
+                R[n * 32] = v;
+                ip *= inv;
             }
         }
+        BLG_TICK(5);
+        // exponent of the column maximum straight from the bit pattern (normal numbers; a subnormal
+        // maximum keeps exponent 0, which only costs range, not correctness)
         int ex = 0;
-        if (!bad && mxv > 0.0) ex = ilogb(mxv);
-        if (live) {
-            double* o = st.out + f;
-            const bool exact = (ex > -1000 && ex < 1000);
-            const double sc = exact ? scalbn(1.0, -ex) : 1.0;          // exact power of two
-            for (int n = 0; n <= X; ++n) o[(size_t)n * ld] = exact ? res[n * 32] * sc : scalbn(res[n * 32], -ex);
-            st.out_scl[f] = sclsum + ex;
+        if (!bad && mxv > 0.0) {
+            const int be = (__double2hiint(mxv) >> 20) & 0x7ff;
+            if (be != 0) ex = be - 1023;
         }
+        {
+            double* o = st.out + f;
+            const double sc = __hiloint2double((1023 - ex) << 20, 0);     // 2^-ex, exact (|ex| <= 1022)
+            for (int n = 0; n <= Xw; ++n) {
+                const double v = R[n * 32] * sc;
+                R[n * 32] = v;
+                if (live && n <= X) o[(size_t)n * ld] = v;
+            }
+            if (live) st.out_scl[f] = sclsum + ex;
+        }
+        prevX = X;
+        prevScl = sclsum + ex;
+        prevR = R;
         __syncwarp();
+        BLG_TICK(6);
     }
 }
 
@@ -848,6 +921,8 @@ struct blg_handle {
     DevBuf<SweepNodeConst> d_nc;
     DevBuf<int> d_fast_ok;
     std::vector<int> fast_ok;            // host copy, refreshed by every rebuild
+    std::vector<SweepNodeConst> h_nc;    // host copies of the device-built per-node scalars (same refresh)
+    std::vector<double> h_eps0;
     std::vector<HostTab> tabs;
     std::vector<NodeTab> tab_stage;
     bool tabs_valid = false;
@@ -855,6 +930,9 @@ struct blg_handle {
     // sweep-kernel plumbing
     int kernel_version = 2;
     int last_kernel = 0;
+    bool order_resident = true;
+    int profile_sweep = 0;
+    DevBuf<unsigned long long> d_prof;
     int slice_cap = 52;                       // doubles per lane of the per-warp shared-memory slice
     std::unique_ptr<SweepList> sweep_list{new SweepList()};
     DevBuf<double> gscratch;
@@ -883,7 +961,7 @@ struct blg_handle {
         weight.free_(); fam_ll.free_(); partial.free_(); result.free_(); rootw.free_(); pascal.free_();
         d_kind.free_(); d_parent.free_(); d_child_off.free_(); d_child_idx.free_(); d_list.free_();
         d_t.free_(); d_lam.free_(); d_mu.free_(); d_q.free_(); d_eps0.free_(); d_eps1.free_(); d_tab.free_();
-        d_nc.free_(); d_fast_ok.free_();
+        d_nc.free_(); d_fast_ok.free_(); d_prof.free_();
         for (auto& e : ev) if (e) cudaEventDestroy(e);
         gscratch.free_();
         if (own_stream && stream) cudaStreamDestroy(stream);
@@ -998,7 +1076,7 @@ struct blg_handle {
         }
         if (same && (tb.Wt || wdim == 0) && (tb.ipow || nrow == 0)) return;
         free_tab(tb);
-        tb.wdim = wdim; tb.wdp = round_up(std::max(wdim, 1), BLG_TS); tb.nrow = nrow; tb.k = k;
+        tb.wdim = wdim; tb.wdp = round_up(std::max(wdim, 1), 16); tb.nrow = nrow; tb.k = k;
         for (int c = 0; c < k; ++c) tb.mo[c] = mo[c];
         if (wdim > 0) CK(cudaMalloc(&tb.Wt, (size_t)wdim * tb.wdp * sizeof(double)));
         if (nrow > 0) {
@@ -1066,7 +1144,11 @@ struct blg_handle {
         // list/tab_stage are host vectors reused by later calls: make sure the copies are done; the
         // per-node "table-free kernel allowed" flags come back with the same synchronisation
         fast_ok.resize(ncols_model, 0);
+        h_nc.resize(ncols_model);
+        h_eps0.resize(ncols_model);
         CK(cudaMemcpyAsync(fast_ok.data(), d_fast_ok.p, (size_t)ncols_model * sizeof(int), cudaMemcpyDeviceToHost, stream));
+        CK(cudaMemcpyAsync(h_nc.data(), d_nc.p, (size_t)ncols_model * sizeof(SweepNodeConst), cudaMemcpyDeviceToHost, stream));
+        CK(cudaMemcpyAsync(h_eps0.data(), d_eps0.p, (size_t)ncols_model * sizeof(double), cudaMemcpyDeviceToHost, stream));
         CK(cudaStreamSynchronize(stream));
         if (list.size() == postorder.size()) tabs_valid = true;
     }
@@ -1128,26 +1210,38 @@ struct blg_handle {
         while (pos < nodes.size()) {
             SweepList& L = *sweep_list;
             memset(&L, 0, sizeof(int) * 4);
-            int nch = 0, worst = 1;
+            int nch = 0, worst = 1, prev_node = -1;
             while (pos < nodes.size() && L.nsteps < BLG_SWEEP_MAXSTEPS) {
                 int u = nodes[pos];
                 int k = (int)children[u].size();
                 if (nch + k > BLG_SWEEP_MAXCHILD) break;
                 NodeStep st = make_step(u);
+                // the node computed by the previous step of this launch goes to merge position 0: its column is
+                // still in shared memory (and its count/exponent must not be prefetched before they exist)
+                for (int c = 1; c < k; ++c)
+                    if (st.child[c].id == prev_node) { std::rotate(st.child, st.child + c, st.child + c + 1); break; }
                 SweepStep& ss = L.step[L.nsteps++];
-                ss.k = k; ss.node = u; ss.first = nch; ss.pad_ = 0;
-                ss.ipow = st.ipow; ss.out = st.out; ss.out_scl = st.out_scl; ss.cnt = st.cnt;
+                ss.k = k; ss.first = nch; ss.pad_ = 0;
+                ss.resident = (L.nsteps >= 2 && prev_node == st.child[0].id && !children[prev_node].empty()) ? 1 : 0;
+                prev_node = u;
+                double raw = 1.0;
+                ss.inv = h_nc[u].inv; ss.ip0 = h_nc[u].ip0;
+                ss.out = st.out; ss.out_scl = st.out_scl; ss.cnt = st.cnt;
                 int sum = 0;
                 bool tiled = false;
                 for (int c = 0; c < k; ++c) {
                     SweepChild& sc = L.child[nch++];
                     const ChildRef& cr = st.child[c];
                     sc.ell = cr.ell; sc.scl = cr.scl; sc.cnt = cr.cnt; sc.Wt = cr.Wt;
-                    sc.wdp = cr.wdp; sc.id = cr.id; sc.table = (kind[cr.id] == BLG_WGDAFTER) ? 1 : 0; sc.pad_ = 0;
+                    sc.wdp = cr.wdp; sc.table = (kind[cr.id] == BLG_WGDAFTER) ? 1 : 0; sc.pad0_ = sc.pad1_ = 0;
+                    sc.e = h_eps0[cr.id]; sc.psi = h_nc[cr.id].psi; sc.cc = h_nc[cr.id].cc;
+                    sc.Epre = raw > 1.0 ? 1.0 : raw;           // clamped prefix of the children merged before this one
+                    raw *= sc.e;
                     int xm = Tp[cr.id].xmax;
                     sum += xm;
                     if (c >= 1 && xm >= 24) tiled = true;
                 }
+                if (k == 2 && std::min(Tp[st.child[0].id].xmax, Tp[st.child[1].id].xmax) < 24) tiled = false;
                 worst = std::max(worst, tiled ? 3 * (sum + 1) : sum + k + 1);
                 ++pos;
             }
@@ -1165,11 +1259,34 @@ struct blg_handle {
             }
             size_t smem = (size_t)cap * 32 * warps_per_block * sizeof(double);
             if (smem > sweep_smem_set) {
-                CK(cudaFuncSetAttribute(sweep_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+                CK(cudaFuncSetAttribute(sweep_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+                CK(cudaFuncSetAttribute(sweep_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
                 sweep_smem_set = smem;
             }
-            sweep_kernel<<<blocks, 32 * warps_per_block, smem, stream>>>(L, d_eps0.p, d_nc.p, N, ld, cap, gs, gstride);
-            CK(cudaGetLastError());
+            if (!profile_sweep) {
+                sweep_kernel<false><<<blocks, 32 * warps_per_block, smem, stream>>>(L, N, ld, cap, gs, gstride, nullptr);
+                CK(cudaGetLastError());
+            } else {
+                d_prof.ensure((size_t)BLG_SWEEP_MAXSTEPS * 8);
+                CK(cudaMemsetAsync(d_prof.p, 0, (size_t)BLG_SWEEP_MAXSTEPS * 8 * sizeof(unsigned long long), stream));
+                sweep_kernel<true><<<blocks, 32 * warps_per_block, smem, stream>>>(L, N, ld, cap, gs, gstride, d_prof.p);
+                CK(cudaGetLastError());
+                std::vector<unsigned long long> hp((size_t)BLG_SWEEP_MAXSTEPS * 8);
+                CK(cudaMemcpyAsync(hp.data(), d_prof.p, hp.size() * sizeof(unsigned long long), cudaMemcpyDeviceToHost, stream));
+                CK(cudaStreamSynchronize(stream));
+                double tot[8] = {0};
+                fprintf(stderr, "[blg sweep profile] warp-cycles per step: node k res | prologue child0 child1 merge tiled scale store\n");
+                for (int i = 0; i < L.nsteps; ++i) {
+                    double rowsum = 0;
+                    for (int p = 0; p < 7; ++p) { tot[p] += (double)hp[i * 8 + p]; rowsum += (double)hp[i * 8 + p]; }
+                    if (profile_sweep > 1)
+                        fprintf(stderr, "  step %3d k%d r%d | %8.0f %8.0f %8.0f %8.0f %8.0f %8.0f %8.0f | %9.0f\n", i, L.step[i].k,
+                                L.step[i].resident, hp[i*8]/1e3, hp[i*8+1]/1e3, hp[i*8+2]/1e3, hp[i*8+3]/1e3, hp[i*8+4]/1e3, hp[i*8+5]/1e3, hp[i*8+6]/1e3, rowsum/1e3);
+                }
+                double all = 0; for (int p = 0; p < 7; ++p) all += tot[p];
+                fprintf(stderr, "  total (Mcycles): prologue %.1f child0 %.1f child1 %.1f merge %.1f tiled %.1f scale %.1f store %.1f | sum %.1f\n",
+                        tot[0]/1e6, tot[1]/1e6, tot[2]/1e6, tot[3]/1e6, tot[4]/1e6, tot[5]/1e6, tot[6]/1e6, all/1e6);
+            }
             last_launches++;
         }
     }
@@ -1200,8 +1317,26 @@ struct blg_handle {
         require((int)Tp.size() >= 1, "logpdf: no profile columns");
         if (timing) { for (auto& e : ev) if (!e) CK(cudaEventCreate(&e)); CK(cudaEventRecord(ev[0], stream)); }
         std::vector<int> nodes;
-        if (mode == 0) {
+        if (mode == 0 && !order_resident) {
             for (int u : postorder) if (!children[u].empty()) nodes.push_back(u);
+        } else if (mode == 0) {
+            // any post-order is valid; visit the child with the larger counts LAST so that its column is
+            // still in shared memory when the parent (the very next step) needs it
+            std::vector<std::pair<int, size_t>> stk;
+            std::vector<std::vector<int>> ord(ncols_model);
+            stk.push_back({0, 0});
+            while (!stk.empty()) {
+                int u = stk.back().first;
+                if (stk.back().second == 0 && ord[u].empty() && !children[u].empty()) {
+                    ord[u] = children[u];
+                    std::stable_sort(ord[u].begin(), ord[u].end(), [&](int a, int b) {
+                        double ca = a < (int)Tp.size() ? Tp[a].colsum : 0.0, cb = b < (int)Tp.size() ? Tp[b].colsum : 0.0;
+                        return ca < cb;
+                    });
+                }
+                if (stk.back().second < ord[u].size()) { int c = ord[u][stk.back().second++]; stk.push_back({c, 0}); }
+                else { if (!children[u].empty()) nodes.push_back(u); stk.pop_back(); }
+            }
         } else if (mode == 1) {
             int u = node - 1;
             require(present(u), "logpdf_from: node id not in the model");
@@ -1266,6 +1401,8 @@ int blg_create(int device, void* stream, blg_handle** out) {
             CK(cudaMemcpyToSymbol(c_inv, iv.data(), n * sizeof(double)));
         }
         if (const char* kv = getenv("BLG_KERNEL")) h->kernel_version = atoi(kv) == 1 ? 1 : 2;
+        if (const char* o = getenv("BLG_ORDER")) h->order_resident = atoi(o) != 0;
+        if (const char* o = getenv("BLG_PROF")) h->profile_sweep = atoi(o);
         if (const char* sc = getenv("BLG_SLICE")) h->slice_cap = std::max(8, std::min(224, atoi(sc)));
         *out = h;
     } catch (const std::exception& e) { g_create_error = e.what(); return 2; }
