@@ -466,10 +466,12 @@ __device__ __forceinline__ int warp_max(int v) { return __reduce_max_sync(0xffff
 // in-place table contraction (branch below a WGD/WGT): col[s] ← Σ_{j=s..Mw} Wt[j*wdp+s]·col[j]
 template <int TS>
 __device__ __noinline__ void sweep_contract_table(double* col, int Mw, const double* __restrict__ Wt, int wdp) {
+#pragma unroll 1
     for (int s0 = 0; s0 <= Mw; s0 += TS) {
         double acc[TS];
 #pragma unroll
         for (int k = 0; k < TS; ++k) acc[k] = 0.0;
+#pragma unroll 1
         for (int j = s0; j <= Mw; ++j) {
             const double x = col[j * 32];
             const double* __restrict__ w = Wt + (size_t)j * wdp + s0;
@@ -485,8 +487,10 @@ __device__ __noinline__ void sweep_contract_table(double* col, int Mw, const dou
 template <int TS>
 __device__ __noinline__ void sweep_contract_fast(double* col, int Mw, double psi, double cc) {
     // u[j] = (j-1)!·ℓ[j]
+#pragma unroll 1
     for (int j = 2; j <= Mw; ++j) col[j * 32] *= c_fact[j - 1];
     double post = cc;                                  // c^n/(n-1)! at n = 1
+#pragma unroll 1
     for (int n0 = 1; n0 <= Mw; n0 += TS) {
         double acc[TS], win[TS];
 #pragma unroll
@@ -496,6 +500,7 @@ __device__ __noinline__ void sweep_contract_fast(double* col, int Mw, double psi
         }
         double g = 1.0;                                // ψ'^d/d!
         const int dmax = Mw - n0;
+#pragma unroll 1
         for (int d = 0; d <= dmax; ++d) {
 #pragma unroll
             for (int k = 0; k < TS; ++k) acc[k] = fma(g, win[k], acc[k]);
@@ -528,6 +533,7 @@ __device__ __noinline__ void sweep_merge_fast(double* O, const double* A, int Sw
     const double invE = 1.0 / E;
     double tf = 1.0;       // 1/(t!·E^t)
     double em = 1.0;       // n!·E^n
+#pragma unroll 1
     for (int t = 0; t <= nmax; ++t) {
         if (t <= Sw) {
             const double a = A[t * 32] * tf;
@@ -552,6 +558,7 @@ __device__ __noinline__ void sweep_merge_tiled(const double* A, int Sw, double* 
     const int ntile = M2w / TS + 1;
     const int nmax = Sw + M2w;
     const double invE = 1.0 / E;
+#pragma unroll 1
     for (int tile = ntile - 1; tile >= 0; --tile) {
         const int s0 = tile * TS;
         const bool top = (tile == ntile - 1);
@@ -565,6 +572,7 @@ __device__ __noinline__ void sweep_merge_tiled(const double* A, int Sw, double* 
         for (int k = 0; k < TS; ++k)
             if (s0 + k <= M2w) O[(s0 + k) * 32] = 0.0;
         double tf = 1.0;
+#pragma unroll 1
         for (int t = 0; t <= Sw + TS - 1; ++t) {
             if (t <= Sw) {
                 const double a = A[t * 32] * tf;
@@ -585,6 +593,7 @@ __device__ __noinline__ void sweep_merge_tiled(const double* A, int Sw, double* 
         }
     }
     double em = 1.0;
+#pragma unroll 1
     for (int n = 0; n <= nmax; ++n) { O[n * 32] *= em; em *= E * (double)(n + 1); }
 }
 
@@ -592,23 +601,21 @@ __device__ __noinline__ void sweep_merge_tiled(const double* A, int Sw, double* 
 __device__ __noinline__ void sweep_child(const SweepChild& c, int f, size_t ld, int M, int Mw, double* col, bool resident) {
     if (c.ell == nullptr) {                        // leaf: column x_c of w* (one-hot likelihood)
         const double* __restrict__ row = c.Wt + (size_t)M * c.wdp;
-#pragma unroll 4
+#pragma unroll 2
         for (int s = 0; s <= Mw; ++s) col[s * 32] = (s <= M) ? row[s] : 0.0;
         return;
     }
     if (!resident) {
         const double* __restrict__ src = c.ell + f;
-#pragma unroll 8
+#pragma unroll 4
         for (int j = 0; j <= Mw; ++j) col[j * 32] = (j <= M) ? src[(size_t)j * ld] : 0.0;
     }
     if (c.table) {
-        if (Mw < 8) sweep_contract_table<8>(col, Mw, c.Wt, c.wdp);
-        else sweep_contract_table<16>(col, Mw, c.Wt, c.wdp);
+        sweep_contract_table<16>(col, Mw, c.Wt, c.wdp);
     } else {
         const double psi = c.psi, cc = c.cc;
         if (Mw <= 4) sweep_contract_fast<4>(col, Mw, psi, cc);
-        else if (Mw <= 12) sweep_contract_fast<12>(col, Mw, psi, cc);
-        else sweep_contract_fast<24>(col, Mw, psi, cc);
+        else sweep_contract_fast<12>(col, Mw, psi, cc);
     }
 }
 
@@ -672,8 +679,10 @@ __global__ void __launch_bounds__(128, 4) sweep_kernel(const __grid_constant__ S
         }
         const int need = tiled ? 3 * (sumw + 1) : sumw + k + 1;
         double* R = (need <= slice_cap) ? sl : gs;
-        if (res0 && R != prevR)
+        if (res0 && R != prevR) {
+#pragma unroll 1
             for (int n = 0; n <= M0w; ++n) R[n * 32] = prevR[n * 32];
+        }
         BLG_TICK(0);
 
         sweep_child(ch[0], f, ld, M0, M0w, R, res0);
@@ -689,12 +698,10 @@ __global__ void __launch_bounds__(128, 4) sweep_kernel(const __grid_constant__ S
                 if (!swap) {
                     const double E = ch[i].Epre, e = ch[i].e;
                     if (Miw < 4) sweep_merge_fast<4>(R, R, Sw, colB, Miw, E, e);
-                    else if (Miw < 12) sweep_merge_fast<12>(R, R, Sw, colB, Miw, E, e);
                     else sweep_merge_fast<24>(R, R, Sw, colB, Miw, E, e);
                 } else {       // k == 2: child 1 is the "t" side, child 0 (at the front) the register-tiled "s" side
                     const double E = fmin(ch[1].e, 1.0), e = ch[0].e;
                     if (Sw < 4) sweep_merge_fast<4>(R, colB, Miw, R, Sw, E, e);
-                    else if (Sw < 12) sweep_merge_fast<12>(R, colB, Miw, R, Sw, E, e);
                     else sweep_merge_fast<24>(R, colB, Miw, R, Sw, E, e);
                 }
                 Sw += Miw;
@@ -709,9 +716,11 @@ __global__ void __launch_bounds__(128, 4) sweep_kernel(const __grid_constant__ S
                 const int Mi = (i == 1) ? M1 : (int)ch[i].cnt[f];
                 const int Miw = (i == 1) ? M1w : warp_max(Mi);
                 sweep_child(ch[i], f, ld, Mi, Miw, rO, false);
+#pragma unroll 1
                 for (int n = Miw + 1; n <= Sw + Miw; ++n) rO[n * 32] = 0.0;
                 sweep_merge_tiled(rA, Sw, rO, Miw, rH, ch[i].Epre, ch[i].e);
                 Sw += Miw;
+#pragma unroll 1
                 for (int n = 0; n <= Sw; ++n) rA[n * 32] = rO[n * 32];     // result back to the front of R
                 BLG_TICK(4);
             }
@@ -723,6 +732,7 @@ __global__ void __launch_bounds__(128, 4) sweep_kernel(const __grid_constant__ S
         {
             double ip = st.ip0;
             const double inv = st.inv;
+#pragma unroll 1
             for (int n = 0; n <= Xw; ++n) {
                 double v = 0.0;
                 if (n <= X) {
@@ -745,6 +755,7 @@ __global__ void __launch_bounds__(128, 4) sweep_kernel(const __grid_constant__ S
         {
             double* o = st.out + f;
             const double sc = __hiloint2double((1023 - ex) << 20, 0);     // 2^-ex, exact (|ex| <= 1022)
+#pragma unroll 2
             for (int n = 0; n <= Xw; ++n) {
                 const double v = R[n * 32] * sc;
                 R[n * 32] = v;
@@ -1428,18 +1439,64 @@ int blg_set_profiles(blg_handle* h, const int32_t* X, const int64_t* weight, int
     if (npatterns == 0) { h->Tc.clear(); h->Tp.clear(); return 0; }
     h->require(X && weight, "set_profiles: null pointer");
     size_t ld = h->ld;
-    // device order: lexicographic on the first columns (ids are pre-order, so these are the root
-    // and the nodes next to it — where the large counts and most of the work are), descending
+    // device order: families that share a warp should have similar count vectors at the heavy nodes, because
+    // every loop of a warp runs to the warp's maximum count.  k-d ordering: recursively split the family set
+    // at a multiple of 32 along the heavy column with the largest spread, until 32 families remain per leaf.
     h->perm.resize(npatterns);
     for (int f = 0; f < npatterns; ++f) h->perm[f] = f;
-    {
-        const int nk = std::min(ncols, 12);
-        std::stable_sort(h->perm.begin(), h->perm.end(), [&](int a, int b) {
-            const int32_t* xa = X + (size_t)a * ncols;
-            const int32_t* xb = X + (size_t)b * ncols;
-            for (int k = 0; k < nk; ++k) if (xa[k] != xb[k]) return xa[k] > xb[k];
-            return false;
-        });
+    if (npatterns > 32) {
+        // candidate columns: largest Σx² first, identical columns (wgd / wgdafter copies) dropped
+        std::vector<double> s1(ncols, 0.0), s2(ncols, 0.0);
+        for (int f = 0; f < npatterns; ++f) {
+            const int32_t* x = X + (size_t)f * ncols;
+            for (int c = 0; c < ncols; ++c) { s1[c] += x[c]; s2[c] += (double)x[c] * x[c]; }
+        }
+        std::vector<int> byw(ncols);
+        for (int c = 0; c < ncols; ++c) byw[c] = c;
+        std::stable_sort(byw.begin(), byw.end(), [&](int a, int b) { return s2[a] > s2[b]; });
+        std::vector<int> keys;
+        for (int c : byw) {
+            bool dup = false;
+            for (int k : keys) if (s1[k] == s1[c] && s2[k] == s2[c]) { dup = true; break; }
+            if (!dup && s2[c] > 0.0) keys.push_back(c);
+            if (keys.size() == 32) break;
+        }
+        const int nk = (int)keys.size();
+        if (nk > 0) {
+            std::vector<float> K((size_t)npatterns * nk);
+            for (int f = 0; f < npatterns; ++f)
+                for (int k = 0; k < nk; ++k) K[(size_t)f * nk + k] = (float)X[(size_t)f * ncols + keys[k]];
+            std::vector<std::pair<int, int>> stk;
+            stk.push_back({0, npatterns});
+            std::vector<double> m1(nk), m2(nk);
+            while (!stk.empty()) {
+                auto seg = stk.back();
+                stk.pop_back();
+                const int lo = seg.first, hi = seg.second, n = hi - lo;
+                if (n <= 32) continue;
+                std::fill(m1.begin(), m1.end(), 0.0);
+                std::fill(m2.begin(), m2.end(), 0.0);
+                for (int i = lo; i < hi; ++i) {
+                    const float* kf = &K[(size_t)h->perm[i] * nk];
+                    for (int k = 0; k < nk; ++k) { m1[k] += kf[k]; m2[k] += (double)kf[k] * kf[k]; }
+                }
+                int best = 0;
+                double bestv = -1.0;
+                for (int k = 0; k < nk; ++k) {
+                    double var = m2[k] / n - (m1[k] / n) * (m1[k] / n);
+                    if (var > bestv) { bestv = var; best = k; }
+                }
+                if (bestv <= 0.0) continue;             // identical on every key: nothing to gain
+                int half = ((n / 2 + 31) / 32) * 32;
+                if (half >= n) half = n / 2;
+                std::nth_element(h->perm.begin() + lo, h->perm.begin() + lo + half, h->perm.begin() + hi, [&](int a, int b) {
+                    float va = K[(size_t)a * nk + best], vb = K[(size_t)b * nk + best];
+                    return va != vb ? va > vb : a < b;
+                });
+                stk.push_back({lo + half, hi});
+                stk.push_back({lo, lo + half});
+            }
+        }
     }
     h->inv.resize(npatterns);
     for (int f = 0; f < npatterns; ++f) h->inv[h->perm[f]] = f;
