@@ -462,6 +462,18 @@ struct SweepList {
 static_assert(sizeof(SweepList) <= 32000, "kernel parameter space");
 
 __device__ __forceinline__ int warp_max(int v) { return __reduce_max_sync(0xffffffffu, v); }
+// loads that must be ISSUED where they are written (software prefetch one step ahead): volatile asm keeps
+// the compiler from sinking them to their first use
+__device__ __forceinline__ int ldg_u16_now(const uint16_t* p) {
+    unsigned short v;
+    asm volatile("ld.global.u16 %0, [%1];" : "=h"(v) : "l"(p));
+    return (int)v;
+}
+__device__ __forceinline__ int ldg_s32_now(const int* p) {
+    int v;
+    asm volatile("ld.global.s32 %0, [%1];" : "=r"(v) : "l"(p));
+    return v;
+}
 
 // in-place table contraction (branch below a WGD/WGT): col[s] ← Σ_{j=s..Mw} Wt[j*wdp+s]·col[j]
 template <int TS>
@@ -486,6 +498,7 @@ __device__ __noinline__ void sweep_contract_table(double* col, int Mw, const dou
 // in-place closed-form contraction over an ordinary branch.  On entry col[j] = ℓ[j] (j = 0..Mw).
 template <int TS>
 __device__ __noinline__ void sweep_contract_fast(double* col, int Mw, double psi, double cc) {
+    // (a node with a single child folds its (1-E)^(-n) normalisation into cc, see the caller)
     // u[j] = (j-1)!·ℓ[j]
 #pragma unroll 1
     for (int j = 2; j <= Mw; ++j) col[j * 32] *= c_fact[j - 1];
@@ -522,7 +535,10 @@ __device__ __noinline__ void sweep_contract_fast(double* col, int Mw, double psi
 // warp's slice); the result Σ_{t+s=n} C(n,s)·E^s·A[t]·B[t,s], n = 0..Sw+M2w, is written to O[n] at step n.
 // O may alias the slice as long as O+n never passes an unread A[t] (O == A, or O below A).
 template <int TS>
-__device__ __noinline__ void sweep_merge_fast(double* O, const double* A, int Sw, const double* B0, int M2w, double E, double e) {
+__device__ __noinline__ double sweep_merge_fast(double* O, const double* A, int Sw, const double* B0, int M2w, double E, double e,
+                                                double em0, double emg, int X) {
+    // em0/emg: the emitted value is acc·n!·E^n·(extra factor em0·emg^n): the last merge of a node passes
+    // the (1-E_k)^(-n) normalisation (and the NaN poison) through them.  Returns max_{n<=X} of the result.
     double B[TS], acc[TS];
 #pragma unroll
     for (int k = 0; k < TS; ++k) {
@@ -531,8 +547,11 @@ __device__ __noinline__ void sweep_merge_fast(double* O, const double* A, int Sw
     }
     const int nmax = Sw + M2w;
     const double invE = 1.0 / E;
+    const double Eg = E * emg;
     double tf = 1.0;       // 1/(t!·E^t)
-    double em = 1.0;       // n!·E^n
+    double em = em0;       // n!·E^n · em0·emg^n
+    double mx = 0.0;
+    bool nan = false;
 #pragma unroll 1
     for (int t = 0; t <= nmax; ++t) {
         if (t <= Sw) {
@@ -544,12 +563,16 @@ __device__ __noinline__ void sweep_merge_fast(double* O, const double* A, int Sw
             B[TS - 1] = e * B[TS - 1];
             tf *= invE * c_inv[t + 1];
         }
-        O[t * 32] = acc[0] * em;
+        const double v = (t <= X) ? acc[0] * em : 0.0;
+        O[t * 32] = v;
+        nan |= !(v == v);
+        mx = fmax(mx, v);
 #pragma unroll
         for (int k = 0; k < TS - 1; ++k) acc[k] = acc[k + 1];
         acc[TS - 1] = 0.0;
-        em *= E * (double)(t + 1);
+        em *= Eg * (double)(t + 1);
     }
+    return nan ? __longlong_as_double(0x7ff8000000000000LL) : mx;
 }
 // general merge for a smaller child with >= 24 counts: 16-wide tiles from high s to low s chained
 // through the history column H.  A[0..Sw]; O[0..M2w] = B[0,·], O[M2w+1..Sw+M2w] = 0 on entry; result in O.
@@ -660,9 +683,9 @@ __global__ void __launch_bounds__(128, 4) sweep_kernel(const __grid_constant__ S
         if (si + 1 < L.nsteps) {                       // prefetch the next step's counts
             const SweepStep& sn = L.step[si + 1];
             const SweepChild* cn = &L.child[sn.first];
-            nX = sn.cnt[f];
-            if (!sn.resident) { nM0 = cn[0].cnt[f]; nS0 = cn[0].scl ? cn[0].scl[f] : 0; }
-            if (sn.k >= 2) { nM1 = cn[1].cnt[f]; nS1 = cn[1].scl ? cn[1].scl[f] : 0; }
+            nX = ldg_u16_now(sn.cnt + f);
+            if (!sn.resident) { nM0 = ldg_u16_now(cn[0].cnt + f); nS0 = cn[0].scl ? ldg_s32_now(cn[0].scl + f) : 0; }
+            if (sn.k >= 2) { nM1 = ldg_u16_now(cn[1].cnt + f); nS1 = cn[1].scl ? ldg_s32_now(cn[1].scl + f) : 0; }
         }
         const int M0w = warp_max(M0);
         const int M1w = warp_max(M1);
@@ -688,6 +711,8 @@ __global__ void __launch_bounds__(128, 4) sweep_kernel(const __grid_constant__ S
         sweep_child(ch[0], f, ld, M0, M0w, R, res0);
         BLG_TICK(1);
         int Sw = M0w;
+        double mxv = 0.0;
+        bool scaled = false;        // has the (1-E_k)^(-n) normalisation already been applied (and mxv taken)?
         if (!tiled) {
             for (int i = 1; i < k; ++i) {
                 const int Mi = (i == 1) ? M1 : (int)ch[i].cnt[f];
@@ -695,16 +720,21 @@ __global__ void __launch_bounds__(128, 4) sweep_kernel(const __grid_constant__ S
                 double* colB = R + (size_t)(Sw + 1) * 32;
                 sweep_child(ch[i], f, ld, Mi, Miw, colB, false);
                 BLG_TICK(2);
+                const bool last = (i == k - 1);
+                const double em0 = last ? st.ip0 : 1.0, emg = last ? st.inv : 1.0;
+                const int Xm = last ? X : 0x7fffffff;
+                double mx;
                 if (!swap) {
                     const double E = ch[i].Epre, e = ch[i].e;
-                    if (Miw < 4) sweep_merge_fast<4>(R, R, Sw, colB, Miw, E, e);
-                    else sweep_merge_fast<24>(R, R, Sw, colB, Miw, E, e);
+                    if (Miw < 4) mx = sweep_merge_fast<4>(R, R, Sw, colB, Miw, E, e, em0, emg, Xm);
+                    else mx = sweep_merge_fast<24>(R, R, Sw, colB, Miw, E, e, em0, emg, Xm);
                 } else {       // k == 2: child 1 is the "t" side, child 0 (at the front) the register-tiled "s" side
                     const double E = fmin(ch[1].e, 1.0), e = ch[0].e;
-                    if (Sw < 4) sweep_merge_fast<4>(R, colB, Miw, R, Sw, E, e);
-                    else sweep_merge_fast<24>(R, colB, Miw, R, Sw, E, e);
+                    if (Sw < 4) mx = sweep_merge_fast<4>(R, colB, Miw, R, Sw, E, e, em0, emg, Xm);
+                    else mx = sweep_merge_fast<24>(R, colB, Miw, R, Sw, E, e, em0, emg, Xm);
                 }
                 Sw += Miw;
+                if (last) { mxv = mx; scaled = true; }
                 BLG_TICK(3);
             }
         } else {
@@ -727,9 +757,12 @@ __global__ void __launch_bounds__(128, 4) sweep_kernel(const __grid_constant__ S
         }
         // ℓ_u[n] = Ã[n]·(1-E_k)^(-n), rescale to a power-of-two exponent, store; the column also stays
         // in R[0..Xw] (zero above the family's own count) for a parent that follows immediately
-        double mxv = 0.0;
         bool bad = false;
-        {
+        if (scaled) {
+            bad = !(mxv == mxv) || isinf(mxv);
+#pragma unroll 1
+            for (int n = Sw + 1; n <= Xw; ++n) R[n * 32] = 0.0;
+        } else {
             double ip = st.ip0;
             const double inv = st.inv;
 #pragma unroll 1
