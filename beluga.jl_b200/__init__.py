@@ -9,7 +9,8 @@ from .model import (BRANCH, NODE, DLWGD as DLWGDModel, ModelNode, closestnode, i
                     postwalk, prewalk, update_)
 from .newick import readnw
 from .parallel import allreduce_sum_, dist_info, shard_range
-from .profile import DLWGD_ as DLWGD, PArray, extend_, logpdf_, logpdfroot, profile, rev_, set_, shrink_
+from .profile import (DLWGD_ as DLWGD, PArray, extend_, gradient, gradient_cr, logpdf_, logpdfroot, profile, rev_, set_,
+                      shrink_)
 
 
 def addwgd_(model, n, t, q):

@@ -883,6 +883,8 @@ __global__ void zero_slab_kernel(double* ell, int* scl, size_t nell, int N) {
     for (size_t k = i; k < (size_t)N; k += stride) scl[k] = 0;
 }
 
+#include "gradient.cuh"
+
 // ------------------------------------------------------------------------------------------------
 // host-side state
 // ------------------------------------------------------------------------------------------------
@@ -1006,6 +1008,7 @@ struct blg_handle {
         d_kind.free_(); d_parent.free_(); d_child_off.free_(); d_child_idx.free_(); d_list.free_();
         d_t.free_(); d_lam.free_(); d_mu.free_(); d_q.free_(); d_eps0.free_(); d_eps1.free_(); d_tab.free_();
         d_nc.free_(); d_fast_ok.free_(); d_prof.free_();
+        gpool_release();
         for (auto& e : ev) if (e) cudaEventDestroy(e);
         gscratch.free_();
         if (own_stream && stream) cudaStreamDestroy(stream);
@@ -1203,7 +1206,7 @@ struct blg_handle {
         prune_node_kernel<CAP><<<blocks, 128, 0, stream>>>(st, d_eps0.p, N, ld);
     }
     // describe the pruning step at node u against the current proposal tables (allocates the output slab)
-    NodeStep make_step(int u) {
+    NodeStep make_step(int u, bool readonly = false) {
         int k = (int)children[u].size();
         require(k >= 1, "prune_node: leaf");
         require(u < (int)Tp.size(), "logpdf: model has more node ids than the profile has columns (call blg_extend)");
@@ -1228,7 +1231,7 @@ struct blg_handle {
             if (i >= 1) require(tabs[u].cdp[i] == round_up(Tp[c].xmax + 1, BLG_TS), "logpdf: merge table does not match the profile (call blg_rebuild)");
         }
         require(tabs[u].nrow == Tp[u].xmax + 1, "logpdf: node table does not match the profile (call blg_rebuild)");
-        Slab* o = writable(u);
+        Slab* o = readonly ? readable(u) : writable(u);
         st.nrow = tabs[u].nrow;
         st.out = o->ell; st.out_scl = o->scl; st.cnt = Tp[u].cnt;
         st.ipow = tabs[u].ipow;
@@ -1334,6 +1337,243 @@ struct blg_handle {
             last_launches++;
         }
     }
+
+    // ---- gradient (forward-mode, path-sparse) ---------------------------------------------------------------
+    std::map<size_t, std::vector<void*>> gpool;          // scratch buffers of the tangent passes, by size
+    void* galloc(size_t bytes) {
+        bytes = (bytes + 255) / 256 * 256;
+        auto& v = gpool[bytes];
+        if (!v.empty()) { void* p = v.back(); v.pop_back(); return p; }
+        void* p = nullptr;
+        CK(cudaMalloc(&p, bytes));
+        return p;
+    }
+    void gfree(void* p, size_t bytes) { bytes = (bytes + 255) / 256 * 256; gpool[bytes].push_back(p); }
+    void gpool_release() {
+        for (auto& kv : gpool) for (void* p : kv.second) cudaFree(p);
+        gpool.clear();
+    }
+    int nonwgdchild_h(int i) const { while (kind[i] == BLG_WGD || kind[i] == BLG_WGT || kind[i] == BLG_WGDAFTER) i = children[i][0]; return i; }
+    int nonwgdparent_h(int i) const { while (kind[i] == BLG_WGD || kind[i] == BLG_WGT || kind[i] == BLG_WGDAFTER) i = parent[i]; return i; }
+
+    template <int CAP> void launch_prune_dual(const NodeStep& st, const DualStep<2>& ds) {
+        int blocks = (N + 63) / 64;
+        prune_dual_kernel<2, CAP><<<blocks, 64, 0, stream>>>(st, ds, d_eps0.p, N, ld);
+    }
+
+    // one tangent pass with two lanes; adds Σ weight·∂logL/∂lane into out2[0..1]
+    void tangent_pass(const Seeds<2>& sd, double out2[2]) {
+        const int n = ncols_model;
+        // ---- which quantities does this parameter group perturb? (post-order dependency walk) ----
+        std::vector<char> e0d(n, 0), e1d(n, 0), wd(n, 0), sdirty(n, 0);
+        auto seeded_rate = [&](int p, int c) {
+            for (int t = 0; t < 2; ++t) {
+                int k = sd.kind[t];
+                if (k == SEED_LAM_ALL || k == SEED_MU_ALL) return true;
+                if (k == SEED_LAM || k == SEED_MU) {
+                    int b = nonwgdchild_h(c);
+                    if (sd.node[t] == b) return true;
+                    if (model_kind == BLG_NODE_MODEL && sd.node[t] == nonwgdparent_h(p)) return true;
+                }
+            }
+            return false;
+        };
+        auto seeded_q = [&](int w) {
+            for (int t = 0; t < 2; ++t) if (sd.kind[t] == SEED_Q && sd.node[t] == w) return true;
+            return false;
+        };
+        std::vector<int> elist, tlist, steps;
+        for (int u : postorder) {
+            if (children[u].empty()) continue;
+            bool any_e0 = false, any_step = false;
+            const bool wg = kind[u] == BLG_WGD || kind[u] == BLG_WGT;
+            for (int c : children[u]) {
+                bool rate = (!wg && kind[c] != BLG_WGDAFTER) ? seeded_rate(u, c) : false;
+                // ϵ[1] of c: ordinary parent → ep(λ,μ,t,ϵ_c[2]); wgd/wgt parent → polynomial in q and ϵ_c[2]
+                e0d[c] = wg ? (seeded_q(u) || e1d[c]) : (rate || e1d[c]);
+                // W of c: wgdafter → (q of its parent, ϵ_c[2]); ordinary → (rates, ϵ_c[2]).  (a wgd's own branch is ordinary)
+                bool rate_w = (kind[c] != BLG_WGDAFTER) ? seeded_rate(u, c) : false;
+                wd[c] = (kind[c] == BLG_WGDAFTER) ? (seeded_q(u) || e1d[c]) : (rate_w || e1d[c]);
+                any_e0 |= e0d[c] != 0;
+                any_step |= wd[c] || e0d[c] || sdirty[c];
+                if (wd[c]) tlist.push_back(c);
+            }
+            e1d[u] = any_e0;
+            if (any_e0) { elist.push_back(u); if (std::find(tlist.begin(), tlist.end(), u) == tlist.end()) tlist.push_back(u); }
+            sdirty[u] = any_step;
+            if (any_step) steps.push_back(u);
+        }
+        // a node can be in tlist both as a child (dWt) and as a parent (merge tables): dedupe, keep order
+        {
+            std::vector<int> uniq;
+            std::vector<char> seen(n, 0);
+            for (int i : tlist) if (!seen[i]) { seen[i] = 1; uniq.push_back(i); }
+            tlist.swap(uniq);
+        }
+        ModelDev m = model_dev();
+        // ---- ε tangents ----
+        size_t debytes = (size_t)2 * n * sizeof(double);
+        double* de0 = (double*)galloc(debytes);
+        double* de1 = (double*)galloc(debytes);
+        CK(cudaMemsetAsync(de0, 0, debytes, stream));
+        CK(cudaMemsetAsync(de1, 0, debytes, stream));
+        std::vector<std::pair<void*, size_t>> temps;
+        temps.push_back({de0, debytes});
+        temps.push_back({de1, debytes});
+        if (!elist.empty()) {
+            int* dl = (int*)galloc(elist.size() * sizeof(int));
+            temps.push_back({dl, elist.size() * sizeof(int)});
+            CK(cudaMemcpyAsync(dl, elist.data(), elist.size() * sizeof(int), cudaMemcpyHostToDevice, stream));
+            eps_dual_kernel<2><<<1, 32, 0, stream>>>(m, sd, dl, (int)elist.size(), de0, de1);
+            CK(cudaGetLastError());
+        }
+        // ---- table tangents ----
+        std::vector<DualTab> dts(tlist.size());
+        std::map<int, DualTab> dt_of;
+        int maxdim = 1;
+        for (size_t i = 0; i < tlist.size(); ++i) {
+            int u = tlist[i];
+            HostTab& tb = tabs[u];
+            DualTab dt;
+            memset(&dt, 0, sizeof(dt));
+            if (tb.Wt) {
+                size_t b = (size_t)2 * tb.wdim * tb.wdp * sizeof(double);
+                dt.dWt = (double*)galloc(b);
+                temps.push_back({dt.dWt, b});
+                maxdim = std::max(maxdim, tb.wdim);
+            }
+            if (tb.ipow) {
+                size_t b = (size_t)2 * tb.nrow * sizeof(double);
+                dt.dipow = (double*)galloc(b);
+                temps.push_back({dt.dipow, b});
+                for (int c = 1; c < tb.k; ++c) {
+                    size_t bc = (size_t)2 * tb.nrow * tb.cdp[c] * sizeof(double);
+                    dt.dcoefD[c] = (double*)galloc(bc);
+                    temps.push_back({dt.dcoefD[c], bc});
+                }
+            }
+            dts[i] = dt;
+            dt_of[u] = dt;
+        }
+        if (!tlist.empty()) {
+            int* dl = (int*)galloc(tlist.size() * sizeof(int));
+            temps.push_back({dl, tlist.size() * sizeof(int)});
+            DualTab* ddt = (DualTab*)galloc(tlist.size() * sizeof(DualTab));
+            temps.push_back({ddt, tlist.size() * sizeof(DualTab)});
+            CK(cudaMemcpyAsync(dl, tlist.data(), tlist.size() * sizeof(int), cudaMemcpyHostToDevice, stream));
+            CK(cudaMemcpyAsync(ddt, dts.data(), tlist.size() * sizeof(DualTab), cudaMemcpyHostToDevice, stream));
+            size_t smem = (size_t)2 * maxdim * 3 * sizeof(double);
+            tables_dual_kernel<2><<<(unsigned)tlist.size(), 128, smem, stream>>>(m, sd, dl, ddt, de0, de1);
+            CK(cudaGetLastError());
+        }
+        // ---- tangent columns up the perturbed steps ----
+        std::map<int, std::pair<double*, size_t>> dcol;      // node -> (tangent column, stride rows*ld)
+        for (int u : steps) {
+            NodeStep st = make_step(u, true);
+            DualStep<2> ds;
+            memset(&ds, 0, sizeof(ds));
+            for (int i = 0; i < st.k; ++i) {
+                int c = st.child[i].id;
+                auto it = dcol.find(c);
+                if (it != dcol.end()) { ds.child[i].dell = it->second.first; ds.child[i].dell_stride = it->second.second; }
+                auto jt = dt_of.find(c);
+                if (jt != dt_of.end() && jt->second.dWt && wd[c]) { ds.child[i].dWt = jt->second.dWt; ds.child[i].dWt_stride = (size_t)tabs[c].wdim * tabs[c].wdp; }
+                auto ut = dt_of.find(u);
+                if (i >= 1 && ut != dt_of.end() && ut->second.dcoefD[i]) { ds.child[i].dcoefD = ut->second.dcoefD[i]; ds.child[i].dcoef_stride = (size_t)tabs[u].nrow * tabs[u].cdp[i]; }
+            }
+            auto ut = dt_of.find(u);
+            if (ut != dt_of.end() && ut->second.dipow) ds.dipow = ut->second.dipow;
+            ds.nrow = tabs[u].nrow;
+            ds.de0 = de0;
+            ds.de_stride = (size_t)n;
+            size_t rows = (size_t)Tp[u].xmax + 1;
+            size_t b = (size_t)2 * rows * ld * sizeof(double);
+            ds.dout = (double*)galloc(b);
+            temps.push_back({ds.dout, b});
+            ds.dout_stride = rows * ld;
+            ds.out_scl = st.out_scl;
+            dcol[u] = {ds.dout, rows * ld};
+            int need = Tp[u].xmax + 1;
+            if (need <= 16) launch_prune_dual<16>(st, ds);
+            else if (need <= 64) launch_prune_dual<64>(st, ds);
+            else if (need <= 256) launch_prune_dual<256>(st, ds);
+            else launch_prune_dual<1024>(st, ds);
+            CK(cudaGetLastError());
+        }
+        // ---- root ----
+        Slab* rs = readable(0);
+        int nrow = Tp[0].xmax + 1;
+        size_t rwb = (size_t)3 * nrow * sizeof(double);
+        double* rw = (double*)galloc(rwb);
+        temps.push_back({rw, rwb});
+        root_tables_dual_kernel<2><<<1, 128, 0, stream>>>(m, sd, de0, de1, rw, nrow);
+        CK(cudaGetLastError());
+        int blocks = (N + 255) / 256;
+        size_t pb = (size_t)2 * blocks * sizeof(double);
+        double* part = (double*)galloc(pb);
+        temps.push_back({part, pb});
+        auto rt = dcol.find(0);
+        root_dual_kernel<2><<<blocks, 256, 0, stream>>>(rs->ell, rt != dcol.end() ? rt->second.first : nullptr,
+                                                        rt != dcol.end() ? rt->second.second : 0, Tp[0].cnt, rw, nrow, weight.p, part, blocks, N, ld);
+        CK(cudaGetLastError());
+        double* dres = (double*)galloc(2 * sizeof(double));
+        temps.push_back({dres, 2 * sizeof(double)});
+        grad_reduce_kernel<<<1, 256, 0, stream>>>(part, blocks, 2, dres);
+        CK(cudaGetLastError());
+        CK(cudaMemcpyAsync(out2, dres, 2 * sizeof(double), cudaMemcpyDeviceToHost, stream));
+        CK(cudaStreamSynchronize(stream));
+        for (auto& t : temps) gfree(t.first, t.second);
+    }
+
+    // g: [λ_1..λ_n, μ_1..μ_n, q (ascending wgd id), η]  (asvector layout, model.jl:541-546) or [λ, μ] for cr
+    void gradient(double* g, int len, double* logpdf_out, bool cr) {
+        require(have_topology && have_params && tabs_valid, "gradient: model not set (topology, params, rebuild)");
+        int nn = 0;
+        while (nn < ncols_model && present(nn) && (kind[nn] == BLG_ROOT || kind[nn] == BLG_SP)) ++nn;
+        std::vector<int> wg;
+        for (int i = nn; i < ncols_model; ++i) {
+            if (!present(i)) continue;
+            require(kind[i] != BLG_ROOT && kind[i] != BLG_SP, "gradient: non-WGD ids must be 1..n (call reindex!)");
+            if (kind[i] == BLG_WGD || kind[i] == BLG_WGT) wg.push_back(i);
+        }
+        const int P = cr ? 2 : 2 * nn + (int)wg.size() + 1;
+        require(len >= P, "gradient: output vector too short");
+        for (int i = 0; i < P; ++i) g[i] = 0.0;
+        if (N == 0) { if (logpdf_out) *logpdf_out = 0.0; return; }
+        // fresh evaluation that leaves the committed/proposal state alone (the reference uses a fresh L, model.jl:395)
+        std::vector<Col> saved = Tp;
+        try {
+            logpdf(0, 1, result.p);
+            double ll;
+            CK(cudaMemcpyAsync(&ll, result.p, sizeof(double), cudaMemcpyDeviceToHost, stream));
+            CK(cudaStreamSynchronize(stream));
+            if (logpdf_out) *logpdf_out = ll;
+            Seeds<2> sd;
+            double o[2];
+            if (cr) {
+                sd.kind[0] = SEED_LAM_ALL; sd.kind[1] = SEED_MU_ALL; sd.node[0] = sd.node[1] = -1;
+                tangent_pass(sd, o);
+                g[0] = o[0]; g[1] = o[1];
+            } else {
+                for (int b = 0; b < nn; ++b) {
+                    if (model_kind == BLG_BRANCH_MODEL && b == 0) continue;     // root rates are unused by Branch models
+                    sd.kind[0] = SEED_LAM; sd.kind[1] = SEED_MU; sd.node[0] = sd.node[1] = b;
+                    tangent_pass(sd, o);
+                    g[b] = o[0]; g[nn + b] = o[1];
+                }
+                for (size_t j = 0; j < wg.size(); ++j) {
+                    sd.kind[0] = SEED_Q; sd.node[0] = wg[j]; sd.kind[1] = SEED_NONE; sd.node[1] = -1;
+                    tangent_pass(sd, o);
+                    g[2 * nn + j] = o[0];
+                }
+                sd.kind[0] = SEED_ETA; sd.node[0] = 0; sd.kind[1] = SEED_NONE; sd.node[1] = -1;
+                tangent_pass(sd, o);
+                g[P - 1] = o[0];
+            }
+        } catch (...) { Tp = saved; throw; }
+        Tp = saved;
+    }
+
     void root_reduce(double* d_out) {
         require(tabs_valid, "logpdf: ε/W tables are stale (call blg_rebuild)");
         require(!children[0].empty(), "logpdf: the root is a leaf");
@@ -1656,20 +1896,28 @@ int blg_logpdf_full_async(blg_handle* h, double* d_out) { return logpdf_async(h,
 int blg_logpdf_from_async(blg_handle* h, int node, double* d_out) { return logpdf_async(h, 1, node, d_out); }
 int blg_logpdf_root_async(blg_handle* h, double* d_out) { return logpdf_async(h, 2, 1, d_out); }
 
-int blg_gradient(blg_handle* h, double*, int, double*) {
-    if (!h) return 1;
-    h->err = "blg_gradient: not built yet in this revision";
-    return 3;
+int blg_gradient(blg_handle* h, double* g, int len, double* logpdf_out) {
+    BLG_ENTER(h)
+    h->require(g != nullptr, "gradient: null output");
+    h->gradient(g, len, logpdf_out, false);
+    BLG_LEAVE(h)
 }
-int blg_gradient_cr(blg_handle* h, double*, double*) {
-    if (!h) return 1;
-    h->err = "blg_gradient_cr: not built yet in this revision";
-    return 3;
+int blg_gradient_cr(blg_handle* h, double* g2, double* logpdf_out) {
+    BLG_ENTER(h)
+    h->require(g2 != nullptr, "gradient_cr: null output");
+    h->gradient(g2, 2, logpdf_out, true);
+    BLG_LEAVE(h)
 }
-int blg_gradient_async(blg_handle* h, double*, int) {
-    if (!h) return 1;
-    h->err = "blg_gradient_async: not built yet in this revision";
-    return 3;
+// d_g[0] = logL, d_g[1..len] = ∇ in device memory on the handle's stream (for an all-reduce behind it).  The
+// tangent passes synchronise internally; only the final placement is asynchronous.
+int blg_gradient_async(blg_handle* h, double* d_g, int len) {
+    BLG_ENTER(h)
+    h->require(d_g != nullptr && len >= 1, "gradient_async: bad arguments");
+    std::vector<double> tmp(len + 1, 0.0);
+    h->gradient(tmp.data() + 1, len, tmp.data(), false);
+    CK(cudaMemcpyAsync(d_g, tmp.data(), (size_t)(len + 1) * sizeof(double), cudaMemcpyHostToDevice, h->stream));
+    CK(cudaStreamSynchronize(h->stream));
+    BLG_LEAVE(h)
 }
 
 int blg_commit(blg_handle* h) {

@@ -165,6 +165,35 @@ class PArray:
         self.sync(n.model)
         return self._run(2, 1)
 
+    # ---- gradient (src/profile.jl:71-75) -----------------------------------------------------------------------
+    def gradient(self, model, cr=False):
+        """-> (g, logpdf).  g is laid out like asvector(model) (src/model.jl:541-546): [λ…, μ…, q in getwgds
+        order, η]; ``cr=True`` gives gradient_cr's [∂λ, ∂μ] with the rates tied across nodes."""
+        n = model.ne() + 1
+        k = model.nwgd()
+        P = 2 if cr else 2 * n + k + 1
+        g = np.zeros(P)
+        if self.N == 0 and not self.distributed:
+            return g, 0.0
+        self.sync(model)
+        ll = C.c_double()
+        if cr:
+            self._ck(self.L.blg_gradient_cr(self.h, _dp(g), C.byref(ll)))
+        else:
+            self._ck(self.L.blg_gradient(self.h, _dp(g), P, C.byref(ll)))
+        llv = ll.value
+        if self.distributed:
+            import torch
+            with torch.cuda.stream(self.torch_stream):
+                t = torch.from_numpy(np.concatenate([[llv], g])).to("cuda:%d" % self.device)
+                allreduce_sum_(t)
+                h = t.cpu().numpy()
+            llv, g = float(h[0]), h[1:].copy()
+        if not cr and k > 1:
+            # the library orders ∂/∂q by ascending wgd id; asvector lists q in getwgds order (descending id)
+            g[2 * n:2 * n + k] = g[2 * n:2 * n + k][::-1].copy()
+        return g, llv
+
     # ---- accept / reject / reversible jump ---------------------------------------------------------------
     def set_(self):
         if self.h is not None:
@@ -293,6 +322,16 @@ def logpdf_(x, p):
 
 def logpdfroot(n, p):
     return p.logpdfroot(n)
+
+
+def gradient(d, p):
+    """gradient(d::DLWGD, p::PArray)  (src/profile.jl:71-72)"""
+    return p.gradient(d)[0]
+
+
+def gradient_cr(d, p):
+    """gradient_cr(d::DLWGD, p::PArray)  (src/profile.jl:74-75)"""
+    return p.gradient(d, cr=True)[0]
 
 
 def set_(x):

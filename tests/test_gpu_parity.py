@@ -291,3 +291,69 @@ def test_synthetic_large_batch_vs_oracle():
     want, pf = orc.logpdf(per_family=True)
     assert close(got, want, 1e-11)
     np.testing.assert_allclose(data.family_logpdf(), pf, rtol=1e-11)
+
+
+# ---- gradient (forward-mode tangent kernels) vs the oracle's dual-number gradient ---------------------------
+GRTOL = 1e-8      # the stated bar (relative to the largest component, plus per-component)
+
+
+def assert_grad_close(g, want, rtol=GRTOL):
+    g, want = np.asarray(g), np.asarray(want)
+    assert g.shape == want.shape
+    scale = np.abs(want).max()
+    np.testing.assert_allclose(g, want, rtol=rtol, atol=rtol * scale)
+
+
+def test_gradient_golden_config(plants1c):                # test/gradient.jl:1-13 (Branch, λ=2 μ=1 η=0.9)
+    from conftest import GRAD_GOLDEN
+    nw, df = plants1c
+    model, data, orc = pair(nw, df, 2.0, 1.0, 0.9, B.BRANCH)
+    g = B.gradient(model, data)
+    np.testing.assert_allclose(g, GRAD_GOLDEN, atol=1e-4, rtol=0)          # the reference's own 5-digit golden
+    assert_grad_close(g, orc.gradient())
+    assert g[0] == 0.0 and g[19] == 0.0                                      # root rates are unused by Branch models
+    # the call leaves the profile state alone
+    l0 = B.logpdf_(model, data)
+    B.set_(data)
+    g2, ll = data.gradient(model)
+    assert ll == pytest.approx(l0, rel=1e-13)
+    np.testing.assert_array_equal(g, g2)
+    assert B.logpdfroot(model[1], data) == pytest.approx(l0, rel=1e-13)
+
+
+@pytest.mark.parametrize("nt", [B.NODE, B.BRANCH])
+def test_gradient_heterogeneous_rates_with_wgd(plants1, nt):
+    nw, df = plants1
+    model, data, orc = pair(nw, df, 0.7, 0.9, 0.8, nt)
+    rng = np.random.default_rng(12)
+    X = np.exp(rng.normal(0, 0.4, size=(2, len(model))))
+    model.setrates_(X); orc.setrates(X)
+    B.addwgd_(model, model[6], 0.3, 0.35); orc.addwgd(6, 0.3, 0.35)
+    B.extend_(data, 6); orc.extend(6)
+    g, ll = data.gradient(model)
+    assert ll == pytest.approx(orc.logpdf(), rel=1e-12)
+    assert_grad_close(g, orc.gradient())                                     # one WGD: literal reference ordering
+    # two WGDs: asvector lists q by descending id; the oracle's self-consistent gradient lists them ascending
+    B.addwgd_(model, model[15], 0.2, 0.15); orc.addwgd(15, 0.2, 0.15)
+    B.extend_(data, 15); orc.extend(15)
+    g = B.gradient(model, data)
+    want = orc.gradient(literal=False)
+    n = model.ne() + 1
+    want[2 * n:2 * n + 2] = want[2 * n:2 * n + 2][::-1]
+    assert_grad_close(g, want)
+
+
+def test_gradient_cr(dicots):
+    nw, df = dicots
+    model, data, orc = pair(nw, df, 1.0, 0.92, 0.66, B.BRANCH)
+    assert_grad_close(B.gradient_cr(model, data), orc.gradient_cr())
+    # equals the sum of the per-branch components
+    g = B.gradient(model, data)
+    n = model.ne() + 1
+    np.testing.assert_allclose(B.gradient_cr(model, data), [g[:n].sum(), g[n:2 * n].sum()], rtol=1e-9)
+
+
+def test_gradient_lambda_equals_mu_branch(monocots):      # λ ≈ μ: both sides differentiate the limit formula
+    nw, df = monocots
+    model, data, orc = pair(nw, df, 0.003, 0.003, 0.9, B.BRANCH)
+    assert_grad_close(B.gradient(model, data), orc.gradient(), rtol=1e-7)
