@@ -132,11 +132,13 @@ __device__ __forceinline__ double d_powi(double b, int n) {   // b^n, n >= 0, by
     return r;
 }
 
-// setϵ! (node.jl:136-162) for the listed nodes, in list order.  Sequential by construction (each
-// node needs its children's ϵ[2]); one thread, a few hundred flops per node.
-__global__ void eps_kernel(ModelDev m, const int* __restrict__ list, int nlist) {
-    if (blockIdx.x != 0 || threadIdx.x != 0) return;
-    for (int li = 0; li < nlist; ++li) {
+// setϵ! (node.jl:136-162) for the listed nodes.  A node needs its children's ϵ[2], so the list is cut into
+// segments (seg[0..nseg]) such that no node depends on another node of its own segment: the host passes either
+// one node per segment (a literal replay of the reference's call order) or the nodes grouped by height above
+// the leaves (set!(d): every level in parallel).  One block; threads of a segment work concurrently.
+__global__ void __launch_bounds__(128) eps_kernel(ModelDev m, const int* __restrict__ list, const int* __restrict__ seg, int nseg) {
+    for (int sg = 0; sg < nseg; ++sg) {
+      for (int li = seg[sg] + (int)threadIdx.x; li < seg[sg + 1]; li += (int)blockDim.x) {
         int n = list[li];
         int c0 = m.child_off[n], c1 = m.child_off[n + 1];
         uint8_t kd = m.kind[n];
@@ -168,6 +170,8 @@ __global__ void eps_kernel(ModelDev m, const int* __restrict__ list, int nlist) 
             }
             m.eps1[n] = d_approx1(e);
         }
+      }
+      __syncthreads();
     }
 }
 
@@ -644,8 +648,8 @@ __device__ __noinline__ void sweep_child(const SweepChild& c, int f, size_t ld, 
 
 // PROF: per-(step, phase) warp-cycle totals into prof[step*8 + phase] (diagnostic build of the same kernel)
 #define BLG_TICK(ph) do { if (PROF) { long long t1_ = clock64(); if (lane == 0) atomicAdd(&prof[si * 8 + (ph)], (unsigned long long)(t1_ - t0_)); t0_ = t1_; } } while (0)
-template <bool PROF>
-__global__ void __launch_bounds__(128, 4) sweep_kernel(const __grid_constant__ SweepList L, int N, size_t ld, int slice_cap,
+template <bool PROF, int MINB>
+__global__ void __launch_bounds__(128, MINB) sweep_kernel(const __grid_constant__ SweepList L, int N, size_t ld, int slice_cap,
                                                        double* gscratch, size_t gs_stride, unsigned long long* prof) {
     extern __shared__ double smem[];
     const unsigned lane = threadIdx.x & 31u;
@@ -961,7 +965,7 @@ struct blg_handle {
     bool have_params = false;
     // device model arrays
     DevBuf<uint8_t> d_kind;
-    DevBuf<int> d_parent, d_child_off, d_child_idx, d_list;
+    DevBuf<int> d_parent, d_child_off, d_child_idx, d_list, d_elist, d_seg;
     DevBuf<double> d_t, d_lam, d_mu, d_q, d_eps0, d_eps1;
     DevBuf<NodeTab> d_tab;
     DevBuf<SweepNodeConst> d_nc;
@@ -977,6 +981,7 @@ struct blg_handle {
     int kernel_version = 2;
     int last_kernel = 0;
     bool order_resident = true;
+    int min_blocks = 4;
     int profile_sweep = 0;
     DevBuf<unsigned long long> d_prof;
     int slice_cap = 52;                       // doubles per lane of the per-warp shared-memory slice
@@ -1005,7 +1010,7 @@ struct blg_handle {
         for (auto* c : count_allocs) cudaFree(c);
         for (auto& tb : tabs) free_tab(tb);
         weight.free_(); fam_ll.free_(); partial.free_(); result.free_(); rootw.free_(); pascal.free_();
-        d_kind.free_(); d_parent.free_(); d_child_off.free_(); d_child_idx.free_(); d_list.free_();
+        d_kind.free_(); d_parent.free_(); d_child_off.free_(); d_child_idx.free_(); d_list.free_(); d_elist.free_(); d_seg.free_();
         d_t.free_(); d_lam.free_(); d_mu.free_(); d_q.free_(); d_eps0.free_(); d_eps1.free_(); d_tab.free_();
         d_nc.free_(); d_fast_ok.free_(); d_prof.free_();
         gpool_release();
@@ -1181,10 +1186,33 @@ struct blg_handle {
         d_nc.ensure((size_t)ncols_model);
         d_fast_ok.ensure((size_t)ncols_model);
         CK(cudaMemcpyAsync(d_tab.p, tab_stage.data(), (size_t)ncols_model * sizeof(NodeTab), cudaMemcpyHostToDevice, stream));
+        // ε segments: a full rebuild groups the nodes by height above the leaves (children always sit in an
+        // earlier segment); a partial list is replayed literally, one node after the other
+        std::vector<int> elist = list, seg;
+        if (list.size() == postorder.size()) {
+            std::vector<int> height(ncols_model, 0);
+            int hmax = 0;
+            for (int u : postorder) {
+                int hh = 0;
+                for (int c : children[u]) hh = std::max(hh, height[c] + 1);
+                height[u] = hh;
+                hmax = std::max(hmax, hh);
+            }
+            std::stable_sort(elist.begin(), elist.end(), [&](int a, int b) { return height[a] < height[b]; });
+            seg.push_back(0);
+            for (size_t i = 1; i < elist.size(); ++i) if (height[elist[i]] != height[elist[i - 1]]) seg.push_back((int)i);
+            seg.push_back((int)elist.size());
+        } else {
+            for (size_t i = 0; i <= elist.size(); ++i) seg.push_back((int)i);
+        }
         d_list.ensure(list.size());
+        d_elist.ensure(elist.size());
+        d_seg.ensure(seg.size());
         CK(cudaMemcpyAsync(d_list.p, list.data(), list.size() * sizeof(int), cudaMemcpyHostToDevice, stream));
+        CK(cudaMemcpyAsync(d_elist.p, elist.data(), elist.size() * sizeof(int), cudaMemcpyHostToDevice, stream));
+        CK(cudaMemcpyAsync(d_seg.p, seg.data(), seg.size() * sizeof(int), cudaMemcpyHostToDevice, stream));
         ModelDev m = model_dev();
-        eps_kernel<<<1, 32, 0, stream>>>(m, d_list.p, (int)list.size());
+        eps_kernel<<<1, 128, 0, stream>>>(m, d_elist.p, d_seg.p, (int)seg.size() - 1);
         CK(cudaGetLastError());
         tables_kernel<<<(unsigned)list.size(), 128, 2 * (size_t)maxdim * sizeof(double), stream>>>(m, d_list.p, (int)list.size());
         CK(cudaGetLastError());
@@ -1306,17 +1334,21 @@ struct blg_handle {
             }
             size_t smem = (size_t)cap * 32 * warps_per_block * sizeof(double);
             if (smem > sweep_smem_set) {
-                CK(cudaFuncSetAttribute(sweep_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-                CK(cudaFuncSetAttribute(sweep_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+                CK(cudaFuncSetAttribute(sweep_kernel<false, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+                CK(cudaFuncSetAttribute(sweep_kernel<false, 5>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+                CK(cudaFuncSetAttribute(sweep_kernel<false, 6>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+                CK(cudaFuncSetAttribute(sweep_kernel<true, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
                 sweep_smem_set = smem;
             }
             if (!profile_sweep) {
-                sweep_kernel<false><<<blocks, 32 * warps_per_block, smem, stream>>>(L, N, ld, cap, gs, gstride, nullptr);
+                if (min_blocks == 6) sweep_kernel<false, 6><<<blocks, 32 * warps_per_block, smem, stream>>>(L, N, ld, cap, gs, gstride, nullptr);
+                else if (min_blocks == 5) sweep_kernel<false, 5><<<blocks, 32 * warps_per_block, smem, stream>>>(L, N, ld, cap, gs, gstride, nullptr);
+                else sweep_kernel<false, 4><<<blocks, 32 * warps_per_block, smem, stream>>>(L, N, ld, cap, gs, gstride, nullptr);
                 CK(cudaGetLastError());
             } else {
                 d_prof.ensure((size_t)BLG_SWEEP_MAXSTEPS * 8);
                 CK(cudaMemsetAsync(d_prof.p, 0, (size_t)BLG_SWEEP_MAXSTEPS * 8 * sizeof(unsigned long long), stream));
-                sweep_kernel<true><<<blocks, 32 * warps_per_block, smem, stream>>>(L, N, ld, cap, gs, gstride, d_prof.p);
+                sweep_kernel<true, 4><<<blocks, 32 * warps_per_block, smem, stream>>>(L, N, ld, cap, gs, gstride, d_prof.p);
                 CK(cudaGetLastError());
                 std::vector<unsigned long long> hp((size_t)BLG_SWEEP_MAXSTEPS * 8);
                 CK(cudaMemcpyAsync(hp.data(), d_prof.p, hp.size() * sizeof(unsigned long long), cudaMemcpyDeviceToHost, stream));
@@ -1686,6 +1718,7 @@ int blg_create(int device, void* stream, blg_handle** out) {
         }
         if (const char* kv = getenv("BLG_KERNEL")) h->kernel_version = atoi(kv) == 1 ? 1 : 2;
         if (const char* o = getenv("BLG_ORDER")) h->order_resident = atoi(o) != 0;
+        if (const char* o = getenv("BLG_MINB")) h->min_blocks = atoi(o);
         if (const char* o = getenv("BLG_PROF")) h->profile_sweep = atoi(o);
         if (const char* sc = getenv("BLG_SLICE")) h->slice_cap = std::max(8, std::min(224, atoi(sc)));
         *out = h;

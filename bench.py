@@ -230,12 +230,12 @@ def main():
         data._ck(data.L.blg_logpdf_full_async(data.h, ptr))
         B.allreduce_sum_(out)
 
+    sampler = ClockSampler(local)          # samples clocks from the warm-up through both timed regions
+    sampler.start()
     for _ in range(args.warmup):
         step_resident()
     data.set_timing(True)
     barrier()
-    sampler = ClockSampler(local)
-    sampler.start()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     prune_ms = []
     e0.record(stream)
