@@ -41,6 +41,9 @@ def parse():
     ap.add_argument("--max-count", type=int, default=50)
     ap.add_argument("--cpu-seconds", type=float, default=15.0, help="target CPU time of the cpu_baseline sample")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-mcmc", action="store_true", help="skip the rjMCMC iterations/s leg")
+    ap.add_argument("--mcmc-families", type=int, default=100_000)
+    ap.add_argument("--mcmc-generations", type=int, default=40)
     return ap.parse_args()
 
 
@@ -168,6 +171,34 @@ def run_reference(args):
         "e2e": {"value": cb["value"], "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     }
     print(json.dumps(line))
+
+
+def mcmc_leg(args, local):
+    """rjMCMC iterations/s (second half of BASELINE.json's metric), config C4: 12monocots tree, 10^5 synthetic
+    families from the model, one GPU, `rjmcmc!` generations (one add/remove jump + one MWG sweep each) replayed
+    through the public API by beluga_b200.mcmc (flat prior, fixed-width proposals)."""
+    import beluga_b200 as B
+    from beluga_b200.mcmc import RevJumpChain
+    from beluga_b200.model import build_model
+    from beluga_b200.sim import rand_profiles_torch
+
+    nw = open(os.path.join(ROOT, "tests", "data", "12monocots.nw")).readline().strip()
+    m0, _, _ = build_model(nw, 0.004, 0.003, 0.9, B.BRANCH)
+    names, counts = rand_profiles_torch(m0, args.mcmc_families, seed=SEED, device="cuda:%d" % local, max_rootsum=60, chunk=1 << 19)
+    model, data = B.DLWGD(nw, (names, counts), 0.004, 0.003, 0.9, B.BRANCH, device=local)
+    chain = RevJumpChain(data, model, seed=SEED, step=0.02).init_()
+    chain.rjmcmc_(5, trace=0)                      # warm-up
+    data.synchronize()
+    e0, p0 = chain.evals, chain.proposed
+    t0 = time.perf_counter()
+    chain.rjmcmc_(args.mcmc_generations, trace=0)
+    data.synchronize()
+    dt = time.perf_counter() - t0
+    return {"metric": "rjMCMC iters/sec", "value": args.mcmc_generations / dt, "unit": "generations/s",
+            "config": {"workload": "C4: 12monocots, %d synthetic families (%d patterns), rjmcmc! generations on 1 GPU" % (args.mcmc_families, len(data)),
+                       "nodes": len(model), "wgds_at_end": model.nwgd()},
+            "likelihood_calls_per_s": (chain.evals - e0) / dt, "proposals_per_s": (chain.proposed - p0) / dt,
+            "acceptance": chain.accepted / max(chain.proposed, 1), "generations": args.mcmc_generations}
 
 
 def workload_config(args, npat, nfam):
@@ -303,6 +334,13 @@ def main():
             "gpu_launches": int(launches * args.steps),
             "clocks": sampler.summary(),
         }
+        if not args.no_mcmc:
+            try:
+                del data
+                torch.cuda.empty_cache()
+                line["mcmc"] = mcmc_leg(args, local)
+            except Exception as e:
+                line["mcmc"] = {"metric": "rjMCMC iters/sec", "value": None, "error": repr(e)}
         if not args.no_cpu_baseline:
             try:
                 line["cpu_baseline"] = {k: v for k, v in cpu_baseline(args, None, args.cpu_seconds).items()

@@ -357,3 +357,40 @@ def test_gradient_lambda_equals_mu_branch(monocots):      # λ ≈ μ: both side
     nw, df = monocots
     model, data, orc = pair(nw, df, 0.003, 0.003, 0.9, B.BRANCH)
     assert_grad_close(B.gradient(model, data), orc.gradient(), rtol=1e-7)
+
+
+# ---- the caller: MCMC move schedule through the device (rjmcmc.jl:275-305) -------------------------------------
+def test_mcmc_and_rjmcmc_keep_device_state_consistent(monocots):
+    from beluga_b200.mcmc import RevJumpChain
+    nw, df = monocots
+    model, data, _ = pair(nw, df, 0.004, 0.003, 0.9, B.BRANCH)
+    chain = RevJumpChain(data, model, seed=5, step=0.08).init_()
+    l0 = chain.state["logp"]
+    chain.mcmc_(3)
+    chain.rjmcmc_(12)
+    assert chain.accepted > 0 and chain.proposed > chain.accepted      # both accept and reject paths ran
+    assert chain.state["k"] == model.nwgd()
+    assert data.ncols() == data.ncols(proposal=False) == max(model.nodes)
+    assert sorted(model.nodes) == list(range(1, max(model.nodes) + 1))  # ids contiguous after the jumps
+    # the running log-likelihood (built from partial recomputes, commits and reverts only) equals a fresh
+    # full evaluation of the final model, on the device and in the oracle
+    lfull = B.logpdf_(model, data)
+    assert chain.state["logp"] == pytest.approx(lfull, rel=1e-11)
+    orc = OracleDLWGD(nw, df[0], df[1], 0.004, 0.003, 0.9, OBRANCH, threads=4)
+    # rebuild the final model in the oracle: WGDs in id order, then all θ
+    for wid in sorted(i for i, n in model.nodes.items() if n.kind == "wgd"):
+        w = model[wid]
+        below = w.c[0].c[0]
+        # insertion point: the node below, at distance t(below) above it (ids are appended in order)
+        orc.addwgd(below.i if below.kind != "wgd" else below.i, below["t"], w["q"])
+        orc.extend(below.i)
+    for i, n in model.nodes.items():
+        for key, field in (("λ", "lam"), ("μ", "mu"), ("q", "q"), ("t", "t")):
+            if key in n.theta:
+                orc.setfield(i, field, n[key])
+    orc.setfield(1, "eta", model[1]["η"])
+    orc.setall()
+    # (child ORDER differs: the chain's insert/remove history permutes siblings, which only changes rounding)
+    assert orc.maxid == max(model.nodes) and orc.nwgd == model.nwgd()
+    assert lfull == pytest.approx(orc.logpdf(), rel=1e-10)
+    assert l0 != lfull
