@@ -201,6 +201,22 @@ def mcmc_leg(args, local):
             "acceptance": chain.accepted / max(chain.proposed, 1), "generations": args.mcmc_generations}
 
 
+def ncu_traffic():
+    """dram read+write bytes of one sweep_kernel launch from the committed ncu --set full capture of this
+    workload (profiles/r01_sweep_kernel_ncu.csv); None if the file is missing."""
+    path = os.path.join(ROOT, "profiles", "r01_sweep_kernel_ncu.csv")
+    try:
+        tot = 0.0
+        for line in open(path):
+            parts = line.strip().split(",")
+            if parts[0] in ("dram__bytes_read.sum", "dram__bytes_write.sum"):
+                mult = {"byte": 1.0, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9}[parts[1]]
+                tot += float(parts[2]) * mult
+        return tot if tot > 0 else None
+    except OSError:
+        return None
+
+
 def workload_config(args, npat, nfam):
     return {"workload": "C5: %d-taxon coalescent tree + %d WGDs, %s families/GPU drawn from the model (max count %d), pattern-compressed; "
                         "full logpdf! sweep" % (args.taxa, args.wgds, args.families, args.max_count),
@@ -326,7 +342,7 @@ def main():
             "weighted_families_per_s": tot_fam / (ms / 1e3),
             "logpdf": total_ll,
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                         "traffic": None, "kernel": "prune_node_kernel (%d launches/step, event-bracketed)" % (launches - 3),
+                         "traffic": ncu_traffic(), "kernel": "sweep_kernel (%d launch/step, event-bracketed)" % (launches - 3),
                          "algorithmic_bytes_per_launch_group": prune_bytes, "algorithmic_bytes_per_step": alg_bytes, "phase_ms": {"prune": pm, "root+reduce": rm},
                          "peak_source": peak_src},
             "e2e": {"value": tot_pat / (e2e_ms / 1e3), "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": 8,

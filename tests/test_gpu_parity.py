@@ -394,3 +394,83 @@ def test_mcmc_and_rjmcmc_keep_device_state_consistent(monocots):
     assert orc.maxid == max(model.nodes) and orc.nwgd == model.nwgd()
     assert lfull == pytest.approx(orc.logpdf(), rel=1e-10)
     assert l0 != lfull
+
+
+# ---- benchmark-shaped workload (C5: 100 taxa + 10 WGDs): oracle on a sample + size-independent properties --------
+def _c5(nfam, seed=20261019):
+    from beluga_b200.sim import add_random_wgds, rand_profiles, random_tree_newick
+    nw = random_tree_newick(100, seed=seed)
+    model, t, l = build_model(nw, 1.0, 1.2, 0.8, B.BRANCH)
+    ext = add_random_wgds(model, 10, seed=seed)
+    names, counts = rand_profiles(model, nfam, seed=seed, max_rootsum=50)
+    return nw, model, ext, t, l, names, counts
+
+
+def test_c5_workload_sample_against_oracle_and_properties():
+    nw, model, ext, t, l, names, counts = _c5(6000)
+    X, w, _ = B.profile(t, l, (names, counts))
+    data = B.PArray(X, w, device=0)
+    for i in ext:
+        B.extend_(data, i)
+    B.set_(data)
+    total = B.logpdf_(model, data)
+    pf = data.family_logpdf()
+    # (a) the total is the weighted sum of the per-family values
+    assert total == pytest.approx(float((w * pf).sum()), rel=1e-12)
+    # (b) oracle on a sample of 300 patterns, rebuilt with the same WGD insertions
+    sel = np.linspace(0, X.shape[0] - 1, 300).astype(int)
+    leaf_ids = sorted(l)
+    rows = X[sel][:, [i - 1 for i in leaf_ids]]
+    orc = OracleDLWGD(nw, [l[i] for i in leaf_ids], rows, 1.0, 1.2, 0.8, OBRANCH, threads=8)
+    m2, _, _ = build_model(nw, 1.0, 1.2, 0.8, B.BRANCH)
+    rng = np.random.default_rng(20261019)
+    for _ in range(10):                                   # replay add_random_wgds in the oracle
+        ids = sorted(m2.nodes)
+        ww = np.array([m2.nodes[i]["t"] for i in ids], dtype=np.float64)
+        i = int(rng.choice(ids, p=ww / ww.sum()))
+        n = m2.nodes[i]
+        tt = rng.random() * n["t"]
+        if not (n["t"] - tt > 0.0):
+            tt = 0.5 * n["t"]
+        q = float(rng.beta(1.0, 3.0))
+        m2.addwgd_(n, tt, q)
+        orc.addwgd(i, tt, q)
+        orc.extend(i)
+    _, opf = orc.logpdf(per_family=True)
+    ow, ox = orc.profile()
+    # the oracle compresses the sampled rows again: match patterns through their leaf counts
+    key = {tuple(r[[i - 1 for i in leaf_ids]]): k for k, r in enumerate(ox)}
+    got = np.array([pf[s] for s in sel])
+    want = np.array([opf[key[tuple(r)]] for r in rows])
+    np.testing.assert_allclose(got, want, rtol=1e-11)
+    # (c) permutation invariance: per-family values do not depend on the order the families arrive in
+    perm = np.random.default_rng(3).permutation(X.shape[0])
+    data2 = B.PArray(X[perm], w[perm], device=0)
+    for i in ext:
+        B.extend_(data2, i)
+    B.set_(data2)
+    total2 = B.logpdf_(model, data2)
+    # (the device groups families into warps by a k-d split whose ties depend on arrival order, and a family's
+    # loop shapes follow its warp's maxima: values may move by an ulp, nothing more)
+    np.testing.assert_allclose(data2.family_logpdf(), pf[perm], rtol=1e-13)
+    assert total2 == pytest.approx(total, rel=1e-13)
+    # (d) bit-reproducible repeat; partial recompute from any node equals the full sweep after the same update
+    assert B.logpdf_(model, data) == total
+    B.update_(model[29], λ=1.3, μ=0.9)
+    lp = B.logpdf_(model[29], data)
+    lf = B.logpdf_(model, data)
+    assert lp == pytest.approx(lf, rel=1e-13)
+    assert lf != total
+    # (e) the general per-node kernels and the sweep kernel agree on the whole batch
+    import os
+    os.environ["BLG_KERNEL"] = "1"
+    try:
+        data3 = B.PArray(X, w, device=0)
+        for i in ext:
+            B.extend_(data3, i)
+        B.set_(data3)
+        l3 = B.logpdf_(model, data3)
+    finally:
+        del os.environ["BLG_KERNEL"]
+    assert l3 == pytest.approx(lf, rel=1e-12)
+    np.testing.assert_allclose(data3.family_logpdf(), data.family_logpdf(), rtol=1e-11)
