@@ -449,7 +449,9 @@ struct SweepChild {
     double psi, cc;        // ψ', (1-ϕ')(1-ψ') of the child's branch
 };
 struct SweepStep {
-    int k, first, resident, pad_;   // resident != 0: child[0] is the node of the previous step (its column is still in shared memory)
+    int k, first, resident, prefact;   // resident != 0: child[0] is the node of the previous step (its column is still in shared memory)
+                                       // prefact != 0: the NEXT step keeps this node's column resident and contracts it in closed
+                                       // form, so leave (n-1)!·ℓ[n] in shared memory
     double inv, ip0;                // 1/(1-E_k); (1-E_k)^0, NaN where the reference's column would be NaN
     double* out;
     int* out_scl;
@@ -502,10 +504,8 @@ __device__ __noinline__ void sweep_contract_table(double* col, int Mw, const dou
 // in-place closed-form contraction over an ordinary branch.  On entry col[j] = ℓ[j] (j = 0..Mw).
 template <int TS>
 __device__ __noinline__ void sweep_contract_fast(double* col, int Mw, double psi, double cc) {
-    // (a node with a single child folds its (1-E)^(-n) normalisation into cc, see the caller)
-    // u[j] = (j-1)!·ℓ[j]
-#pragma unroll 1
-    for (int j = 2; j <= Mw; ++j) col[j * 32] *= c_fact[j - 1];
+    // On entry col[j] = u[j] = (j-1)!·ℓ[j] (j >= 1; the factor is applied by whoever put the column there:
+    // the staging load, or the previous step's final write when the column stayed resident).
     double post = cc;                                  // c^n/(n-1)! at n = 1
 #pragma unroll 1
     for (int n0 = 1; n0 <= Mw; n0 += TS) {
@@ -634,8 +634,13 @@ __device__ __noinline__ void sweep_child(const SweepChild& c, int f, size_t ld, 
     }
     if (!resident) {
         const double* __restrict__ src = c.ell + f;
+        if (c.table) {
 #pragma unroll 4
-        for (int j = 0; j <= Mw; ++j) col[j * 32] = (j <= M) ? src[(size_t)j * ld] : 0.0;
+            for (int j = 0; j <= Mw; ++j) col[j * 32] = (j <= M) ? src[(size_t)j * ld] : 0.0;
+        } else {                                   // closed-form contraction wants u[j] = (j-1)!·ℓ[j]
+#pragma unroll 4
+            for (int j = 0; j <= Mw; ++j) col[j * 32] = (j <= M) ? src[(size_t)j * ld] * c_fact[j > 0 ? j - 1 : 0] : 0.0;
+        }
     }
     if (c.table) {
         sweep_contract_table<16>(col, Mw, c.Wt, c.wdp);
@@ -731,10 +736,12 @@ __global__ void __launch_bounds__(128, MINB) sweep_kernel(const __grid_constant_
                 if (!swap) {
                     const double E = ch[i].Epre, e = ch[i].e;
                     if (Miw < 4) mx = sweep_merge_fast<4>(R, R, Sw, colB, Miw, E, e, em0, emg, Xm);
+                    else if (Miw < 12) mx = sweep_merge_fast<12>(R, R, Sw, colB, Miw, E, e, em0, emg, Xm);
                     else mx = sweep_merge_fast<24>(R, R, Sw, colB, Miw, E, e, em0, emg, Xm);
                 } else {       // k == 2: child 1 is the "t" side, child 0 (at the front) the register-tiled "s" side
                     const double E = fmin(ch[1].e, 1.0), e = ch[0].e;
                     if (Sw < 4) mx = sweep_merge_fast<4>(R, colB, Miw, R, Sw, E, e, em0, emg, Xm);
+                    else if (Sw < 12) mx = sweep_merge_fast<12>(R, colB, Miw, R, Sw, E, e, em0, emg, Xm);
                     else mx = sweep_merge_fast<24>(R, colB, Miw, R, Sw, E, e, em0, emg, Xm);
                 }
                 Sw += Miw;
@@ -792,10 +799,11 @@ __global__ void __launch_bounds__(128, MINB) sweep_kernel(const __grid_constant_
         {
             double* o = st.out + f;
             const double sc = __hiloint2double((1023 - ex) << 20, 0);     // 2^-ex, exact (|ex| <= 1022)
+            const bool pfact = st.prefact != 0;
 #pragma unroll 2
             for (int n = 0; n <= Xw; ++n) {
                 const double v = R[n * 32] * sc;
-                R[n * 32] = v;
+                R[n * 32] = pfact ? v * c_fact[n > 0 ? n - 1 : 0] : v;
                 if (live && n <= X) o[(size_t)n * ld] = v;
             }
             if (live) st.out_scl[f] = sclsum + ex;
@@ -1296,8 +1304,10 @@ struct blg_handle {
                 for (int c = 1; c < k; ++c)
                     if (st.child[c].id == prev_node) { std::rotate(st.child, st.child + c, st.child + c + 1); break; }
                 SweepStep& ss = L.step[L.nsteps++];
-                ss.k = k; ss.first = nch; ss.pad_ = 0;
+                ss.k = k; ss.first = nch; ss.prefact = 0;
                 ss.resident = (L.nsteps >= 2 && prev_node == st.child[0].id && !children[prev_node].empty()) ? 1 : 0;
+                // a resident column that will be contracted in closed form is left pre-multiplied by (n-1)!
+                if (ss.resident && kind[prev_node] != BLG_WGDAFTER) L.step[L.nsteps - 2].prefact = 1;
                 prev_node = u;
                 double raw = 1.0;
                 ss.inv = h_nc[u].inv; ss.ip0 = h_nc[u].ip0;
