@@ -443,7 +443,8 @@ struct SweepChild {
     const int* scl;
     const uint16_t* cnt;
     const double* Wt;      // transposed w* of the child's branch (leaf gather, WGD/WGT-after contraction)
-    int wdp, table, pad0_, pad1_;   // table != 0: contract with Wt (branch below a WGD/WGT)
+    int wdp, table;        // table != 0: contract with Wt (branch below a WGD/WGT)
+    double invEself;       // 1/min(e, 1)
     double e;              // ϵ[1] of the child (extinction probability at the top of its branch)
     double Epre;           // clamped product of the e's of the children merged before this one (1 for the first)
     double psi, cc;        // ψ', (1-ϕ')(1-ψ') of the child's branch
@@ -475,6 +476,14 @@ __device__ __forceinline__ int ldg_u16_now(const uint16_t* p) {
     asm volatile("ld.global.u16 %0, [%1];" : "=h"(v) : "l"(p));
     return (int)v;
 }
+// asynchronous global→shared copy of one double (zero-filled when !take), tracked by cp.async groups
+__device__ __forceinline__ void cp_async_f64(double* smem_dst, const double* gsrc, bool take) {
+    const unsigned d = (unsigned)__cvta_generic_to_shared(smem_dst);
+    const int n = take ? 8 : 0;
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 8, %2;" ::"r"(d), "l"(gsrc), "r"(n) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+__device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_group 0;" ::: "memory"); }
 __device__ __forceinline__ int ldg_s32_now(const int* p) {
     int v;
     asm volatile("ld.global.s32 %0, [%1];" : "=r"(v) : "l"(p));
@@ -503,9 +512,13 @@ __device__ __noinline__ void sweep_contract_table(double* col, int Mw, const dou
 }
 // in-place closed-form contraction over an ordinary branch.  On entry col[j] = ℓ[j] (j = 0..Mw).
 template <int TS>
-__device__ __noinline__ void sweep_contract_fast(double* col, int Mw, double psi, double cc) {
+__device__ __noinline__ void sweep_contract_fast(double* col, int Mw, double psi, double cc, bool need_fact) {
     // On entry col[j] = u[j] = (j-1)!·ℓ[j] (j >= 1; the factor is applied by whoever put the column there:
-    // the staging load, or the previous step's final write when the column stayed resident).
+    // the staging load, or the previous step's final write when the column stayed resident) unless need_fact.
+    if (need_fact) {
+#pragma unroll 1
+        for (int j = 2; j <= Mw; ++j) col[j * 32] *= c_fact[j - 1];
+    }
     double post = cc;                                  // c^n/(n-1)! at n = 1
 #pragma unroll 1
     for (int n0 = 1; n0 <= Mw; n0 += TS) {
@@ -539,8 +552,8 @@ __device__ __noinline__ void sweep_contract_fast(double* col, int Mw, double psi
 // warp's slice); the result Σ_{t+s=n} C(n,s)·E^s·A[t]·B[t,s], n = 0..Sw+M2w, is written to O[n] at step n.
 // O may alias the slice as long as O+n never passes an unread A[t] (O == A, or O below A).
 template <int TS>
-__device__ __noinline__ double sweep_merge_fast(double* O, const double* A, int Sw, const double* B0, int M2w, double E, double e,
-                                                double em0, double emg, int X) {
+__device__ __noinline__ double sweep_merge_fast(double* O, const double* A, int Sw, const double* B0, int M2w, double E, double invE,
+                                                double e, double em0, double emg, int X) {
     // em0/emg: the emitted value is acc·n!·E^n·(extra factor em0·emg^n): the last merge of a node passes
     // the (1-E_k)^(-n) normalisation (and the NaN poison) through them.  Returns max_{n<=X} of the result.
     double B[TS], acc[TS];
@@ -550,12 +563,10 @@ __device__ __noinline__ double sweep_merge_fast(double* O, const double* A, int 
         acc[k] = 0.0;
     }
     const int nmax = Sw + M2w;
-    const double invE = 1.0 / E;
     const double Eg = E * emg;
     double tf = 1.0;       // 1/(t!·E^t)
     double em = em0;       // n!·E^n · em0·emg^n
     double mx = 0.0;
-    bool nan = false;
 #pragma unroll 1
     for (int t = 0; t <= nmax; ++t) {
         if (t <= Sw) {
@@ -569,14 +580,13 @@ __device__ __noinline__ double sweep_merge_fast(double* O, const double* A, int 
         }
         const double v = (t <= X) ? acc[0] * em : 0.0;
         O[t * 32] = v;
-        nan |= !(v == v);
-        mx = fmax(mx, v);
+        mx = fmax(mx, v);                         // (a NaN column leaves mx = 0: stored as it is, exponent 0)
 #pragma unroll
         for (int k = 0; k < TS - 1; ++k) acc[k] = acc[k + 1];
         acc[TS - 1] = 0.0;
         em *= Eg * (double)(t + 1);
     }
-    return nan ? __longlong_as_double(0x7ff8000000000000LL) : mx;
+    return mx;
 }
 // general merge for a smaller child with >= 24 counts: 16-wide tiles from high s to low s chained
 // through the history column H.  A[0..Sw]; O[0..M2w] = B[0,·], O[M2w+1..Sw+M2w] = 0 on entry; result in O.
@@ -625,8 +635,12 @@ __device__ __noinline__ void sweep_merge_tiled(const double* A, int Sw, double* 
 }
 
 // stage (unless the column is already resident in col) + contract one child into col[0..Mw]
-__device__ __noinline__ void sweep_child(const SweepChild& c, int f, size_t ld, int M, int Mw, double* col, bool resident) {
+// have: 0 = load the child's input column; 1 = it is in col already, pre-multiplied by (j-1)! where the closed form
+// wants that; 2 = it is in col already, plain (copied by cp.async)
+__device__ __noinline__ void sweep_child(const SweepChild& c, int f, size_t ld, int M, int Mw, double* col, int have) {
+    const bool resident = have != 0;
     if (c.ell == nullptr) {                        // leaf: column x_c of w* (one-hot likelihood)
+        if (have) return;
         const double* __restrict__ row = c.Wt + (size_t)M * c.wdp;
 #pragma unroll 2
         for (int s = 0; s <= Mw; ++s) col[s * 32] = (s <= M) ? row[s] : 0.0;
@@ -646,8 +660,8 @@ __device__ __noinline__ void sweep_child(const SweepChild& c, int f, size_t ld, 
         sweep_contract_table<16>(col, Mw, c.Wt, c.wdp);
     } else {
         const double psi = c.psi, cc = c.cc;
-        if (Mw <= 4) sweep_contract_fast<4>(col, Mw, psi, cc);
-        else sweep_contract_fast<12>(col, Mw, psi, cc);
+        if (Mw <= 4) sweep_contract_fast<4>(col, Mw, psi, cc, have == 2);
+        else sweep_contract_fast<12>(col, Mw, psi, cc, have == 2);
     }
 }
 
@@ -717,7 +731,23 @@ __global__ void __launch_bounds__(128, MINB) sweep_kernel(const __grid_constant_
         }
         BLG_TICK(0);
 
-        sweep_child(ch[0], f, ld, M0, M0w, R, res0);
+        // child 1's input column is copied asynchronously while child 0 is being contracted
+        const bool async1 = (k >= 2) && !tiled && R == sl;
+        if (async1) {
+            double* dst = R + (size_t)(M0w + 1) * 32;
+            if (ch[1].ell == nullptr) {
+                const double* row = ch[1].Wt + (size_t)M1 * ch[1].wdp;
+#pragma unroll 1
+                for (int s = 0; s <= M1w; ++s) cp_async_f64(dst + s * 32, (s <= M1) ? row + s : row, s <= M1);
+            } else {
+                const double* src = ch[1].ell + f;
+#pragma unroll 1
+                for (int j = 0; j <= M1w; ++j) cp_async_f64(dst + j * 32, (j <= M1) ? src + (size_t)j * ld : src, j <= M1);
+            }
+            cp_async_commit();
+        }
+        sweep_child(ch[0], f, ld, M0, M0w, R, res0 ? 1 : 0);
+        if (async1) cp_async_wait_all();
         BLG_TICK(1);
         int Sw = M0w;
         double mxv = 0.0;
@@ -727,7 +757,7 @@ __global__ void __launch_bounds__(128, MINB) sweep_kernel(const __grid_constant_
                 const int Mi = (i == 1) ? M1 : (int)ch[i].cnt[f];
                 const int Miw = (i == 1) ? M1w : warp_max(Mi);
                 double* colB = R + (size_t)(Sw + 1) * 32;
-                sweep_child(ch[i], f, ld, Mi, Miw, colB, false);
+                sweep_child(ch[i], f, ld, Mi, Miw, colB, (i == 1 && async1) ? 2 : 0);
                 BLG_TICK(2);
                 const bool last = (i == k - 1);
                 const double em0 = last ? st.ip0 : 1.0, emg = last ? st.inv : 1.0;
@@ -735,14 +765,15 @@ __global__ void __launch_bounds__(128, MINB) sweep_kernel(const __grid_constant_
                 double mx;
                 if (!swap) {
                     const double E = ch[i].Epre, e = ch[i].e;
-                    if (Miw < 4) mx = sweep_merge_fast<4>(R, R, Sw, colB, Miw, E, e, em0, emg, Xm);
-                    else if (Miw < 12) mx = sweep_merge_fast<12>(R, R, Sw, colB, Miw, E, e, em0, emg, Xm);
-                    else mx = sweep_merge_fast<24>(R, R, Sw, colB, Miw, E, e, em0, emg, Xm);
+                    const double invE = (k == 2) ? ch[0].invEself : 1.0 / E;
+                    if (Miw < 4) mx = sweep_merge_fast<4>(R, R, Sw, colB, Miw, E, invE, e, em0, emg, Xm);
+                    else if (Miw < 12) mx = sweep_merge_fast<12>(R, R, Sw, colB, Miw, E, invE, e, em0, emg, Xm);
+                    else mx = sweep_merge_fast<24>(R, R, Sw, colB, Miw, E, invE, e, em0, emg, Xm);
                 } else {       // k == 2: child 1 is the "t" side, child 0 (at the front) the register-tiled "s" side
-                    const double E = fmin(ch[1].e, 1.0), e = ch[0].e;
-                    if (Sw < 4) mx = sweep_merge_fast<4>(R, colB, Miw, R, Sw, E, e, em0, emg, Xm);
-                    else if (Sw < 12) mx = sweep_merge_fast<12>(R, colB, Miw, R, Sw, E, e, em0, emg, Xm);
-                    else mx = sweep_merge_fast<24>(R, colB, Miw, R, Sw, E, e, em0, emg, Xm);
+                    const double E = fmin(ch[1].e, 1.0), e = ch[0].e, invE = ch[1].invEself;
+                    if (Sw < 4) mx = sweep_merge_fast<4>(R, colB, Miw, R, Sw, E, invE, e, em0, emg, Xm);
+                    else if (Sw < 12) mx = sweep_merge_fast<12>(R, colB, Miw, R, Sw, E, invE, e, em0, emg, Xm);
+                    else mx = sweep_merge_fast<24>(R, colB, Miw, R, Sw, E, invE, e, em0, emg, Xm);
                 }
                 Sw += Miw;
                 if (last) { mxv = mx; scaled = true; }
@@ -756,7 +787,7 @@ __global__ void __launch_bounds__(128, MINB) sweep_kernel(const __grid_constant_
             for (int i = 1; i < k; ++i) {
                 const int Mi = (i == 1) ? M1 : (int)ch[i].cnt[f];
                 const int Miw = (i == 1) ? M1w : warp_max(Mi);
-                sweep_child(ch[i], f, ld, Mi, Miw, rO, false);
+                sweep_child(ch[i], f, ld, Mi, Miw, rO, 0);
 #pragma unroll 1
                 for (int n = Miw + 1; n <= Sw + Miw; ++n) rO[n * 32] = 0.0;
                 sweep_merge_tiled(rA, Sw, rO, Miw, rH, ch[i].Epre, ch[i].e);
@@ -768,9 +799,7 @@ __global__ void __launch_bounds__(128, MINB) sweep_kernel(const __grid_constant_
         }
         // ℓ_u[n] = Ã[n]·(1-E_k)^(-n), rescale to a power-of-two exponent, store; the column also stays
         // in R[0..Xw] (zero above the family's own count) for a parent that follows immediately
-        bool bad = false;
         if (scaled) {
-            bad = !(mxv == mxv) || isinf(mxv);
 #pragma unroll 1
             for (int n = Sw + 1; n <= Xw; ++n) R[n * 32] = 0.0;
         } else {
@@ -781,7 +810,6 @@ __global__ void __launch_bounds__(128, MINB) sweep_kernel(const __grid_constant_
                 double v = 0.0;
                 if (n <= X) {
                     v = (n <= Sw ? R[n * 32] : 0.0) * ip;
-                    if (!(v == v) || isinf(v)) bad = true;
                     mxv = fmax(mxv, v);
                 }
                 R[n * 32] = v;
@@ -792,19 +820,26 @@ __global__ void __launch_bounds__(128, MINB) sweep_kernel(const __grid_constant_
         // exponent of the column maximum straight from the bit pattern (normal numbers; a subnormal
         // maximum keeps exponent 0, which only costs range, not correctness)
         int ex = 0;
-        if (!bad && mxv > 0.0) {
+        if (mxv > 0.0) {                               // (fmax skips NaNs; an infinite maximum keeps exponent 0)
             const int be = (__double2hiint(mxv) >> 20) & 0x7ff;
-            if (be != 0) ex = be - 1023;
+            if (be != 0 && be != 0x7ff) ex = be - 1023;
         }
         {
             double* o = st.out + f;
             const double sc = __hiloint2double((1023 - ex) << 20, 0);     // 2^-ex, exact (|ex| <= 1022)
-            const bool pfact = st.prefact != 0;
+            const int keep = st.prefact;               // 0: the next step does not reuse the column; 1: plain; 2: times (n-1)!
+            if (keep == 0) {
+                if (live) {
 #pragma unroll 2
-            for (int n = 0; n <= Xw; ++n) {
-                const double v = R[n * 32] * sc;
-                R[n * 32] = pfact ? v * c_fact[n > 0 ? n - 1 : 0] : v;
-                if (live && n <= X) o[(size_t)n * ld] = v;
+                    for (int n = 0; n <= X; ++n) o[(size_t)n * ld] = R[n * 32] * sc;
+                }
+            } else {
+#pragma unroll 2
+                for (int n = 0; n <= Xw; ++n) {
+                    const double v = R[n * 32] * sc;
+                    R[n * 32] = (keep == 2) ? v * c_fact[n > 0 ? n - 1 : 0] : v;
+                    if (live && n <= X) o[(size_t)n * ld] = v;
+                }
             }
             if (live) st.out_scl[f] = sclsum + ex;
         }
@@ -1307,7 +1342,7 @@ struct blg_handle {
                 ss.k = k; ss.first = nch; ss.prefact = 0;
                 ss.resident = (L.nsteps >= 2 && prev_node == st.child[0].id && !children[prev_node].empty()) ? 1 : 0;
                 // a resident column that will be contracted in closed form is left pre-multiplied by (n-1)!
-                if (ss.resident && kind[prev_node] != BLG_WGDAFTER) L.step[L.nsteps - 2].prefact = 1;
+                if (ss.resident) L.step[L.nsteps - 2].prefact = (kind[prev_node] != BLG_WGDAFTER) ? 2 : 1;
                 prev_node = u;
                 double raw = 1.0;
                 ss.inv = h_nc[u].inv; ss.ip0 = h_nc[u].ip0;
@@ -1318,8 +1353,9 @@ struct blg_handle {
                     SweepChild& sc = L.child[nch++];
                     const ChildRef& cr = st.child[c];
                     sc.ell = cr.ell; sc.scl = cr.scl; sc.cnt = cr.cnt; sc.Wt = cr.Wt;
-                    sc.wdp = cr.wdp; sc.table = (kind[cr.id] == BLG_WGDAFTER) ? 1 : 0; sc.pad0_ = sc.pad1_ = 0;
+                    sc.wdp = cr.wdp; sc.table = (kind[cr.id] == BLG_WGDAFTER) ? 1 : 0;
                     sc.e = h_eps0[cr.id]; sc.psi = h_nc[cr.id].psi; sc.cc = h_nc[cr.id].cc;
+                    sc.invEself = 1.0 / (sc.e > 1.0 ? 1.0 : sc.e);
                     sc.Epre = raw > 1.0 ? 1.0 : raw;           // clamped prefix of the children merged before this one
                     raw *= sc.e;
                     int xm = Tp[cr.id].xmax;
