@@ -469,26 +469,18 @@ struct SweepList {
 static_assert(sizeof(SweepList) <= 32000, "kernel parameter space");
 
 __device__ __forceinline__ int warp_max(int v) { return __reduce_max_sync(0xffffffffu, v); }
-// loads that must be ISSUED where they are written (software prefetch one step ahead): volatile asm keeps
-// the compiler from sinking them to their first use
-__device__ __forceinline__ int ldg_u16_now(const uint16_t* p) {
-    unsigned short v;
-    asm volatile("ld.global.u16 %0, [%1];" : "=h"(v) : "l"(p));
-    return (int)v;
-}
 // asynchronous global→shared copy of one double (zero-filled when !take), tracked by cp.async groups
 __device__ __forceinline__ void cp_async_f64(double* smem_dst, const double* gsrc, bool take) {
     const unsigned d = (unsigned)__cvta_generic_to_shared(smem_dst);
     const int n = take ? 8 : 0;
     asm volatile("cp.async.ca.shared.global [%0], [%1], 8, %2;" ::"r"(d), "l"(gsrc), "r"(n) : "memory");
 }
+__device__ __forceinline__ void cp_async_b32(int* smem_dst, const void* gsrc) {
+    const unsigned d = (unsigned)__cvta_generic_to_shared(smem_dst);
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(d), "l"(gsrc) : "memory");
+}
 __device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
 __device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_group 0;" ::: "memory"); }
-__device__ __forceinline__ int ldg_s32_now(const int* p) {
-    int v;
-    asm volatile("ld.global.s32 %0, [%1];" : "=r"(v) : "l"(p));
-    return v;
-}
 
 // in-place table contraction (branch below a WGD/WGT): col[s] ← Σ_{j=s..Mw} Wt[j*wdp+s]·col[j]
 template <int TS>
@@ -678,37 +670,43 @@ __global__ void __launch_bounds__(128, MINB) sweep_kernel(const __grid_constant_
     int f = wg * 32 + (int)lane;
     const bool live = f < N;
     if (!live) f = N - 1;            // idle lanes shadow the last family (loads stay in bounds; they never store)
-    double* sl = smem + (size_t)warp * slice_cap * 32 + lane;
+    // [4 warps][5 slots][32 lanes] ints: the next step's counts and exponents land here by cp.async (registers that
+    // are live across the helper calls get spilled right after their load, which made a register prefetch block)
+    int* cb = reinterpret_cast<int*>(smem) + (size_t)warp * 160 + lane;
+    double* sl = smem + (size_t)(blockDim.x >> 5) * 80 + (size_t)warp * slice_cap * 32 + lane;
     double* gs = gscratch ? gscratch + (size_t)wg * gs_stride + lane : nullptr;
+    const int fe = f & ~1;                 // the aligned 4-byte word holding this lane's uint16 count
+    const int fsh = (f & 1) * 16;
 
     int prevX = 0, prevScl = 0;      // count and exponent of the column left in the slice by the previous step
     double* prevR = sl;
     long long t0_ = PROF ? clock64() : 0;
-    // counts / exponents of the first two children and the node's own count are loaded one step ahead
-    int nX = 0, nM0 = 0, nM1 = 0, nS0 = 0, nS1 = 0;
     {
         const SweepStep& st = L.step[0];
         const SweepChild* ch = &L.child[st.first];
-        nX = st.cnt[f];
-        nM0 = ch[0].cnt[f];
-        nS0 = ch[0].scl ? ch[0].scl[f] : 0;
-        if (st.k >= 2) { nM1 = ch[1].cnt[f]; nS1 = ch[1].scl ? ch[1].scl[f] : 0; }
+        cp_async_b32(cb + 0 * 32, st.cnt + fe);
+        cp_async_b32(cb + 1 * 32, ch[0].cnt + fe);
+        if (ch[0].scl) cp_async_b32(cb + 3 * 32, ch[0].scl + f);
+        if (st.k >= 2) { cp_async_b32(cb + 2 * 32, ch[1].cnt + fe); if (ch[1].scl) cp_async_b32(cb + 4 * 32, ch[1].scl + f); }
+        cp_async_commit();
     }
     for (int si = 0; si < L.nsteps; ++si) {
         const SweepStep& st = L.step[si];
         const int k = st.k;
         const SweepChild* ch = &L.child[st.first];
         const bool res0 = st.resident != 0;
-        const int X = nX;
-        const int M0 = res0 ? prevX : nM0;
-        const int M1 = (k >= 2) ? nM1 : 0;
-        int sclsum = (res0 ? prevScl : nS0) + ((k >= 2) ? nS1 : 0);
-        if (si + 1 < L.nsteps) {                       // prefetch the next step's counts
+        cp_async_wait_all();
+        const int X = (cb[0 * 32] >> fsh) & 0xffff;
+        const int M0 = res0 ? prevX : ((cb[1 * 32] >> fsh) & 0xffff);
+        const int M1 = (k >= 2) ? ((cb[2 * 32] >> fsh) & 0xffff) : 0;
+        int sclsum = (res0 ? prevScl : (ch[0].scl ? cb[3 * 32] : 0)) + ((k >= 2 && ch[1].scl) ? cb[4 * 32] : 0);
+        if (si + 1 < L.nsteps) {                       // prefetch the next step's counts (asynchronously, into cb)
             const SweepStep& sn = L.step[si + 1];
             const SweepChild* cn = &L.child[sn.first];
-            nX = ldg_u16_now(sn.cnt + f);
-            if (!sn.resident) { nM0 = ldg_u16_now(cn[0].cnt + f); nS0 = cn[0].scl ? ldg_s32_now(cn[0].scl + f) : 0; }
-            if (sn.k >= 2) { nM1 = ldg_u16_now(cn[1].cnt + f); nS1 = cn[1].scl ? ldg_s32_now(cn[1].scl + f) : 0; }
+            cp_async_b32(cb + 0 * 32, sn.cnt + fe);
+            if (!sn.resident) { cp_async_b32(cb + 1 * 32, cn[0].cnt + fe); if (cn[0].scl) cp_async_b32(cb + 3 * 32, cn[0].scl + f); }
+            if (sn.k >= 2) { cp_async_b32(cb + 2 * 32, cn[1].cnt + fe); if (cn[1].scl) cp_async_b32(cb + 4 * 32, cn[1].scl + f); }
+            cp_async_commit();
         }
         const int M0w = warp_max(M0);
         const int M1w = warp_max(M1);
@@ -1027,7 +1025,7 @@ struct blg_handle {
     int min_blocks = 4;
     int profile_sweep = 0;
     DevBuf<unsigned long long> d_prof;
-    int slice_cap = 52;                       // doubles per lane of the per-warp shared-memory slice
+    int slice_cap = 50;                       // doubles per lane of the per-warp shared-memory slice
     std::unique_ptr<SweepList> sweep_list{new SweepList()};
     DevBuf<double> gscratch;
     size_t sweep_smem_set = 0;
@@ -1378,7 +1376,7 @@ struct blg_handle {
                 gscratch.ensure(gstride * (size_t)nwarps);
                 gs = gscratch.p;
             }
-            size_t smem = (size_t)cap * 32 * warps_per_block * sizeof(double);
+            size_t smem = ((size_t)cap * 32 + 80) * warps_per_block * sizeof(double);
             if (smem > sweep_smem_set) {
                 CK(cudaFuncSetAttribute(sweep_kernel<false, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
                 CK(cudaFuncSetAttribute(sweep_kernel<false, 5>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
