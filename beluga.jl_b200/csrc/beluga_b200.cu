@@ -659,21 +659,31 @@ __device__ __noinline__ void sweep_child(const SweepChild& c, int f, size_t ld, 
 
 // PROF: per-(step, phase) warp-cycle totals into prof[step*8 + phase] (diagnostic build of the same kernel)
 #define BLG_TICK(ph) do { if (PROF) { long long t1_ = clock64(); if (lane == 0) atomicAdd(&prof[si * 8 + (ph)], (unsigned long long)(t1_ - t0_)); t0_ = t1_; } } while (0)
-template <bool PROF, int MINB>
+template <bool PROF, int MINB, bool PERSIST>
 __global__ void __launch_bounds__(128, MINB) sweep_kernel(const __grid_constant__ SweepList L, int N, size_t ld, int slice_cap,
-                                                       double* gscratch, size_t gs_stride, unsigned long long* prof) {
+                                                       double* gscratch, size_t gs_stride, unsigned long long* prof,
+                                                       unsigned int* tile_counter) {
     extern __shared__ double smem[];
     const unsigned lane = threadIdx.x & 31u;
     const int warp = threadIdx.x >> 5;
-    const int wg = blockIdx.x * (blockDim.x >> 5) + warp;
-    if ((long long)wg * 32 >= N) return;
-    int f = wg * 32 + (int)lane;
-    const bool live = f < N;
-    if (!live) f = N - 1;            // idle lanes shadow the last family (loads stay in bounds; they never store)
     // [4 warps][5 slots][32 lanes] ints: the next step's counts and exponents land here by cp.async (registers that
     // are live across the helper calls get spilled right after their load, which made a register prefetch block)
     int* cb = reinterpret_cast<int*>(smem) + (size_t)warp * 160 + lane;
     double* sl = smem + (size_t)(blockDim.x >> 5) * 80 + (size_t)warp * slice_cap * 32 + lane;
+    const int ntiles = (N + 31) / 32;
+    // persistent grid, warp-granular work stealing: tiles (32 families, heaviest first) are handed out by an atomic
+    // counter, so a batch that is a little more than one wave does not pay for a nearly empty second wave
+    // (PERSIST == false: one tile per warp, grid sized to the batch — better for many waves)
+    for (int round = 0; PERSIST || round == 0; ++round) {
+    int wg = blockIdx.x * (blockDim.x >> 5) + warp;
+    if (PERSIST) {
+        if (lane == 0) wg = (int)atomicAdd(tile_counter, 1u);
+        wg = __shfl_sync(0xffffffffu, wg, 0);
+    }
+    if (wg >= ntiles) break;
+    int f = wg * 32 + (int)lane;
+    const bool live = f < N;
+    if (!live) f = N - 1;            // idle lanes shadow the last family (loads stay in bounds; they never store)
     double* gs = gscratch ? gscratch + (size_t)wg * gs_stride + lane : nullptr;
     const int fe = f & ~1;                 // the aligned 4-byte word holding this lane's uint16 count
     const int fsh = (f & 1) * 16;
@@ -847,6 +857,7 @@ __global__ void __launch_bounds__(128, MINB) sweep_kernel(const __grid_constant_
         __syncwarp();
         BLG_TICK(6);
     }
+    }   // next tile
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -1027,6 +1038,8 @@ struct blg_handle {
     DevBuf<unsigned long long> d_prof;
     int slice_cap = 50;                       // doubles per lane of the per-warp shared-memory slice
     std::unique_ptr<SweepList> sweep_list{new SweepList()};
+    DevBuf<unsigned int> d_tilectr;
+    int sm_count = 148;
     DevBuf<double> gscratch;
     size_t sweep_smem_set = 0;
 
@@ -1056,7 +1069,7 @@ struct blg_handle {
         d_nc.free_(); d_fast_ok.free_(); d_prof.free_();
         gpool_release();
         for (auto& e : ev) if (e) cudaEventDestroy(e);
-        gscratch.free_();
+        gscratch.free_(); d_tilectr.free_();
         if (own_stream && stream) cudaStreamDestroy(stream);
     }
     static void free_tab(HostTab& tb) {
@@ -1368,6 +1381,12 @@ struct blg_handle {
             const int warps_per_block = 4;
             int nwarps = (N + 31) / 32;
             int blocks = (nwarps + warps_per_block - 1) / warps_per_block;
+            // small batches (up to ~3 waves): persistent grid with tile stealing, so a fractional last wave costs a
+            // fraction; large batches: plain grid (measured 10 % faster on the 5-wave benchmark)
+            const bool persist = blocks <= sm_count * 4 * 3 && blocks > sm_count * 4;
+            if (persist) blocks = sm_count * 4;
+            d_tilectr.ensure(1);
+            if (persist) CK(cudaMemsetAsync(d_tilectr.p, 0, sizeof(unsigned int), stream));
             int cap = std::min(slice_cap, worst);            // doubles per lane in the shared slice
             double* gs = nullptr;
             size_t gstride = 0;
@@ -1378,21 +1397,20 @@ struct blg_handle {
             }
             size_t smem = ((size_t)cap * 32 + 80) * warps_per_block * sizeof(double);
             if (smem > sweep_smem_set) {
-                CK(cudaFuncSetAttribute(sweep_kernel<false, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-                CK(cudaFuncSetAttribute(sweep_kernel<false, 5>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-                CK(cudaFuncSetAttribute(sweep_kernel<false, 6>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-                CK(cudaFuncSetAttribute(sweep_kernel<true, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+                CK(cudaFuncSetAttribute(sweep_kernel<false, 4, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+                CK(cudaFuncSetAttribute(sweep_kernel<false, 4, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+                CK(cudaFuncSetAttribute(sweep_kernel<true, 4, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
                 sweep_smem_set = smem;
             }
             if (!profile_sweep) {
-                if (min_blocks == 6) sweep_kernel<false, 6><<<blocks, 32 * warps_per_block, smem, stream>>>(L, N, ld, cap, gs, gstride, nullptr);
-                else if (min_blocks == 5) sweep_kernel<false, 5><<<blocks, 32 * warps_per_block, smem, stream>>>(L, N, ld, cap, gs, gstride, nullptr);
-                else sweep_kernel<false, 4><<<blocks, 32 * warps_per_block, smem, stream>>>(L, N, ld, cap, gs, gstride, nullptr);
+                if (persist) sweep_kernel<false, 4, true><<<blocks, 32 * warps_per_block, smem, stream>>>(L, N, ld, cap, gs, gstride, nullptr, d_tilectr.p);
+                else sweep_kernel<false, 4, false><<<blocks, 32 * warps_per_block, smem, stream>>>(L, N, ld, cap, gs, gstride, nullptr, d_tilectr.p);
                 CK(cudaGetLastError());
             } else {
                 d_prof.ensure((size_t)BLG_SWEEP_MAXSTEPS * 8);
                 CK(cudaMemsetAsync(d_prof.p, 0, (size_t)BLG_SWEEP_MAXSTEPS * 8 * sizeof(unsigned long long), stream));
-                sweep_kernel<true, 4><<<blocks, 32 * warps_per_block, smem, stream>>>(L, N, ld, cap, gs, gstride, d_prof.p);
+                if (persist) { blocks = (nwarps + warps_per_block - 1) / warps_per_block; }
+                sweep_kernel<true, 4, false><<<blocks, 32 * warps_per_block, smem, stream>>>(L, N, ld, cap, gs, gstride, d_prof.p, d_tilectr.p);
                 CK(cudaGetLastError());
                 std::vector<unsigned long long> hp((size_t)BLG_SWEEP_MAXSTEPS * 8);
                 CK(cudaMemcpyAsync(hp.data(), d_prof.p, hp.size() * sizeof(unsigned long long), cudaMemcpyDeviceToHost, stream));
@@ -1746,6 +1764,7 @@ int blg_create(int device, void* stream, blg_handle** out) {
         if (stream) h->stream = (cudaStream_t)stream;
         else { CK(cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking)); h->own_stream = true; }
         h->result.ensure(16);
+        { int smc = 0; if (cudaDeviceGetAttribute(&smc, cudaDevAttrMultiProcessorCount, device) == cudaSuccess && smc > 0) h->sm_count = smc; }
         {   // factorial tables of the table-free kernel (per device, idempotent)
             const int n = BLG_FAST_MAXCOUNT + 72;
             std::vector<double> f(n), fi(n), iv(n);
