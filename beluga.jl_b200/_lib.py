@@ -15,7 +15,7 @@ SYMBOLS = [
     "blg_logpdf_from_async", "blg_logpdf_root_async", "blg_gradient", "blg_gradient_cr", "blg_gradient_async",
     "blg_commit", "blg_revert", "blg_extend", "blg_shrink", "blg_get_column", "blg_get_family_logpdf",
     "blg_get_eps", "blg_get_W", "blg_ncols", "blg_npatterns", "blg_last_algorithmic", "blg_sync",
-    "blg_set_timing", "blg_last_timing",
+    "blg_set_timing", "blg_last_timing", "blg_family_order",
 ]
 
 
@@ -55,6 +55,7 @@ def lib():
     for f in ("blg_commit", "blg_revert", "blg_sync", "blg_npatterns"):
         getattr(L, f).argtypes = [vp]
     L.blg_extend.argtypes = [vp, C.c_int]
+    L.blg_family_order.argtypes = [C.POINTER(C.c_int32), C.c_int, C.c_int, C.POINTER(C.c_int32)]
     L.blg_shrink.argtypes = [vp, C.c_int]
     L.blg_get_column.argtypes = [vp, C.c_int, C.c_int, C.c_int, dp, C.c_int, ip]
     L.blg_get_family_logpdf.argtypes = [vp, dp, C.c_int]

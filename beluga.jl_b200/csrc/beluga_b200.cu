@@ -1017,11 +1017,19 @@ struct blg_handle {
     bool have_params = false;
     // device model arrays
     DevBuf<uint8_t> d_kind;
-    DevBuf<int> d_parent, d_child_off, d_child_idx, d_list, d_elist, d_seg;
-    DevBuf<double> d_t, d_lam, d_mu, d_q, d_eps0, d_eps1;
+    DevBuf<int> d_parent, d_child_off, d_child_idx, d_lists;
+    DevBuf<double> d_par, d_eps1;        // d_par: [t | λ | μ | q], one upload per parameter change
     DevBuf<NodeTab> d_tab;
-    DevBuf<SweepNodeConst> d_nc;
-    DevBuf<int> d_fast_ok;
+    // what every rebuild reads back travels as ONE block: [ε[0] | per-node sweep scalars | table-free flags]
+    DevBuf<unsigned char> d_back;
+    unsigned char* h_back = nullptr;     // pinned mirror of d_back
+    size_t h_back_cap = 0;
+    struct { double* p = nullptr; } d_eps0;
+    struct { SweepNodeConst* p = nullptr; } d_nc;
+    struct { int* p = nullptr; } d_fast_ok;
+    NodeTab* d_tab_seen = nullptr;       // device table-descriptor array the last upload went to
+    std::vector<double> par_stage;
+    std::vector<int> lists_stage;
     std::vector<int> fast_ok;            // host copy, refreshed by every rebuild
     std::vector<SweepNodeConst> h_nc;    // host copies of the device-built per-node scalars (same refresh)
     std::vector<double> h_eps0;
@@ -1064,9 +1072,11 @@ struct blg_handle {
         for (auto* c : count_allocs) cudaFree(c);
         for (auto& tb : tabs) free_tab(tb);
         weight.free_(); fam_ll.free_(); partial.free_(); result.free_(); rootw.free_(); pascal.free_();
-        d_kind.free_(); d_parent.free_(); d_child_off.free_(); d_child_idx.free_(); d_list.free_(); d_elist.free_(); d_seg.free_();
-        d_t.free_(); d_lam.free_(); d_mu.free_(); d_q.free_(); d_eps0.free_(); d_eps1.free_(); d_tab.free_();
-        d_nc.free_(); d_fast_ok.free_(); d_prof.free_();
+        d_kind.free_(); d_parent.free_(); d_child_off.free_(); d_child_idx.free_(); d_lists.free_();
+        d_par.free_(); d_eps1.free_(); d_tab.free_(); d_back.free_();
+        if (h_back) cudaFreeHost(h_back);
+        h_back = nullptr;
+        d_prof.free_();
         gpool_release();
         for (auto& e : ev) if (e) cudaEventDestroy(e);
         gscratch.free_(); d_tilectr.free_();
@@ -1148,7 +1158,8 @@ struct blg_handle {
         ModelDev m;
         m.n = ncols_model; m.model_kind = model_kind;
         m.kind = d_kind.p; m.parent = d_parent.p; m.child_off = d_child_off.p; m.child_idx = d_child_idx.p;
-        m.t = d_t.p; m.lam = d_lam.p; m.mu = d_mu.p; m.q = d_q.p; m.eta = eta;
+        m.t = d_par.p; m.lam = d_par.p + ncols_model; m.mu = d_par.p + 2 * (size_t)ncols_model;
+        m.q = d_par.p + 3 * (size_t)ncols_model; m.eta = eta;
         m.eps0 = d_eps0.p; m.eps1 = d_eps1.p; m.tab = d_tab.p; m.pascal = pascal.p; m.pdim = pdim;
         m.nc = d_nc.p; m.fast_ok = d_fast_ok.p;
         return m;
@@ -1200,12 +1211,35 @@ struct blg_handle {
         require(have_topology, "set_params/rebuild: call blg_set_topology first");
         require(have_params, "rebuild: call blg_set_params first");
         size_t n = (size_t)ncols_model;
-        d_lam.ensure(n); d_mu.ensure(n); d_q.ensure(n); d_t.ensure(n); d_eps0.ensure(n); d_eps1.ensure(n);
-        CK(cudaMemcpyAsync(d_t.p, t.data(), n * sizeof(double), cudaMemcpyHostToDevice, stream));
-        CK(cudaMemcpyAsync(d_lam.p, lam.data(), n * sizeof(double), cudaMemcpyHostToDevice, stream));
-        CK(cudaMemcpyAsync(d_mu.p, mu.data(), n * sizeof(double), cudaMemcpyHostToDevice, stream));
-        CK(cudaMemcpyAsync(d_q.p, q.data(), n * sizeof(double), cudaMemcpyHostToDevice, stream));
-        // pageable sources: the copies are staged before the call returns
+        d_par.ensure(4 * n); d_eps1.ensure(n);
+        ensure_back(n);
+        par_stage.resize(4 * n);
+        std::copy(t.begin(), t.begin() + n, par_stage.begin());
+        std::copy(lam.begin(), lam.begin() + n, par_stage.begin() + n);
+        std::copy(mu.begin(), mu.begin() + n, par_stage.begin() + 2 * n);
+        std::copy(q.begin(), q.begin() + n, par_stage.begin() + 3 * n);
+        // pageable source: the copy is staged before the call returns
+        CK(cudaMemcpyAsync(d_par.p, par_stage.data(), 4 * n * sizeof(double), cudaMemcpyHostToDevice, stream));
+    }
+
+    // layout of the read-back block for n node ids (doubles first, so everything stays aligned)
+    static size_t back_bytes(size_t n) { return n * (sizeof(double) + sizeof(SweepNodeConst) + sizeof(int)); }
+    void ensure_back(size_t n) {
+        size_t need = back_bytes(n);
+        if (need > d_back.cap) {
+            // ε[0] of the previous arena is still needed by nobody: every size change comes with a full rebuild
+            d_back.ensure(need + need / 2);
+        }
+        if (need > h_back_cap) {
+            if (h_back) cudaFreeHost(h_back);
+            h_back = nullptr;
+            h_back_cap = 0;
+            CK(cudaMallocHost(&h_back, need + need / 2));
+            h_back_cap = need + need / 2;
+        }
+        d_eps0.p = reinterpret_cast<double*>(d_back.p);
+        d_nc.p = reinterpret_cast<SweepNodeConst*>(d_back.p + n * sizeof(double));
+        d_fast_ok.p = reinterpret_cast<int*>(d_back.p + n * (sizeof(double) + sizeof(SweepNodeConst)));
     }
 
     void rebuild(const int32_t* nodes, int n) {
@@ -1225,6 +1259,7 @@ struct blg_handle {
         if ((int)tabs.size() < ncols_model) tabs.resize(ncols_model);
         if ((int)tab_stage.size() < ncols_model) tab_stage.resize(ncols_model);
         int maxdim = 1;
+        bool tab_dirty = false;
         for (int i : list) {
             ensure_tab(i);
             HostTab& tb = tabs[i];
@@ -1232,14 +1267,16 @@ struct blg_handle {
             memset(&nt, 0, sizeof(nt));
             nt.Wt = tb.Wt; nt.wdim = tb.wdim; nt.wdp = tb.wdp; nt.ipow = tb.ipow; nt.nrow = tb.nrow;
             for (int c = 0; c < BLG_MAXK; ++c) { nt.coefD[c] = tb.coefD[c]; nt.cdp[c] = tb.cdp[c]; nt.mo[c] = tb.mo[c]; }
-            tab_stage[i] = nt;
+            if (memcmp(&tab_stage[i], &nt, sizeof(nt)) != 0) { tab_stage[i] = nt; tab_dirty = true; }
             tb.built = true;
             maxdim = std::max(maxdim, tb.wdim);
         }
         d_tab.ensure((size_t)ncols_model);
-        d_nc.ensure((size_t)ncols_model);
-        d_fast_ok.ensure((size_t)ncols_model);
-        CK(cudaMemcpyAsync(d_tab.p, tab_stage.data(), (size_t)ncols_model * sizeof(NodeTab), cudaMemcpyHostToDevice, stream));
+        ensure_back((size_t)ncols_model);
+        if (tab_dirty || d_tab.p != d_tab_seen || list.size() == postorder.size()) {
+            CK(cudaMemcpyAsync(d_tab.p, tab_stage.data(), (size_t)ncols_model * sizeof(NodeTab), cudaMemcpyHostToDevice, stream));
+            d_tab_seen = d_tab.p;
+        }
         // ε segments: a full rebuild groups the nodes by height above the leaves (children always sit in an
         // earlier segment); a partial list is replayed literally, one node after the other
         std::vector<int> elist = list, seg;
@@ -1259,26 +1296,34 @@ struct blg_handle {
         } else {
             for (size_t i = 0; i <= elist.size(); ++i) seg.push_back((int)i);
         }
-        d_list.ensure(list.size());
-        d_elist.ensure(elist.size());
-        d_seg.ensure(seg.size());
-        CK(cudaMemcpyAsync(d_list.p, list.data(), list.size() * sizeof(int), cudaMemcpyHostToDevice, stream));
-        CK(cudaMemcpyAsync(d_elist.p, elist.data(), elist.size() * sizeof(int), cudaMemcpyHostToDevice, stream));
-        CK(cudaMemcpyAsync(d_seg.p, seg.data(), seg.size() * sizeof(int), cudaMemcpyHostToDevice, stream));
+        // [list | elist | seg] in one upload
+        lists_stage.clear();
+        lists_stage.insert(lists_stage.end(), list.begin(), list.end());
+        lists_stage.insert(lists_stage.end(), elist.begin(), elist.end());
+        lists_stage.insert(lists_stage.end(), seg.begin(), seg.end());
+        d_lists.ensure(lists_stage.size());
+        CK(cudaMemcpyAsync(d_lists.p, lists_stage.data(), lists_stage.size() * sizeof(int), cudaMemcpyHostToDevice, stream));
+        const int* d_list_p = d_lists.p;
+        const int* d_elist_p = d_lists.p + list.size();
+        const int* d_seg_p = d_elist_p + elist.size();
         ModelDev m = model_dev();
-        eps_kernel<<<1, 128, 0, stream>>>(m, d_elist.p, d_seg.p, (int)seg.size() - 1);
+        eps_kernel<<<1, 128, 0, stream>>>(m, d_elist_p, d_seg_p, (int)seg.size() - 1);
         CK(cudaGetLastError());
-        tables_kernel<<<(unsigned)list.size(), 128, 2 * (size_t)maxdim * sizeof(double), stream>>>(m, d_list.p, (int)list.size());
+        tables_kernel<<<(unsigned)list.size(), 128, 2 * (size_t)maxdim * sizeof(double), stream>>>(m, d_list_p, (int)list.size());
         CK(cudaGetLastError());
         // list/tab_stage are host vectors reused by later calls: make sure the copies are done; the
         // per-node "table-free kernel allowed" flags come back with the same synchronisation
         fast_ok.resize(ncols_model, 0);
         h_nc.resize(ncols_model);
         h_eps0.resize(ncols_model);
-        CK(cudaMemcpyAsync(fast_ok.data(), d_fast_ok.p, (size_t)ncols_model * sizeof(int), cudaMemcpyDeviceToHost, stream));
-        CK(cudaMemcpyAsync(h_nc.data(), d_nc.p, (size_t)ncols_model * sizeof(SweepNodeConst), cudaMemcpyDeviceToHost, stream));
-        CK(cudaMemcpyAsync(h_eps0.data(), d_eps0.p, (size_t)ncols_model * sizeof(double), cudaMemcpyDeviceToHost, stream));
-        CK(cudaStreamSynchronize(stream));
+        {
+            size_t nn = (size_t)ncols_model;
+            CK(cudaMemcpyAsync(h_back, d_back.p, back_bytes(nn), cudaMemcpyDeviceToHost, stream));
+            CK(cudaStreamSynchronize(stream));
+            memcpy(h_eps0.data(), h_back, nn * sizeof(double));
+            memcpy(h_nc.data(), h_back + nn * sizeof(double), nn * sizeof(SweepNodeConst));
+            memcpy(fast_ok.data(), h_back + nn * (sizeof(double) + sizeof(SweepNodeConst)), nn * sizeof(int));
+        }
         if (list.size() == postorder.size()) tabs_valid = true;
     }
 
@@ -1791,28 +1836,13 @@ int blg_create(int device, void* stream, blg_handle** out) {
 int blg_destroy(blg_handle* h) { delete h; return 0; }
 const char* blg_last_error(blg_handle* h) { return h ? h->err.c_str() : g_create_error.c_str(); }
 
-int blg_set_profiles(blg_handle* h, const int32_t* X, const int64_t* weight, int ncols, int npatterns) {
-    BLG_ENTER(h)
-    h->require(ncols >= 0 && npatterns >= 0, "set_profiles: negative size");
-    CK(cudaStreamSynchronize(h->stream));
-    h->Tc.clear(); h->Tp.clear();
-    h->pool.clear();
-    for (auto* s : h->all_slabs) { cudaFree(s->ell); cudaFree(s->scl); delete s; }
-    h->all_slabs.clear();
-    for (auto* c : h->count_allocs) cudaFree(c);
-    h->count_allocs.clear();
-    h->N = npatterns;
-    h->ld = ((size_t)npatterns + 127) / 128 * 128;
-    h->tabs_valid = false;
-    for (auto& tb : h->tabs) blg_handle::free_tab(tb);
-    if (npatterns == 0) { h->Tc.clear(); h->Tp.clear(); return 0; }
-    h->require(X && weight, "set_profiles: null pointer");
-    size_t ld = h->ld;
+// ----------------------------------------------------------------------------------------------------
+static void family_order(const int32_t* X, int ncols, int npatterns, std::vector<int>& perm) {
     // device order: families that share a warp should have similar count vectors at the heavy nodes, because
     // every loop of a warp runs to the warp's maximum count.  k-d ordering: recursively split the family set
     // at a multiple of 32 along the heavy column with the largest spread, until 32 families remain per leaf.
-    h->perm.resize(npatterns);
-    for (int f = 0; f < npatterns; ++f) h->perm[f] = f;
+    perm.resize(npatterns);
+    for (int f = 0; f < npatterns; ++f) perm[f] = f;
     if (npatterns > 32) {
         // candidate columns: largest Σx² first, identical columns (wgd / wgdafter copies) dropped
         std::vector<double> s1(ncols, 0.0), s2(ncols, 0.0);
@@ -1846,7 +1876,7 @@ int blg_set_profiles(blg_handle* h, const int32_t* X, const int64_t* weight, int
                 std::fill(m1.begin(), m1.end(), 0.0);
                 std::fill(m2.begin(), m2.end(), 0.0);
                 for (int i = lo; i < hi; ++i) {
-                    const float* kf = &K[(size_t)h->perm[i] * nk];
+                    const float* kf = &K[(size_t)perm[i] * nk];
                     for (int k = 0; k < nk; ++k) { m1[k] += kf[k]; m2[k] += (double)kf[k] * kf[k]; }
                 }
                 int best = 0;
@@ -1858,7 +1888,7 @@ int blg_set_profiles(blg_handle* h, const int32_t* X, const int64_t* weight, int
                 if (bestv <= 0.0) continue;             // identical on every key: nothing to gain
                 int half = ((n / 2 + 31) / 32) * 32;
                 if (half >= n) half = n / 2;
-                std::nth_element(h->perm.begin() + lo, h->perm.begin() + lo + half, h->perm.begin() + hi, [&](int a, int b) {
+                std::nth_element(perm.begin() + lo, perm.begin() + lo + half, perm.begin() + hi, [&](int a, int b) {
                     float va = K[(size_t)a * nk + best], vb = K[(size_t)b * nk + best];
                     return va != vb ? va > vb : a < b;
                 });
@@ -1867,6 +1897,26 @@ int blg_set_profiles(blg_handle* h, const int32_t* X, const int64_t* weight, int
             }
         }
     }
+}
+
+int blg_set_profiles(blg_handle* h, const int32_t* X, const int64_t* weight, int ncols, int npatterns) {
+    BLG_ENTER(h)
+    h->require(ncols >= 0 && npatterns >= 0, "set_profiles: negative size");
+    CK(cudaStreamSynchronize(h->stream));
+    h->Tc.clear(); h->Tp.clear();
+    h->pool.clear();
+    for (auto* s : h->all_slabs) { cudaFree(s->ell); cudaFree(s->scl); delete s; }
+    h->all_slabs.clear();
+    for (auto* c : h->count_allocs) cudaFree(c);
+    h->count_allocs.clear();
+    h->N = npatterns;
+    h->ld = ((size_t)npatterns + 127) / 128 * 128;
+    h->tabs_valid = false;
+    for (auto& tb : h->tabs) blg_handle::free_tab(tb);
+    if (npatterns == 0) { h->Tc.clear(); h->Tp.clear(); return 0; }
+    h->require(X && weight, "set_profiles: null pointer");
+    size_t ld = h->ld;
+    family_order(X, ncols, npatterns, h->perm);
     h->inv.resize(npatterns);
     for (int f = 0; f < npatterns; ++f) h->inv[h->perm[f]] = f;
     std::vector<uint16_t> stage((size_t)ncols * ld, 0);
@@ -2103,6 +2153,15 @@ int blg_get_W(blg_handle* h, int node, double* out, int cap, int* dim) {
 }
 int blg_ncols(blg_handle* h, int which) { return h ? (int)(which ? h->Tp.size() : h->Tc.size()) : -1; }
 int blg_npatterns(blg_handle* h) { return h ? h->N : -1; }
+int blg_family_order(const int32_t* X, int ncols, int npatterns, int32_t* perm_out) {
+    if (!X || !perm_out || ncols < 0 || npatterns < 0) return 1;
+    try {
+        std::vector<int> perm;
+        family_order(X, ncols, npatterns, perm);
+        for (int f = 0; f < npatterns; ++f) perm_out[f] = perm[f];
+    } catch (...) { return 1; }
+    return 0;
+}
 int blg_last_algorithmic(blg_handle* h, double* bytes_total, double* bytes_prune, int* launches) {
     if (!h) return 1;
     if (bytes_total) *bytes_total = h->last_bytes;

@@ -21,6 +21,9 @@ KIND_CODE = {"root": 0, "sp": 1, "wgd": 2, "wgt": 3, "wgdafter": 4}
 ABSENT = 255
 
 
+_FLAT_ROW = {"λ": 0, "μ": 1, "q": 2, "t": 3}   # rows of DLWGD._flat
+
+
 class ModelNode:
     """TreeNode{Node{T}} / TreeNode{Branch{T}} (src/node.jl:12-28): id ``i``, payload θ + kind,
     parent ``p``, ordered children ``c``."""
@@ -42,9 +45,16 @@ class ModelNode:
         return self.theta[key]
 
     def __setitem__(self, key, v):
-        self.theta[key] = float(v)
-        if self.model is not None:
-            self.model._param_version += 1
+        v = float(v)
+        self.theta[key] = v
+        m = self.model
+        if m is not None:
+            m._param_version += 1
+            f = m._flat
+            if f is not None and m._flat_topo == m._topo_version:
+                r = _FLAT_ROW.get(key)
+                if r is not None:
+                    f[r, self.i - 1] = v
 
     def __repr__(self):
         return "ModelNode(%d, %s)" % (self.i, self.kind)
@@ -148,6 +158,8 @@ class DLWGD:
         # (None = all nodes in post-order).  Each PArray remembers how far it has replayed the log.
         self._topo_version = 0
         self._param_version = 0
+        self._flat = None        # [λ; μ; q; t] × node id, kept current by ModelNode.__setitem__
+        self._flat_topo = -1
         self._seq = 0
         self._log = []
         self._log_start = 0      # requests with seq <= _log_start have been trimmed away
@@ -345,15 +357,15 @@ class DLWGD:
         return n, parent, kind, cpos
 
     def flat_params(self):
-        n = max(self.nodes)
-        lam, mu, q, t = (np.zeros(n) for _ in range(4))
-        for i, nd in self.nodes.items():
-            th = nd.theta
-            lam[i - 1] = th.get("λ", 0.0)
-            mu[i - 1] = th.get("μ", 0.0)
-            q[i - 1] = th.get("q", 0.0)
-            t[i - 1] = th.get("t", 0.0)
-        return lam, mu, q, t, float(self.nodes[1]["η"])
+        if self._flat is None or self._flat_topo != self._topo_version:
+            f = np.zeros((4, max(self.nodes)))
+            for i, nd in self.nodes.items():
+                th = nd.theta
+                for k, r in _FLAT_ROW.items():
+                    f[r, i - 1] = th.get(k, 0.0)
+            self._flat, self._flat_topo = f, self._topo_version
+        f = self._flat
+        return f[0], f[1], f[2], f[3], float(self.nodes[1].theta["η"])
 
 
 # --- update!, src/node.jl:99-116 ---------------------------------------------------------------------

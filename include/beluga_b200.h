@@ -116,6 +116,9 @@ int blg_get_eps(blg_handle* h, double* eps_top, double* eps_node, int ncols);  /
 int blg_get_W(blg_handle* h, int node, double* out, int cap, int* dim);        /* row-major [n][j] */
 int blg_ncols(blg_handle* h, int which);
 int blg_npatterns(blg_handle* h);
+/* host-only diagnostic: the device order blg_set_profiles gives the rows of X (perm_out[slot] = row); the
+ * reference keeps families in input order (src/model.jl:40-49) — the order is invisible through the ABI */
+int blg_family_order(const int32_t* X, int ncols, int npatterns, int32_t* perm_out);
 /* algorithmic bytes (definition of SURVEY.md §8(d): each internal column written once and read once by
  * its parent, 2 B per leaf count, 4 B per stored scale exponent, 8 B per family result) — in total and
  * for the pruning launches alone — and the number of kernels the last likelihood call launched */
