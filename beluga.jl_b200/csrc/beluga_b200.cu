@@ -17,6 +17,7 @@
 
 #include <algorithm>
 #include <cmath>
+#include <limits>
 #include <cstdint>
 #include <cstdio>
 #include <cstring>
@@ -718,9 +719,22 @@ __global__ void __launch_bounds__(128, MINB) sweep_kernel(const __grid_constant_
             if (sn.k >= 2) { cp_async_b32(cb + 2 * 32, cn[1].cnt + fe); if (cn[1].scl) cp_async_b32(cb + 4 * 32, cn[1].scl + f); }
             cp_async_commit();
         }
+        const int Xw = warp_max(X);
+        if (Xw == 0) {
+            // no family of this warp has a gene below the node: ℓ = [1] whatever the parameters are (n = 0 lineages
+            // leave no descendants with probability 1) — or the reference's NaN, which the host folded into ip0
+            const double v = st.ip0;
+            if (live) { st.out[f] = v; st.out_scl[f] = 0; }
+            sl[0] = v;
+            prevX = 0;
+            prevScl = 0;
+            prevR = sl;
+            __syncwarp();
+            BLG_TICK(0);
+            continue;
+        }
         const int M0w = warp_max(M0);
         const int M1w = warp_max(M1);
-        const int Xw = warp_max(X);
         int sumw = M0w + M1w;
         // which side of a binary merge is register-tiled: the child with the smaller bound in THIS warp
         const bool swap = (k == 2) && (M0w < M1w);
@@ -1033,6 +1047,7 @@ struct blg_handle {
     std::vector<int> fast_ok;            // host copy, refreshed by every rebuild
     std::vector<SweepNodeConst> h_nc;    // host copies of the device-built per-node scalars (same refresh)
     std::vector<double> h_eps0;
+    std::vector<char> poison_below;      // some node of the subtree (the node included) has a NaN column
     std::vector<HostTab> tabs;
     std::vector<NodeTab> tab_stage;
     bool tabs_valid = false;
@@ -1324,6 +1339,14 @@ struct blg_handle {
             memcpy(h_nc.data(), h_back + nn * sizeof(double), nn * sizeof(SweepNodeConst));
             memcpy(fast_ok.data(), h_back + nn * (sizeof(double) + sizeof(SweepNodeConst)), nn * sizeof(int));
         }
+        // a NaN column (reference: a prefix of the children's ε equal to 1) makes every column above it NaN; the
+        // sweep carries that in ip0, so that warps whose families are all empty below a node need not look down
+        poison_below.assign(ncols_model, 0);
+        for (int u : postorder) {
+            bool p = !children[u].empty() && std::isnan(h_nc[u].ip0);
+            for (int c : children[u]) p = p || poison_below[c];
+            poison_below[u] = p ? 1 : 0;
+        }
         if (list.size() == postorder.size()) tabs_valid = true;
     }
 
@@ -1401,7 +1424,7 @@ struct blg_handle {
                 if (ss.resident) L.step[L.nsteps - 2].prefact = (kind[prev_node] != BLG_WGDAFTER) ? 2 : 1;
                 prev_node = u;
                 double raw = 1.0;
-                ss.inv = h_nc[u].inv; ss.ip0 = h_nc[u].ip0;
+                ss.inv = h_nc[u].inv; ss.ip0 = poison_below[u] ? std::numeric_limits<double>::quiet_NaN() : h_nc[u].ip0;
                 ss.out = st.out; ss.out_scl = st.out_scl; ss.cnt = st.cnt;
                 int sum = 0;
                 bool tiled = false;
