@@ -523,15 +523,29 @@ __device__ __noinline__ void sweep_contract_fast(double* col, int Mw, double psi
         }
         double g = 1.0;                                // ψ'^d/d!
         const int dmax = Mw - n0;
+        // the wide tile takes two diagonals per trip, so that the window slides by two registers at once (sliding one by
+        // one costs two moves per output and diagonal — as many instructions as the FMAs); a diagonal past dmax only
+        // sees zeros.  Measured: U = 2 here -1.7 %; U = 4, or the same trick in the merges, slower (longer loop bodies
+        // cost more in instruction fetch than the moves they save)
+        constexpr int U = (TS == 4) ? 1 : 2;
 #pragma unroll 1
-        for (int d = 0; d <= dmax; ++d) {
+        for (int d = 0; d <= dmax; d += U) {
+            double ext[TS + U];
 #pragma unroll
-            for (int k = 0; k < TS; ++k) acc[k] = fma(g, win[k], acc[k]);
+            for (int k = 0; k < TS; ++k) ext[k] = win[k];
 #pragma unroll
-            for (int k = 0; k < TS - 1; ++k) win[k] = win[k + 1];
-            const int j = n0 + TS + d;
-            win[TS - 1] = (j <= Mw) ? col[j * 32] : 0.0;
-            g *= psi * c_inv[d + 1];
+            for (int u = 0; u < U; ++u) {
+                const int j = n0 + TS + d + u;
+                ext[TS + u] = (j <= Mw) ? col[j * 32] : 0.0;
+            }
+#pragma unroll
+            for (int u = 0; u < U; ++u) {
+#pragma unroll
+                for (int k = 0; k < TS; ++k) acc[k] = fma(g, ext[u + k], acc[k]);
+                g *= psi * c_inv[d + u + 1];
+            }
+#pragma unroll
+            for (int k = 0; k < TS; ++k) win[k] = ext[k + U];
         }
 #pragma unroll
         for (int k = 0; k < TS; ++k) {
@@ -635,17 +649,17 @@ __device__ __noinline__ void sweep_child(const SweepChild& c, int f, size_t ld, 
     if (c.ell == nullptr) {                        // leaf: column x_c of w* (one-hot likelihood)
         if (have) return;
         const double* __restrict__ row = c.Wt + (size_t)M * c.wdp;
-#pragma unroll 2
+#pragma unroll 1
         for (int s = 0; s <= Mw; ++s) col[s * 32] = (s <= M) ? row[s] : 0.0;
         return;
     }
     if (!resident) {
         const double* __restrict__ src = c.ell + f;
         if (c.table) {
-#pragma unroll 4
+#pragma unroll 1
             for (int j = 0; j <= Mw; ++j) col[j * 32] = (j <= M) ? src[(size_t)j * ld] : 0.0;
         } else {                                   // closed-form contraction wants u[j] = (j-1)!·ℓ[j]
-#pragma unroll 4
+#pragma unroll 1
             for (int j = 0; j <= Mw; ++j) col[j * 32] = (j <= M) ? src[(size_t)j * ld] * c_fact[j > 0 ? j - 1 : 0] : 0.0;
         }
     }
@@ -739,6 +753,7 @@ __global__ void __launch_bounds__(128, MINB) sweep_kernel(const __grid_constant_
         // which side of a binary merge is register-tiled: the child with the smaller bound in THIS warp
         const bool swap = (k == 2) && (M0w < M1w);
         bool tiled = (k == 2) ? (min(M0w, M1w) >= 24) : (M1w >= 24);
+#pragma unroll 1
         for (int i = 2; i < k; ++i) {
             const int Miw = warp_max((int)ch[i].cnt[f]);
             sumw += Miw;
@@ -775,6 +790,7 @@ __global__ void __launch_bounds__(128, MINB) sweep_kernel(const __grid_constant_
         double mxv = 0.0;
         bool scaled = false;        // has the (1-E_k)^(-n) normalisation already been applied (and mxv taken)?
         if (!tiled) {
+#pragma unroll 1
             for (int i = 1; i < k; ++i) {
                 const int Mi = (i == 1) ? M1 : (int)ch[i].cnt[f];
                 const int Miw = (i == 1) ? M1w : warp_max(Mi);
@@ -784,19 +800,18 @@ __global__ void __launch_bounds__(128, MINB) sweep_kernel(const __grid_constant_
                 const bool last = (i == k - 1);
                 const double em0 = last ? st.ip0 : 1.0, emg = last ? st.inv : 1.0;
                 const int Xm = last ? X : 0x7fffffff;
+                // the register-tiled "s" side is child i — or, in a binary merge whose child 0 has the smaller bound in
+                // this warp, child 0 (already at the front), with child i as the "t" side
+                const double* tA = swap ? colB : R;
+                const double* sB = swap ? R : colB;
+                const int tW = swap ? Miw : Sw, sW = swap ? Sw : Miw;
+                const double E = swap ? fmin(ch[1].e, 1.0) : ch[i].Epre;
+                const double e = swap ? ch[0].e : ch[i].e;
+                const double invE = swap ? ch[1].invEself : ((k == 2) ? ch[0].invEself : 1.0 / E);
                 double mx;
-                if (!swap) {
-                    const double E = ch[i].Epre, e = ch[i].e;
-                    const double invE = (k == 2) ? ch[0].invEself : 1.0 / E;
-                    if (Miw < 4) mx = sweep_merge_fast<4>(R, R, Sw, colB, Miw, E, invE, e, em0, emg, Xm);
-                    else if (Miw < 12) mx = sweep_merge_fast<12>(R, R, Sw, colB, Miw, E, invE, e, em0, emg, Xm);
-                    else mx = sweep_merge_fast<24>(R, R, Sw, colB, Miw, E, invE, e, em0, emg, Xm);
-                } else {       // k == 2: child 1 is the "t" side, child 0 (at the front) the register-tiled "s" side
-                    const double E = fmin(ch[1].e, 1.0), e = ch[0].e, invE = ch[1].invEself;
-                    if (Sw < 4) mx = sweep_merge_fast<4>(R, colB, Miw, R, Sw, E, invE, e, em0, emg, Xm);
-                    else if (Sw < 12) mx = sweep_merge_fast<12>(R, colB, Miw, R, Sw, E, invE, e, em0, emg, Xm);
-                    else mx = sweep_merge_fast<24>(R, colB, Miw, R, Sw, E, invE, e, em0, emg, Xm);
-                }
+                if (sW < 4) mx = sweep_merge_fast<4>(R, tA, tW, sB, sW, E, invE, e, em0, emg, Xm);
+                else if (sW < 12) mx = sweep_merge_fast<12>(R, tA, tW, sB, sW, E, invE, e, em0, emg, Xm);
+                else mx = sweep_merge_fast<24>(R, tA, tW, sB, sW, E, invE, e, em0, emg, Xm);
                 Sw += Miw;
                 if (last) { mxv = mx; scaled = true; }
                 BLG_TICK(3);
@@ -806,6 +821,7 @@ __global__ void __launch_bounds__(128, MINB) sweep_kernel(const __grid_constant_
             double* rA = R;
             double* rH = R + (size_t)cap * 32;
             double* rO = R + (size_t)2 * cap * 32;
+#pragma unroll 1
             for (int i = 1; i < k; ++i) {
                 const int Mi = (i == 1) ? M1 : (int)ch[i].cnt[f];
                 const int Miw = (i == 1) ? M1w : warp_max(Mi);
@@ -852,11 +868,11 @@ __global__ void __launch_bounds__(128, MINB) sweep_kernel(const __grid_constant_
             const int keep = st.prefact;               // 0: the next step does not reuse the column; 1: plain; 2: times (n-1)!
             if (keep == 0) {
                 if (live) {
-#pragma unroll 2
+#pragma unroll 1
                     for (int n = 0; n <= X; ++n) o[(size_t)n * ld] = R[n * 32] * sc;
                 }
             } else {
-#pragma unroll 2
+#pragma unroll 1
                 for (int n = 0; n <= Xw; ++n) {
                     const double v = R[n * 32] * sc;
                     R[n * 32] = (keep == 2) ? v * c_fact[n > 0 ? n - 1 : 0] : v;
