@@ -644,7 +644,11 @@ __device__ __noinline__ void sweep_merge_tiled(const double* A, int Sw, double* 
 // stage (unless the column is already resident in col) + contract one child into col[0..Mw]
 // have: 0 = load the child's input column; 1 = it is in col already, pre-multiplied by (j-1)! where the closed form
 // wants that; 2 = it is in col already, plain (copied by cp.async)
-__device__ __noinline__ void sweep_child(const SweepChild& c, int f, size_t ld, int M, int Mw, double* col, int have) {
+// (the descriptor fields travel by value: read through a reference, inside a noinline function, they were generic loads
+// from the parameter bank that missed the carved-down L1 — a long-scoreboard stall at the top of every call)
+struct ChildArgs { const double* ell; const double* Wt; int wdp, table; double psi, cc; };
+__device__ __forceinline__ ChildArgs child_args(const SweepChild& c) { return ChildArgs{c.ell, c.Wt, c.wdp, c.table, c.psi, c.cc}; }
+__device__ __noinline__ void sweep_child(const ChildArgs c, int f, size_t ld, int M, int Mw, double* col, int have) {
     const bool resident = have != 0;
     if (c.ell == nullptr) {                        // leaf: column x_c of w* (one-hot likelihood)
         if (have) return;
@@ -783,7 +787,7 @@ __global__ void __launch_bounds__(128, MINB) sweep_kernel(const __grid_constant_
             }
             cp_async_commit();
         }
-        sweep_child(ch[0], f, ld, M0, M0w, R, res0 ? 1 : 0);
+        sweep_child(child_args(ch[0]), f, ld, M0, M0w, R, res0 ? 1 : 0);
         if (async1) cp_async_wait_all();
         BLG_TICK(1);
         int Sw = M0w;
@@ -795,7 +799,7 @@ __global__ void __launch_bounds__(128, MINB) sweep_kernel(const __grid_constant_
                 const int Mi = (i == 1) ? M1 : (int)ch[i].cnt[f];
                 const int Miw = (i == 1) ? M1w : warp_max(Mi);
                 double* colB = R + (size_t)(Sw + 1) * 32;
-                sweep_child(ch[i], f, ld, Mi, Miw, colB, (i == 1 && async1) ? 2 : 0);
+                sweep_child(child_args(ch[i]), f, ld, Mi, Miw, colB, (i == 1 && async1) ? 2 : 0);
                 BLG_TICK(2);
                 const bool last = (i == k - 1);
                 const double em0 = last ? st.ip0 : 1.0, emg = last ? st.inv : 1.0;
@@ -825,7 +829,7 @@ __global__ void __launch_bounds__(128, MINB) sweep_kernel(const __grid_constant_
             for (int i = 1; i < k; ++i) {
                 const int Mi = (i == 1) ? M1 : (int)ch[i].cnt[f];
                 const int Miw = (i == 1) ? M1w : warp_max(Mi);
-                sweep_child(ch[i], f, ld, Mi, Miw, rO, 0);
+                sweep_child(child_args(ch[i]), f, ld, Mi, Miw, rO, 0);
 #pragma unroll 1
                 for (int n = Miw + 1; n <= Sw + Miw; ++n) rO[n * 32] = 0.0;
                 sweep_merge_tiled(rA, Sw, rO, Miw, rH, ch[i].Epre, ch[i].e);
