@@ -293,6 +293,72 @@ def test_synthetic_large_batch_vs_oracle():
     np.testing.assert_allclose(data.family_logpdf(), pf, rtol=1e-11)
 
 
+def test_high_counts_scratch_and_general_fallback():
+    # counts beyond the shared-memory slice (global scratch), beyond the register tiles (chained 16-wide tiles) and
+    # beyond the table-free kernel's bound (per-node general kernels); ragged family counts (1, 33, 70)
+    nw = "((A:0.4,B:0.5):0.3,(C:0.6,(D:0.2,E:0.3):0.2):0.25);"
+    names = list("ABCDE")
+    rng = np.random.default_rng(77)
+    for hi, nfam in ((30, 33), (70, 70), (130, 1), (130, 40)):
+        counts = rng.integers(0, hi // 4 + 1, size=(nfam, 5)).astype(np.int64)
+        counts[0] = [hi // 5] * 5                                # one heavy family: root count = hi
+        counts[-1] = [hi // 2, 0, 0, hi // 2, 0]
+        model, data, orc = pair(nw, (names, counts), 0.9, 1.0, 0.8, B.BRANCH)
+        got = B.logpdf_(model, data)
+        want, pf = orc.logpdf(per_family=True)
+        assert close(got, want, 1e-11), (hi, nfam, got, want)
+        np.testing.assert_allclose(data.family_logpdf(), pf, rtol=1e-11)
+        B.set_(data); orc.set()
+        B.update_(model[4], λ=1.3, μ=0.7); orc.update(4, lam=1.3, mu=0.7)
+        assert close(B.logpdf_(model[4], data), orc.logpdf_from(4), 1e-11), (hi, nfam)
+
+
+def test_sparse_profiles_empty_subtrees_and_partial_paths():
+    # most families have no gene in most clades: the sweep skips a node for a warp whose 32 families are all empty
+    # below it; every partial path and the commit/revert cycle must still agree with the oracle
+    from beluga_b200.sim import random_tree_newick
+    nw = random_tree_newick(24, seed=11)
+    model0, _, _ = build_model(nw, 0.5, 0.6, 0.8, B.BRANCH)
+    names = [model0.leaves[i] for i in sorted(model0.leaves)]
+    rng = np.random.default_rng(5)
+    counts = np.zeros((500, len(names)), dtype=np.int64)
+    for f in range(500):                                         # 1-3 non-empty leaves per family
+        for j in rng.choice(len(names), size=rng.integers(1, 4), replace=False):
+            counts[f, j] = rng.integers(1, 5)
+    model, data, orc = pair(nw, (names, counts), 0.5, 0.6, 0.8, B.BRANCH)
+    assert close(B.logpdf_(model, data), orc.logpdf(), 1e-11)
+    B.set_(data); orc.set()
+    ids = sorted(i for i, n in model.nodes.items() if n.p is not None)
+    for i in ids[:: max(1, len(ids) // 12)]:
+        B.update_(model[i], λ=0.7, μ=0.4); orc.update(i, lam=0.7, mu=0.4)
+        got = B.logpdf_(model[i], data)
+        want, pf = orc.logpdf_from(i, per_family=True)
+        assert close(got, want, 1e-11), i
+        np.testing.assert_allclose(data.family_logpdf(), pf, rtol=1e-11)
+        B.update_(model[i], λ=0.5, μ=0.6); orc.update(i, lam=0.5, mu=0.6)
+        B.rev_(data); orc.rev()
+    assert close(B.logpdf_(model, data), orc.logpdf(), 1e-11)
+
+
+def test_wgt_likelihood_and_partial(dicots):
+    nw, df = dicots
+    model, data, orc = pair(nw, df, 0.6, 0.7, 0.85, B.BRANCH)
+    B.logpdf_(model, data); B.set_(data)
+    orc.logpdf(); orc.set()
+    leaf = next(i for i, n in sorted(model.nodes.items()) if not n.c)
+    w = B.addwgt_(model, model[leaf], 0.05, 0.3); orc.addwgt(leaf, 0.05, 0.3)
+    B.extend_(data, leaf); orc.extend(leaf)
+    got = B.logpdf_(model, data)
+    want, pf = orc.logpdf(per_family=True)
+    assert close(got, want, 1e-11)
+    np.testing.assert_allclose(data.family_logpdf(), pf, rtol=1e-11)
+    B.set_(data); orc.set()
+    w["q"] = 0.6; orc.setfield(w.i, "q", 0.6)
+    c = B.nonwgdchild(w)
+    B.update_(c); orc.update_node(c.i)
+    assert close(B.logpdf_(c, data), orc.logpdf_from(c.i), 1e-11)
+
+
 # ---- gradient (forward-mode tangent kernels) vs the oracle's dual-number gradient ---------------------------
 GRTOL = 1e-8      # the stated bar (relative to the largest component, plus per-component)
 
