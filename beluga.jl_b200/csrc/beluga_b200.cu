@@ -894,6 +894,19 @@ __global__ void __launch_bounds__(128, MINB) sweep_kernel(const __grid_constant_
     }   // next tile
 }
 
+// eight independent DFMA chains per thread: what the fp64 pipe sustains (blg_fp64_peak)
+__global__ void __launch_bounds__(256) fp64_peak_kernel(double* sink, int iters, double seed) {
+    double a0 = seed, a1 = seed + 1, a2 = seed + 2, a3 = seed + 3, a4 = seed + 4, a5 = seed + 5, a6 = seed + 6, a7 = seed + 7;
+    const double m = 0.999999 + 1e-9 * threadIdx.x, c = 1e-7;
+#pragma unroll 4
+    for (int i = 0; i < iters; ++i) {
+        a0 = fma(a0, m, c); a1 = fma(a1, m, c); a2 = fma(a2, m, c); a3 = fma(a3, m, c);
+        a4 = fma(a4, m, c); a5 = fma(a5, m, c); a6 = fma(a6, m, c); a7 = fma(a7, m, c);
+    }
+    const double r = ((a0 + a1) + (a2 + a3)) + ((a4 + a5) + (a6 + a7));
+    if (r == 123.456) *sink = r;           // never true: keeps the chains alive
+}
+
 // ------------------------------------------------------------------------------------------------
 // root: integrate_root (model.jl:465-475), condition_oib (model.jl:492-501), weighted reduction
 // ------------------------------------------------------------------------------------------------
@@ -2229,6 +2242,29 @@ int blg_last_timing(blg_handle* h, float* prune_ms, float* root_ms) {
 int blg_sync(blg_handle* h) {
     BLG_ENTER(h)
     CK(cudaStreamSynchronize(h->stream));
+    BLG_LEAVE(h)
+}
+// fp64 FMA throughput of this GPU, measured: the denominator of the "fraction of the fp64 roofline" figure
+int blg_fp64_peak(blg_handle* h, double* tflops) {
+    BLG_ENTER(h)
+    h->require(tflops != nullptr, "fp64_peak: null output");
+    DevBuf<double> sink;
+    sink.ensure(1);
+    cudaEvent_t a = nullptr, b = nullptr;
+    CK(cudaEventCreate(&a));
+    CK(cudaEventCreate(&b));
+    const int iters = 8192, blocks = h->sm_count * 8, threads = 256;
+    fp64_peak_kernel<<<blocks, threads, 0, h->stream>>>(sink.p, 256, 1.0);                 // warm-up
+    CK(cudaEventRecord(a, h->stream));
+    fp64_peak_kernel<<<blocks, threads, 0, h->stream>>>(sink.p, iters, 1.0);
+    CK(cudaEventRecord(b, h->stream));
+    CK(cudaEventSynchronize(b));
+    float ms = 0.f;
+    CK(cudaEventElapsedTime(&ms, a, b));
+    cudaEventDestroy(a);
+    cudaEventDestroy(b);
+    sink.free_();
+    *tflops = 2.0 * 8.0 * (double)iters * blocks * threads / (ms * 1e-3) / 1e12;
     BLG_LEAVE(h)
 }
 

@@ -254,6 +254,12 @@ class PArray:
         self._ck(self.L.blg_last_timing(self.h, C.byref(a), C.byref(b)))
         return a.value, b.value
 
+    def fp64_peak(self):
+        """Measured fp64 FMA throughput of this handle's GPU in TFLOP/s (diagnostic, not in the reference)."""
+        out = C.c_double()
+        self._ck(self.L.blg_fp64_peak(self.h, C.byref(out)))
+        return out.value
+
     def synchronize(self):
         if self.h is not None:
             self._ck(self.L.blg_sync(self.h))

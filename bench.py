@@ -201,6 +201,105 @@ def mcmc_leg(args, local):
             "acceptance": chain.accepted / max(chain.proposed, 1), "generations": args.mcmc_generations}
 
 
+def algorithmic_fma(model, X):
+    """Algorithmic fp64 FMAs of one full sweep over the patterns in X: per internal node with
+    children counts M_1..M_k, S_i = M_1+…+M_i:  Σ_i [c_i internal ? (M_i+1)(M_i+2)/2 : 0]
+    + Σ_{i>=2} [S_{i-1}(M_i+1) + (S_{i-1}+1)(M_i+1)] + Σ_i (S_i+1);  the root adds 3·x_root."""
+    from beluga_b200.model import nonwgdchild
+    nb = X.shape[1]
+
+    def col(n):                       # inserted WGD nodes alias the counts of the species node below them
+        return X[:, (n.i if n.i <= nb else nonwgdchild(n).i) - 1].astype(np.float64)
+
+    tot = 0.0
+    for n in model.nodes.values():
+        if not n.c:
+            continue
+        S = None
+        for i, c in enumerate(n.c):
+            M = col(c)
+            if c.c:
+                tot += float(((M + 1) * (M + 2) / 2).sum())
+            if i >= 1:
+                tot += float((S * (M + 1) + (S + 1) * (M + 1)).sum())
+            S = M if S is None else S + M
+            tot += float((S + 1).sum())
+    tot += 3.0 * float(X[:, 0].astype(np.float64).sum())
+    return tot
+
+
+def node_local_leg(args, local):
+    """Config C3: 9dicots + 3 WGDs (23 nodes), 10^5 synthetic families; `logpdf!(model[i], data)` for
+    every node i through the public API (θ update on the host, ε/W rebuild of the path, partial sweep, scalar back),
+    then `rev!`; reports the mean over nodes and the time of `set!`/`rev!`."""
+    import beluga_b200 as B
+    from beluga_b200.model import build_model, update_
+    from beluga_b200.sim import rand_profiles_torch
+
+    nw = open(os.path.join(ROOT, "tests", "data", "9dicots.nw")).readline().strip()
+    m0, _, _ = build_model(nw, 1.0, 0.92, 0.66, B.BRANCH)
+    for i, t, q in ((6, 0.01, 0.25), (14, 0.02, 0.5), (10, 0.05, 0.3)):
+        m0.addwgd_(m0[i], t, q)
+    names, counts = rand_profiles_torch(m0, 100_000, seed=SEED, device="cuda:%d" % local, max_rootsum=60, chunk=1 << 19)
+    model, data = B.DLWGD(nw, (names, counts), 1.0, 0.92, 0.66, B.BRANCH, device=local)
+    for i, t, q in ((6, 0.01, 0.25), (14, 0.02, 0.5), (10, 0.05, 0.3)):
+        model.addwgd_(model[i], t, q)
+        B.extend_(data, i)
+    B.logpdf_(model, data)
+    B.set_(data)
+    ids = sorted(i for i, n in model.nodes.items() if n.p is not None and "λ" in n.theta)
+    per = {}
+    reps = 5
+    for i in ids:
+        n = model[i]
+        lam = n["λ"]
+        for r in range(reps + 1):
+            if r == 1:
+                data.synchronize()
+                t0 = time.perf_counter()
+            update_(n, λ=lam * (1.0 + 1e-4 * (r + 1)), μ=n["μ"])
+            B.logpdf_(n, data)
+            update_(n, λ=lam, μ=n["μ"])
+            B.rev_(data)
+        per[i] = (time.perf_counter() - t0) / reps
+    t0 = time.perf_counter()
+    for _ in range(200):
+        B.set_(data)
+        B.rev_(data)
+    cr = (time.perf_counter() - t0) / 400
+    mean = float(np.mean(list(per.values())))
+    return {"metric": "family-likelihood evals/sec (logpdf!(model[i]) node-local recompute)", "value": len(data) / mean, "unit": UNIT,
+            "config": {"workload": "C3: 9dicots + 3 WGDs (%d nodes), 100000 synthetic families (%d patterns); update! + logpdf!(model[i]) + rev! for every node i, host in / host out" % (len(model), len(data))},
+            "mean_ms": mean * 1e3, "min_ms": min(per.values()) * 1e3, "max_ms": max(per.values()) * 1e3,
+            "commit_or_revert_us": cr * 1e6}
+
+
+def gradient_leg(args, local):
+    """`gradient(model, data)`: C1 (README example, 9dicots × 25 families, P = 35) and the C4 tree with 10^4 families."""
+    import beluga_b200 as B
+    from beluga_b200.model import build_model
+    from beluga_b200.sim import rand_profiles_torch
+    out = {}
+    nw = open(os.path.join(ROOT, "tests", "data", "9dicots.nw")).readline().strip()
+    rows = [ln.strip().split(",") for ln in open(os.path.join(ROOT, "tests", "data", "9dicots-f01-25.csv"))]
+    names, counts = rows[0], np.array(rows[1:], dtype=np.int64)
+    model, data = B.DLWGD(nw, (names, counts), 1.0, 0.92, 0.66, B.BRANCH, device=local)
+    B.gradient(model, data)
+    t0 = time.perf_counter()
+    for _ in range(3):
+        g = B.gradient(model, data)
+    out["C1"] = {"ms": (time.perf_counter() - t0) / 3 * 1e3, "P": int(len(g)), "patterns": len(data)}
+    nw = open(os.path.join(ROOT, "tests", "data", "12monocots.nw")).readline().strip()
+    m0, _, _ = build_model(nw, 0.004, 0.003, 0.9, B.BRANCH)
+    names, counts = rand_profiles_torch(m0, 10_000, seed=SEED, device="cuda:%d" % local, max_rootsum=60, chunk=1 << 19)
+    model, data = B.DLWGD(nw, (names, counts), 0.004, 0.003, 0.9, B.BRANCH, device=local)
+    B.gradient(model, data)
+    t0 = time.perf_counter()
+    g = B.gradient(model, data)
+    out["C4-tree"] = {"ms": (time.perf_counter() - t0) * 1e3, "P": int(len(g)), "patterns": len(data)}
+    return out
+
+
 def ncu_traffic():
     """dram read+write bytes of one sweep_kernel launch from the committed ncu --set full capture of this
     workload (profiles/r01_sweep_kernel_ncu.csv); None if the file is missing."""
@@ -253,6 +352,7 @@ def main():
     X, w, m = B.profile(t, l, (names, counts))
     X = np.ascontiguousarray(X, dtype=np.int32)
     npat, nfam = X.shape[0], int(w.sum())
+    alg_fma = algorithmic_fma(model, X)
     data = B.PArray(X, w, device=local, distributed=True)
     for i in ext:                 # extend!(data, i) for every inserted WGD (src/profile.jl:108), then set!(data)
         B.extend_(data, i)
@@ -350,6 +450,20 @@ def main():
             "gpu_launches": int(launches * args.steps),
             "clocks": sampler.summary(),
         }
+        try:                                 # the same step against the fp64 roofline (evidence of the regime)
+            fp64_peak = data.fp64_peak()
+            tf = 2.0 * alg_fma / (pm / 1e3) / 1e12
+            line["roofline_fp64"] = {"bound": "fp64", "achieved": tf, "peak": fp64_peak, "unit": "TFLOP/s", "frac": tf / fp64_peak,
+                                     "algorithmic_fma_per_step": alg_fma, "flop_per_byte": 2.0 * alg_fma / prune_bytes,
+                                     "peak_source": "measured on this GPU (blg_fp64_peak: 8 DFMA chains/thread)"}
+        except Exception as e:
+            line["roofline_fp64"] = {"error": repr(e)}
+        if not args.no_mcmc:
+            for key, leg in (("node_local", node_local_leg), ("gradient", gradient_leg)):
+                try:
+                    line[key] = leg(args, local)
+                except Exception as e:
+                    line[key] = {"error": repr(e)}
         if not args.no_mcmc:
             try:
                 del data

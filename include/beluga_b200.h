@@ -129,6 +129,9 @@ int blg_sync(blg_handle* h);
  * the two device durations of the last call in milliseconds. */
 int blg_set_timing(blg_handle* h, int on);
 int blg_last_timing(blg_handle* h, float* prune_ms, float* root_ms);
+/* measured fp64 FMA throughput of the device (TFLOP/s, 8 independent DFMA chains per thread): the fp64-roofline
+ * denominator SURVEY.md §8(d) asks for; not part of the reference's API */
+int blg_fp64_peak(blg_handle* h, double* tflops);
 
 #ifdef __cplusplus
 }
