@@ -987,6 +987,7 @@ __global__ void zero_slab_kernel(double* ell, int* scl, size_t nell, int N) {
 }
 
 #include "gradient.cuh"
+#include "adjoint.cuh"
 
 // ------------------------------------------------------------------------------------------------
 // host-side state
@@ -1089,6 +1090,8 @@ struct blg_handle {
     int kernel_version = 2;
     int last_kernel = 0;
     bool order_resident = true;
+    double weight_total = 0.0;           // Σ_f w_f
+    int grad_mode = 1;                   // 1: reverse-mode sweep where the tree allows it; 0: forward-mode tangent passes (BLG_GRAD=forward)
     int min_blocks = 4;
     int profile_sweep = 0;
     DevBuf<unsigned long long> d_prof;
@@ -1720,6 +1723,116 @@ struct blg_handle {
         for (auto& t : temps) gfree(t.first, t.second);
     }
 
+    // ---- gradient, reverse mode (adjoint.cuh) -------------------------------------------------------------------
+    bool adjoint_eligible() const {
+        if (children[0].size() != 2) return false;
+        for (int u : postorder) {
+            if (children[u].size() > 2) return false;
+            if (u < (int)Tp.size() && Tp[u].xmax > 255) return false;
+        }
+        return true;
+    }
+    template <int CAP> void launch_adjoint(const AdjStep& as) {
+        int blocks = (N + 127) / 128;
+        adjoint_node_kernel<CAP><<<blocks, 128, 0, stream>>>(as, pascal.p, pdim, N, ld);
+    }
+    // res[2·i + lane] = ∂logL/∂(parameter of lane `lane` of group i); the caller has just run a full logpdf
+    void gradient_adjoint(const std::vector<Seeds<2>>& groups, std::vector<double>& res) {
+        const int n = ncols_model;
+        ModelDev m = model_dev();
+        std::vector<std::pair<void*, size_t>> temps;
+        auto ga = [&](size_t b) { void* p = galloc(b); temps.push_back({p, b}); return p; };
+        std::vector<double*> adj(n, nullptr);
+        std::vector<int*> adjs(n, nullptr);
+        for (int u : postorder) {
+            if (children[u].empty()) continue;
+            adj[u] = (double*)ga((size_t)(Tp[u].xmax + 1) * ld * sizeof(double));
+            adjs[u] = (int*)ga(ld * sizeof(int));
+        }
+        double* sadj = (double*)ga((size_t)n * 4 * sizeof(double));
+        CK(cudaMemsetAsync(sadj, 0, (size_t)n * 4 * sizeof(double), stream));
+        const int nrow = Tp[0].xmax + 1;
+        double* rwbar = (double*)ga((size_t)nrow * sizeof(double));
+        CK(cudaMemsetAsync(rwbar, 0, (size_t)nrow * sizeof(double), stream));
+        // tangent inputs of the dual W tables below a WGD/WGT: lane 0 = ∂/∂q (no ε tangent), lane 1 = ∂/∂ε of the child
+        double* dez = (double*)ga((size_t)2 * n * sizeof(double));
+        double* de1c = (double*)ga((size_t)2 * n * sizeof(double));
+        CK(cudaMemsetAsync(dez, 0, (size_t)2 * n * sizeof(double), stream));
+        // stage 1: root, then every internal node, parents before children
+        {
+            Slab* rs = readable(0);
+            int blocks = (N + 255) / 256;
+            double* rpart = (double*)ga((size_t)nrow * blocks * sizeof(double));
+            root_adjoint_kernel<<<blocks, 256, 0, stream>>>(rs->ell, Tp[0].cnt, rootw.p, weight.p, adj[0], adjs[0], rpart, blocks, nrow, N, ld);
+            CK(cudaGetLastError());
+            grad_reduce_kernel<<<1, 256, 0, stream>>>(rpart, blocks, nrow, rwbar);
+            CK(cudaGetLastError());
+        }
+        const int nblk = (N + 127) / 128;
+        double* npart = (double*)ga((size_t)6 * nblk * sizeof(double));
+        std::vector<std::vector<double>> keep_host;          // staging of the one-hot tangent vectors (must outlive the copies)
+        for (auto it = postorder.rbegin(); it != postorder.rend(); ++it) {
+            const int u = *it;
+            if (children[u].empty()) continue;
+            NodeStep ns = make_step(u, true);
+            AdjStep as;
+            memset(&as, 0, sizeof(as));
+            as.k = ns.k;
+            for (int i = 0; i < ns.k; ++i) {
+                const ChildRef& cr = ns.child[i];
+                AdjChild& c = as.child[i];
+                c.ell = cr.ell; c.scl = cr.scl; c.cnt = cr.cnt; c.Wt = cr.Wt; c.wdp = cr.wdp; c.id = cr.id;
+                c.adj = adj[cr.id]; c.adj_scl = adjs[cr.id];
+                c.e = h_eps0[cr.id]; c.cc = h_nc[cr.id].cc;
+                if (kind[cr.id] == BLG_WGDAFTER) {
+                    const HostTab& tb = tabs[cr.id];
+                    const size_t wsz = (size_t)tb.wdim * tb.wdp;
+                    double* dW = (double*)ga(2 * wsz * sizeof(double));
+                    DualTab dt;
+                    memset(&dt, 0, sizeof(dt));
+                    dt.dWt = dW;
+                    DualTab* ddt = (DualTab*)ga(sizeof(DualTab));
+                    int* dl = (int*)ga(sizeof(int));
+                    keep_host.emplace_back((size_t)2 * n, 0.0);
+                    keep_host.back()[(size_t)n + cr.id] = 1.0;
+                    CK(cudaMemcpyAsync(de1c, keep_host.back().data(), (size_t)2 * n * sizeof(double), cudaMemcpyHostToDevice, stream));
+                    CK(cudaMemcpyAsync(ddt, &dt, sizeof(DualTab), cudaMemcpyHostToDevice, stream));
+                    CK(cudaMemcpyAsync(dl, &cr.id, sizeof(int), cudaMemcpyHostToDevice, stream));
+                    Seeds<2> sd;
+                    sd.kind[0] = SEED_Q; sd.node[0] = u; sd.kind[1] = SEED_NONE; sd.node[1] = -1;
+                    size_t smem = (size_t)2 * std::max(tb.wdim, 1) * 3 * sizeof(double);
+                    tables_dual_kernel<2><<<1, 128, smem, stream>>>(m, sd, dl, ddt, dez, de1c);
+                    CK(cudaGetLastError());
+                    CK(cudaStreamSynchronize(stream));       // ddt/dl/de1c are reused by the next WGD
+                    c.dW = dW;
+                    c.dW_stride = wsz;
+                }
+            }
+            as.ell = ns.out; as.scl = ns.out_scl; as.cnt = ns.cnt;
+            as.adj = adj[u]; as.adj_scl = adjs[u];
+            as.ipow = ns.ipow; as.inv = h_nc[u].inv; as.partial = npart;
+            const int need = Tp[u].xmax + 1;
+            if (need <= 16) launch_adjoint<16>(as);
+            else if (need <= 64) launch_adjoint<64>(as);
+            else launch_adjoint<256>(as);
+            CK(cudaGetLastError());
+            adjoint_reduce_kernel<<<1, 256, 0, stream>>>(npart, nblk, as.k, as.child[0].id, as.k == 2 ? as.child[1].id : 0, sadj);
+            CK(cudaGetLastError());
+        }
+        // stage 2: chain rule per parameter group
+        Seeds<2>* dg = (Seeds<2>*)ga(groups.size() * sizeof(Seeds<2>));
+        int* dpost = (int*)ga(postorder.size() * sizeof(int));
+        double* dout = (double*)ga(groups.size() * 2 * sizeof(double));
+        CK(cudaMemcpyAsync(dg, groups.data(), groups.size() * sizeof(Seeds<2>), cudaMemcpyHostToDevice, stream));
+        CK(cudaMemcpyAsync(dpost, postorder.data(), postorder.size() * sizeof(int), cudaMemcpyHostToDevice, stream));
+        adjoint_params_kernel<<<(unsigned)groups.size(), 32, (size_t)4 * n * sizeof(double), stream>>>(m, dg, dpost, (int)postorder.size(), sadj, rwbar,
+                                                                                                   nrow, weight_total, dout);
+        CK(cudaGetLastError());
+        CK(cudaMemcpyAsync(res.data(), dout, groups.size() * 2 * sizeof(double), cudaMemcpyDeviceToHost, stream));
+        CK(cudaStreamSynchronize(stream));
+        for (auto& t : temps) gfree(t.first, t.second);
+    }
+
     // g: [λ_1..λ_n, μ_1..μ_n, q (ascending wgd id), η]  (asvector layout, model.jl:541-546) or [λ, μ] for cr
     void gradient(double* g, int len, double* logpdf_out, bool cr) {
         require(have_topology && have_params && tabs_valid, "gradient: model not set (topology, params, rebuild)");
@@ -1743,27 +1856,34 @@ struct blg_handle {
             CK(cudaMemcpyAsync(&ll, result.p, sizeof(double), cudaMemcpyDeviceToHost, stream));
             CK(cudaStreamSynchronize(stream));
             if (logpdf_out) *logpdf_out = ll;
-            Seeds<2> sd;
-            double o[2];
+            // parameter groups (two tangent lanes each) and where their results go
+            std::vector<Seeds<2>> groups;
+            std::vector<std::pair<int, int>> dest;
+            auto add_group = [&](int k0, int n0, int d0, int k1, int n1, int d1) {
+                Seeds<2> sd;
+                sd.kind[0] = k0; sd.node[0] = n0; sd.kind[1] = k1; sd.node[1] = n1;
+                groups.push_back(sd);
+                dest.push_back({d0, d1});
+            };
             if (cr) {
-                sd.kind[0] = SEED_LAM_ALL; sd.kind[1] = SEED_MU_ALL; sd.node[0] = sd.node[1] = -1;
-                tangent_pass(sd, o);
-                g[0] = o[0]; g[1] = o[1];
+                add_group(SEED_LAM_ALL, -1, 0, SEED_MU_ALL, -1, 1);
             } else {
                 for (int b = 0; b < nn; ++b) {
                     if (model_kind == BLG_BRANCH_MODEL && b == 0) continue;     // root rates are unused by Branch models
-                    sd.kind[0] = SEED_LAM; sd.kind[1] = SEED_MU; sd.node[0] = sd.node[1] = b;
-                    tangent_pass(sd, o);
-                    g[b] = o[0]; g[nn + b] = o[1];
+                    add_group(SEED_LAM, b, b, SEED_MU, b, nn + b);
                 }
-                for (size_t j = 0; j < wg.size(); ++j) {
-                    sd.kind[0] = SEED_Q; sd.node[0] = wg[j]; sd.kind[1] = SEED_NONE; sd.node[1] = -1;
-                    tangent_pass(sd, o);
-                    g[2 * nn + j] = o[0];
-                }
-                sd.kind[0] = SEED_ETA; sd.node[0] = 0; sd.kind[1] = SEED_NONE; sd.node[1] = -1;
-                tangent_pass(sd, o);
-                g[P - 1] = o[0];
+                for (size_t j = 0; j < wg.size(); ++j) add_group(SEED_Q, wg[j], 2 * nn + (int)j, SEED_NONE, -1, -1);
+                add_group(SEED_ETA, 0, P - 1, SEED_NONE, -1, -1);
+            }
+            std::vector<double> res(2 * groups.size(), 0.0);
+            if (grad_mode == 1 && adjoint_eligible()) {
+                gradient_adjoint(groups, res);
+            } else {
+                for (size_t i = 0; i < groups.size(); ++i) tangent_pass(groups[i], &res[2 * i]);
+            }
+            for (size_t i = 0; i < groups.size(); ++i) {
+                if (dest[i].first >= 0) g[dest[i].first] = res[2 * i];
+                if (dest[i].second >= 0) g[dest[i].second] = res[2 * i + 1];
             }
         } catch (...) { Tp = saved; throw; }
         Tp = saved;
@@ -1884,6 +2004,7 @@ int blg_create(int device, void* stream, blg_handle** out) {
         if (const char* o = getenv("BLG_ORDER")) h->order_resident = atoi(o) != 0;
         if (const char* o = getenv("BLG_MINB")) h->min_blocks = atoi(o);
         if (const char* o = getenv("BLG_PROF")) h->profile_sweep = atoi(o);
+        if (const char* o = getenv("BLG_GRAD")) h->grad_mode = (strcmp(o, "forward") == 0) ? 0 : 1;
         if (const char* sc = getenv("BLG_SLICE")) h->slice_cap = std::max(8, std::min(224, atoi(sc)));
         *out = h;
     } catch (const std::exception& e) { g_create_error = e.what(); return 2; }
@@ -2000,6 +2121,8 @@ int blg_set_profiles(blg_handle* h, const int32_t* X, const int64_t* weight, int
     for (int c = 0; c < ncols; ++c) cols[c].cnt = dcnt + (size_t)c * ld;
     std::vector<double> w(ld, 0.0);
     for (int f = 0; f < npatterns; ++f) w[f] = (double)weight[h->perm[f]];
+    h->weight_total = 0.0;
+    for (int f = 0; f < npatterns; ++f) h->weight_total += w[f];
     h->weight.ensure(ld);
     h->fam_ll.ensure(ld);
     CK(cudaMemcpyAsync(h->weight.p, w.data(), ld * sizeof(double), cudaMemcpyHostToDevice, h->stream));

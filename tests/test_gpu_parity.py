@@ -387,6 +387,29 @@ def test_gradient_golden_config(plants1c):                # test/gradient.jl:1-1
     assert B.logpdfroot(model[1], data) == pytest.approx(l0, rel=1e-13)
 
 
+def test_gradient_forward_mode_path_and_polytomy_fallback(dicots, monkeypatch):
+    # the reverse-mode sweep is the default for binary trees; the forward-mode tangent passes stay as the path for
+    # polytomies (and BLG_GRAD=forward): both must give the oracle's gradient
+    nw, df = dicots
+    monkeypatch.setenv("BLG_GRAD", "forward")
+    model, data, orc = pair(nw, df, 1.0, 0.92, 0.66, B.BRANCH)
+    w = B.addwgd_(model, model[6], 0.01, 0.25); orc.addwgd(6, 0.01, 0.25)
+    B.extend_(data, 6); orc.extend(6)
+    gf = B.gradient(model, data)
+    assert_grad_close(gf, orc.gradient())
+    monkeypatch.delenv("BLG_GRAD")
+    model2, data2 = B.DLWGD(nw, df, 1.0, 0.92, 0.66, B.BRANCH, device=0)
+    B.addwgd_(model2, model2[6], 0.01, 0.25); B.extend_(data2, 6)
+    ga = B.gradient(model2, data2)
+    np.testing.assert_allclose(ga, gf, rtol=1e-12, atol=1e-12 * np.abs(gf).max())
+    # polytomy: not eligible for the adjoint sweep
+    nwp = "((A:1.0,B:1.2,C:0.7):0.5,(D:0.9,E:0.9):0.6);"
+    rng = np.random.default_rng(12)
+    counts = rng.poisson(1.5, size=(60, 5)).astype(np.int64) + 1
+    modelp, datap, orcp = pair(nwp, (list("ABCDE"), counts), 0.8, 1.1, 0.7, B.BRANCH)
+    assert_grad_close(B.gradient(modelp, datap), orcp.gradient())
+
+
 @pytest.mark.parametrize("nt", [B.NODE, B.BRANCH])
 def test_gradient_heterogeneous_rates_with_wgd(plants1, nt):
     nw, df = plants1
