@@ -458,12 +458,23 @@ def main():
                                      "peak_source": "measured on this GPU (blg_fp64_peak: 8 DFMA chains/thread)"}
         except Exception as e:
             line["roofline_fp64"] = {"error": repr(e)}
+        c5_grad = None
+        if not args.no_mcmc and world == 1:
+            try:                             # gradient(model, data) on the headline workload itself (reverse-mode sweep)
+                data.gradient(model)
+                t0 = time.perf_counter()
+                gg, _ = data.gradient(model)
+                c5_grad = {"ms": (time.perf_counter() - t0) * 1e3, "P": int(len(gg)), "patterns": int(npat)}
+            except Exception as e:
+                c5_grad = {"error": repr(e)}
         if not args.no_mcmc:
             for key, leg in (("node_local", node_local_leg), ("gradient", gradient_leg)):
                 try:
                     line[key] = leg(args, local)
                 except Exception as e:
                     line[key] = {"error": repr(e)}
+            if c5_grad is not None and isinstance(line.get("gradient"), dict):
+                line["gradient"]["C5"] = c5_grad
         if not args.no_mcmc:
             try:
                 del data
