@@ -203,12 +203,26 @@ class DLWGD:
     # --- rates, src/model.jl:69-99 --------------------------------------------------------------
     def setrates_(self, X):
         X = np.asarray(X, dtype=np.float64)
-        for i in sorted(self.nodes):
-            n = self.nodes[i]
+        lam, mu = X[0].tolist(), X[1].tolist()
+        nodes = self.nodes
+        nn = cnt = 0
+        for i in sorted(nodes):
+            n = nodes[i]
             if isawgd(n):
                 break
-            n["λ"] = X[0, i - 1]
-            n["μ"] = X[1, i - 1]
+            th = n.theta                     # (same effect as n["λ"] = …; n["μ"] = … for every node, in bulk)
+            th["λ"] = lam[i - 1]
+            th["μ"] = mu[i - 1]
+            nn = i
+            cnt += 1
+        self._param_version += 1
+        f = self._flat
+        if f is not None and self._flat_topo == self._topo_version:
+            if cnt == nn:                    # ids 1..nn are the non-WGD nodes (the reference's invariant, model.jl:69-76)
+                f[0, :nn] = X[0, :nn]
+                f[1, :nn] = X[1, :nn]
+            else:
+                self._flat = None
         self.set_()
 
     def getrates(self):

@@ -111,6 +111,41 @@ def test_update_records_reference_refresh_order():
         assert model[1]["η"] == 0.91
 
 
+def test_flat_parameter_cache_tracks_updates_and_topology_edits():
+    # flat_params() serves the per-proposal θ upload from an array that ModelNode.__setitem__ keeps current; it must
+    # equal a fresh walk over the graph after any mix of updates, WGD insertions/removals and reindexing
+    nw = read_nw("9dicots.nw")
+    model, _, _ = build_model(nw, 1.0, 0.92, 0.66, B.BRANCH)
+
+    def fresh():
+        n = max(model.nodes)
+        out = np.zeros((4, n))
+        for i, nd in model.nodes.items():
+            for r, k in enumerate(("λ", "μ", "q", "t")):
+                out[r, i - 1] = nd.theta.get(k, 0.0)
+        return out
+
+    def check():
+        lam, mu, q, t, eta = model.flat_params()
+        np.testing.assert_array_equal(np.vstack([lam, mu, q, t]), fresh())
+        assert eta == model[1]["η"]
+
+    check()
+    B.update_(model[5], λ=1.7, μ=0.3); check()
+    model[9]["t"] = 0.123; check()
+    w = B.addwgd_(model, model[6], 0.01, 0.25); check()
+    w["q"] = 0.9; model[6]["λ"] = 2.5; check()
+    w2 = B.addwgt_(model, model[12], 0.02, 0.4); check()
+    B.removewgd_(model, w); check()                      # reindexes the WGT pair down by two
+    B.update_(model[1], "η", 0.5); check()
+    X = model.getrates() * 1.3
+    model.setrates_(X); check()
+    np.testing.assert_array_equal(model.getrates(), X)
+    m2 = model(model.asvector() * 1.1)                   # the functor builds an independent model
+    assert m2 is not model and m2._flat is not model._flat
+    check()
+
+
 def test_mock_profile_returns_zero():             # profile.jl:28,31,56; test/rjmcmc.jl:3-24 relies on it
     model, data = B.DLWGD(read_nw("plants1.nw"), None, 1.0, 1.0, 0.9)
     assert len(data) == 0
