@@ -419,7 +419,7 @@ __global__ void __launch_bounds__(128) prune_node_kernel(const NodeStep st, cons
 //   * step descriptors travel as a __grid_constant__ kernel parameter (constant bank: uniform,
 //     cache-resident reads that streaming data cannot evict);
 //   * the per-family working column lives in a per-warp shared-memory slice laid out [index][lane]
-//     (conflict-free 64-bit accesses); a node needs S+2 doubles per family because both inner loops
+//     (conflict-free 64-bit accesses); a node needs S+3 doubles per family because both inner loops
 //     run IN PLACE;
 //   * NO coefficient tables are read in the inner loops.  They are generated in registers:
 //       contraction over an ordinary branch: w*(n|j) = C(j-1,n-1)·ψ'^(j-n)·c^n, c = (1-ϕ')(1-ψ')
@@ -434,7 +434,10 @@ __global__ void __launch_bounds__(128) prune_node_kernel(const NodeStep st, cons
 //     the branch below a WGD/WGT keeps its (banded) table, read from global memory;
 //   * the factorial scalings limit this kernel to count bounds <= BLG_FAST_MAXCOUNT and to parameter
 //     ranges where they stay inside fp64 (checked per node on the device when ε/W are built);
-//     otherwise the per-node general kernels above are used.
+//     otherwise the per-node general kernels above are used;
+//   * the code is kept SMALL on purpose (rolled loops, noinline helpers, one merge dispatch): with 16 warps per SM
+//     at different places of the sweep, the kernel's speed follows its instruction-cache footprint more closely than
+//     anything else (80 KB of SASS: 12.0 ms per benchmark sweep; 54 KB: 2.7 ms; 41 KB: 2.3 ms — same arithmetic).
 __constant__ double c_fact[BLG_FAST_MAXCOUNT + 72];      // n!
 __constant__ double c_invfact[BLG_FAST_MAXCOUNT + 72];   // 1/n!
 __constant__ double c_inv[BLG_FAST_MAXCOUNT + 72];       // 1/n (c_inv[0] = 0)
@@ -1092,7 +1095,6 @@ struct blg_handle {
     bool order_resident = true;
     double weight_total = 0.0;           // Σ_f w_f
     int grad_mode = 1;                   // 1: reverse-mode sweep where the tree allows it; 0: forward-mode tangent passes (BLG_GRAD=forward)
-    int min_blocks = 4;
     int profile_sweep = 0;
     DevBuf<unsigned long long> d_prof;
     int slice_cap = 50;                       // doubles per lane of the per-warp shared-memory slice
@@ -2002,7 +2004,6 @@ int blg_create(int device, void* stream, blg_handle** out) {
         }
         if (const char* kv = getenv("BLG_KERNEL")) h->kernel_version = atoi(kv) == 1 ? 1 : 2;
         if (const char* o = getenv("BLG_ORDER")) h->order_resident = atoi(o) != 0;
-        if (const char* o = getenv("BLG_MINB")) h->min_blocks = atoi(o);
         if (const char* o = getenv("BLG_PROF")) h->profile_sweep = atoi(o);
         if (const char* o = getenv("BLG_GRAD")) h->grad_mode = (strcmp(o, "forward") == 0) ? 0 : 1;
         if (const char* sc = getenv("BLG_SLICE")) h->slice_cap = std::max(8, std::min(224, atoi(sc)));

@@ -194,7 +194,14 @@ def mcmc_leg(args, local):
     chain.rjmcmc_(args.mcmc_generations, trace=0)
     data.synchronize()
     dt = time.perf_counter() - t0
-    return {"metric": "rjMCMC iters/sec", "value": args.mcmc_generations / dt, "unit": "generations/s",
+    try:                                           # BASELINE.json's "gradient-based" wording: one gradient(model, data) on the chain's state
+        data.gradient(model)
+        t1 = time.perf_counter()
+        gg, _ = data.gradient(model)
+        grad_ms, grad_p = (time.perf_counter() - t1) * 1e3, int(len(gg))
+    except Exception:
+        grad_ms, grad_p = None, None
+    return {"metric": "rjMCMC iters/sec", "value": args.mcmc_generations / dt, "unit": "generations/s", "gradient_ms": grad_ms, "gradient_P": grad_p,
             "config": {"workload": "C4: 12monocots, %d synthetic families (%d patterns), rjmcmc! generations on 1 GPU" % (args.mcmc_families, len(data)),
                        "nodes": len(model), "wgds_at_end": model.nwgd()},
             "likelihood_calls_per_s": (chain.evals - e0) / dt, "proposals_per_s": (chain.proposed - p0) / dt,
