@@ -402,6 +402,19 @@ def test_gradient_forward_mode_path_and_polytomy_fallback(dicots, monkeypatch):
     B.addwgd_(model2, model2[6], 0.01, 0.25); B.extend_(data2, 6)
     ga = B.gradient(model2, data2)
     np.testing.assert_allclose(ga, gf, rtol=1e-12, atol=1e-12 * np.abs(gf).max())
+    # larger counts (the 256-entry instantiation of the adjoint step) against both the oracle and the forward mode
+    nwb = "((A:0.4,B:0.5):0.3,(C:0.6,(D:0.2,E:0.3):0.2):0.25);"
+    rng = np.random.default_rng(21)
+    countsb = rng.integers(0, 9, size=(40, 5)).astype(np.int64)
+    countsb[0] = [14] * 5
+    countsb[1] = [30, 0, 0, 35, 1]
+    modelb, datab, orcb = pair(nwb, (list("ABCDE"), countsb), 0.9, 1.0, 0.8, B.NODE)
+    gb = B.gradient(modelb, datab)
+    assert_grad_close(gb, orcb.gradient())
+    monkeypatch.setenv("BLG_GRAD", "forward")
+    modelb2, datab2 = B.DLWGD(nwb, (list("ABCDE"), countsb), 0.9, 1.0, 0.8, B.NODE, device=0)
+    np.testing.assert_allclose(B.gradient(modelb2, datab2), gb, rtol=1e-11, atol=1e-11 * np.abs(gb).max())
+    monkeypatch.delenv("BLG_GRAD")
     # polytomy: not eligible for the adjoint sweep
     nwp = "((A:1.0,B:1.2,C:0.7):0.5,(D:0.9,E:0.9):0.6);"
     rng = np.random.default_rng(12)
