@@ -1814,7 +1814,9 @@ struct blg_handle {
             as.adj = adj[u]; as.adj_scl = adjs[u];
             as.ipow = ns.ipow; as.inv = h_nc[u].inv; as.partial = npart;
             const int need = Tp[u].xmax + 1;
-            if (need <= 16) launch_adjoint<16>(as);
+            if (need <= 8) launch_adjoint<8>(as);
+            else if (need <= 16) launch_adjoint<16>(as);
+            else if (need <= 32) launch_adjoint<32>(as);
             else if (need <= 64) launch_adjoint<64>(as);
             else launch_adjoint<256>(as);
             CK(cudaGetLastError());
