@@ -109,7 +109,8 @@ def cpu_baseline(args, threads, target_seconds, steps=None, warmup=1):
     sample of the same workload.  Test infrastructure used as a yard-stick, never as the product."""
     from oracle.oracle import BRANCH as OBRANCH, OracleDLWGD, max_threads
 
-    threads = threads or max_threads()
+    # all the host cores this process may use — not OMP_NUM_THREADS, which torchrun pins to 1
+    threads = threads or max(max_threads(), len(os.sched_getaffinity(0)))
     nw, model, ext, t, l, names, counts = build_workload(args, 0, device=None, families=4000)
 
     # the oracle API inserts a WGD at distance t above a node; replay in insertion order
@@ -160,7 +161,7 @@ def run_reference(args):
     if rank != 0:
         return
     from oracle.oracle import max_threads
-    threads = max_threads()
+    threads = max(max_threads(), len(os.sched_getaffinity(0)))
     cb = cpu_baseline(args, threads, target_seconds=max(30.0, args.cpu_seconds), steps=args.steps, warmup=args.warmup)
     line = {
         "impl": "reference", "metric": METRIC, "value": cb["value"], "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
