@@ -88,6 +88,8 @@ struct ModelDev {
     int pdim;
     SweepNodeConst* nc;        // per-node scalars of the table-free sweep kernel
     int* fast_ok;              // per node: 1 if the factorial-scaled forms stay inside fp64 here
+    double* rootw;             // root integration weights, rebuilt with the root's tables (nullptr: not now)
+    int rootw_n;
 };
 
 __device__ __forceinline__ bool d_isapprox(double a, double b) {
@@ -173,6 +175,38 @@ __global__ void __launch_bounds__(128) eps_kernel(ModelDev m, const int* __restr
         }
       }
       __syncthreads();
+    }
+}
+
+__device__ __forceinline__ double d_log1mexp(double x) { return x < -0.6931471805599453 ? log1p(-exp(x)) : log(-expm1(x)); }
+
+// rootw[n] = exp((n)·log1mexp(lε) + log η + (n-1)·log(1-η) - (n+1)·log1mexp(log(1-η)+lε)), n >= 1;
+// rootw[0] holds the conditioning constant log(1-r_1) + log(1-r_2) (+Inf marks "invalid").
+// (integrate_root model.jl:465-475, condition_oib model.jl:492-501; one block, tid of nt threads)
+__device__ void d_root_tables(const ModelDev& m, double* rootw, int nrow, int tid, int nt) {
+    int root = 0;
+    double eta = m.eta;
+    double le = log(m.eps1[root]);
+    double a = d_log1mexp(le), b = log(eta), c = log(1.0 - eta), d = d_log1mexp(log(1.0 - eta) + le);
+    for (int n = 1 + tid; n < nrow; n += nt) {
+        double f = (double)n * a + b + (double)(n - 1) * c;
+        f -= (double)(n + 1) * d;
+        rootw[n] = exp(f);
+    }
+    if (tid == 0) {
+        int c0 = m.child_off[root], c1 = m.child_off[root + 1];
+        double cond = __longlong_as_double(0x7ff8000000000000LL);
+        if (c1 - c0 >= 2) {
+            double leta = log(eta);
+            double lr[2];
+            for (int i = 0; i < 2; ++i) {
+                double e = log(m.eps0[m.child_idx[c0 + i]]);
+                lr[i] = leta + e - d_log1mexp(d_log1mexp(leta) + e);           // utils.jl:22-23
+            }
+            if (lr[0] > 0.0 || lr[1] > 0.0) cond = -INFINITY;                   // model.jl:495-497
+            else cond = d_log1mexp(lr[0]) + d_log1mexp(lr[1]);
+        }
+        rootw[0] = cond;
     }
 }
 
@@ -298,6 +332,7 @@ __global__ void __launch_bounds__(128) tables_kernel(ModelDev m, const int* __re
         }
     }
     if (tid == 0) m.fast_ok[n] = ok ? 1 : 0;
+    if (kd == BLG_ROOT && m.rootw != nullptr) d_root_tables(m, m.rootw, m.rootw_n, tid, nt);   // ϵ of the root's children is final here
 }
 
 // Pascal triangle C(n,s), n,s < dim, by the addition recurrence (exact while < 2^53).
@@ -913,42 +948,15 @@ __global__ void __launch_bounds__(256) fp64_peak_kernel(double* sink, int iters,
 // ------------------------------------------------------------------------------------------------
 // root: integrate_root (model.jl:465-475), condition_oib (model.jl:492-501), weighted reduction
 // ------------------------------------------------------------------------------------------------
-__device__ __forceinline__ double d_log1mexp(double x) { return x < -0.6931471805599453 ? log1p(-exp(x)) : log(-expm1(x)); }
-
-// rootw[n] = exp((n)·log1mexp(lε) + log η + (n-1)·log(1-η) - (n+1)·log1mexp(log(1-η)+lε)), n >= 1;
-// rootw[0] holds the conditioning constant log(1-r_1) + log(1-r_2) (+Inf marks "invalid").
-__global__ void root_tables_kernel(ModelDev m, double* rootw, int nrow) {
-    int root = 0;
-    double eta = m.eta;
-    double le = log(m.eps1[root]);
-    double a = d_log1mexp(le), b = log(eta), c = log(1.0 - eta), d = d_log1mexp(log(1.0 - eta) + le);
-    for (int n = 1 + threadIdx.x; n < nrow; n += blockDim.x) {
-        double f = (double)n * a + b + (double)(n - 1) * c;
-        f -= (double)(n + 1) * d;
-        rootw[n] = exp(f);
-    }
-    if (threadIdx.x == 0) {
-        int c0 = m.child_off[root], c1 = m.child_off[root + 1];
-        double cond = __longlong_as_double(0x7ff8000000000000LL);
-        if (c1 - c0 >= 2) {
-            double leta = log(eta);
-            double lr[2];
-            for (int i = 0; i < 2; ++i) {
-                double e = log(m.eps0[m.child_idx[c0 + i]]);
-                lr[i] = leta + e - d_log1mexp(d_log1mexp(leta) + e);           // utils.jl:22-23
-            }
-            if (lr[0] > 0.0 || lr[1] > 0.0) cond = -INFINITY;                   // model.jl:495-497
-            else cond = d_log1mexp(lr[0]) + d_log1mexp(lr[1]);
-        }
-        rootw[0] = cond;
-    }
-}
+__global__ void root_tables_kernel(ModelDev m, double* rootw, int nrow) { d_root_tables(m, rootw, nrow, (int)threadIdx.x, (int)blockDim.x); }
 
 __global__ void __launch_bounds__(256) root_kernel(const double* __restrict__ ell, const int* __restrict__ scl,
                                                    const uint16_t* __restrict__ cnt, const double* __restrict__ rootw,
                                                    const double* __restrict__ weight, double* __restrict__ fam_ll,
-                                                   double* __restrict__ partial, int N, size_t ld) {
+                                                   double* __restrict__ partial, int N, size_t ld,
+                                                   unsigned int* __restrict__ ticket, double* __restrict__ out) {
     __shared__ double red[256];
+    __shared__ bool last_block;
     int f = blockIdx.x * blockDim.x + threadIdx.x;
     double contrib = 0.0;
     if (f < N) {
@@ -966,20 +974,25 @@ __global__ void __launch_bounds__(256) root_kernel(const double* __restrict__ el
         if ((int)threadIdx.x < s) red[threadIdx.x] += red[threadIdx.x + s];
         __syncthreads();
     }
-    if (threadIdx.x == 0) partial[blockIdx.x] = red[0];
-}
-
-__global__ void __launch_bounds__(256) final_reduce_kernel(const double* __restrict__ partial, int nparts, double* __restrict__ out) {
-    __shared__ double red[256];
-    double s = 0.0;
-    for (int i = threadIdx.x; i < nparts; i += 256) s += partial[i];
-    red[threadIdx.x] = s;
-    __syncthreads();
-    for (int k = 128; k > 0; k >>= 1) {
-        if ((int)threadIdx.x < k) red[threadIdx.x] += red[threadIdx.x + k];
-        __syncthreads();
+    if (threadIdx.x == 0) {
+        partial[blockIdx.x] = red[0];
+        __threadfence();
+        last_block = atomicAdd(ticket, 1u) == gridDim.x - 1;
     }
-    if (threadIdx.x == 0) out[0] = red[0];
+    __syncthreads();
+    if (last_block) {                       // the last block to finish adds the partial sums, in a fixed order
+        __threadfence();
+        const volatile double* vp = partial;
+        double s = 0.0;
+        for (int i = threadIdx.x; i < (int)gridDim.x; i += 256) s += vp[i];
+        red[threadIdx.x] = s;
+        __syncthreads();
+        for (int k = 128; k > 0; k >>= 1) {
+            if ((int)threadIdx.x < k) red[threadIdx.x] += red[threadIdx.x + k];
+            __syncthreads();
+        }
+        if (threadIdx.x == 0) { out[0] = red[0]; *ticket = 0u; }
+    }
 }
 
 __global__ void zero_slab_kernel(double* ell, int* scl, size_t nell, int N) {
@@ -1088,6 +1101,8 @@ struct blg_handle {
     std::vector<HostTab> tabs;
     std::vector<NodeTab> tab_stage;
     bool tabs_valid = false;
+    bool rootw_valid = false;            // the root integration weights match the current parameters
+    DevBuf<unsigned int> d_ticket;       // last-block-done counter of root_kernel (self-resetting)
 
     // sweep-kernel plumbing
     int kernel_version = 2;
@@ -1132,7 +1147,7 @@ struct blg_handle {
         d_prof.free_();
         gpool_release();
         for (auto& e : ev) if (e) cudaEventDestroy(e);
-        gscratch.free_(); d_tilectr.free_();
+        gscratch.free_(); d_tilectr.free_(); d_ticket.free_();
         if (own_stream && stream) cudaStreamDestroy(stream);
     }
     static void free_tab(HostTab& tb) {
@@ -1215,6 +1230,7 @@ struct blg_handle {
         m.q = d_par.p + 3 * (size_t)ncols_model; m.eta = eta;
         m.eps0 = d_eps0.p; m.eps1 = d_eps1.p; m.tab = d_tab.p; m.pascal = pascal.p; m.pdim = pdim;
         m.nc = d_nc.p; m.fast_ok = d_fast_ok.p;
+        m.rootw = nullptr; m.rootw_n = 0;
         return m;
     }
 
@@ -1360,6 +1376,16 @@ struct blg_handle {
         const int* d_elist_p = d_lists.p + list.size();
         const int* d_seg_p = d_elist_p + elist.size();
         ModelDev m = model_dev();
+        bool root_listed = false;
+        for (int i : list) root_listed = root_listed || i == 0;
+        rootw_valid = false;
+        if (root_listed && !Tp.empty() && !children[0].empty()) {      // the block of the root also builds the root weights
+            const int nrow = Tp[0].xmax + 1;
+            rootw.ensure((size_t)nrow + 1);
+            m.rootw = rootw.p;
+            m.rootw_n = nrow;
+            rootw_valid = true;
+        }
         eps_kernel<<<1, 128, 0, stream>>>(m, d_elist_p, d_seg_p, (int)seg.size() - 1);
         CK(cudaGetLastError());
         tables_kernel<<<(unsigned)list.size(), 128, 2 * (size_t)maxdim * sizeof(double), stream>>>(m, d_list_p, (int)list.size());
@@ -1898,18 +1924,21 @@ struct blg_handle {
         require(!children[0].empty(), "logpdf: the root is a leaf");
         Slab* s = readable(0);
         int nrow = Tp[0].xmax + 1;
-        rootw.ensure((size_t)nrow + 1);
-        ModelDev m = model_dev();
-        root_tables_kernel<<<1, 128, 0, stream>>>(m, rootw.p, nrow);
-        CK(cudaGetLastError());
+        if (!rootw_valid) {                  // normally built by tables_kernel together with the root's tables
+            rootw.ensure((size_t)nrow + 1);
+            ModelDev m = model_dev();
+            root_tables_kernel<<<1, 128, 0, stream>>>(m, rootw.p, nrow);
+            CK(cudaGetLastError());
+            rootw_valid = true;
+            last_launches += 1;
+        }
         int blocks = (N + 255) / 256;
         partial.ensure((size_t)blocks);
-        root_kernel<<<blocks, 256, 0, stream>>>(s->ell, s->scl, Tp[0].cnt, rootw.p, weight.p, fam_ll.p, partial.p, N, ld);
-        CK(cudaGetLastError());
-        final_reduce_kernel<<<1, 256, 0, stream>>>(partial.p, blocks, d_out);
+        if (!d_ticket.p) { d_ticket.ensure(1); CK(cudaMemsetAsync(d_ticket.p, 0, sizeof(unsigned int), stream)); }
+        root_kernel<<<blocks, 256, 0, stream>>>(s->ell, s->scl, Tp[0].cnt, rootw.p, weight.p, fam_ll.p, partial.p, N, ld, d_ticket.p, d_out);
         CK(cudaGetLastError());
         last_bytes += 8.0 * Tp[0].colsum + 4.0 * N + 8.0 * N;
-        last_launches += 3;
+        last_launches += 1;
     }
     void logpdf(int mode, int node, double* d_out) {
         // mode 0 full, 1 from node, 2 root only
@@ -2092,6 +2121,7 @@ int blg_set_profiles(blg_handle* h, const int32_t* X, const int64_t* weight, int
     h->N = npatterns;
     h->ld = ((size_t)npatterns + 127) / 128 * 128;
     h->tabs_valid = false;
+    h->rootw_valid = false;
     for (auto& tb : h->tabs) blg_handle::free_tab(tb);
     if (npatterns == 0) { h->Tc.clear(); h->Tp.clear(); return 0; }
     h->require(X && weight, "set_profiles: null pointer");
@@ -2176,6 +2206,7 @@ int blg_set_topology(blg_handle* h, int ncols, const int32_t* parent, const uint
     h->have_topology = true;
     h->have_params = false;
     h->tabs_valid = false;
+    h->rootw_valid = false;
     for (auto& tb : h->tabs) tb.built = false;
     BLG_LEAVE(h)
 }
@@ -2193,6 +2224,7 @@ int blg_set_params(blg_handle* h, int model_kind, const double* lambda, const do
     h->t.assign(t, t + n);
     h->eta = eta;
     h->have_params = true;
+    h->rootw_valid = false;
     h->upload_params();
     BLG_LEAVE(h)
 }
