@@ -440,8 +440,8 @@ def main():
 
     if rank == 0:
         peak, peak_src = peaks()
-        # dominant kernel: prune_node_kernel (one launch per internal node).  Its algorithmic bytes are the
-        # sweep's minus the root/reduction share; its duration is the event-bracketed pruning phase.
+        # dominant kernel: sweep_kernel (one launch per likelihood call; the other launch is root_kernel).  Its algorithmic
+        # bytes are the sweep's minus the root/reduction share; its duration is the event-bracketed pruning phase.
         achieved = (prune_bytes / 1e9) / (pm / 1e3)
         line = {
             "metric": METRIC, "value": tot_pat / (ms / 1e3), "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
@@ -450,7 +450,7 @@ def main():
             "weighted_families_per_s": tot_fam / (ms / 1e3),
             "logpdf": total_ll,
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                         "traffic": ncu_traffic(), "kernel": "sweep_kernel (%d launch/step, event-bracketed)" % (launches - 3),
+                         "traffic": ncu_traffic(), "kernel": "sweep_kernel (%d launch/step, event-bracketed)" % (launches - 1),
                          "algorithmic_bytes_per_launch_group": prune_bytes, "algorithmic_bytes_per_step": alg_bytes, "phase_ms": {"prune": pm, "root+reduce": rm},
                          "peak_source": peak_src},
             "e2e": {"value": tot_pat / (e2e_ms / 1e3), "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": 8,
