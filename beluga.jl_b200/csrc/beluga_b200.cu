@@ -316,8 +316,17 @@ __global__ void __launch_bounds__(128) tables_kernel(ModelDev m, const int* __re
             m.nc[n].ip0 = poison ? __longlong_as_double(0x7ff8000000000000LL) : 1.0;
         }
         if (tb.nrow - 1 > BLG_FAST_MAXCOUNT) ok = false;
+        // the fast merge scales the "t" side by E^-t (E: prefix product; in a binary merge the e of whichever child is
+        // the "t" side in a warp) and the register-tiled side by e^-n (that child's own e): both must stay inside fp64
+        // over the count bound of this node
         for (int i = 1; i < k; ++i)
             if (!poison && !(E[i] > 0.0 && -(double)tb.nrow * log(E[i]) < 600.0)) ok = false;
+        if (k >= 2) {
+            for (int i = 0; i < k; ++i) {
+                const double ei = m.eps0[tb.mo[i]];
+                if (!poison && !(ei > 0.0 && ei <= 1.0 && -(double)tb.nrow * log(ei) < 600.0)) ok = false;
+            }
+        }
         for (int r = tid; r < tb.nrow; r += nt) tb.ipow[r] = poison ? __longlong_as_double(0x7ff8000000000000LL) : d_powi(inv, r);
         for (int i = 1; i < k; ++i) {
             double* cf = tb.coefD[i];
@@ -490,8 +499,8 @@ struct SweepChild {
 };
 struct SweepStep {
     int k, first, resident, prefact;   // resident != 0: child[0] is the node of the previous step (its column is still in shared memory)
-                                       // prefact != 0: the NEXT step keeps this node's column resident and contracts it in closed
-                                       // form, so leave (n-1)!·ℓ[n] in shared memory
+                                       // prefact != 0: the NEXT step reuses this node's column, which therefore stays in
+                                       // shared memory (rescaled) after the final write
     double inv, ip0;                // 1/(1-E_k); (1-E_k)^0, NaN where the reference's column would be NaN
     double* out;
     int* out_scl;
@@ -523,7 +532,7 @@ __device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wai
 
 // in-place table contraction (branch below a WGD/WGT): col[s] ← Σ_{j=s..Mw} Wt[j*wdp+s]·col[j]
 template <int TS>
-__device__ __noinline__ void sweep_contract_table(double* col, int Mw, const double* __restrict__ Wt, int wdp) {
+__device__ __noinline__ void sweep_contract_table(double* col, int Mw, const double* __restrict__ Wt, int wdp, double osc) {
 #pragma unroll 1
     for (int s0 = 0; s0 <= Mw; s0 += TS) {
         double acc[TS];
@@ -538,58 +547,40 @@ __device__ __noinline__ void sweep_contract_table(double* col, int Mw, const dou
         }
 #pragma unroll
         for (int k = 0; k < TS; ++k)
-            if (s0 + k <= Mw) col[(s0 + k) * 32] = acc[k];
+            if (s0 + k <= Mw) col[(s0 + k) * 32] = acc[k] * osc;
     }
 }
-// in-place closed-form contraction over an ordinary branch.  On entry col[j] = ℓ[j] (j = 0..Mw).
+// in-place contraction over an ordinary branch, col[j] = ℓ[j] → col[n] = b[n] (j, n = 0..Mw; b[0] = ℓ[0]).
+// The columns of w* obey v_j = T·v_{j-1}, (T v)[n] = ψ'·v[n] + c·v[n-1], v_1 = c·δ_{n1} (wstar!, node.jl:181-192), so
+// b = Σ_j ℓ[j]·T^(j-1)·v_1 is evaluated by Horner's rule from j = Mw down to 1.  With r[n] = (partial b[n])/c^n a stage is
+//     r[n] ← ψ'·r[n] + r[n-1]   (n descending, r[0] := ℓ[j])
+// — ONE DFMA per element, in place, the shift is the FMA's addend: no register moves, no coefficient, no factorial
+// scaling (r is bounded by 2^Mw·max ℓ whatever the parameters are).  TS consecutive n live in registers; a tile hands the
+// old value of its top element to the tile above through the column itself: at stage j tile `base` reads col[base+j]
+// (ℓ[j] for the first tile) and leaves its top element in col[base+TS+j], a slot it has already consumed.
 template <int TS>
-__device__ __noinline__ void sweep_contract_fast(double* col, int Mw, double psi, double cc, bool need_fact) {
-    // On entry col[j] = u[j] = (j-1)!·ℓ[j] (j >= 1; the factor is applied by whoever put the column there:
-    // the staging load, or the previous step's final write when the column stayed resident) unless need_fact.
-    if (need_fact) {
+__device__ __noinline__ void sweep_contract_horner(double* col, int Mw, double psi, double cc, double osc) {
+    double cpow = cc * osc;                            // c^n (times the pending power-of-two rescale of a resident column) at the tile's first output
 #pragma unroll 1
-        for (int j = 2; j <= Mw; ++j) col[j * 32] *= c_fact[j - 1];
-    }
-    double post = cc;                                  // c^n/(n-1)! at n = 1
+    for (int base = 0; base < Mw; base += TS) {        // outputs n = base+1 .. base+TS
+        double r[TS];
+#pragma unroll
+        for (int k = 0; k < TS; ++k) r[k] = 0.0;
+        const int lim = Mw - base - TS;                // stages j <= lim feed the next tile
 #pragma unroll 1
-    for (int n0 = 1; n0 <= Mw; n0 += TS) {
-        double acc[TS], win[TS];
+        for (int j = Mw - base; j >= 1; --j) {
+            const double h = col[(base + j) * 32];
+            const double top = r[TS - 1];
 #pragma unroll
-        for (int k = 0; k < TS; ++k) {
-            acc[k] = 0.0;
-            win[k] = (n0 + k <= Mw) ? col[(n0 + k) * 32] : 0.0;
-        }
-        double g = 1.0;                                // ψ'^d/d!
-        const int dmax = Mw - n0;
-        // the wide tile takes two diagonals per trip, so that the window slides by two registers at once (sliding one by
-        // one costs two moves per output and diagonal — as many instructions as the FMAs); a diagonal past dmax only
-        // sees zeros.  Measured: U = 2 here -1.7 %; U = 4, or the same trick in the merges, slower (longer loop bodies
-        // cost more in instruction fetch than the moves they save)
-        constexpr int U = (TS == 4) ? 1 : 2;
-#pragma unroll 1
-        for (int d = 0; d <= dmax; d += U) {
-            double ext[TS + U];
-#pragma unroll
-            for (int k = 0; k < TS; ++k) ext[k] = win[k];
-#pragma unroll
-            for (int u = 0; u < U; ++u) {
-                const int j = n0 + TS + d + u;
-                ext[TS + u] = (j <= Mw) ? col[j * 32] : 0.0;
-            }
-#pragma unroll
-            for (int u = 0; u < U; ++u) {
-#pragma unroll
-                for (int k = 0; k < TS; ++k) acc[k] = fma(g, ext[u + k], acc[k]);
-                g *= psi * c_inv[d + u + 1];
-            }
-#pragma unroll
-            for (int k = 0; k < TS; ++k) win[k] = ext[k + U];
+            for (int k = TS - 1; k >= 1; --k) r[k] = fma(psi, r[k], r[k - 1]);
+            r[0] = fma(psi, r[0], h);
+            if (j <= lim) col[(base + TS + j) * 32] = top;
         }
 #pragma unroll
         for (int k = 0; k < TS; ++k) {
-            const int n = n0 + k;
-            if (n <= Mw) col[n * 32] = acc[k] * post;
-            post *= cc * c_inv[n];                     // → c^(n+1)/n!
+            const int n = base + 1 + k;
+            if (n <= Mw) col[n * 32] = r[k] * cpow;
+            cpow *= cc;
         }
     }
 }
@@ -598,38 +589,51 @@ __device__ __noinline__ void sweep_contract_fast(double* col, int Mw, double psi
 // O may alias the slice as long as O+n never passes an unread A[t] (O == A, or O below A).
 template <int TS>
 __device__ __noinline__ double sweep_merge_fast(double* O, const double* A, int Sw, const double* B0, int M2w, double E, double invE,
-                                                double e, double em0, double emg, int X) {
+                                                double e, double inve, double em0, double emg, int X) {
     // em0/emg: the emitted value is acc·n!·E^n·(extra factor em0·emg^n): the last merge of a node passes
     // the (1-E_k)^(-n) normalisation (and the NaN poison) through them.  Returns max_{n<=X} of the result.
+    // The row is kept as B‡[t,s] = B†[t,s]·e^-(t+s): its recurrence B‡[t,s] = (s+1)·B‡[t-1,s+1] + B‡[t-1,s] is ONE
+    // DFMA with an immediate multiplier (the plain form needs a DMUL and a DFMA), and the factor e^(t+s) = e^n that
+    // every term of output n is missing is applied when the output is emitted (as a separate factor: multiplied into
+    // n!·E^n it could underflow on short branches, where e is tiny).  |B‡| <= 2^t·e^-M2w·max|b|; inve = 1/e; the range
+    // of e^-n over the count bound is part of the per-node range check (tables_kernel).
+    // The accumulators slide by one output per step; that shift is fused into the accumulation of the NEXT step's terms,
+    // acc[k] ← acc[k+1] + a[t+1]·B‡[t+1,k] in ascending k (in place: one DFMA, no register moves); once the "t" side is
+    // exhausted the same statement runs with a = 0 and only drains the accumulators.
     double B[TS], acc[TS];
+    double tf = 1.0;       // 1/(t!·E^t)
+    {
+        const double a0 = A[0];
+        double ek = 1.0;
 #pragma unroll
-    for (int k = 0; k < TS; ++k) {
-        B[k] = (k <= M2w) ? B0[k * 32] * c_invfact[k] : 0.0;
-        acc[k] = 0.0;
+        for (int k = 0; k < TS; ++k) {
+            B[k] = (k <= M2w) ? B0[k * 32] * (c_invfact[k] * ek) : 0.0;
+            acc[k] = a0 * B[k];
+            ek *= inve;
+        }
     }
     const int nmax = Sw + M2w;
     const double Eg = E * emg;
-    double tf = 1.0;       // 1/(t!·E^t)
     double em = em0;       // n!·E^n · em0·emg^n
+    double ee = 1.0;       // e^n
     double mx = 0.0;
 #pragma unroll 1
     for (int t = 0; t <= nmax; ++t) {
-        if (t <= Sw) {
-            const double a = A[t * 32] * tf;
-#pragma unroll
-            for (int k = 0; k < TS; ++k) acc[k] = fma(a, B[k], acc[k]);
-#pragma unroll
-            for (int k = 0; k < TS - 1; ++k) B[k] = fma(e, B[k], (double)(k + 1) * B[k + 1]);
-            B[TS - 1] = e * B[TS - 1];
-            tf *= invE * c_inv[t + 1];
-        }
-        const double v = (t <= X) ? acc[0] * em : 0.0;
+        const double v = (t <= X) ? (acc[0] * ee) * em : 0.0;
         O[t * 32] = v;
         mx = fmax(mx, v);                         // (a NaN column leaves mx = 0: stored as it is, exponent 0)
-#pragma unroll
-        for (int k = 0; k < TS - 1; ++k) acc[k] = acc[k + 1];
-        acc[TS - 1] = 0.0;
         em *= Eg * (double)(t + 1);
+        ee *= e;
+        double a = 0.0;
+        if (t < Sw) {
+#pragma unroll
+            for (int k = 0; k < TS - 1; ++k) B[k] = fma((double)(k + 1), B[k + 1], B[k]);
+            tf *= invE * c_inv[t + 1];
+            a = A[(t + 1) * 32] * tf;
+        }
+#pragma unroll
+        for (int k = 0; k < TS - 1; ++k) acc[k] = fma(a, B[k], acc[k + 1]);
+        acc[TS - 1] = a * B[TS - 1];
     }
     return mx;
 }
@@ -680,13 +684,13 @@ __device__ __noinline__ void sweep_merge_tiled(const double* A, int Sw, double* 
 }
 
 // stage (unless the column is already resident in col) + contract one child into col[0..Mw]
-// have: 0 = load the child's input column; 1 = it is in col already, pre-multiplied by (j-1)! where the closed form
-// wants that; 2 = it is in col already, plain (copied by cp.async)
+// have: 0 = load the child's input column; 1 = it is in col already, left there by the previous step and still to be
+// multiplied by the power of two osc (applied to the outputs); 2 = it is in col already (copied by cp.async)
 // (the descriptor fields travel by value: read through a reference, inside a noinline function, they were generic loads
 // from the parameter bank that missed the carved-down L1 — a long-scoreboard stall at the top of every call)
 struct ChildArgs { const double* ell; const double* Wt; int wdp, table; double psi, cc; };
 __device__ __forceinline__ ChildArgs child_args(const SweepChild& c) { return ChildArgs{c.ell, c.Wt, c.wdp, c.table, c.psi, c.cc}; }
-__device__ __noinline__ void sweep_child(const ChildArgs c, int f, size_t ld, int M, int Mw, double* col, int have) {
+__device__ __noinline__ void sweep_child(const ChildArgs c, int f, size_t ld, int M, int Mw, double* col, int have, double osc) {
     const bool resident = have != 0;
     if (c.ell == nullptr) {                        // leaf: column x_c of w* (one-hot likelihood)
         if (have) return;
@@ -697,20 +701,17 @@ __device__ __noinline__ void sweep_child(const ChildArgs c, int f, size_t ld, in
     }
     if (!resident) {
         const double* __restrict__ src = c.ell + f;
-        if (c.table) {
 #pragma unroll 1
-            for (int j = 0; j <= Mw; ++j) col[j * 32] = (j <= M) ? src[(size_t)j * ld] : 0.0;
-        } else {                                   // closed-form contraction wants u[j] = (j-1)!·ℓ[j]
-#pragma unroll 1
-            for (int j = 0; j <= Mw; ++j) col[j * 32] = (j <= M) ? src[(size_t)j * ld] * c_fact[j > 0 ? j - 1 : 0] : 0.0;
-        }
+        for (int j = 0; j <= Mw; ++j) col[j * 32] = (j <= M) ? src[(size_t)j * ld] : 0.0;
     }
     if (c.table) {
-        sweep_contract_table<16>(col, Mw, c.Wt, c.wdp);
+        sweep_contract_table<16>(col, Mw, c.Wt, c.wdp, osc);
     } else {
         const double psi = c.psi, cc = c.cc;
-        if (Mw <= 4) sweep_contract_fast<4>(col, Mw, psi, cc, have == 2);
-        else sweep_contract_fast<12>(col, Mw, psi, cc, have == 2);
+        if (have == 1) col[0] *= osc;              // b[0] = ℓ[0]
+        if (Mw <= 4) sweep_contract_horner<4>(col, Mw, psi, cc, osc);
+        else if (Mw <= 8) sweep_contract_horner<8>(col, Mw, psi, cc, osc);
+        else sweep_contract_horner<16>(col, Mw, psi, cc, osc);
     }
 }
 
@@ -746,6 +747,7 @@ __global__ void __launch_bounds__(128, MINB) sweep_kernel(const __grid_constant_
     const int fsh = (f & 1) * 16;
 
     int prevX = 0, prevScl = 0;      // count and exponent of the column left in the slice by the previous step
+    double prevSc = 1.0;             // ... which is still to be multiplied by this power of two (its stored copy already is)
     double* prevR = sl;
     long long t0_ = PROF ? clock64() : 0;
     {
@@ -784,6 +786,7 @@ __global__ void __launch_bounds__(128, MINB) sweep_kernel(const __grid_constant_
             sl[0] = v;
             prevX = 0;
             prevScl = 0;
+            prevSc = 1.0;
             prevR = sl;
             __syncwarp();
             BLG_TICK(0);
@@ -825,7 +828,7 @@ __global__ void __launch_bounds__(128, MINB) sweep_kernel(const __grid_constant_
             }
             cp_async_commit();
         }
-        sweep_child(child_args(ch[0]), f, ld, M0, M0w, R, res0 ? 1 : 0);
+        sweep_child(child_args(ch[0]), f, ld, M0, M0w, R, res0 ? 1 : 0, res0 ? prevSc : 1.0);
         if (async1) cp_async_wait_all();
         BLG_TICK(1);
         int Sw = M0w;
@@ -837,7 +840,7 @@ __global__ void __launch_bounds__(128, MINB) sweep_kernel(const __grid_constant_
                 const int Mi = (i == 1) ? M1 : (int)ch[i].cnt[f];
                 const int Miw = (i == 1) ? M1w : warp_max(Mi);
                 double* colB = R + (size_t)(Sw + 1) * 32;
-                sweep_child(child_args(ch[i]), f, ld, Mi, Miw, colB, (i == 1 && async1) ? 2 : 0);
+                sweep_child(child_args(ch[i]), f, ld, Mi, Miw, colB, (i == 1 && async1) ? 2 : 0, 1.0);
                 BLG_TICK(2);
                 const bool last = (i == k - 1);
                 const double em0 = last ? st.ip0 : 1.0, emg = last ? st.inv : 1.0;
@@ -850,10 +853,11 @@ __global__ void __launch_bounds__(128, MINB) sweep_kernel(const __grid_constant_
                 const double E = swap ? fmin(ch[1].e, 1.0) : ch[i].Epre;
                 const double e = swap ? ch[0].e : ch[i].e;
                 const double invE = swap ? ch[1].invEself : ((k == 2) ? ch[0].invEself : 1.0 / E);
+                const double inve = swap ? ch[0].invEself : ch[i].invEself;
                 double mx;
-                if (sW < 4) mx = sweep_merge_fast<4>(R, tA, tW, sB, sW, E, invE, e, em0, emg, Xm);
-                else if (sW < 12) mx = sweep_merge_fast<12>(R, tA, tW, sB, sW, E, invE, e, em0, emg, Xm);
-                else mx = sweep_merge_fast<24>(R, tA, tW, sB, sW, E, invE, e, em0, emg, Xm);
+                if (sW < 4) mx = sweep_merge_fast<4>(R, tA, tW, sB, sW, E, invE, e, inve, em0, emg, Xm);
+                else if (sW < 12) mx = sweep_merge_fast<12>(R, tA, tW, sB, sW, E, invE, e, inve, em0, emg, Xm);
+                else mx = sweep_merge_fast<24>(R, tA, tW, sB, sW, E, invE, e, inve, em0, emg, Xm);
                 Sw += Miw;
                 if (last) { mxv = mx; scaled = true; }
                 BLG_TICK(3);
@@ -867,7 +871,7 @@ __global__ void __launch_bounds__(128, MINB) sweep_kernel(const __grid_constant_
             for (int i = 1; i < k; ++i) {
                 const int Mi = (i == 1) ? M1 : (int)ch[i].cnt[f];
                 const int Miw = (i == 1) ? M1w : warp_max(Mi);
-                sweep_child(child_args(ch[i]), f, ld, Mi, Miw, rO, 0);
+                sweep_child(child_args(ch[i]), f, ld, Mi, Miw, rO, 0, 1.0);
 #pragma unroll 1
                 for (int n = Miw + 1; n <= Sw + Miw; ++n) rO[n * 32] = 0.0;
                 sweep_merge_tiled(rA, Sw, rO, Miw, rH, ch[i].Epre, ch[i].e);
@@ -904,25 +908,16 @@ __global__ void __launch_bounds__(128, MINB) sweep_kernel(const __grid_constant_
             const int be = (__double2hiint(mxv) >> 20) & 0x7ff;
             if (be != 0 && be != 0x7ff) ex = be - 1023;
         }
-        {
+        // the stored column is rescaled; the copy in R stays as it is — a parent that follows immediately applies the
+        // same power of two to the outputs of its contraction (exact, so both routes give the same bits)
+        const double sc = __hiloint2double((1023 - ex) << 20, 0);         // 2^-ex, exact (|ex| <= 1022)
+        if (live) {
             double* o = st.out + f;
-            const double sc = __hiloint2double((1023 - ex) << 20, 0);     // 2^-ex, exact (|ex| <= 1022)
-            const int keep = st.prefact;               // 0: the next step does not reuse the column; 1: plain; 2: times (n-1)!
-            if (keep == 0) {
-                if (live) {
 #pragma unroll 1
-                    for (int n = 0; n <= X; ++n) o[(size_t)n * ld] = R[n * 32] * sc;
-                }
-            } else {
-#pragma unroll 1
-                for (int n = 0; n <= Xw; ++n) {
-                    const double v = R[n * 32] * sc;
-                    R[n * 32] = (keep == 2) ? v * c_fact[n > 0 ? n - 1 : 0] : v;
-                    if (live && n <= X) o[(size_t)n * ld] = v;
-                }
-            }
-            if (live) st.out_scl[f] = sclsum + ex;
+            for (int n = 0; n <= X; ++n) o[(size_t)n * ld] = R[n * 32] * sc;
+            st.out_scl[f] = sclsum + ex;
         }
+        prevSc = sc;
         prevX = X;
         prevScl = sclsum + ex;
         prevR = R;
@@ -1484,8 +1479,7 @@ struct blg_handle {
                 SweepStep& ss = L.step[L.nsteps++];
                 ss.k = k; ss.first = nch; ss.prefact = 0;
                 ss.resident = (L.nsteps >= 2 && prev_node == st.child[0].id && !children[prev_node].empty()) ? 1 : 0;
-                // a resident column that will be contracted in closed form is left pre-multiplied by (n-1)!
-                if (ss.resident) L.step[L.nsteps - 2].prefact = (kind[prev_node] != BLG_WGDAFTER) ? 2 : 1;
+                if (ss.resident) L.step[L.nsteps - 2].prefact = 1;
                 prev_node = u;
                 double raw = 1.0;
                 ss.inv = h_nc[u].inv; ss.ip0 = poison_below[u] ? std::numeric_limits<double>::quiet_NaN() : h_nc[u].ip0;
