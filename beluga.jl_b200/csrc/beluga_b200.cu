@@ -529,6 +529,7 @@ __device__ __forceinline__ void cp_async_b32(int* smem_dst, const void* gsrc) {
 }
 __device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
 __device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_group 0;" ::: "memory"); }
+__device__ __forceinline__ void cp_async_wait_but_one() { asm volatile("cp.async.wait_group 1;" ::: "memory"); }
 
 // in-place table contraction (branch below a WGD/WGT): col[s] ← Σ_{j=s..Mw} Wt[j*wdp+s]·col[j]
 template <int TS>
@@ -637,7 +638,7 @@ __device__ __noinline__ double sweep_merge_fast(double* O, const double* A, int 
     }
     return mx;
 }
-// general merge for a smaller child with >= 24 counts: 16-wide tiles from high s to low s chained
+// general merge for a smaller child with >= 20 counts: 16-wide tiles from high s to low s chained
 // through the history column H.  A[0..Sw]; O[0..M2w] = B[0,·], O[M2w+1..Sw+M2w] = 0 on entry; result in O.
 __device__ __noinline__ void sweep_merge_tiled(const double* A, int Sw, double* O, int M2w, double* H, double E, double e) {
     constexpr int TS = 16;
@@ -724,10 +725,12 @@ __global__ void __launch_bounds__(128, MINB) sweep_kernel(const __grid_constant_
     extern __shared__ double smem[];
     const unsigned lane = threadIdx.x & 31u;
     const int warp = threadIdx.x >> 5;
-    // [4 warps][5 slots][32 lanes] ints: the next step's counts and exponents land here by cp.async (registers that
-    // are live across the helper calls get spilled right after their load, which made a register prefetch block)
-    int* cb = reinterpret_cast<int*>(smem) + (size_t)warp * 160 + lane;
-    double* sl = smem + (size_t)(blockDim.x >> 5) * 80 + (size_t)warp * slice_cap * 32 + lane;
+    // [warps][2 buffers][5 slots][32 lanes] ints: counts and exponents of the coming steps land here by cp.async, in the
+    // buffer of the step's parity.  Counts (static data) are requested TWO steps ahead, so that a run of empty steps
+    // — each far shorter than a trip to HBM — does not wait for every single one; exponents (written by earlier steps of
+    // this very launch) one step ahead.  Step j commits one group {counts(j+2), exponents(j+1)}.
+    int* cb = reinterpret_cast<int*>(smem) + (size_t)warp * 320 + lane;
+    double* sl = smem + (size_t)(blockDim.x >> 5) * 160 + (size_t)warp * slice_cap * 32 + lane;
     const int ntiles = (N + 31) / 32;
     // persistent grid, warp-granular work stealing: tiles (32 families, heaviest first) are handed out by an atomic
     // counter, so a batch that is a little more than one wave does not pay for a nearly empty second wave
@@ -750,34 +753,50 @@ __global__ void __launch_bounds__(128, MINB) sweep_kernel(const __grid_constant_
     double prevSc = 1.0;             // ... which is still to be multiplied by this power of two (its stored copy already is)
     double* prevR = sl;
     long long t0_ = PROF ? clock64() : 0;
-    {
-        const SweepStep& st = L.step[0];
-        const SweepChild* ch = &L.child[st.first];
-        cp_async_b32(cb + 0 * 32, st.cnt + fe);
-        cp_async_b32(cb + 1 * 32, ch[0].cnt + fe);
-        if (ch[0].scl) cp_async_b32(cb + 3 * 32, ch[0].scl + f);
-        if (st.k >= 2) { cp_async_b32(cb + 2 * 32, ch[1].cnt + fe); if (ch[1].scl) cp_async_b32(cb + 4 * 32, ch[1].scl + f); }
-        cp_async_commit();
-    }
+    auto request_counts = [&](int s) {
+        if (s < L.nsteps) {
+            const SweepStep& sn = L.step[s];
+            const SweepChild* cn = &L.child[sn.first];
+            int* b = cb + (s & 1) * 160;
+            cp_async_b32(b + 0 * 32, sn.cnt + fe);
+            if (!sn.resident) cp_async_b32(b + 1 * 32, cn[0].cnt + fe);
+            if (sn.k >= 2) cp_async_b32(b + 2 * 32, cn[1].cnt + fe);
+        }
+    };
+    auto request_exponents = [&](int s) {
+        if (s < L.nsteps) {
+            const SweepStep& sn = L.step[s];
+            const SweepChild* cn = &L.child[sn.first];
+            int* b = cb + (s & 1) * 160;
+            if (!sn.resident && cn[0].scl) cp_async_b32(b + 3 * 32, cn[0].scl + f);
+            if (sn.k >= 2 && cn[1].scl) cp_async_b32(b + 4 * 32, cn[1].scl + f);
+        }
+    };
+    cp_async_wait_all();
+    request_counts(0);
+    cp_async_commit();
+    request_counts(1);
+    request_exponents(0);
+    cp_async_commit();
     for (int si = 0; si < L.nsteps; ++si) {
         const SweepStep& st = L.step[si];
         const int k = st.k;
         const SweepChild* ch = &L.child[st.first];
         const bool res0 = st.resident != 0;
-        cp_async_wait_all();
-        const int X = (cb[0 * 32] >> fsh) & 0xffff;
-        const int M0 = res0 ? prevX : ((cb[1 * 32] >> fsh) & 0xffff);
-        const int M1 = (k >= 2) ? ((cb[2 * 32] >> fsh) & 0xffff) : 0;
-        int sclsum = (res0 ? prevScl : (ch[0].scl ? cb[3 * 32] : 0)) + ((k >= 2 && ch[1].scl) ? cb[4 * 32] : 0);
-        if (si + 1 < L.nsteps) {                       // prefetch the next step's counts (asynchronously, into cb)
-            const SweepStep& sn = L.step[si + 1];
-            const SweepChild* cn = &L.child[sn.first];
-            cp_async_b32(cb + 0 * 32, sn.cnt + fe);
-            if (!sn.resident) { cp_async_b32(cb + 1 * 32, cn[0].cnt + fe); if (cn[0].scl) cp_async_b32(cb + 3 * 32, cn[0].scl + f); }
-            if (sn.k >= 2) { cp_async_b32(cb + 2 * 32, cn[1].cnt + fe); if (cn[1].scl) cp_async_b32(cb + 4 * 32, cn[1].scl + f); }
-            cp_async_commit();
-        }
+        const int* b = cb + (si & 1) * 160;
+        cp_async_wait_but_one();                       // this step's counts are here; its exponents may still be on their way
+        const int X = (b[0 * 32] >> fsh) & 0xffff;
         const int Xw = warp_max(X);
+        int M0 = 0, M1 = 0, sclsum = 0;
+        if (Xw != 0) {
+            cp_async_wait_all();
+            M0 = res0 ? prevX : ((b[1 * 32] >> fsh) & 0xffff);
+            M1 = (k >= 2) ? ((b[2 * 32] >> fsh) & 0xffff) : 0;
+            sclsum = (res0 ? prevScl : (ch[0].scl ? b[3 * 32] : 0)) + ((k >= 2 && ch[1].scl) ? b[4 * 32] : 0);
+        }
+        request_counts(si + 2);                        // into the buffer just read
+        request_exponents(si + 1);
+        cp_async_commit();
         if (Xw == 0) {
             // no family of this warp has a gene below the node: ℓ = [1] whatever the parameters are (n = 0 lineages
             // leave no descendants with probability 1) — or the reference's NaN, which the host folded into ip0
@@ -797,12 +816,12 @@ __global__ void __launch_bounds__(128, MINB) sweep_kernel(const __grid_constant_
         int sumw = M0w + M1w;
         // which side of a binary merge is register-tiled: the child with the smaller bound in THIS warp
         const bool swap = (k == 2) && (M0w < M1w);
-        bool tiled = (k == 2) ? (min(M0w, M1w) >= 24) : (M1w >= 24);
+        bool tiled = (k == 2) ? (min(M0w, M1w) >= 20) : (M1w >= 20);
 #pragma unroll 1
         for (int i = 2; i < k; ++i) {
             const int Miw = warp_max((int)ch[i].cnt[f]);
             sumw += Miw;
-            if (Miw >= 24) tiled = true;
+            if (Miw >= 20) tiled = true;
             if (ch[i].scl) sclsum += ch[i].scl[f];
         }
         const int need = tiled ? 3 * (sumw + 1) : sumw + k + 1;
@@ -856,8 +875,9 @@ __global__ void __launch_bounds__(128, MINB) sweep_kernel(const __grid_constant_
                 const double inve = swap ? ch[0].invEself : ch[i].invEself;
                 double mx;
                 if (sW < 4) mx = sweep_merge_fast<4>(R, tA, tW, sB, sW, E, invE, e, inve, em0, emg, Xm);
+                else if (sW < 8) mx = sweep_merge_fast<8>(R, tA, tW, sB, sW, E, invE, e, inve, em0, emg, Xm);
                 else if (sW < 12) mx = sweep_merge_fast<12>(R, tA, tW, sB, sW, E, invE, e, inve, em0, emg, Xm);
-                else mx = sweep_merge_fast<24>(R, tA, tW, sB, sW, E, invE, e, inve, em0, emg, Xm);
+                else mx = sweep_merge_fast<20>(R, tA, tW, sB, sW, E, invE, e, inve, em0, emg, Xm);
                 Sw += Miw;
                 if (last) { mxv = mx; scaled = true; }
                 BLG_TICK(3);
@@ -913,8 +933,14 @@ __global__ void __launch_bounds__(128, MINB) sweep_kernel(const __grid_constant_
         const double sc = __hiloint2double((1023 - ex) << 20, 0);         // 2^-ex, exact (|ex| <= 1022)
         if (live) {
             double* o = st.out + f;
+            int n = 0;
 #pragma unroll 1
-            for (int n = 0; n <= X; ++n) o[(size_t)n * ld] = R[n * 32] * sc;
+            for (; n < X; n += 2) {                    // two loads in flight
+                const double v0 = R[n * 32], v1 = R[(n + 1) * 32];
+                o[(size_t)n * ld] = v0 * sc;
+                o[(size_t)(n + 1) * ld] = v1 * sc;
+            }
+            if (n == X) o[(size_t)n * ld] = R[n * 32] * sc;
             st.out_scl[f] = sclsum + ex;
         }
         prevSc = sc;
@@ -1108,6 +1134,7 @@ struct blg_handle {
     int profile_sweep = 0;
     DevBuf<unsigned long long> d_prof;
     int slice_cap = 50;                       // doubles per lane of the per-warp shared-memory slice
+    int sweep_wpb = 4;                        // warps per block of the sweep kernel (BLG_WPB: 1, 2 or 4)
     std::unique_ptr<SweepList> sweep_list{new SweepList()};
     DevBuf<unsigned int> d_tilectr;
     int sm_count = 148;
@@ -1497,20 +1524,21 @@ struct blg_handle {
                     raw *= sc.e;
                     int xm = Tp[cr.id].xmax;
                     sum += xm;
-                    if (c >= 1 && xm >= 24) tiled = true;
+                    if (c >= 1 && xm >= 20) tiled = true;
                 }
-                if (k == 2 && std::min(Tp[st.child[0].id].xmax, Tp[st.child[1].id].xmax) < 24) tiled = false;
+                if (k == 2 && std::min(Tp[st.child[0].id].xmax, Tp[st.child[1].id].xmax) < 20) tiled = false;
                 worst = std::max(worst, tiled ? 3 * (sum + 1) : sum + k + 1);
                 ++pos;
             }
             require(L.nsteps > 0, "sweep: a node has more children than one launch can describe");
-            const int warps_per_block = 4;
+            const int warps_per_block = sweep_wpb;            // 4 blocks of 4 warps, or 8 blocks of 2 warps, per SM
+            const int per_wave = sm_count * (16 / warps_per_block);
             int nwarps = (N + 31) / 32;
             int blocks = (nwarps + warps_per_block - 1) / warps_per_block;
             // small batches (up to ~3 waves): persistent grid with tile stealing, so a fractional last wave costs a
             // fraction; large batches: plain grid (measured 10 % faster on the 5-wave benchmark)
-            const bool persist = blocks <= sm_count * 4 * 3 && blocks > sm_count * 4;
-            if (persist) blocks = sm_count * 4;
+            const bool persist = blocks <= per_wave * 3 && blocks > per_wave;
+            if (persist) blocks = per_wave;
             d_tilectr.ensure(1);
             if (persist) CK(cudaMemsetAsync(d_tilectr.p, 0, sizeof(unsigned int), stream));
             int cap = std::min(slice_cap, worst);            // doubles per lane in the shared slice
@@ -1521,7 +1549,7 @@ struct blg_handle {
                 gscratch.ensure(gstride * (size_t)nwarps);
                 gs = gscratch.p;
             }
-            size_t smem = ((size_t)cap * 32 + 80) * warps_per_block * sizeof(double);
+            size_t smem = ((size_t)cap * 32 + 160) * warps_per_block * sizeof(double);
             if (smem > sweep_smem_set) {
                 CK(cudaFuncSetAttribute(sweep_kernel<false, 4, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
                 CK(cudaFuncSetAttribute(sweep_kernel<false, 4, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
@@ -2031,6 +2059,7 @@ int blg_create(int device, void* stream, blg_handle** out) {
         if (const char* o = getenv("BLG_ORDER")) h->order_resident = atoi(o) != 0;
         if (const char* o = getenv("BLG_PROF")) h->profile_sweep = atoi(o);
         if (const char* o = getenv("BLG_GRAD")) h->grad_mode = (strcmp(o, "forward") == 0) ? 0 : 1;
+        if (const char* w = getenv("BLG_WPB")) { int v = atoi(w); if (v == 1 || v == 2 || v == 4) h->sweep_wpb = v; }
         if (const char* sc = getenv("BLG_SLICE")) h->slice_cap = std::max(8, std::min(224, atoi(sc)));
         *out = h;
     } catch (const std::exception& e) { g_create_error = e.what(); return 2; }
