@@ -465,23 +465,25 @@ __global__ void __launch_bounds__(128) prune_node_kernel(const NodeStep st, cons
 //   * the per-family working column lives in a per-warp shared-memory slice laid out [index][lane]
 //     (conflict-free 64-bit accesses); a node needs S+3 doubles per family because both inner loops
 //     run IN PLACE;
-//   * NO coefficient tables are read in the inner loops.  They are generated in registers:
-//       contraction over an ordinary branch: w*(n|j) = C(j-1,n-1)·ψ'^(j-n)·c^n, c = (1-ϕ')(1-ψ')
-//         (closed form of the recurrence in wstar!, node.jl:181-192), hence for n >= 1
-//           b[n] = c^n/(n-1)! · Σ_{d>=0} [ψ'^d/d!] · [(n+d-1)!·ℓ[n+d]]
-//         — a sliding-window correlation: TS outputs and a TS-wide window stay in registers, one
-//         shared-memory load and TS FMAs per step;
+//   * NO coefficient tables are read in the inner loops and no register is moved there:
+//       contraction over an ordinary branch: Horner's rule on the recurrence of wstar! (node.jl:181-192),
+//           r[n] ← ψ'·r[n] + r[n-1]  for j = M..1 (r[0] := ℓ[j]),   b[n] = c^n·r[n],   c = (1-ϕ')(1-ψ')
+//         — one DFMA per element, TS accumulators in registers, tiles chained through the column itself
+//         (sweep_contract_horner);
 //       merge: C(n,s)·E^s = n!·E^n · 1/(t!·E^t) · 1/s!  (t+s = n), hence with a'[t] = A[t]/(t!E^t) and
-//         B†[t,s] = B[t,s]/s!:   B†[t,s] = (s+1)·B†[t-1,s+1] + e·B†[t-1,s]
-//                                 Ã[n]   = n!E^n · Σ_{t+s=n} a'[t]·B†[t,s]
-//         with the B† row and the anti-diagonal accumulators of the smaller child in registers;
+//         B‡[t,s] = B[t,s]·e^-(t+s)/s!:   B‡[t,s] = (s+1)·B‡[t-1,s+1] + B‡[t-1,s]      (one DFMA, immediate multiplier)
+//                                          acc[k] ← acc[k+1] + a'[t+1]·B‡[t+1,k]         (the slide is the FMA's addend)
+//                                          Ã[n]   = n!E^n · e^n · acc[0] at step n
+//         with the B‡ row and the anti-diagonal accumulators of the smaller child in registers (sweep_merge_fast);
 //     the branch below a WGD/WGT keeps its (banded) table, read from global memory;
-//   * the factorial scalings limit this kernel to count bounds <= BLG_FAST_MAXCOUNT and to parameter
+//   * the scalings (1/t!E^t, e^-n) limit this kernel to count bounds <= BLG_FAST_MAXCOUNT and to parameter
 //     ranges where they stay inside fp64 (checked per node on the device when ε/W are built);
 //     otherwise the per-node general kernels above are used;
 //   * the code is kept SMALL on purpose (rolled loops, noinline helpers, one merge dispatch): with 16 warps per SM
 //     at different places of the sweep, the kernel's speed follows its instruction-cache footprint more closely than
-//     anything else (80 KB of SASS: 12.0 ms per benchmark sweep; 54 KB: 2.7 ms; 41 KB: 2.3 ms — same arithmetic).
+//     anything else (80 KB of SASS: 12.0 ms per benchmark sweep; 54 KB: 2.7 ms; 41 KB: 2.3 ms — same arithmetic);
+//   * no helper may use so many registers that the kernel's loop invariants get spilled around the calls (the widest
+//     merge is 20 for that reason): a spill reload here is an L2 round trip.
 __constant__ double c_fact[BLG_FAST_MAXCOUNT + 72];      // n!
 __constant__ double c_invfact[BLG_FAST_MAXCOUNT + 72];   // 1/n!
 __constant__ double c_inv[BLG_FAST_MAXCOUNT + 72];       // 1/n (c_inv[0] = 0)
@@ -499,8 +501,8 @@ struct SweepChild {
 };
 struct SweepStep {
     int k, first, resident, prefact;   // resident != 0: child[0] is the node of the previous step (its column is still in shared memory)
-                                       // prefact != 0: the NEXT step reuses this node's column, which therefore stays in
-                                       // shared memory (rescaled) after the final write
+                                       // prefact != 0: the NEXT step reuses this node's column (informational: the column
+                                       // always stays in the slice, unscaled, see prevSc)
     double inv, ip0;                // 1/(1-E_k); (1-E_k)^0, NaN where the reference's column would be NaN
     double* out;
     int* out_scl;
