@@ -313,6 +313,30 @@ def test_high_counts_scratch_and_general_fallback():
         assert close(B.logpdf_(model[4], data), orc.logpdf_from(4), 1e-11), (hi, nfam)
 
 
+def test_short_branches_tiny_extinction_probabilities():
+    # ϵ of a child on a very short branch is tiny and the table-free merge scales its row by ϵ^-n: inside the per-node
+    # range rule (tables_kernel) the sweep kernel must still agree with the oracle, outside of it the general per-node
+    # kernels must take over — same answer either way
+    names = list("ABCDE")
+    rng = np.random.default_rng(123)
+    counts = rng.integers(0, 9, size=(70, 5)).astype(np.int64)
+    counts[0] = [20, 20, 1, 2, 3]                                # the cherry (A,B) reaches 40 lineages
+    counts[1] = [0, 19, 0, 18, 1]
+    counts[-1] = [17, 0, 3, 0, 0]
+    for tshort, fast in ((1e-4, True), (1e-8, False)):
+        nw = "((A:%g,B:%g):0.3,(C:0.6,(D:%g,E:0.3):0.2):0.25);" % (tshort, 2 * tshort, 3 * tshort)
+        model, data, orc = pair(nw, (names, counts), 0.9, 1.0, 0.8, B.BRANCH)
+        got = B.logpdf_(model, data)
+        want, pf = orc.logpdf(per_family=True)
+        assert close(got, want, 1e-10), (tshort, got, want)
+        np.testing.assert_allclose(data.family_logpdf(), pf, rtol=1e-10)
+        launches = data.last_algorithmic()[2]
+        assert (launches == 2) == fast, (tshort, launches)       # 2 = sweep_kernel + root_kernel
+        B.set_(data); orc.set()
+        B.update_(model[3], λ=1.4, μ=0.6); orc.update(3, lam=1.4, mu=0.6)
+        assert close(B.logpdf_(model[3], data), orc.logpdf_from(3), 1e-10), tshort
+
+
 def test_sparse_profiles_empty_subtrees_and_partial_paths():
     # most families have no gene in most clades: the sweep skips a node for a warp whose 32 families are all empty
     # below it; every partial path and the commit/revert cycle must still agree with the oracle
