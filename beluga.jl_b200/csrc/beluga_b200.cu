@@ -484,7 +484,7 @@ __global__ void __launch_bounds__(128) prune_node_kernel(const NodeStep st, cons
 //     anything else (80 KB of SASS: 12.0 ms per benchmark sweep; 54 KB: 2.7 ms; 41 KB: 2.3 ms — same arithmetic);
 //   * no helper may use so many registers that the kernel's loop invariants get spilled around the calls (the widest
 //     merge is 20 for that reason): a spill reload here is an L2 round trip.
-__constant__ double c_fact[BLG_FAST_MAXCOUNT + 72];      // n!
+__constant__ double c_fact[BLG_FAST_MAXCOUNT + 72];      // n! (not read any more since the Horner contraction; removing it perturbs ptxas scheduling of the profiled kernel: next round)
 __constant__ double c_invfact[BLG_FAST_MAXCOUNT + 72];   // 1/n!
 __constant__ double c_inv[BLG_FAST_MAXCOUNT + 72];       // 1/n (c_inv[0] = 0)
 
