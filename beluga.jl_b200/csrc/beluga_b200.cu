@@ -30,8 +30,8 @@
 #include "beluga_b200.h"
 
 #define BLG_MAXK 8          // max children of one node (polytomies)
-#define BLG_MAXCOUNT 1023   // largest extended count supported (binomials stay finite in fp64)
-#define BLG_FAST_MAXCOUNT 100   // largest count bound the table-free sweep kernel handles
+#define BLG_MAXCOUNT 4095   // largest extended count supported (general kernel: probability-form recursion, no tables)
+#define BLG_FAST_MAXCOUNT 100   // largest count bound the table-free sweep kernel handles (families above it: heavy shard)
 
 namespace {
 
@@ -55,7 +55,8 @@ struct NodeTab {        // per node id, device-resident tables
     int wdim;           // xmax + 1
     int wdp;            // row stride, wdim rounded up to BLG_TS (padding is zero)
     double* ipow;       // (1-E_k)^(-n), n = 0..nrow-1  (NaN-poisoned when the reference would be)
-    int nrow;           // xmax_u + 1
+    int nrow;           // xmax_u + 1 (fast shard; 0 when it holds no family)
+    int xfast;          // count bound of this column in the fast shard
     // merge coefficients for the child in merge position i >= 1, diagonal-major:
     // coefD[i][t*cdp[i] + s] = C(t+s, s)·E_{i-1}^s  (0 where t+s > xmax_u or s > xmax of that child)
     double* coefD[BLG_MAXK];
@@ -63,11 +64,23 @@ struct NodeTab {        // per node id, device-resident tables
     int mo[BLG_MAXK];   // merge order: node indices of the children in the order they are merged
 };
 
-struct SweepNodeConst {       // per node id, written by tables_kernel, read by sweep_kernel
-    double psi, cc;           // ψ', (1-ϕ')(1-ψ') of the (ordinary) branch above the node
-    double E[BLG_MAXK];       // clamped prefix products of the children's ϵ[1] in merge order (E[0] = 1)
-    double inv, ip0;          // 1/(1-E_k) and (1-E_k)^0 — ip0 is NaN when the reference's column would be NaN
+// per node id, DEVICE-RESIDENT: written by tables_kernel at every parameter update, read by the pruning kernels by node
+// index (the host never needs these numbers, so a parameter update involves no read-back).  80 bytes, 16-byte aligned:
+// the sweep kernel stages {e, inve, psi, cc} and {inv, ip0} with 16-byte cp.async.
+struct NodeK {
+    // the node as a CHILD (the branch above it)
+    double e;                 // ϵ[1]: extinction probability of one lineage at the top of the branch
+    double inve;              // 1/min(e, 1)
+    double psi, cc;           // ψ', c = (1-ϕ')(1-ψ') of an ordinary branch
+    double chat;              // c/(1-e) (ordinary branch);  a/(1-e) below a WGD  (general kernel)
+    double bhat;              // b/(1-e) below a WGD
+    // the node as a PARENT
+    double inv;               // 1/(1-E_k)
+    double ip0;               // 1, or NaN when the reference's column is NaN here or anywhere below (model.jl:433-435)
+    double ip0raw;            // the same for this node alone
+    double pad_;
 };
+static_assert(sizeof(NodeK) == 80, "NodeK layout");
 
 struct ModelDev {
     int n;                     // ncols (max id)
@@ -86,10 +99,16 @@ struct ModelDev {
     NodeTab* tab;
     const double* pascal;      // C(n,s), row stride pdim
     int pdim;
-    SweepNodeConst* nc;        // per-node scalars of the table-free sweep kernel
-    int* fast_ok;              // per node: 1 if the factorial-scaled forms stay inside fp64 here
+    NodeK* nk;                 // per-node scalars of the pruning kernels
+    int* fast_ok;              // per node: 1 if the factorial-scaled forms of the sweep kernel stay inside fp64 here
     double* rootw;             // root integration weights, rebuilt with the root's tables (nullptr: not now)
+    double* rootlw;            // ... in log form (heavy shard; nullptr: not needed)
     int rootw_n;
+    // summary written by the last block of tables_kernel: flags[0] = every present node is fast_ok
+    int* flags;
+    unsigned int* ticket;
+    const int* post;           // all present nodes in post-order
+    int npost;
 };
 
 __device__ __forceinline__ bool d_isapprox(double a, double b) {
@@ -183,7 +202,9 @@ __device__ __forceinline__ double d_log1mexp(double x) { return x < -0.693147180
 // rootw[n] = exp((n)·log1mexp(lε) + log η + (n-1)·log(1-η) - (n+1)·log1mexp(log(1-η)+lε)), n >= 1;
 // rootw[0] holds the conditioning constant log(1-r_1) + log(1-r_2) (+Inf marks "invalid").
 // (integrate_root model.jl:465-475, condition_oib model.jl:492-501; one block, tid of nt threads)
-__device__ void d_root_tables(const ModelDev& m, double* rootw, int nrow, int tid, int nt) {
+// rootlw (optional): the same weights in log form, n >= 1 — the heavy shard's root kernel needs them: with root counts in the
+// hundreds the linear weights underflow long before the products ℓ[n]·weight[n] do.
+__device__ void d_root_tables(const ModelDev& m, double* rootw, double* rootlw, int nrow, int tid, int nt) {
     int root = 0;
     double eta = m.eta;
     double le = log(m.eps1[root]);
@@ -192,6 +213,7 @@ __device__ void d_root_tables(const ModelDev& m, double* rootw, int nrow, int ti
         double f = (double)n * a + b + (double)(n - 1) * c;
         f -= (double)(n + 1) * d;
         rootw[n] = exp(f);
+        if (rootlw) rootlw[n] = f;
     }
     if (tid == 0) {
         int c0 = m.child_off[root], c1 = m.child_off[root + 1];
@@ -210,18 +232,24 @@ __device__ void d_root_tables(const ModelDev& m, double* rootw, int nrow, int ti
     }
 }
 
-// setW! (node.jl:164-218) and the per-node merge tables, one block per listed node.
+// setW! (node.jl:164-218), the per-node scalars of the pruning kernels (NodeK) and the merge tables of the gradient
+// kernels, one block per listed node (the list holds every node once).  The W table is only filled where one is
+// allocated (tb.Wt != nullptr: dimensions of the FAST shard, i.e. counts <= BLG_FAST_MAXCOUNT; the branch below a WGT keeps
+// a table for both shards); the general kernel needs no table for ordinary branches and branches below a WGD.
+// The last block to finish folds the NaN rule over the tree (a NaN column makes every column above it NaN) and publishes
+// flags[0] = "every node is inside the table-free sweep kernel's range" — no host round trip.
 __global__ void __launch_bounds__(128) tables_kernel(ModelDev m, const int* __restrict__ list, int nlist) {
-    extern __shared__ double sm[];   // 2 * maxdim doubles
+    extern __shared__ double sm[];   // max(2 * maxdim doubles, ncols ints)
+    __shared__ bool last_block;
     int n = list[blockIdx.x];
     const NodeTab tb = m.tab[n];
     const int tid = threadIdx.x, nt = blockDim.x;
     uint8_t kd = m.kind[n];
     bool ok = true;                 // may the table-free sweep kernel be used at this node?
-    if (tid == 0) { m.nc[n].psi = 0.0; m.nc[n].cc = 0.0; }
-    // ---- W of the branch above n -------------------------------------------------------------
-    if (kd != BLG_ROOT && tb.Wt != nullptr) {
-        const int d = tb.wdim;
+    const double NaN = __longlong_as_double(0x7ff8000000000000LL);
+    // ---- the branch above n ---------------------------------------------------------------------
+    if (kd != BLG_ROOT) {
+        const int d = tb.Wt ? tb.wdim : 0;
         const int dp = tb.wdp;
         double* W = tb.Wt;            // element (row n, column j) of w* lives at W[j*dp + n]
 #define WT(n_, j_) W[(size_t)(j_) * dp + (n_)]
@@ -229,16 +257,26 @@ __global__ void __launch_bounds__(128) tables_kernel(ModelDev m, const int* __re
         __syncthreads();
         int par = m.parent[n];
         double e = m.eps1[n];
+        const double etop = m.eps0[n];           // ϵ[1] of n: final, eps_kernel has finished
+        if (tid == 0) {
+            NodeK& k_ = m.nk[n];
+            k_.e = etop;
+            k_.inve = 1.0 / (etop > 1.0 ? 1.0 : etop);
+            k_.psi = 0.0; k_.cc = 0.0; k_.chat = 0.0; k_.bhat = 0.0;
+        }
         if (kd == BLG_WGDAFTER && m.kind[par] == BLG_WGD) {                         // wstar_wgd!
             double q = m.q[par];
             double a = ((1.0 - q) + 2.0 * q * e) * (1.0 - e);
             double b = q * ((1.0 - e) * (1.0 - e));
-            if (tid == 0) { WT(0, 0) = 1.0; if (d > 1) WT(1, 1) = a; if (d > 2) WT(1, 2) = b; }
-            __syncthreads();
-            for (int i = 1; i < d; ++i) {
-                for (int j = 2 + tid; j < d; j += nt)
-                    WT(i, j) = a * WT(i - 1, j - 1) + b * WT(i - 1, j - 2);
+            if (tid == 0) { m.nk[n].chat = a / (1.0 - etop); m.nk[n].bhat = b / (1.0 - etop); }
+            if (d > 0) {
+                if (tid == 0) { WT(0, 0) = 1.0; if (d > 1) WT(1, 1) = a; if (d > 2) WT(1, 2) = b; }
                 __syncthreads();
+                for (int i = 1; i < d; ++i) {
+                    for (int j = 2 + tid; j < d; j += nt)
+                        WT(i, j) = a * WT(i - 1, j - 1) + b * WT(i - 1, j - 2);
+                    __syncthreads();
+                }
             }
         } else if (kd == BLG_WGDAFTER && m.kind[par] == BLG_WGT) {                  // wstar_wgt! (literal, j from 3)
             double q = m.q[par];
@@ -246,12 +284,14 @@ __global__ void __launch_bounds__(128) tables_kernel(ModelDev m, const int* __re
             double a = q1 * ome + 2.0 * q2 * e * ome + 3.0 * q3 * (e * e) * ome;
             double b = q2 * (ome * ome) + 3.0 * q3 * e * (ome * ome);
             double c = q3 * (ome * ome * ome);
-            if (tid == 0) { WT(0, 0) = 1.0; if (d > 1) WT(1, 1) = a; if (d > 2) WT(1, 2) = b; if (d > 3) WT(1, 3) = c; }
-            __syncthreads();
-            for (int i = 1; i < d; ++i) {
-                for (int j = 3 + tid; j < d; j += nt)
-                    WT(i, j) = a * WT(i - 1, j - 1) + b * WT(i - 1, j - 2) + c * WT(i - 1, j - 3);
+            if (d > 0) {
+                if (tid == 0) { WT(0, 0) = 1.0; if (d > 1) WT(1, 1) = a; if (d > 2) WT(1, 2) = b; if (d > 3) WT(1, 3) = c; }
                 __syncthreads();
+                for (int i = 1; i < d; ++i) {
+                    for (int j = 3 + tid; j < d; j += nt)
+                        WT(i, j) = a * WT(i - 1, j - 1) + b * WT(i - 1, j - 2) + c * WT(i - 1, j - 3);
+                    __syncthreads();
+                }
             }
         } else {                                                                     // wstar!
             double l, mu;
@@ -262,43 +302,46 @@ __global__ void __launch_bounds__(128) tables_kernel(ModelDev m, const int* __re
             double phip = d_approx1((phi * (1.0 - e) + (1.0 - psi) * e) / nn);
             double psip = d_approx1(psi * (1.0 - e) / nn);
             double cc = (1.0 - phip) * (1.0 - psip);
-            if (tid == 0) { m.nc[n].psi = psip; m.nc[n].cc = cc; }
-            {   // range of ψ'^d/d! and c^n/(n-1)! over the count bound of this column
-                const int xm = d - 1;
+            if (tid == 0) { m.nk[n].psi = psip; m.nk[n].cc = cc; m.nk[n].chat = cc / (1.0 - etop); }
+            {   // range of ψ'^d/d! and c^n/(n-1)! over the count bound of this column (fast shard)
+                const int xm = tb.xfast;
                 if (xm > BLG_FAST_MAXCOUNT) ok = false;
                 if (!(psip >= 0.0 && psip <= 1.0 && cc >= 0.0 && cc <= 1.0)) ok = false;
                 if (psip > 0.0 && xm * log(psip) - lgamma(xm + 1.0) < -640.0) ok = false;
                 if (cc > 0.0 && xm * log(cc) - lgamma((double)(xm > 0 ? xm : 1)) < -640.0) ok = false;
             }
-            double* prev = sm;
-            double* cur = sm + d;
-            for (int i = tid; i < d; i += nt) prev[i] = (i == 0) ? 1.0 : 0.0;   // column 0
-            if (tid == 0) WT(0, 0) = 1.0;
-            __syncthreads();
-            for (int j = 1; j < d; ++j) {
-                for (int r = tid; r < d; r += nt) {
-                    double v = 0.0;
-                    if (r >= 1 && r <= j) v = psip * prev[r] + cc * prev[r - 1];
-                    cur[r] = v;
-                    if (r >= 1 && r <= j) WT(r, j) = v;
-                }
+            if (d > 0) {
+                double* prev = sm;
+                double* cur = sm + d;
+                for (int i = tid; i < d; i += nt) prev[i] = (i == 0) ? 1.0 : 0.0;   // column 0
+                if (tid == 0) WT(0, 0) = 1.0;
                 __syncthreads();
-                double* tmp = prev; prev = cur; cur = tmp;
+                for (int j = 1; j < d; ++j) {
+                    for (int r = tid; r < d; r += nt) {
+                        double v = 0.0;
+                        if (r >= 1 && r <= j) v = psip * prev[r] + cc * prev[r - 1];
+                        cur[r] = v;
+                        if (r >= 1 && r <= j) WT(r, j) = v;
+                    }
+                    __syncthreads();
+                    double* tmp = prev; prev = cur; cur = tmp;
+                }
             }
         }
 #undef WT
     }
-    // ---- merge tables of n (internal nodes) -----------------------------------------------------
+    // ---- n as a parent: normalisation, NaN rule, range rule, merge tables of the gradient kernels -----------------------
     int c0 = m.child_off[n], c1 = m.child_off[n + 1];
     int k = c1 - c0;
-    if (k > 0 && tb.ipow != nullptr) {
+    if (k > 0) {
         // _ϵ = cumprod([1; ϵ_c[1]...]) then clamp >1 to 1 (model.jl:415-419)
         double E[BLG_MAXK + 1];
         double raw = 1.0;
         bool poison = false;
         E[0] = 1.0;
+        const bool have_mo = tb.ipow != nullptr;
         for (int i = 0; i < k; ++i) {          // prefixes in MERGE order: what the merge coefficients use
-            raw *= m.eps0[tb.mo[i]];
+            raw *= m.eps0[have_mo ? tb.mo[i] : m.child_idx[c0 + i]];
             E[i + 1] = raw > 1.0 ? 1.0 : raw;
         }
         raw = 1.0;
@@ -311,37 +354,70 @@ __global__ void __launch_bounds__(128) tables_kernel(ModelDev m, const int* __re
         }
         double inv = 1.0 / (1.0 - E[k]);
         if (tid == 0) {
-            for (int i = 0; i < k; ++i) m.nc[n].E[i] = E[i];
-            m.nc[n].inv = inv;
-            m.nc[n].ip0 = poison ? __longlong_as_double(0x7ff8000000000000LL) : 1.0;
+            m.nk[n].inv = inv;
+            m.nk[n].ip0raw = poison ? NaN : 1.0;
         }
-        if (tb.nrow - 1 > BLG_FAST_MAXCOUNT) ok = false;
+        const int nrow = tb.nrow;              // fast-shard bound of this column + 1 (0: no fast families)
+        if (nrow - 1 > BLG_FAST_MAXCOUNT) ok = false;
         // the fast merge scales the "t" side by E^-t (E: prefix product; in a binary merge the e of whichever child is
         // the "t" side in a warp) and the register-tiled side by e^-n (that child's own e): both must stay inside fp64
         // over the count bound of this node
         for (int i = 1; i < k; ++i)
-            if (!poison && !(E[i] > 0.0 && -(double)tb.nrow * log(E[i]) < 600.0)) ok = false;
+            if (!poison && !(E[i] > 0.0 && -(double)nrow * log(E[i]) < 600.0)) ok = false;
         if (k >= 2) {
             for (int i = 0; i < k; ++i) {
-                const double ei = m.eps0[tb.mo[i]];
-                if (!poison && !(ei > 0.0 && ei <= 1.0 && -(double)tb.nrow * log(ei) < 600.0)) ok = false;
+                const double ei = m.eps0[m.child_idx[c0 + i]];
+                if (!poison && !(ei > 0.0 && ei <= 1.0 && -(double)nrow * log(ei) < 600.0)) ok = false;
             }
         }
-        for (int r = tid; r < tb.nrow; r += nt) tb.ipow[r] = poison ? __longlong_as_double(0x7ff8000000000000LL) : d_powi(inv, r);
-        for (int i = 1; i < k; ++i) {
-            double* cf = tb.coefD[i];
-            int cs = tb.cdp[i];
-            int smax = m.tab[tb.mo[i]].wdim - 1;      // xmax of that child
-            double p = E[i];
-            for (int idx = tid; idx < tb.nrow * cs; idx += nt) {
-                int t = idx / cs, s = idx - t * cs;
-                int r = t + s;
-                cf[idx] = (r < tb.nrow && s <= smax) ? m.pascal[(size_t)r * m.pdim + s] * d_powi(p, s) : 0.0;
+        if (tb.ipow != nullptr) {
+            for (int r = tid; r < nrow; r += nt) tb.ipow[r] = poison ? NaN : d_powi(inv, r);
+            for (int i = 1; i < k; ++i) {
+                double* cf = tb.coefD[i];
+                if (cf == nullptr) continue;
+                int cs = tb.cdp[i];
+                int smax = m.tab[tb.mo[i]].xfast;      // fast-shard bound of that child
+                double p = E[i];
+                for (int idx = tid; idx < nrow * cs; idx += nt) {
+                    int t = idx / cs, s = idx - t * cs;
+                    int r = t + s;
+                    cf[idx] = (r < nrow && s <= smax) ? m.pascal[(size_t)r * m.pdim + s] * d_powi(p, s) : 0.0;
+                }
             }
         }
+    } else if (tid == 0) {
+        m.nk[n].inv = 1.0;
+        m.nk[n].ip0raw = 1.0;
     }
     if (tid == 0) m.fast_ok[n] = ok ? 1 : 0;
-    if (kd == BLG_ROOT && m.rootw != nullptr) d_root_tables(m, m.rootw, m.rootw_n, tid, nt);   // ϵ of the root's children is final here
+    if (kd == BLG_ROOT && m.rootw != nullptr) d_root_tables(m, m.rootw, m.rootlw, m.rootw_n, tid, nt);   // ϵ of the root's children is final here
+    // ---- last block: NaN rule over the tree, fast-path summary ------------------------------------------------------
+    __syncthreads();
+    if (tid == 0) {
+        __threadfence();
+        last_block = atomicAdd(m.ticket, 1u) == gridDim.x - 1;
+    }
+    __syncthreads();
+    if (last_block) {
+        __threadfence();
+        int* pz = reinterpret_cast<int*>(sm);
+        for (int i = tid; i < m.n; i += nt) pz[i] = isnan(__ldcg(&m.nk[i].ip0raw)) ? 1 : 0;
+        __syncthreads();
+        if (tid == 0) {
+            int all_ok = 1;
+            for (int li = 0; li < m.npost; ++li) {
+                const int u = m.post[li];
+                int p = (m.child_off[u + 1] > m.child_off[u]) ? pz[u] : 0;
+                for (int ci = m.child_off[u]; ci < m.child_off[u + 1]; ++ci) p |= pz[m.child_idx[ci]];
+                pz[u] = p;
+                if (__ldcg(&m.fast_ok[u]) == 0) all_ok = 0;
+            }
+            m.flags[0] = all_ok;
+            *m.ticket = 0u;
+        }
+        __syncthreads();
+        for (int li = tid; li < m.npost; li += nt) { const int u = m.post[li]; m.nk[u].ip0 = pz[u] ? NaN : 1.0; }
+    }
 }
 
 // Pascal triangle C(n,s), n,s < dim, by the addition recurrence (exact while < 2^53).
@@ -397,66 +473,6 @@ struct NodeStep {
 // The children of a node may be merged in any order (ℓ_u does not depend on it); the host puts
 // the child with the smaller counts first.
 
-// ---- v1: one launch per node, per-thread arrays in local memory.  Kept as the general fallback
-// (any count up to BLG_MAXCOUNT) and as an A/B reference for the sweep kernel below. ---------------
-template <int CAP>
-__global__ void __launch_bounds__(128) prune_node_kernel(const NodeStep st, const double* __restrict__ eps0, int N, size_t ld) {
-    int f = blockIdx.x * blockDim.x + threadIdx.x;
-    if (f >= N) return;
-    double A0[CAP], A1[CAP], Bc[CAP], lc[CAP];
-    double* Acur = A0;
-    double* Anew = A1;
-    int S = 0;
-    int sclsum = 0;
-    for (int i = 0; i < st.k; ++i) {
-        const ChildRef& c = st.child[i];
-        const int Mi = c.cnt[f];
-        const double* __restrict__ Wt = c.Wt;
-        const int wd = c.wdp;
-        if (c.ell == nullptr) {
-            for (int s = 0; s <= Mi; ++s) Bc[s] = Wt[(size_t)Mi * wd + s];
-        } else {
-            for (int j = 0; j <= Mi; ++j) lc[j] = c.ell[(size_t)j * ld + f];
-            sclsum += c.scl[f];
-            for (int s = 0; s <= Mi; ++s) {
-                double acc = 0.0;
-                for (int j = s; j <= Mi; ++j) acc = fma(Wt[(size_t)j * wd + s], lc[j], acc);
-                Bc[s] = acc;
-            }
-        }
-        if (i == 0) {
-            for (int n = 0; n <= Mi; ++n) Acur[n] = Bc[n];
-            S = Mi;
-        } else {
-            const double e = eps0[c.id];
-            const double* __restrict__ cf = c.coefD;
-            const int cs = c.cdp;
-            for (int n = 0; n <= S + Mi; ++n) Anew[n] = 0.0;
-            for (int t = 0; t <= S; ++t) {
-                const double a = Acur[t];
-                for (int s = 0; s <= Mi; ++s) Anew[t + s] = fma(cf[(size_t)t * cs + s], a * Bc[s], Anew[t + s]);
-                for (int s = 0; s < Mi; ++s) Bc[s] = fma(e, Bc[s], Bc[s + 1]);
-                Bc[Mi] = e * Bc[Mi];
-            }
-            double* tmp = Acur; Acur = Anew; Anew = tmp;
-            S += Mi;
-        }
-    }
-    const int X = st.cnt[f];   // == S for a consistent extended profile
-    double mxv = 0.0;
-    bool bad = false;
-    for (int n = 0; n <= X; ++n) {
-        double v = (n <= S ? Acur[n] : 0.0) * st.ipow[n];
-        Acur[n] = v;
-        if (!(v == v) || isinf(v)) bad = true;
-        mxv = fmax(mxv, v);
-    }
-    int ex = 0;
-    if (!bad && mxv > 0.0) ex = ilogb(mxv);
-    for (int n = 0; n <= X; ++n) st.out[(size_t)n * ld + f] = (ex != 0) ? scalbn(Acur[n], -ex) : Acur[n];
-    st.out_scl[f] = sclsum + ex;
-}
-
 // ---- the sweep kernel.  ONE launch walks a list of nodes (a full post-order sweep, or the path
 // node→root of a partial recompute).  A warp owns 32 consecutive families for the whole list and never
 // synchronises with another warp: a parent only reads what the same thread wrote.
@@ -484,9 +500,8 @@ __global__ void __launch_bounds__(128) prune_node_kernel(const NodeStep st, cons
 //     anything else (80 KB of SASS: 12.0 ms per benchmark sweep; 54 KB: 2.7 ms; 41 KB: 2.3 ms — same arithmetic);
 //   * no helper may use so many registers that the kernel's loop invariants get spilled around the calls (the widest
 //     merge is 20 for that reason): a spill reload here is an L2 round trip.
-__constant__ double c_fact[BLG_FAST_MAXCOUNT + 72];      // n! (not read any more since the Horner contraction; removing it perturbs ptxas scheduling of the profiled kernel: next round)
 __constant__ double c_invfact[BLG_FAST_MAXCOUNT + 72];   // 1/n!
-__constant__ double c_inv[BLG_FAST_MAXCOUNT + 72];       // 1/n (c_inv[0] = 0)
+__constant__ double c_inv[BLG_MAXCOUNT + 9];             // 1/n (c_inv[0] = 0)
 
 struct SweepChild {
     const double* ell;     // nullptr: leaf
@@ -494,22 +509,17 @@ struct SweepChild {
     const uint16_t* cnt;
     const double* Wt;      // transposed w* of the child's branch (leaf gather, WGD/WGT-after contraction)
     int wdp, table;        // table != 0: contract with Wt (branch below a WGD/WGT)
-    double invEself;       // 1/min(e, 1)
-    double e;              // ϵ[1] of the child (extinction probability at the top of its branch)
-    double Epre;           // clamped product of the e's of the children merged before this one (1 for the first)
-    double psi, cc;        // ψ', (1-ϕ')(1-ψ') of the child's branch
+    int node, pad_;        // node index of the child: its scalars {e, 1/min(e,1), ψ', c} are read from NodeK on the device
 };
 struct SweepStep {
-    int k, first, resident, prefact;   // resident != 0: child[0] is the node of the previous step (its column is still in shared memory)
-                                       // prefact != 0: the NEXT step reuses this node's column (informational: the column
-                                       // always stays in the slice, unscaled, see prevSc)
-    double inv, ip0;                // 1/(1-E_k); (1-E_k)^0, NaN where the reference's column would be NaN
+    int k, first, resident, node;      // resident != 0: child[0] is the node of the previous step (its column is still in shared memory)
+                                       // node: index of the node itself: {1/(1-E_k), NaN flag} are read from NodeK on the device
     double* out;
     int* out_scl;
     const uint16_t* cnt;
 };
-#define BLG_SWEEP_MAXSTEPS 160
-#define BLG_SWEEP_MAXCHILD 280
+#define BLG_SWEEP_MAXSTEPS 224
+#define BLG_SWEEP_MAXCHILD 400
 struct SweepList {
     int nsteps;
     int pad_[3];
@@ -528,6 +538,10 @@ __device__ __forceinline__ void cp_async_f64(double* smem_dst, const double* gsr
 __device__ __forceinline__ void cp_async_b32(int* smem_dst, const void* gsrc) {
     const unsigned d = (unsigned)__cvta_generic_to_shared(smem_dst);
     asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(d), "l"(gsrc) : "memory");
+}
+__device__ __forceinline__ void cp_async_b128(double* smem_dst, const double* gsrc) {
+    const unsigned d = (unsigned)__cvta_generic_to_shared(smem_dst);
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 16;" ::"r"(d), "l"(gsrc) : "memory");
 }
 __device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
 __device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_group 0;" ::: "memory"); }
@@ -692,7 +706,7 @@ __device__ __noinline__ void sweep_merge_tiled(const double* A, int Sw, double* 
 // (the descriptor fields travel by value: read through a reference, inside a noinline function, they were generic loads
 // from the parameter bank that missed the carved-down L1 — a long-scoreboard stall at the top of every call)
 struct ChildArgs { const double* ell; const double* Wt; int wdp, table; double psi, cc; };
-__device__ __forceinline__ ChildArgs child_args(const SweepChild& c) { return ChildArgs{c.ell, c.Wt, c.wdp, c.table, c.psi, c.cc}; }
+__device__ __forceinline__ ChildArgs child_args(const SweepChild& c, double psi, double cc) { return ChildArgs{c.ell, c.Wt, c.wdp, c.table, psi, cc}; }
 __device__ __noinline__ void sweep_child(const ChildArgs c, int f, size_t ld, int M, int Mw, double* col, int have, double osc) {
     const bool resident = have != 0;
     if (c.ell == nullptr) {                        // leaf: column x_c of w* (one-hot likelihood)
@@ -721,18 +735,27 @@ __device__ __noinline__ void sweep_child(const ChildArgs c, int f, size_t ld, in
 // PROF: per-(step, phase) warp-cycle totals into prof[step*8 + phase] (diagnostic build of the same kernel)
 #define BLG_TICK(ph) do { if (PROF) { long long t1_ = clock64(); if (lane == 0) atomicAdd(&prof[si * 8 + (ph)], (unsigned long long)(t1_ - t0_)); t0_ = t1_; } } while (0)
 template <bool PROF, int MINB, bool PERSIST>
-__global__ void __launch_bounds__(128, MINB) sweep_kernel(const __grid_constant__ SweepList L, int N, size_t ld, int slice_cap,
+__global__ void __launch_bounds__(128, MINB) sweep_kernel(const __grid_constant__ SweepList L, const NodeK* __restrict__ nk,
+                                                       const int* __restrict__ flags, unsigned int* __restrict__ ran,
+                                                       int N, size_t ld, int slice_cap,
                                                        double* gscratch, size_t gs_stride, unsigned long long* prof,
                                                        unsigned int* tile_counter) {
     extern __shared__ double smem[];
+    if (flags[0] == 0) return;        // some node is outside the table-free forms' range: the general kernel (launched next) does the work
+    if (blockIdx.x == 0 && threadIdx.x == 0) atomicAdd(&ran[0], 1u);
     const unsigned lane = threadIdx.x & 31u;
     const int warp = threadIdx.x >> 5;
     // [warps][2 buffers][5 slots][32 lanes] ints: counts and exponents of the coming steps land here by cp.async, in the
     // buffer of the step's parity.  Counts (static data) are requested TWO steps ahead, so that a run of empty steps
     // — each far shorter than a trip to HBM — does not wait for every single one; exponents (written by earlier steps of
-    // this very launch) one step ahead.  Step j commits one group {counts(j+2), exponents(j+1)}.
+    // this very launch) one step ahead.  Step j commits one group {counts(j+2), scalars(j+2), exponents(j+1)}.
+    // [warps][2 buffers][10] doubles behind them: the per-node scalars of the step (NodeK, device-resident: built by
+    // tables_kernel, never seen by the host): child 0 {e, 1/min(e,1), ψ', c}, child 1 the same, the node {1/(1-E_k), NaN flag}.
+    // (three scalar buffers, indexed by step mod 3: the request for step s+2 must not land on the scalars of step s,
+    // which are read throughout the step)
     int* cb = reinterpret_cast<int*>(smem) + (size_t)warp * 320 + lane;
-    double* sl = smem + (size_t)(blockDim.x >> 5) * 160 + (size_t)warp * slice_cap * 32 + lane;
+    double* sb = smem + (size_t)(blockDim.x >> 5) * 160 + (size_t)warp * 30;
+    double* sl = smem + (size_t)(blockDim.x >> 5) * 190 + (size_t)warp * slice_cap * 32 + lane;
     const int ntiles = (N + 31) / 32;
     // persistent grid, warp-granular work stealing: tiles (32 families, heaviest first) are handed out by an atomic
     // counter, so a batch that is a little more than one wave does not pay for a nearly empty second wave
@@ -763,6 +786,13 @@ __global__ void __launch_bounds__(128, MINB) sweep_kernel(const __grid_constant_
             cp_async_b32(b + 0 * 32, sn.cnt + fe);
             if (!sn.resident) cp_async_b32(b + 1 * 32, cn[0].cnt + fe);
             if (sn.k >= 2) cp_async_b32(b + 2 * 32, cn[1].cnt + fe);
+            // the step's scalars, 16 bytes per lane: lanes 0,1 child 0; lanes 2,3 child 1; lane 4 the node itself
+            if (lane < 5) {
+                const int ci = (int)(lane >> 1);
+                double* d = sb + (s % 3) * 10;
+                if (lane == 4) cp_async_b128(d + 8, &nk[sn.node].inv);
+                else if (ci < sn.k) cp_async_b128(d + lane * 2, &nk[cn[ci].node].e + (lane & 1) * 2);
+            }
         }
     };
     auto request_exponents = [&](int s) {
@@ -786,7 +816,8 @@ __global__ void __launch_bounds__(128, MINB) sweep_kernel(const __grid_constant_
         const SweepChild* ch = &L.child[st.first];
         const bool res0 = st.resident != 0;
         const int* b = cb + (si & 1) * 160;
-        cp_async_wait_but_one();                       // this step's counts are here; its exponents may still be on their way
+        const double* sc_ = sb + (si % 3) * 10;        // {e, 1/min(e,1), ψ', c} of child 0, of child 1, {1/(1-E_k), NaN flag} of the node
+        cp_async_wait_but_one();                       // this step's counts and scalars are here; its exponents may still be on their way
         const int X = (b[0 * 32] >> fsh) & 0xffff;
         const int Xw = warp_max(X);
         int M0 = 0, M1 = 0, sclsum = 0;
@@ -801,8 +832,8 @@ __global__ void __launch_bounds__(128, MINB) sweep_kernel(const __grid_constant_
         cp_async_commit();
         if (Xw == 0) {
             // no family of this warp has a gene below the node: ℓ = [1] whatever the parameters are (n = 0 lineages
-            // leave no descendants with probability 1) — or the reference's NaN, which the host folded into ip0
-            const double v = st.ip0;
+            // leave no descendants with probability 1) — or the reference's NaN, folded over the subtree by tables_kernel
+            const double v = sc_[9];
             if (live) { st.out[f] = v; st.out_scl[f] = 0; }
             sl[0] = v;
             prevX = 0;
@@ -849,32 +880,39 @@ __global__ void __launch_bounds__(128, MINB) sweep_kernel(const __grid_constant_
             }
             cp_async_commit();
         }
-        sweep_child(child_args(ch[0]), f, ld, M0, M0w, R, res0 ? 1 : 0, res0 ? prevSc : 1.0);
+        sweep_child(child_args(ch[0], sc_[2], sc_[3]), f, ld, M0, M0w, R, res0 ? 1 : 0, res0 ? prevSc : 1.0);
         if (async1) cp_async_wait_all();
         BLG_TICK(1);
         int Sw = M0w;
         double mxv = 0.0;
         bool scaled = false;        // has the (1-E_k)^(-n) normalisation already been applied (and mxv taken)?
+        double Eraw = sc_[0];       // product of the e's of the children merged so far (polytomies: clamped when used)
         if (!tiled) {
 #pragma unroll 1
             for (int i = 1; i < k; ++i) {
                 const int Mi = (i == 1) ? M1 : (int)ch[i].cnt[f];
                 const int Miw = (i == 1) ? M1w : warp_max(Mi);
                 double* colB = R + (size_t)(Sw + 1) * 32;
-                sweep_child(child_args(ch[i]), f, ld, Mi, Miw, colB, (i == 1 && async1) ? 2 : 0, 1.0);
+                // scalars of child i: staged for i == 1, straight from NodeK for the further children of a polytomy
+                const double ei = (i == 1) ? sc_[4] : nk[ch[i].node].e;
+                const double invei = (i == 1) ? sc_[5] : nk[ch[i].node].inve;
+                sweep_child(child_args(ch[i], (i == 1) ? sc_[6] : nk[ch[i].node].psi, (i == 1) ? sc_[7] : nk[ch[i].node].cc), f, ld, Mi, Miw, colB,
+                            (i == 1 && async1) ? 2 : 0, 1.0);
                 BLG_TICK(2);
                 const bool last = (i == k - 1);
-                const double em0 = last ? st.ip0 : 1.0, emg = last ? st.inv : 1.0;
+                const double em0 = last ? sc_[9] : 1.0, emg = last ? sc_[8] : 1.0;
                 const int Xm = last ? X : 0x7fffffff;
                 // the register-tiled "s" side is child i — or, in a binary merge whose child 0 has the smaller bound in
                 // this warp, child 0 (already at the front), with child i as the "t" side
                 const double* tA = swap ? colB : R;
                 const double* sB = swap ? R : colB;
                 const int tW = swap ? Miw : Sw, sW = swap ? Sw : Miw;
-                const double E = swap ? fmin(ch[1].e, 1.0) : ch[i].Epre;
-                const double e = swap ? ch[0].e : ch[i].e;
-                const double invE = swap ? ch[1].invEself : ((k == 2) ? ch[0].invEself : 1.0 / E);
-                const double inve = swap ? ch[0].invEself : ch[i].invEself;
+                const double Epre = fmin(Eraw, 1.0);              // clamped prefix of the children merged before this one
+                const double E = swap ? fmin(ei, 1.0) : Epre;
+                const double e = swap ? sc_[0] : ei;
+                const double invE = swap ? invei : ((k == 2) ? sc_[1] : 1.0 / E);
+                const double inve = swap ? sc_[1] : invei;
+                Eraw *= ei;
                 double mx;
                 if (sW < 4) mx = sweep_merge_fast<4>(R, tA, tW, sB, sW, E, invE, e, inve, em0, emg, Xm);
                 else if (sW < 8) mx = sweep_merge_fast<8>(R, tA, tW, sB, sW, E, invE, e, inve, em0, emg, Xm);
@@ -893,10 +931,12 @@ __global__ void __launch_bounds__(128, MINB) sweep_kernel(const __grid_constant_
             for (int i = 1; i < k; ++i) {
                 const int Mi = (i == 1) ? M1 : (int)ch[i].cnt[f];
                 const int Miw = (i == 1) ? M1w : warp_max(Mi);
-                sweep_child(child_args(ch[i]), f, ld, Mi, Miw, rO, 0, 1.0);
+                const double ei = (i == 1) ? sc_[4] : nk[ch[i].node].e;
+                sweep_child(child_args(ch[i], (i == 1) ? sc_[6] : nk[ch[i].node].psi, (i == 1) ? sc_[7] : nk[ch[i].node].cc), f, ld, Mi, Miw, rO, 0, 1.0);
 #pragma unroll 1
                 for (int n = Miw + 1; n <= Sw + Miw; ++n) rO[n * 32] = 0.0;
-                sweep_merge_tiled(rA, Sw, rO, Miw, rH, ch[i].Epre, ch[i].e);
+                sweep_merge_tiled(rA, Sw, rO, Miw, rH, fmin(Eraw, 1.0), ei);
+                Eraw *= ei;
                 Sw += Miw;
 #pragma unroll 1
                 for (int n = 0; n <= Sw; ++n) rA[n * 32] = rO[n * 32];     // result back to the front of R
@@ -909,8 +949,8 @@ __global__ void __launch_bounds__(128, MINB) sweep_kernel(const __grid_constant_
 #pragma unroll 1
             for (int n = Sw + 1; n <= Xw; ++n) R[n * 32] = 0.0;
         } else {
-            double ip = st.ip0;
-            const double inv = st.inv;
+            double ip = sc_[9];
+            const double inv = sc_[8];
 #pragma unroll 1
             for (int n = 0; n <= Xw; ++n) {
                 double v = 0.0;
@@ -971,13 +1011,13 @@ __global__ void __launch_bounds__(256) fp64_peak_kernel(double* sink, int iters,
 // ------------------------------------------------------------------------------------------------
 // root: integrate_root (model.jl:465-475), condition_oib (model.jl:492-501), weighted reduction
 // ------------------------------------------------------------------------------------------------
-__global__ void root_tables_kernel(ModelDev m, double* rootw, int nrow) { d_root_tables(m, rootw, nrow, (int)threadIdx.x, (int)blockDim.x); }
+__global__ void root_tables_kernel(ModelDev m, double* rootw, double* rootlw, int nrow) { d_root_tables(m, rootw, rootlw, nrow, (int)threadIdx.x, (int)blockDim.x); }
 
 __global__ void __launch_bounds__(256) root_kernel(const double* __restrict__ ell, const int* __restrict__ scl,
                                                    const uint16_t* __restrict__ cnt, const double* __restrict__ rootw,
                                                    const double* __restrict__ weight, double* __restrict__ fam_ll,
                                                    double* __restrict__ partial, int N, size_t ld,
-                                                   unsigned int* __restrict__ ticket, double* __restrict__ out) {
+                                                   unsigned int* __restrict__ ticket, unsigned int nblocks_total, double* __restrict__ out) {
     __shared__ double red[256];
     __shared__ bool last_block;
     int f = blockIdx.x * blockDim.x + threadIdx.x;
@@ -1000,14 +1040,14 @@ __global__ void __launch_bounds__(256) root_kernel(const double* __restrict__ el
     if (threadIdx.x == 0) {
         partial[blockIdx.x] = red[0];
         __threadfence();
-        last_block = atomicAdd(ticket, 1u) == gridDim.x - 1;
+        last_block = atomicAdd(ticket, 1u) == nblocks_total - 1;
     }
     __syncthreads();
-    if (last_block) {                       // the last block to finish adds the partial sums, in a fixed order
-        __threadfence();
+    if (last_block) {                       // the last block of the call's root launches (this one for the fast shard,
+        __threadfence();                    // root_ragged_kernel for the heavy shard) adds the partial sums, in a fixed order
         const volatile double* vp = partial;
         double s = 0.0;
-        for (int i = threadIdx.x; i < (int)gridDim.x; i += 256) s += vp[i];
+        for (int i = threadIdx.x; i < (int)nblocks_total; i += 256) s += vp[i];
         red[threadIdx.x] = s;
         __syncthreads();
         for (int k = 128; k > 0; k >>= 1) {
@@ -1025,6 +1065,7 @@ __global__ void zero_slab_kernel(double* ell, int* scl, size_t nell, int N) {
     for (size_t k = i; k < (size_t)N; k += stride) scl[k] = 0;
 }
 
+#include "general.cuh"
 #include "gradient.cuh"
 #include "adjoint.cuh"
 
@@ -1034,16 +1075,17 @@ __global__ void zero_slab_kernel(double* ell, int* scl, size_t nell, int N) {
 struct Slab {
     double* ell = nullptr;
     int* scl = nullptr;
-    int rows = 0;
+    size_t nd = 0;                   // doubles in ell
 };
 struct Col {
     const uint16_t* cnt = nullptr;   // device counts of this column (shared between aliases)
     int xmax = 0;
-    double colsum = 0.0;             // Σ_f (x_f + 1), for the algorithmic byte count
+    double colsum = 0.0;             // Σ_f (x_f + 1): the algorithmic byte count, and the size of a ragged slab
     std::shared_ptr<Slab> slab;      // null: never computed ("-Inf")
+    const uint32_t* off = nullptr;   // ragged (heavy) shard: per-family offsets of the column, prefix sums of (count+1); shared between aliases
 };
 struct HostTab {                     // host mirror of NodeTab allocations
-    int wdim = 0, wdp = 0, nrow = 0, k = 0;
+    int wdim = 0, wdp = 0, nrow = 0, k = 0, xfast = 0;
     int cdp[BLG_MAXK] = {0};
     int mo[BLG_MAXK] = {0};          // merge order (node indices)
     double* Wt = nullptr;
@@ -1069,6 +1111,39 @@ template <class T> struct DevBuf {
     void free_() { if (p) cudaFree(p); p = nullptr; cap = 0; }
 };
 
+// One of the two family sets of a handle.  The FAST shard holds the families whose root count is at most
+// BLG_FAST_MAXCOUNT: node-major SoA slabs ell[n][family] padded to the shard's per-node bound, k-d family order, walked by
+// sweep_kernel (32 families per warp).  The HEAVY shard holds the rest: ragged slabs (family f's column starts at
+// off[f], exactly x_f+1 doubles, no padding), heaviest family first, walked by gsweep_kernel (one warp per family).
+struct Shard {
+    bool ragged = false;
+    int N = 0;               // families
+    size_t ld = 0;           // stride of the count rows (and of the SoA slabs), N rounded up to 128
+    std::vector<Col> Tc, Tp; // committed / proposal column tables (by id-1)
+    std::vector<uint16_t*> count_allocs;
+    DevBuf<double> weight, fam_ll;
+    std::map<size_t, std::vector<Slab*>> pool;   // free slabs by size
+    std::vector<Slab*> all_slabs;
+    std::vector<uint32_t*> off_allocs;
+    std::vector<int> perm;   // perm[device index] = caller's pattern index
+    double weight_total = 0.0;
+    struct Class { int f0, f1, maxroot; };
+    std::vector<Class> classes;                  // heavy shard: launch groups by root count (shared memory per warp follows it)
+
+    void release() {
+        Tc.clear();          // the slab deleters push into `pool`: run them while it is still alive
+        Tp.clear();
+        pool.clear();
+        for (auto* sl : all_slabs) { cudaFree(sl->ell); cudaFree(sl->scl); delete sl; }
+        all_slabs.clear();
+        for (auto* o : off_allocs) cudaFree(o);
+        off_allocs.clear();
+        for (auto* c : count_allocs) cudaFree(c);
+        count_allocs.clear();
+        N = 0; ld = 0; perm.clear(); classes.clear(); weight_total = 0.0;
+    }
+};
+
 }  // namespace
 
 struct blg_handle {
@@ -1077,14 +1152,19 @@ struct blg_handle {
     bool own_stream = false;
     std::string err;
 
-    // profiles
-    int N = 0;           // patterns in this shard
-    size_t ld = 0;       // padded family stride
-    std::vector<Col> Tc, Tp;                 // committed / proposal column tables (by id-1)
-    std::vector<uint16_t*> count_allocs;
-    DevBuf<double> weight, fam_ll, partial, result, rootw;
-    std::map<int, std::vector<Slab*>> pool;  // free slabs by row count
-    std::vector<Slab*> all_slabs;
+    // profiles: two family sets (see Shard); the members below alias the FAST shard (the gradient kernels work on it)
+    Shard F, H;
+    int& N = F.N;
+    size_t& ld = F.ld;
+    std::vector<Col>& Tc = F.Tc;
+    std::vector<Col>& Tp = F.Tp;
+    DevBuf<double>& weight = F.weight;
+    DevBuf<double>& fam_ll = F.fam_ll;
+    double& weight_total = F.weight_total;
+    int Ntot = 0;                            // patterns of this handle (both shards)
+    std::vector<int> loc;                    // caller's pattern index -> device index (fast) or -1 - index (heavy)
+    int heavy_min = BLG_FAST_MAXCOUNT + 1;   // families whose root count reaches this go to the heavy shard (BLG_HEAVY_MIN)
+    DevBuf<double> partial, result, rootw;
     int maxcount = 0;
     DevBuf<double> pascal;
     int pdim = 0;
@@ -1104,44 +1184,39 @@ struct blg_handle {
     bool have_params = false;
     // device model arrays
     DevBuf<uint8_t> d_kind;
-    DevBuf<int> d_parent, d_child_off, d_child_idx, d_lists;
-    DevBuf<double> d_par, d_eps1;        // d_par: [t | λ | μ | q], one upload per parameter change
+    DevBuf<int> d_parent, d_child_off, d_child_idx, d_lists, d_post;
+    DevBuf<double> d_par, d_eps0, d_eps1;   // d_par: [t | λ | μ | q], one upload per parameter change
     DevBuf<NodeTab> d_tab;
-    // what every rebuild reads back travels as ONE block: [ε[0] | per-node sweep scalars | table-free flags]
-    DevBuf<unsigned char> d_back;
-    unsigned char* h_back = nullptr;     // pinned mirror of d_back
-    size_t h_back_cap = 0;
-    struct { double* p = nullptr; } d_eps0;
-    struct { SweepNodeConst* p = nullptr; } d_nc;
-    struct { int* p = nullptr; } d_fast_ok;
+    DevBuf<NodeK> d_nk;                  // per-node scalars of the pruning kernels: device-resident, never read back by a likelihood call
+    DevBuf<int> d_fast_ok, d_flags;
+    DevBuf<unsigned int> d_tticket;      // last-block-done counter of tables_kernel (self-resetting)
+    DevBuf<unsigned int> d_ran;          // [0] sweep_kernel launches that did the work, [1] gsweep_kernel ones (cumulative)
     NodeTab* d_tab_seen = nullptr;       // device table-descriptor array the last upload went to
     std::vector<double> par_stage;
     std::vector<int> lists_stage;
-    std::vector<int> fast_ok;            // host copy, refreshed by every rebuild
-    std::vector<SweepNodeConst> h_nc;    // host copies of the device-built per-node scalars (same refresh)
+    std::vector<NodeK> h_nk;             // host copy for the gradient (fetched by gradient() only)
     std::vector<double> h_eps0;
-    std::vector<char> poison_below;      // some node of the subtree (the node included) has a NaN column
     std::vector<HostTab> tabs;
     std::vector<NodeTab> tab_stage;
     bool tabs_valid = false;
     bool rootw_valid = false;            // the root integration weights match the current parameters
-    DevBuf<unsigned int> d_ticket;       // last-block-done counter of root_kernel (self-resetting)
+    int rootw_rows = 0;
+    DevBuf<unsigned int> d_ticket;       // last-block-done counter of the root kernels (self-resetting)
 
     // sweep-kernel plumbing
     int kernel_version = 2;
-    int last_kernel = 0;
     bool order_resident = true;
-    double weight_total = 0.0;           // Σ_f w_f
     int grad_mode = 1;                   // 1: reverse-mode sweep where the tree allows it; 0: forward-mode tangent passes (BLG_GRAD=forward)
     int profile_sweep = 0;
     DevBuf<unsigned long long> d_prof;
     int slice_cap = 50;                       // doubles per lane of the per-warp shared-memory slice
     int sweep_wpb = 4;                        // warps per block of the sweep kernel (BLG_WPB: 1, 2 or 4)
     std::unique_ptr<SweepList> sweep_list{new SweepList()};
-    DevBuf<unsigned int> d_tilectr;
+    std::unique_ptr<GList> glist{new GList()};
+    DevBuf<unsigned int> d_tilectr, d_gctr;
     int sm_count = 148;
     DevBuf<double> gscratch;
-    size_t sweep_smem_set = 0;
+    size_t sweep_smem_set = 0, g4_smem_set = 0, g16_smem_set = 0;
 
     // accounting of the last likelihood call
     double last_bytes = 0.0, last_prune_bytes = 0.0;
@@ -1150,28 +1225,21 @@ struct blg_handle {
     cudaEvent_t ev[3] = {nullptr, nullptr, nullptr};
     bool ev_valid = false;
 
-    // family order on the device (sorted by count profile so that the 32 families of a warp have
-    // similar loop bounds); perm[device index] = caller's pattern index
-    std::vector<int> perm, inv;
-
     ~blg_handle() {
         cudaSetDevice(device);
         if (stream) cudaStreamSynchronize(stream);
-        Tc.clear();      // the slab deleters push into `pool`: run them while it is still alive
-        Tp.clear();
-        pool.clear();
-        for (auto* s : all_slabs) { cudaFree(s->ell); cudaFree(s->scl); delete s; }
-        for (auto* c : count_allocs) cudaFree(c);
+        F.release();
+        H.release();
+        F.weight.free_(); F.fam_ll.free_(); H.weight.free_(); H.fam_ll.free_();
         for (auto& tb : tabs) free_tab(tb);
-        weight.free_(); fam_ll.free_(); partial.free_(); result.free_(); rootw.free_(); pascal.free_();
-        d_kind.free_(); d_parent.free_(); d_child_off.free_(); d_child_idx.free_(); d_lists.free_();
-        d_par.free_(); d_eps1.free_(); d_tab.free_(); d_back.free_();
-        if (h_back) cudaFreeHost(h_back);
-        h_back = nullptr;
+        partial.free_(); result.free_(); rootw.free_(); pascal.free_();
+        d_kind.free_(); d_parent.free_(); d_child_off.free_(); d_child_idx.free_(); d_lists.free_(); d_post.free_();
+        d_par.free_(); d_eps0.free_(); d_eps1.free_(); d_tab.free_(); d_nk.free_(); d_fast_ok.free_(); d_flags.free_();
+        d_tticket.free_(); d_ran.free_();
         d_prof.free_();
         gpool_release();
         for (auto& e : ev) if (e) cudaEventDestroy(e);
-        gscratch.free_(); d_tilectr.free_(); d_ticket.free_();
+        gscratch.free_(); d_tilectr.free_(); d_gctr.free_(); d_ticket.free_();
         if (own_stream && stream) cudaStreamDestroy(stream);
     }
     static void free_tab(HostTab& tb) {
@@ -1182,37 +1250,42 @@ struct blg_handle {
     }
 
     // ---- slabs ---------------------------------------------------------------------------------
-    std::shared_ptr<Slab> new_slab(int rows) {
+    static size_t slab_doubles(const Shard& S, const Col& col) {
+        return S.ragged ? (size_t)col.colsum + 8 : (size_t)(col.xmax + 1) * S.ld;
+    }
+    std::shared_ptr<Slab> new_slab(Shard& S, size_t nd) {
         Slab* s = nullptr;
-        auto it = pool.find(rows);
-        if (it != pool.end() && !it->second.empty()) { s = it->second.back(); it->second.pop_back(); }
+        auto it = S.pool.find(nd);
+        if (it != S.pool.end() && !it->second.empty()) { s = it->second.back(); it->second.pop_back(); }
         else {
             s = new Slab();
-            s->rows = rows;
-            CK(cudaMalloc(&s->ell, (size_t)rows * ld * sizeof(double)));
-            cudaError_t e = cudaMalloc(&s->scl, ld * sizeof(int));
+            s->nd = nd;
+            CK(cudaMalloc(&s->ell, nd * sizeof(double)));
+            cudaError_t e = cudaMalloc(&s->scl, S.ld * sizeof(int));
             if (e != cudaSuccess) { cudaFree(s->ell); delete s; throw CudaError(std::string("cudaMalloc: ") + cudaGetErrorString(e)); }
-            all_slabs.push_back(s);
+            S.all_slabs.push_back(s);
         }
-        blg_handle* self = this;
-        return std::shared_ptr<Slab>(s, [self](Slab* p) { self->pool[p->rows].push_back(p); });
+        Shard* sp = &S;
+        return std::shared_ptr<Slab>(s, [sp](Slab* p) { sp->pool[p->nd].push_back(p); });
     }
     // slab the proposal may overwrite for column c (copy-on-write without the copy: a pruning step
     // rewrites the whole column for every family)
-    Slab* writable(int c) {
-        Col& col = Tp[c];
-        if (!col.slab || col.slab.use_count() > 1) col.slab = new_slab(col.xmax + 1);
+    Slab* writable(Shard& S, int c) {
+        Col& col = S.Tp[c];
+        if (!col.slab || col.slab.use_count() > 1) col.slab = new_slab(S, slab_doubles(S, col));
         return col.slab.get();
     }
-    Slab* readable(int c) {
-        Col& col = Tp[c];
+    Slab* readable(Shard& S, int c) {
+        Col& col = S.Tp[c];
         if (!col.slab) {   // never computed: the reference holds -Inf there, i.e. ℓ = 0
-            col.slab = new_slab(col.xmax + 1);
-            zero_slab_kernel<<<296, 256, 0, stream>>>(col.slab->ell, col.slab->scl, (size_t)(col.xmax + 1) * ld, (int)ld);
+            col.slab = new_slab(S, slab_doubles(S, col));
+            zero_slab_kernel<<<296, 256, 0, stream>>>(col.slab->ell, col.slab->scl, col.slab->nd, (int)S.ld);
             CK(cudaGetLastError());
         }
         return col.slab.get();
     }
+    Slab* writable(int c) { return writable(F, c); }
+    Slab* readable(int c) { return readable(F, c); }
 
     void require(bool c, const char* msg) { if (!c) throw std::runtime_error(msg); }
 
@@ -1253,47 +1326,56 @@ struct blg_handle {
         m.t = d_par.p; m.lam = d_par.p + ncols_model; m.mu = d_par.p + 2 * (size_t)ncols_model;
         m.q = d_par.p + 3 * (size_t)ncols_model; m.eta = eta;
         m.eps0 = d_eps0.p; m.eps1 = d_eps1.p; m.tab = d_tab.p; m.pascal = pascal.p; m.pdim = pdim;
-        m.nc = d_nc.p; m.fast_ok = d_fast_ok.p;
-        m.rootw = nullptr; m.rootw_n = 0;
+        m.nk = d_nk.p; m.fast_ok = d_fast_ok.p;
+        m.rootw = nullptr; m.rootlw = nullptr; m.rootw_n = 0;
+        m.flags = d_flags.p; m.ticket = d_tticket.p; m.post = d_post.p; m.npost = (int)postorder.size();
         return m;
     }
+
+    // count bound of column i in a shard (0 when the shard is empty or the column does not exist yet)
+    static int xmax_of(const Shard& S, int i) { return (S.N > 0 && i < (int)S.Tp.size()) ? S.Tp[i].xmax : 0; }
+    static double colsum_of(const Shard& S, int i) { return (S.N > 0 && i < (int)S.Tp.size()) ? S.Tp[i].colsum : 0.0; }
 
     // merge order of node i's children: the child with the larger counts first (the "t" side of the
     // merge, whose column lives in shared memory); the smaller one is the register-tiled "s" side
     std::vector<int> merge_order(int i) {
         std::vector<int> mo = children[i];
         if (mo.size() == 2) {
-            double a = mo[0] < (int)Tp.size() ? Tp[mo[0]].colsum : 0.0;
-            double b = mo[1] < (int)Tp.size() ? Tp[mo[1]].colsum : 0.0;
+            double a = colsum_of(F, mo[0]);
+            double b = colsum_of(F, mo[1]);
             if (b > a) std::swap(mo[0], mo[1]);
         }
         return mo;
     }
-    // (re)allocate the tables of node i for the current proposal column dims
+    // (re)allocate the tables of node i for the current proposal column dims.  Tables exist for the FAST shard's count
+    // bounds only (<= BLG_FAST_MAXCOUNT); the branch below a WGT keeps its literal table for both shards.
     void ensure_tab(int i) {
         HostTab& tb = tabs[i];
         int k = (int)children[i].size();
-        int xm = (i < (int)Tp.size()) ? Tp[i].xmax : 0;
-        int wdim = (kind[i] == BLG_ROOT) ? 0 : xm + 1;
-        int nrow = k > 0 ? xm + 1 : 0;
+        const bool havef = F.N > 0 && i < (int)F.Tp.size();
+        int xm = xmax_of(F, i);
+        int wdim = (kind[i] == BLG_ROOT || !havef) ? 0 : xm + 1;
+        if (kind[i] == BLG_WGDAFTER && parent[i] >= 0 && kind[parent[i]] == BLG_WGT && H.N > 0 && i < (int)H.Tp.size())
+            wdim = std::max(wdim, xmax_of(H, i) + 1);
+        int nrow = (k > 0 && havef) ? xm + 1 : 0;
         std::vector<int> mo = merge_order(i);
-        bool same = tb.wdim == wdim && tb.nrow == nrow && tb.k == k;
+        bool same = tb.wdim == wdim && tb.nrow == nrow && tb.k == k && tb.xfast == xm;
         for (int c = 0; c < k && same; ++c) {
             int ci = mo[c];
-            int cx = (ci < (int)Tp.size()) ? Tp[ci].xmax : 0;
+            int cx = xmax_of(F, ci);
             if (tb.mo[c] != ci) same = false;
-            if (c >= 1 && tb.cdp[c] != round_up(cx + 1, BLG_TS)) same = false;
+            if (c >= 1 && nrow > 0 && tb.cdp[c] != round_up(cx + 1, BLG_TS)) same = false;
         }
         if (same && (tb.Wt || wdim == 0) && (tb.ipow || nrow == 0)) return;
         free_tab(tb);
-        tb.wdim = wdim; tb.wdp = round_up(std::max(wdim, 1), 16); tb.nrow = nrow; tb.k = k;
+        tb.wdim = wdim; tb.wdp = round_up(std::max(wdim, 1), 16); tb.nrow = nrow; tb.k = k; tb.xfast = xm;
         for (int c = 0; c < k; ++c) tb.mo[c] = mo[c];
         if (wdim > 0) CK(cudaMalloc(&tb.Wt, (size_t)wdim * tb.wdp * sizeof(double)));
         if (nrow > 0) {
             CK(cudaMalloc(&tb.ipow, (size_t)nrow * sizeof(double)));
             for (int c = 1; c < k; ++c) {
                 int ci = mo[c];
-                int cx = (ci < (int)Tp.size()) ? Tp[ci].xmax : 0;
+                int cx = xmax_of(F, ci);
                 tb.cdp[c] = round_up(cx + 1, BLG_TS);
                 CK(cudaMalloc(&tb.coefD[c], (size_t)nrow * tb.cdp[c] * sizeof(double)));
             }
@@ -1304,8 +1386,7 @@ struct blg_handle {
         require(have_topology, "set_params/rebuild: call blg_set_topology first");
         require(have_params, "rebuild: call blg_set_params first");
         size_t n = (size_t)ncols_model;
-        d_par.ensure(4 * n); d_eps1.ensure(n);
-        ensure_back(n);
+        d_par.ensure(4 * n); d_eps1.ensure(n); d_eps0.ensure(n);
         par_stage.resize(4 * n);
         std::copy(t.begin(), t.begin() + n, par_stage.begin());
         std::copy(lam.begin(), lam.begin() + n, par_stage.begin() + n);
@@ -1315,26 +1396,10 @@ struct blg_handle {
         CK(cudaMemcpyAsync(d_par.p, par_stage.data(), 4 * n * sizeof(double), cudaMemcpyHostToDevice, stream));
     }
 
-    // layout of the read-back block for n node ids (doubles first, so everything stays aligned)
-    static size_t back_bytes(size_t n) { return n * (sizeof(double) + sizeof(SweepNodeConst) + sizeof(int)); }
-    void ensure_back(size_t n) {
-        size_t need = back_bytes(n);
-        if (need > d_back.cap) {
-            // ε[0] of the previous arena is still needed by nobody: every size change comes with a full rebuild
-            d_back.ensure(need + need / 2);
-        }
-        if (need > h_back_cap) {
-            if (h_back) cudaFreeHost(h_back);
-            h_back = nullptr;
-            h_back_cap = 0;
-            CK(cudaMallocHost(&h_back, need + need / 2));
-            h_back_cap = need + need / 2;
-        }
-        d_eps0.p = reinterpret_cast<double*>(d_back.p);
-        d_nc.p = reinterpret_cast<SweepNodeConst*>(d_back.p + n * sizeof(double));
-        d_fast_ok.p = reinterpret_cast<int*>(d_back.p + n * (sizeof(double) + sizeof(SweepNodeConst)));
-    }
+    int root_rows() const { return std::max(xmax_of(F, 0), xmax_of(H, 0)) + 1; }
 
+    // set!(n) for the listed ids in the listed order (nodes == nullptr: set!(d), every node).  Everything stays on the
+    // device: ε (eps_kernel), W / per-node scalars / range flags / NaN rule (tables_kernel); nothing is read back.
     void rebuild(const int32_t* nodes, int n) {
         require(have_topology && have_params, "rebuild: topology and params must be set first");
         std::vector<int> list;
@@ -1346,41 +1411,49 @@ struct blg_handle {
                 list.push_back(i);
             }
         }
-        if (!tabs_valid) {
-            require(list.size() == postorder.size(), "rebuild: the topology changed; a full rebuild (nodes = NULL) is required");
-        }
+        const bool full = list.size() == postorder.size() && (nodes == nullptr || n <= 0);
+        if (!tabs_valid) require(full, "rebuild: the topology changed; a full rebuild (nodes = NULL) is required");
         if ((int)tabs.size() < ncols_model) tabs.resize(ncols_model);
         if ((int)tab_stage.size() < ncols_model) tab_stage.resize(ncols_model);
+        // the tables are built once per node: a literal update! replay may list a node several times
+        // (tables_kernel's blocks must not build the same table concurrently)
+        std::vector<int> tlist;
+        {
+            std::vector<char> seen(ncols_model, 0);
+            for (int i : list) if (!seen[i]) { seen[i] = 1; tlist.push_back(i); }
+        }
         int maxdim = 1;
         bool tab_dirty = false;
-        for (int i : list) {
+        for (int i : tlist) {
             ensure_tab(i);
             HostTab& tb = tabs[i];
             NodeTab nt;
             memset(&nt, 0, sizeof(nt));
-            nt.Wt = tb.Wt; nt.wdim = tb.wdim; nt.wdp = tb.wdp; nt.ipow = tb.ipow; nt.nrow = tb.nrow;
+            nt.Wt = tb.Wt; nt.wdim = tb.wdim; nt.wdp = tb.wdp; nt.ipow = tb.ipow; nt.nrow = tb.nrow; nt.xfast = tb.xfast;
             for (int c = 0; c < BLG_MAXK; ++c) { nt.coefD[c] = tb.coefD[c]; nt.cdp[c] = tb.cdp[c]; nt.mo[c] = tb.mo[c]; }
             if (memcmp(&tab_stage[i], &nt, sizeof(nt)) != 0) { tab_stage[i] = nt; tab_dirty = true; }
             tb.built = true;
             maxdim = std::max(maxdim, tb.wdim);
         }
-        d_tab.ensure((size_t)ncols_model);
-        ensure_back((size_t)ncols_model);
-        if (tab_dirty || d_tab.p != d_tab_seen || list.size() == postorder.size()) {
-            CK(cudaMemcpyAsync(d_tab.p, tab_stage.data(), (size_t)ncols_model * sizeof(NodeTab), cudaMemcpyHostToDevice, stream));
+        const size_t nn = (size_t)ncols_model;
+        d_tab.ensure(nn);
+        d_nk.ensure(nn); d_fast_ok.ensure(nn); d_eps0.ensure(nn); d_eps1.ensure(nn);
+        if (!d_flags.p) { d_flags.ensure(4); CK(cudaMemsetAsync(d_flags.p, 0, 4 * sizeof(int), stream)); }
+        if (!d_tticket.p) { d_tticket.ensure(1); CK(cudaMemsetAsync(d_tticket.p, 0, sizeof(unsigned int), stream)); }
+        if (!d_ran.p) { d_ran.ensure(4); CK(cudaMemsetAsync(d_ran.p, 0, 4 * sizeof(unsigned int), stream)); }
+        if (tab_dirty || d_tab.p != d_tab_seen || full) {
+            CK(cudaMemcpyAsync(d_tab.p, tab_stage.data(), nn * sizeof(NodeTab), cudaMemcpyHostToDevice, stream));
             d_tab_seen = d_tab.p;
         }
         // ε segments: a full rebuild groups the nodes by height above the leaves (children always sit in an
         // earlier segment); a partial list is replayed literally, one node after the other
         std::vector<int> elist = list, seg;
-        if (list.size() == postorder.size()) {
+        if (full) {
             std::vector<int> height(ncols_model, 0);
-            int hmax = 0;
             for (int u : postorder) {
                 int hh = 0;
                 for (int c : children[u]) hh = std::max(hh, height[c] + 1);
                 height[u] = hh;
-                hmax = std::max(hmax, hh);
             }
             std::stable_sort(elist.begin(), elist.end(), [&](int a, int b) { return height[a] < height[b]; });
             seg.push_back(0);
@@ -1389,62 +1462,42 @@ struct blg_handle {
         } else {
             for (size_t i = 0; i <= elist.size(); ++i) seg.push_back((int)i);
         }
-        // [list | elist | seg] in one upload
+        // [tlist | elist | seg] in one upload
         lists_stage.clear();
-        lists_stage.insert(lists_stage.end(), list.begin(), list.end());
+        lists_stage.insert(lists_stage.end(), tlist.begin(), tlist.end());
         lists_stage.insert(lists_stage.end(), elist.begin(), elist.end());
         lists_stage.insert(lists_stage.end(), seg.begin(), seg.end());
         d_lists.ensure(lists_stage.size());
         CK(cudaMemcpyAsync(d_lists.p, lists_stage.data(), lists_stage.size() * sizeof(int), cudaMemcpyHostToDevice, stream));
         const int* d_list_p = d_lists.p;
-        const int* d_elist_p = d_lists.p + list.size();
+        const int* d_elist_p = d_lists.p + tlist.size();
         const int* d_seg_p = d_elist_p + elist.size();
         ModelDev m = model_dev();
         bool root_listed = false;
-        for (int i : list) root_listed = root_listed || i == 0;
-        rootw_valid = false;
-        if (root_listed && !Tp.empty() && !children[0].empty()) {      // the block of the root also builds the root weights
-            const int nrow = Tp[0].xmax + 1;
-            rootw.ensure((size_t)nrow + 1);
+        for (int i : tlist) root_listed = root_listed || i == 0;
+        if (root_listed && Ntot > 0 && !children[0].empty()) {      // the block of the root also builds the root weights
+            const int nrow = root_rows();
+            rootw.ensure(2 * ((size_t)nrow + 1));
             m.rootw = rootw.p;
+            m.rootlw = H.N > 0 ? rootw.p + nrow + 1 : nullptr;
             m.rootw_n = nrow;
             rootw_valid = true;
+            rootw_rows = nrow;
+        } else {
+            rootw_valid = false;
         }
         eps_kernel<<<1, 128, 0, stream>>>(m, d_elist_p, d_seg_p, (int)seg.size() - 1);
         CK(cudaGetLastError());
-        tables_kernel<<<(unsigned)list.size(), 128, 2 * (size_t)maxdim * sizeof(double), stream>>>(m, d_list_p, (int)list.size());
+        const size_t tsm = std::max(2 * (size_t)maxdim * sizeof(double), nn * sizeof(int));
+        tables_kernel<<<(unsigned)tlist.size(), 128, tsm, stream>>>(m, d_list_p, (int)tlist.size());
         CK(cudaGetLastError());
-        // list/tab_stage are host vectors reused by later calls: make sure the copies are done; the
-        // per-node "table-free kernel allowed" flags come back with the same synchronisation
-        fast_ok.resize(ncols_model, 0);
-        h_nc.resize(ncols_model);
-        h_eps0.resize(ncols_model);
-        {
-            size_t nn = (size_t)ncols_model;
-            CK(cudaMemcpyAsync(h_back, d_back.p, back_bytes(nn), cudaMemcpyDeviceToHost, stream));
-            CK(cudaStreamSynchronize(stream));
-            memcpy(h_eps0.data(), h_back, nn * sizeof(double));
-            memcpy(h_nc.data(), h_back + nn * sizeof(double), nn * sizeof(SweepNodeConst));
-            memcpy(fast_ok.data(), h_back + nn * (sizeof(double) + sizeof(SweepNodeConst)), nn * sizeof(int));
-        }
-        // a NaN column (reference: a prefix of the children's ε equal to 1) makes every column above it NaN; the
-        // sweep carries that in ip0, so that warps whose families are all empty below a node need not look down
-        poison_below.assign(ncols_model, 0);
-        for (int u : postorder) {
-            bool p = !children[u].empty() && std::isnan(h_nc[u].ip0);
-            for (int c : children[u]) p = p || poison_below[c];
-            poison_below[u] = p ? 1 : 0;
-        }
-        if (list.size() == postorder.size()) tabs_valid = true;
+        if (full) tabs_valid = true;
     }
 
     // ---- pruning -----------------------------------------------------------------------------------
-    template <int CAP> void launch_prune(const NodeStep& st) {
-        int blocks = (N + 127) / 128;
-        prune_node_kernel<CAP><<<blocks, 128, 0, stream>>>(st, d_eps0.p, N, ld);
-    }
-    // describe the pruning step at node u against the current proposal tables (allocates the output slab)
-    NodeStep make_step(int u, bool readonly = false) {
+    // describe the pruning step at node u against the current proposal tables of the FAST shard (allocates the output
+    // slab); the table pointers are for the gradient kernels, the sweep kernel only takes the slabs from here
+    NodeStep make_step(int u, bool readonly = false, bool count_bytes = true) {
         int k = (int)children[u].size();
         require(k >= 1, "prune_node: leaf");
         require(u < (int)Tp.size(), "logpdf: model has more node ids than the profile has columns (call blg_extend)");
@@ -1456,10 +1509,10 @@ struct blg_handle {
         for (int i = 0; i < k; ++i) {
             int c = tabs[u].mo[i];
             require(c >= 0 && c < (int)Tp.size(), "logpdf: child id beyond the profile columns");
-            require(tabs[c].built && tabs[c].wdim == Tp[c].xmax + 1, "logpdf: W table of a child does not match the profile (call blg_rebuild)");
+            require(tabs[c].built && tabs[c].wdim >= Tp[c].xmax + 1 && tabs[c].xfast == Tp[c].xmax, "logpdf: W table of a child does not match the profile (call blg_rebuild)");
             ChildRef& cr = st.child[i];
-            if (children[c].empty()) { cr.ell = nullptr; cr.scl = nullptr; last_bytes += 2.0 * N; }
-            else { Slab* s = readable(c); cr.ell = s->ell; cr.scl = s->scl; last_bytes += 8.0 * Tp[c].colsum + 4.0 * N; }
+            if (children[c].empty()) { cr.ell = nullptr; cr.scl = nullptr; if (count_bytes) last_bytes += 2.0 * N; }
+            else { Slab* s = readable(c); cr.ell = s->ell; cr.scl = s->scl; if (count_bytes) last_bytes += 8.0 * Tp[c].colsum + 4.0 * N; }
             cr.cnt = Tp[c].cnt;
             cr.Wt = tabs[c].Wt;
             cr.wdp = tabs[c].wdp;
@@ -1473,23 +1526,12 @@ struct blg_handle {
         st.nrow = tabs[u].nrow;
         st.out = o->ell; st.out_scl = o->scl; st.cnt = Tp[u].cnt;
         st.ipow = tabs[u].ipow;
-        last_bytes += 8.0 * Tp[u].colsum + 4.0 * N;
+        if (count_bytes) last_bytes += 8.0 * Tp[u].colsum + 4.0 * N;
         return st;
     }
-    void prune_node_v1(int u) {
-        NodeStep st = make_step(u);
-        int need = Tp[u].xmax + 1;
-        if (need <= 16) launch_prune<16>(st);
-        else if (need <= 32) launch_prune<32>(st);
-        else if (need <= 64) launch_prune<64>(st);
-        else if (need <= 128) launch_prune<128>(st);
-        else if (need <= 256) launch_prune<256>(st);
-        else if (need <= 512) launch_prune<512>(st);
-        else launch_prune<1024>(st);
-        CK(cudaGetLastError());
-        last_launches++;
-    }
-    // one launch for a whole list of nodes (chunked only if the list exceeds the parameter space)
+    // one launch for a whole list of nodes (chunked only if the list exceeds the parameter space): the FAST shard through
+    // the table-free sweep kernel.  The kernel leaves at once when some node is outside its range (flags[0], decided on
+    // the device); the general kernel launched right behind it then does the work (general_sweep(F, nodes, 1)).
     void sweep(const std::vector<int>& nodes) {
         size_t pos = 0;
         while (pos < nodes.size()) {
@@ -1506,12 +1548,9 @@ struct blg_handle {
                 for (int c = 1; c < k; ++c)
                     if (st.child[c].id == prev_node) { std::rotate(st.child, st.child + c, st.child + c + 1); break; }
                 SweepStep& ss = L.step[L.nsteps++];
-                ss.k = k; ss.first = nch; ss.prefact = 0;
+                ss.k = k; ss.first = nch; ss.node = u;
                 ss.resident = (L.nsteps >= 2 && prev_node == st.child[0].id && !children[prev_node].empty()) ? 1 : 0;
-                if (ss.resident) L.step[L.nsteps - 2].prefact = 1;
                 prev_node = u;
-                double raw = 1.0;
-                ss.inv = h_nc[u].inv; ss.ip0 = poison_below[u] ? std::numeric_limits<double>::quiet_NaN() : h_nc[u].ip0;
                 ss.out = st.out; ss.out_scl = st.out_scl; ss.cnt = st.cnt;
                 int sum = 0;
                 bool tiled = false;
@@ -1520,10 +1559,7 @@ struct blg_handle {
                     const ChildRef& cr = st.child[c];
                     sc.ell = cr.ell; sc.scl = cr.scl; sc.cnt = cr.cnt; sc.Wt = cr.Wt;
                     sc.wdp = cr.wdp; sc.table = (kind[cr.id] == BLG_WGDAFTER) ? 1 : 0;
-                    sc.e = h_eps0[cr.id]; sc.psi = h_nc[cr.id].psi; sc.cc = h_nc[cr.id].cc;
-                    sc.invEself = 1.0 / (sc.e > 1.0 ? 1.0 : sc.e);
-                    sc.Epre = raw > 1.0 ? 1.0 : raw;           // clamped prefix of the children merged before this one
-                    raw *= sc.e;
+                    sc.node = cr.id; sc.pad_ = 0;
                     int xm = Tp[cr.id].xmax;
                     sum += xm;
                     if (c >= 1 && xm >= 20) tiled = true;
@@ -1551,7 +1587,7 @@ struct blg_handle {
                 gscratch.ensure(gstride * (size_t)nwarps);
                 gs = gscratch.p;
             }
-            size_t smem = ((size_t)cap * 32 + 160) * warps_per_block * sizeof(double);
+            size_t smem = ((size_t)cap * 32 + 190) * warps_per_block * sizeof(double);
             if (smem > sweep_smem_set) {
                 CK(cudaFuncSetAttribute(sweep_kernel<false, 4, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
                 CK(cudaFuncSetAttribute(sweep_kernel<false, 4, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
@@ -1559,14 +1595,14 @@ struct blg_handle {
                 sweep_smem_set = smem;
             }
             if (!profile_sweep) {
-                if (persist) sweep_kernel<false, 4, true><<<blocks, 32 * warps_per_block, smem, stream>>>(L, N, ld, cap, gs, gstride, nullptr, d_tilectr.p);
-                else sweep_kernel<false, 4, false><<<blocks, 32 * warps_per_block, smem, stream>>>(L, N, ld, cap, gs, gstride, nullptr, d_tilectr.p);
+                if (persist) sweep_kernel<false, 4, true><<<blocks, 32 * warps_per_block, smem, stream>>>(L, d_nk.p, d_flags.p, d_ran.p, N, ld, cap, gs, gstride, nullptr, d_tilectr.p);
+                else sweep_kernel<false, 4, false><<<blocks, 32 * warps_per_block, smem, stream>>>(L, d_nk.p, d_flags.p, d_ran.p, N, ld, cap, gs, gstride, nullptr, d_tilectr.p);
                 CK(cudaGetLastError());
             } else {
                 d_prof.ensure((size_t)BLG_SWEEP_MAXSTEPS * 8);
                 CK(cudaMemsetAsync(d_prof.p, 0, (size_t)BLG_SWEEP_MAXSTEPS * 8 * sizeof(unsigned long long), stream));
                 if (persist) { blocks = (nwarps + warps_per_block - 1) / warps_per_block; }
-                sweep_kernel<true, 4, false><<<blocks, 32 * warps_per_block, smem, stream>>>(L, N, ld, cap, gs, gstride, d_prof.p, d_tilectr.p);
+                sweep_kernel<true, 4, false><<<blocks, 32 * warps_per_block, smem, stream>>>(L, d_nk.p, d_flags.p, d_ran.p, N, ld, cap, gs, gstride, d_prof.p, d_tilectr.p);
                 CK(cudaGetLastError());
                 std::vector<unsigned long long> hp((size_t)BLG_SWEEP_MAXSTEPS * 8);
                 CK(cudaMemcpyAsync(hp.data(), d_prof.p, hp.size() * sizeof(unsigned long long), cudaMemcpyDeviceToHost, stream));
@@ -1585,6 +1621,91 @@ struct blg_handle {
                         tot[0]/1e6, tot[1]/1e6, tot[2]/1e6, tot[3]/1e6, tot[4]/1e6, tot[5]/1e6, tot[6]/1e6, all/1e6);
             }
             last_launches++;
+        }
+    }
+
+    // the general kernel over a shard: one warp per family, any counts, any parameters.
+    // when = 0: always; when = 1: only if the device-side range flag says the sweep kernel could not run (fast shard).
+    void general_sweep(Shard& S, const std::vector<int>& nodes, int when, bool count_bytes) {
+        require(tabs_valid, "logpdf: ε/W tables are stale (call blg_rebuild)");
+        size_t pos = 0;
+        while (pos < nodes.size()) {
+            GList& L = *glist;
+            memset(&L, 0, sizeof(int) * 4);
+            int nch = 0, prev_node = -1;
+            while (pos < nodes.size() && L.nsteps < BLG_G_MAXSTEPS) {
+                const int u = nodes[pos];
+                const int k = (int)children[u].size();
+                require(k >= 1, "prune_node: leaf");
+                if (nch + k > BLG_G_MAXCHILD) break;
+                require(u < (int)S.Tp.size(), "logpdf: model has more node ids than the profile has columns (call blg_extend)");
+                std::vector<int> ord = children[u];
+                for (int c = 1; c < k; ++c)
+                    if (ord[c] == prev_node) { std::rotate(ord.begin(), ord.begin() + c, ord.begin() + c + 1); break; }
+                GStep& gs = L.step[L.nsteps++];
+                gs.k = k; gs.first = nch; gs.node = u;
+                gs.resident = (L.nsteps >= 2 && prev_node == ord[0] && !children[prev_node].empty()) ? 1 : 0;
+                for (int c : ord) {
+                    require(c >= 0 && c < (int)S.Tp.size(), "logpdf: child id beyond the profile columns");
+                    GChild& gc = L.child[nch++];
+                    memset(&gc, 0, sizeof(gc));
+                    if (children[c].empty()) { if (count_bytes) last_bytes += 2.0 * S.N; }
+                    else {
+                        Slab* sl = readable(S, c);
+                        gc.ell = sl->ell; gc.scl = sl->scl;
+                        gc.off = S.ragged ? S.Tp[c].off : nullptr;
+                        if (count_bytes) last_bytes += 8.0 * S.Tp[c].colsum + 4.0 * S.N;
+                    }
+                    gc.cnt = S.Tp[c].cnt;
+                    gc.node = c;
+                    gc.mode = 0;
+                    if (kind[c] == BLG_WGDAFTER) {
+                        if (kind[u] == BLG_WGD) gc.mode = 1;
+                        else {
+                            gc.mode = 2;
+                            require(tabs[c].built && tabs[c].Wt && tabs[c].wdim >= S.Tp[c].xmax + 1, "logpdf: W table below a WGT does not match the profile (call blg_rebuild)");
+                            gc.Wt = tabs[c].Wt; gc.wdp = tabs[c].wdp;
+                        }
+                    }
+                }
+                Slab* o = writable(S, u);
+                gs.out = o->ell; gs.out_scl = o->scl; gs.cnt = S.Tp[u].cnt;
+                gs.out_off = S.ragged ? S.Tp[u].off : nullptr;
+                if (count_bytes) last_bytes += 8.0 * S.Tp[u].colsum + 4.0 * S.N;
+                prev_node = u;
+                ++pos;
+            }
+            require(L.nsteps > 0, "sweep: a node has more children than one launch can describe");
+            // launch groups: the fast shard is one group; the heavy shard one per root-count class
+            std::vector<Shard::Class> groups = S.classes;
+            if (groups.empty()) groups.push_back({0, S.N, xmax_of(S, 0)});
+            d_gctr.ensure(16);
+            require(groups.size() <= 16, "general_sweep: too many launch groups");
+            CK(cudaMemsetAsync(d_gctr.p, 0, 16 * sizeof(unsigned int), stream));
+            int gi = 0;
+            for (const auto& g : groups) {
+                const int nfam = g.f1 - g.f0;
+                if (nfam <= 0) { ++gi; continue; }
+                const int cap = round_up(g.maxroot + 4, 2);
+                const bool small = g.maxroot < 128;                // every merge fits 4 registers per lane
+                const int cmax = small ? 4 : 16;
+                const int nbuf = (g.maxroot >= 32 * cmax) ? 3 : 2;
+                int wpb = 4;
+                while (wpb > 1 && (size_t)wpb * nbuf * cap * sizeof(double) > 200 * 1024) wpb >>= 1;
+                const size_t smem = (size_t)wpb * nbuf * cap * sizeof(double);
+                require(smem <= 227 * 1024, "general_sweep: count bound too large for the shared-memory columns");
+                int blocks = std::min((nfam + wpb - 1) / wpb, sm_count * 16);
+                if (small) {
+                    if (smem > g4_smem_set) { CK(cudaFuncSetAttribute(gsweep_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); g4_smem_set = smem; }
+                    gsweep_kernel<4><<<blocks, 32 * wpb, smem, stream>>>(L, d_nk.p, d_flags.p, when, d_ran.p, g.f0, g.f1, S.ld, cap, nbuf, d_gctr.p + gi);
+                } else {
+                    if (smem > g16_smem_set) { CK(cudaFuncSetAttribute(gsweep_kernel<16>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); g16_smem_set = smem; }
+                    gsweep_kernel<16><<<blocks, 32 * wpb, smem, stream>>>(L, d_nk.p, d_flags.p, when, d_ran.p, g.f0, g.f1, S.ld, cap, nbuf, d_gctr.p + gi);
+                }
+                CK(cudaGetLastError());
+                last_launches++;
+                ++gi;
+            }
         }
     }
 
@@ -1835,7 +1956,7 @@ struct blg_handle {
                 AdjChild& c = as.child[i];
                 c.ell = cr.ell; c.scl = cr.scl; c.cnt = cr.cnt; c.Wt = cr.Wt; c.wdp = cr.wdp; c.id = cr.id;
                 c.adj = adj[cr.id]; c.adj_scl = adjs[cr.id];
-                c.e = h_eps0[cr.id]; c.cc = h_nc[cr.id].cc;
+                c.e = h_nk[cr.id].e; c.cc = h_nk[cr.id].cc;
                 if (kind[cr.id] == BLG_WGDAFTER) {
                     const HostTab& tb = tabs[cr.id];
                     const size_t wsz = (size_t)tb.wdim * tb.wdp;
@@ -1862,7 +1983,7 @@ struct blg_handle {
             }
             as.ell = ns.out; as.scl = ns.out_scl; as.cnt = ns.cnt;
             as.adj = adj[u]; as.adj_scl = adjs[u];
-            as.ipow = ns.ipow; as.inv = h_nc[u].inv; as.partial = npart;
+            as.ipow = ns.ipow; as.inv = h_nk[u].inv; as.partial = npart;
             const int need = Tp[u].xmax + 1;
             if (need <= 8) launch_adjoint<8>(as);
             else if (need <= 16) launch_adjoint<16>(as);
@@ -1901,7 +2022,9 @@ struct blg_handle {
         const int P = cr ? 2 : 2 * nn + (int)wg.size() + 1;
         require(len >= P, "gradient: output vector too short");
         for (int i = 0; i < P; ++i) g[i] = 0.0;
-        if (N == 0) { if (logpdf_out) *logpdf_out = 0.0; return; }
+        if (Ntot == 0) { if (logpdf_out) *logpdf_out = 0.0; return; }
+        require(H.N == 0, "gradient: families with a root count above the fast bound are not supported by the gradient kernels "
+                          "(raise BLG_HEAVY_MIN up to 256 to keep them in the table-based shard)");
         // fresh evaluation that leaves the committed/proposal state alone (the reference uses a fresh L, model.jl:395)
         std::vector<Col> saved = Tp;
         try {
@@ -1910,6 +2033,10 @@ struct blg_handle {
             CK(cudaMemcpyAsync(&ll, result.p, sizeof(double), cudaMemcpyDeviceToHost, stream));
             CK(cudaStreamSynchronize(stream));
             if (logpdf_out) *logpdf_out = ll;
+            // the per-node scalars live on the device; the gradient's host-side step descriptions need a copy
+            h_nk.resize(ncols_model);
+            CK(cudaMemcpyAsync(h_nk.data(), d_nk.p, (size_t)ncols_model * sizeof(NodeK), cudaMemcpyDeviceToHost, stream));
+            CK(cudaStreamSynchronize(stream));
             // parameter groups (two tangent lanes each) and where their results go
             std::vector<Seeds<2>> groups;
             std::vector<std::pair<int, int>> dest;
@@ -1946,66 +2073,85 @@ struct blg_handle {
     void root_reduce(double* d_out) {
         require(tabs_valid, "logpdf: ε/W tables are stale (call blg_rebuild)");
         require(!children[0].empty(), "logpdf: the root is a leaf");
-        Slab* s = readable(0);
-        int nrow = Tp[0].xmax + 1;
-        if (!rootw_valid) {                  // normally built by tables_kernel together with the root's tables
-            rootw.ensure((size_t)nrow + 1);
+        const int nrow = root_rows();
+        if (!rootw_valid || rootw_rows != nrow) {   // normally built by tables_kernel together with the root's tables
+            rootw.ensure(2 * ((size_t)nrow + 1));
             ModelDev m = model_dev();
-            root_tables_kernel<<<1, 128, 0, stream>>>(m, rootw.p, nrow);
+            root_tables_kernel<<<1, 128, 0, stream>>>(m, rootw.p, H.N > 0 ? rootw.p + nrow + 1 : nullptr, nrow);
             CK(cudaGetLastError());
             rootw_valid = true;
+            rootw_rows = nrow;
             last_launches += 1;
         }
-        int blocks = (N + 255) / 256;
-        partial.ensure((size_t)blocks);
+        const int bF = (F.N + 255) / 256, bH = (H.N + 7) / 8;
+        partial.ensure((size_t)(bF + bH));
         if (!d_ticket.p) { d_ticket.ensure(1); CK(cudaMemsetAsync(d_ticket.p, 0, sizeof(unsigned int), stream)); }
-        root_kernel<<<blocks, 256, 0, stream>>>(s->ell, s->scl, Tp[0].cnt, rootw.p, weight.p, fam_ll.p, partial.p, N, ld, d_ticket.p, d_out);
-        CK(cudaGetLastError());
-        last_bytes += 8.0 * Tp[0].colsum + 4.0 * N + 8.0 * N;
-        last_launches += 1;
+        if (F.N > 0) {
+            Slab* s = readable(F, 0);
+            root_kernel<<<bF, 256, 0, stream>>>(s->ell, s->scl, F.Tp[0].cnt, rootw.p, F.weight.p, F.fam_ll.p, partial.p, F.N, F.ld, d_ticket.p,
+                                                (unsigned)(bF + bH), d_out);
+            CK(cudaGetLastError());
+            last_bytes += 8.0 * F.Tp[0].colsum + 4.0 * F.N + 8.0 * F.N;
+            last_launches += 1;
+        }
+        if (H.N > 0) {
+            Slab* s = readable(H, 0);
+            root_ragged_kernel<<<bH, 256, 0, stream>>>(s->ell, s->scl, H.Tp[0].cnt, H.Tp[0].off, rootw.p + nrow + 1, rootw.p, H.weight.p, H.fam_ll.p,
+                                                       partial.p, bF, H.N, d_ticket.p, (unsigned)(bF + bH), d_out);
+            CK(cudaGetLastError());
+            last_bytes += 8.0 * H.Tp[0].colsum + 4.0 * H.N + 8.0 * H.N;
+            last_launches += 1;
+        }
+    }
+    // any post-order is valid; visit the child with the larger counts LAST so that its column is still in shared
+    // memory when the parent (the very next step) needs it
+    std::vector<int> resident_order(const Shard& S) {
+        std::vector<int> nodes;
+        std::vector<std::pair<int, size_t>> stk;
+        std::vector<std::vector<int>> ord(ncols_model);
+        stk.push_back({0, 0});
+        while (!stk.empty()) {
+            int u = stk.back().first;
+            if (stk.back().second == 0 && ord[u].empty() && !children[u].empty()) {
+                ord[u] = children[u];
+                std::stable_sort(ord[u].begin(), ord[u].end(), [&](int a, int b) { return colsum_of(S, a) < colsum_of(S, b); });
+            }
+            if (stk.back().second < ord[u].size()) { int c = ord[u][stk.back().second++]; stk.push_back({c, 0}); }
+            else { if (!children[u].empty()) nodes.push_back(u); stk.pop_back(); }
+        }
+        return nodes;
     }
     void logpdf(int mode, int node, double* d_out) {
         // mode 0 full, 1 from node, 2 root only
         require(have_topology, "logpdf: no topology");
         last_bytes = 0.0;
         last_launches = 0;
-        if (N == 0) { CK(cudaMemsetAsync(d_out, 0, sizeof(double), stream)); return; }   // profile.jl:56
-        require((int)Tp.size() >= 1, "logpdf: no profile columns");
+        if (Ntot == 0) { CK(cudaMemsetAsync(d_out, 0, sizeof(double), stream)); return; }   // profile.jl:56
+        require(have_params && tabs_valid, "logpdf: ε/W tables are stale (call blg_rebuild)");
         if (timing) { for (auto& e : ev) if (!e) CK(cudaEventCreate(&e)); CK(cudaEventRecord(ev[0], stream)); }
-        std::vector<int> nodes;
-        if (mode == 0 && !order_resident) {
-            for (int u : postorder) if (!children[u].empty()) nodes.push_back(u);
-        } else if (mode == 0) {
-            // any post-order is valid; visit the child with the larger counts LAST so that its column is
-            // still in shared memory when the parent (the very next step) needs it
-            std::vector<std::pair<int, size_t>> stk;
-            std::vector<std::vector<int>> ord(ncols_model);
-            stk.push_back({0, 0});
-            while (!stk.empty()) {
-                int u = stk.back().first;
-                if (stk.back().second == 0 && ord[u].empty() && !children[u].empty()) {
-                    ord[u] = children[u];
-                    std::stable_sort(ord[u].begin(), ord[u].end(), [&](int a, int b) {
-                        double ca = a < (int)Tp.size() ? Tp[a].colsum : 0.0, cb = b < (int)Tp.size() ? Tp[b].colsum : 0.0;
-                        return ca < cb;
-                    });
-                }
-                if (stk.back().second < ord[u].size()) { int c = ord[u][stk.back().second++]; stk.push_back({c, 0}); }
-                else { if (!children[u].empty()) nodes.push_back(u); stk.pop_back(); }
+        for (Shard* S : {&F, &H}) {
+            if (S->N == 0) continue;
+            require((int)S->Tp.size() >= 1, "logpdf: no profile columns");
+            std::vector<int> nodes;
+            if (mode == 0 && !order_resident) {
+                for (int u : postorder) if (!children[u].empty()) nodes.push_back(u);
+            } else if (mode == 0) {
+                nodes = resident_order(*S);
+            } else if (mode == 1) {
+                int u = node - 1;
+                require(present(u), "logpdf_from: node id not in the model");
+                while (u >= 0) { if (!children[u].empty()) nodes.push_back(u); u = parent[u]; }
             }
-        } else if (mode == 1) {
-            int u = node - 1;
-            require(present(u), "logpdf_from: node id not in the model");
-            while (u >= 0) { if (!children[u].empty()) nodes.push_back(u); u = parent[u]; }
+            if (nodes.empty()) continue;
+            if (S == &H) general_sweep(H, nodes, 0, true);
+            else if (kernel_version == 1) general_sweep(F, nodes, 0, true);
+            else {
+                // the table-free kernel, and right behind it the general one, which only works when the device-side
+                // range flag says the first could not (no host round trip decides this)
+                sweep(nodes);
+                general_sweep(F, nodes, 1, false);
+            }
         }
-        bool v1 = kernel_version == 1;
-        for (int u : nodes) {          // outside the table-free kernel's range: the general per-node kernels
-            if (!fast_ok[u]) v1 = true;
-            for (int c : children[u]) if (!fast_ok[c]) v1 = true;
-        }
-        last_kernel = v1 ? 1 : 2;
-        if (v1) { for (int u : nodes) prune_node_v1(u); }
-        else sweep(nodes);
         if (timing) CK(cudaEventRecord(ev[1], stream));
         last_prune_bytes = last_bytes;
         root_reduce(d_out);
@@ -2043,19 +2189,19 @@ int blg_create(int device, void* stream, blg_handle** out) {
         else { CK(cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking)); h->own_stream = true; }
         h->result.ensure(16);
         { int smc = 0; if (cudaDeviceGetAttribute(&smc, cudaDevAttrMultiProcessorCount, device) == cudaSuccess && smc > 0) h->sm_count = smc; }
-        {   // factorial tables of the table-free kernel (per device, idempotent)
+        {   // 1/n! (table-free kernel) and 1/n (both pruning kernels); per device, idempotent
             const int n = BLG_FAST_MAXCOUNT + 72;
-            std::vector<double> f(n), fi(n), iv(n);
+            std::vector<double> fi(n);
             long double acc = 1.0L;
             for (int i = 0; i < n; ++i) {
                 if (i > 0) acc *= (long double)i;
-                f[i] = (double)acc;
                 fi[i] = (double)(1.0L / acc);
-                iv[i] = i > 0 ? 1.0 / (double)i : 0.0;
             }
-            CK(cudaMemcpyToSymbol(c_fact, f.data(), n * sizeof(double)));
             CK(cudaMemcpyToSymbol(c_invfact, fi.data(), n * sizeof(double)));
-            CK(cudaMemcpyToSymbol(c_inv, iv.data(), n * sizeof(double)));
+            const int ni = BLG_MAXCOUNT + 9;
+            std::vector<double> iv(ni);
+            for (int i = 0; i < ni; ++i) iv[i] = i > 0 ? 1.0 / (double)i : 0.0;
+            CK(cudaMemcpyToSymbol(c_inv, iv.data(), ni * sizeof(double)));
         }
         if (const char* kv = getenv("BLG_KERNEL")) h->kernel_version = atoi(kv) == 1 ? 1 : 2;
         if (const char* o = getenv("BLG_ORDER")) h->order_resident = atoi(o) != 0;
@@ -2063,6 +2209,9 @@ int blg_create(int device, void* stream, blg_handle** out) {
         if (const char* o = getenv("BLG_GRAD")) h->grad_mode = (strcmp(o, "forward") == 0) ? 0 : 1;
         if (const char* w = getenv("BLG_WPB")) { int v = atoi(w); if (v == 1 || v == 2 || v == 4) h->sweep_wpb = v; }
         if (const char* sc = getenv("BLG_SLICE")) h->slice_cap = std::max(8, std::min(224, atoi(sc)));
+        // families whose root count reaches this go to the heavy shard; above BLG_FAST_MAXCOUNT+1 the fast shard leaves the
+        // table-free kernel's range (general kernel on SoA slabs) but stays inside the table-based gradient kernels' (<= 256)
+        if (const char* hm = getenv("BLG_HEAVY_MIN")) h->heavy_min = std::max(1, std::min(256, atoi(hm)));
         *out = h;
     } catch (const std::exception& e) { g_create_error = e.what(); return 2; }
     return 0;
@@ -2071,16 +2220,16 @@ int blg_destroy(blg_handle* h) { delete h; return 0; }
 const char* blg_last_error(blg_handle* h) { return h ? h->err.c_str() : g_create_error.c_str(); }
 
 // ----------------------------------------------------------------------------------------------------
-static void family_order(const int32_t* X, int ncols, int npatterns, std::vector<int>& perm) {
+// perm: on entry the rows of X (caller's pattern indices) that form the set; on return the same rows in device order
+static void family_order(const int32_t* X, int ncols, std::vector<int>& perm) {
     // device order: families that share a warp should have similar count vectors at the heavy nodes, because
     // every loop of a warp runs to the warp's maximum count.  k-d ordering: recursively split the family set
     // at a multiple of 32 along the heavy column with the largest spread, until 32 families remain per leaf.
-    perm.resize(npatterns);
-    for (int f = 0; f < npatterns; ++f) perm[f] = f;
+    const int npatterns = (int)perm.size();
     if (npatterns > 32) {
         // candidate columns: largest Σx² first, identical columns (wgd / wgdafter copies) dropped
         std::vector<double> s1(ncols, 0.0), s2(ncols, 0.0);
-        for (int f = 0; f < npatterns; ++f) {
+        for (int f : perm) {
             const int32_t* x = X + (size_t)f * ncols;
             for (int c = 0; c < ncols; ++c) { s1[c] += x[c]; s2[c] += (double)x[c] * x[c]; }
         }
@@ -2096,9 +2245,12 @@ static void family_order(const int32_t* X, int ncols, int npatterns, std::vector
         }
         const int nk = (int)keys.size();
         if (nk > 0) {
+            // K is indexed by position in the ORIGINAL perm; `idx` is what gets permuted
             std::vector<float> K((size_t)npatterns * nk);
-            for (int f = 0; f < npatterns; ++f)
-                for (int k = 0; k < nk; ++k) K[(size_t)f * nk + k] = (float)X[(size_t)f * ncols + keys[k]];
+            for (int i = 0; i < npatterns; ++i)
+                for (int k = 0; k < nk; ++k) K[(size_t)i * nk + k] = (float)X[(size_t)perm[i] * ncols + keys[k]];
+            std::vector<int> idx(npatterns);
+            for (int i = 0; i < npatterns; ++i) idx[i] = i;
             std::vector<std::pair<int, int>> stk;
             stk.push_back({0, npatterns});
             std::vector<double> m1(nk), m2(nk);
@@ -2110,7 +2262,7 @@ static void family_order(const int32_t* X, int ncols, int npatterns, std::vector
                 std::fill(m1.begin(), m1.end(), 0.0);
                 std::fill(m2.begin(), m2.end(), 0.0);
                 for (int i = lo; i < hi; ++i) {
-                    const float* kf = &K[(size_t)perm[i] * nk];
+                    const float* kf = &K[(size_t)idx[i] * nk];
                     for (int k = 0; k < nk; ++k) { m1[k] += kf[k]; m2[k] += (double)kf[k] * kf[k]; }
                 }
                 int best = 0;
@@ -2122,69 +2274,123 @@ static void family_order(const int32_t* X, int ncols, int npatterns, std::vector
                 if (bestv <= 0.0) continue;             // identical on every key: nothing to gain
                 int half = ((n / 2 + 31) / 32) * 32;
                 if (half >= n) half = n / 2;
-                std::nth_element(perm.begin() + lo, perm.begin() + lo + half, perm.begin() + hi, [&](int a, int b) {
+                std::nth_element(idx.begin() + lo, idx.begin() + lo + half, idx.begin() + hi, [&](int a, int b) {
                     float va = K[(size_t)a * nk + best], vb = K[(size_t)b * nk + best];
                     return va != vb ? va > vb : a < b;
                 });
                 stk.push_back({lo + half, hi});
                 stk.push_back({lo, lo + half});
             }
+            std::vector<int> out(npatterns);
+            for (int i = 0; i < npatterns; ++i) out[i] = perm[idx[i]];
+            perm.swap(out);
         }
     }
 }
 
-int blg_set_profiles(blg_handle* h, const int32_t* X, const int64_t* weight, int ncols, int npatterns) {
-    BLG_ENTER(h)
-    h->require(ncols >= 0 && npatterns >= 0, "set_profiles: negative size");
-    CK(cudaStreamSynchronize(h->stream));
-    h->Tc.clear(); h->Tp.clear();
-    h->pool.clear();
-    for (auto* s : h->all_slabs) { cudaFree(s->ell); cudaFree(s->scl); delete s; }
-    h->all_slabs.clear();
-    for (auto* c : h->count_allocs) cudaFree(c);
-    h->count_allocs.clear();
-    h->N = npatterns;
-    h->ld = ((size_t)npatterns + 127) / 128 * 128;
-    h->tabs_valid = false;
-    h->rootw_valid = false;
-    for (auto& tb : h->tabs) blg_handle::free_tab(tb);
-    if (npatterns == 0) { h->Tc.clear(); h->Tp.clear(); return 0; }
-    h->require(X && weight, "set_profiles: null pointer");
-    size_t ld = h->ld;
-    family_order(X, ncols, npatterns, h->perm);
-    h->inv.resize(npatterns);
-    for (int f = 0; f < npatterns; ++f) h->inv[h->perm[f]] = f;
+// upload one family set: counts [column][family] (uint16), weights, column tables
+static void upload_shard(blg_handle* h, Shard& S, const int32_t* X, const int64_t* weight, int ncols) {
+    S.N = (int)S.perm.size();
+    S.ld = ((size_t)S.N + 127) / 128 * 128;
+    if (S.N == 0) return;
+    const size_t ld = S.ld;
     std::vector<uint16_t> stage((size_t)ncols * ld, 0);
     std::vector<Col> cols(ncols);
-    int gmax = 0;
     for (int c = 0; c < ncols; ++c) {
         int mx = 0;
         double cs = 0.0;
         uint16_t* dst = stage.data() + (size_t)c * ld;
-        for (int f = 0; f < npatterns; ++f) {
-            int32_t v = X[(size_t)h->perm[f] * ncols + c];
-            if (v < 0 || v > BLG_MAXCOUNT) throw std::runtime_error("set_profiles: count outside [0, 1023]");
+        for (int f = 0; f < S.N; ++f) {
+            const int32_t v = X[(size_t)S.perm[f] * ncols + c];
             dst[f] = (uint16_t)v;
             mx = std::max(mx, (int)v);
             cs += (double)v + 1.0;
         }
         cols[c].xmax = mx;
         cols[c].colsum = cs;
-        gmax = std::max(gmax, mx);
     }
     uint16_t* dcnt = nullptr;
     CK(cudaMalloc(&dcnt, stage.size() * sizeof(uint16_t)));
-    h->count_allocs.push_back(dcnt);
+    S.count_allocs.push_back(dcnt);
     CK(cudaMemcpyAsync(dcnt, stage.data(), stage.size() * sizeof(uint16_t), cudaMemcpyHostToDevice, h->stream));
     for (int c = 0; c < ncols; ++c) cols[c].cnt = dcnt + (size_t)c * ld;
+    if (S.ragged) {
+        // ragged slabs: family f's column starts at off[f] and holds exactly count+1 doubles
+        std::vector<uint32_t> ostage((size_t)ncols * ld, 0);
+        for (int c = 0; c < ncols; ++c) {
+            if (cols[c].colsum >= 4.0e9) throw std::runtime_error("set_profiles: heavy column too large for 32-bit offsets");
+            const uint16_t* src = stage.data() + (size_t)c * ld;
+            uint32_t* dst = ostage.data() + (size_t)c * ld;
+            uint32_t run = 0;
+            for (int f = 0; f < S.N; ++f) { dst[f] = run; run += (uint32_t)src[f] + 1u; }
+        }
+        uint32_t* doff = nullptr;
+        CK(cudaMalloc(&doff, ostage.size() * sizeof(uint32_t)));
+        S.off_allocs.push_back(doff);
+        CK(cudaMemcpy(doff, ostage.data(), ostage.size() * sizeof(uint32_t), cudaMemcpyHostToDevice));
+        for (int c = 0; c < ncols; ++c) cols[c].off = doff + (size_t)c * ld;
+    }
     std::vector<double> w(ld, 0.0);
-    for (int f = 0; f < npatterns; ++f) w[f] = (double)weight[h->perm[f]];
-    h->weight_total = 0.0;
-    for (int f = 0; f < npatterns; ++f) h->weight_total += w[f];
-    h->weight.ensure(ld);
-    h->fam_ll.ensure(ld);
-    CK(cudaMemcpyAsync(h->weight.p, w.data(), ld * sizeof(double), cudaMemcpyHostToDevice, h->stream));
-    CK(cudaMemsetAsync(h->fam_ll.p, 0, ld * sizeof(double), h->stream));
+    S.weight_total = 0.0;
+    for (int f = 0; f < S.N; ++f) { w[f] = (double)weight[S.perm[f]]; S.weight_total += w[f]; }
+    S.weight.ensure(ld);
+    S.fam_ll.ensure(ld);
+    CK(cudaMemcpyAsync(S.weight.p, w.data(), ld * sizeof(double), cudaMemcpyHostToDevice, h->stream));
+    CK(cudaMemsetAsync(S.fam_ll.p, 0, ld * sizeof(double), h->stream));
+    CK(cudaStreamSynchronize(h->stream));       // the staging vectors die here
+    S.Tc = cols;
+    S.Tp = cols;
+}
+
+int blg_set_profiles(blg_handle* h, const int32_t* X, const int64_t* weight, int ncols, int npatterns) {
+    BLG_ENTER(h)
+    h->require(ncols >= 0 && npatterns >= 0, "set_profiles: negative size");
+    CK(cudaStreamSynchronize(h->stream));
+    h->F.release();
+    h->H.release();
+    h->F.ragged = false;
+    h->H.ragged = true;
+    h->Ntot = npatterns;
+    h->loc.clear();
+    h->tabs_valid = false;
+    h->rootw_valid = false;
+    for (auto& tb : h->tabs) blg_handle::free_tab(tb);
+    if (npatterns == 0) return 0;
+    h->require(X && weight && ncols >= 1, "set_profiles: null pointer");
+    // split by the family's largest count (its root count, for an extended profile)
+    std::vector<int> rootc(npatterns);
+    for (int f = 0; f < npatterns; ++f) {
+        int mx = 0;
+        const int32_t* x = X + (size_t)f * ncols;
+        for (int c = 0; c < ncols; ++c) {
+            if (x[c] < 0 || x[c] > BLG_MAXCOUNT) throw std::runtime_error("set_profiles: count outside [0, " + std::to_string(BLG_MAXCOUNT) + "]");
+            mx = std::max(mx, (int)x[c]);
+        }
+        rootc[f] = mx;
+        (mx >= h->heavy_min ? h->H.perm : h->F.perm).push_back(f);
+    }
+    family_order(X, ncols, h->F.perm);
+    // heavy shard: heaviest first (the general kernel hands families out one per warp), launch groups by root count
+    std::stable_sort(h->H.perm.begin(), h->H.perm.end(), [&](int a, int b) { return rootc[a] > rootc[b]; });
+    {
+        static const int bounds[] = {4095, 2047, 1023, 511, 255, 127};
+        size_t pos = 0;
+        for (int bi = 0; bi < 6 && pos < h->H.perm.size(); ++bi) {
+            const int lo = bi + 1 < 6 ? bounds[bi + 1] : -1;      // this class holds root counts in (lo, bounds[bi]]
+            size_t end = pos;
+            while (end < h->H.perm.size() && rootc[h->H.perm[end]] > lo) ++end;
+            if (end > pos) h->H.classes.push_back({(int)pos, (int)end, rootc[h->H.perm[pos]]});
+            pos = end;
+        }
+    }
+    upload_shard(h, h->F, X, weight, ncols);
+    upload_shard(h, h->H, X, weight, ncols);
+    h->loc.assign(npatterns, 0);
+    for (int i = 0; i < h->F.N; ++i) h->loc[h->F.perm[i]] = i;
+    for (int i = 0; i < h->H.N; ++i) h->loc[h->H.perm[i]] = -1 - i;
+    // Pascal triangle for the merge tables of the gradient kernels (fast shard bounds only)
+    int gmax = 0;
+    for (const Col& c : h->F.Tp) gmax = std::max(gmax, c.xmax);
     h->maxcount = gmax;
     int pd = gmax + 1;
     if (pd > h->pdim) {
@@ -2194,8 +2400,6 @@ int blg_set_profiles(blg_handle* h, const int32_t* X, const int64_t* weight, int
         CK(cudaGetLastError());
     }
     CK(cudaStreamSynchronize(h->stream));
-    h->Tc = cols;
-    h->Tp = cols;
     BLG_LEAVE(h)
 }
 
@@ -2227,6 +2431,8 @@ int blg_set_topology(blg_handle* h, int ncols, const int32_t* parent, const uint
     CK(cudaMemcpyAsync(h->d_parent.p, h->parent.data(), n * sizeof(int), cudaMemcpyHostToDevice, h->stream));
     CK(cudaMemcpyAsync(h->d_child_off.p, off.data(), (n + 1) * sizeof(int), cudaMemcpyHostToDevice, h->stream));
     if (!idx.empty()) CK(cudaMemcpyAsync(h->d_child_idx.p, idx.data(), idx.size() * sizeof(int), cudaMemcpyHostToDevice, h->stream));
+    h->d_post.ensure(h->postorder.size());
+    CK(cudaMemcpyAsync(h->d_post.p, h->postorder.data(), h->postorder.size() * sizeof(int), cudaMemcpyHostToDevice, h->stream));
     CK(cudaStreamSynchronize(h->stream));
     h->have_topology = true;
     h->have_params = false;
@@ -2307,64 +2513,87 @@ int blg_gradient_async(blg_handle* h, double* d_g, int len) {
 
 int blg_commit(blg_handle* h) {
     BLG_ENTER(h)
-    h->Tc = h->Tp;
+    h->F.Tc = h->F.Tp;
+    h->H.Tc = h->H.Tp;
     BLG_LEAVE(h)
 }
 int blg_revert(blg_handle* h) {
     BLG_ENTER(h)
-    h->Tp = h->Tc;
+    h->F.Tp = h->F.Tc;
+    h->H.Tp = h->H.Tc;
     BLG_LEAVE(h)
 }
 int blg_extend(blg_handle* h, int i) {
     BLG_ENTER(h)
-    if (h->N == 0) return 0;
-    h->require(i >= 1 && i <= (int)h->Tp.size(), "extend: column out of range");
-    Col c = h->Tp[i - 1];
-    c.slab.reset();
-    h->Tp.push_back(c);
-    h->Tp.push_back(c);
+    if (h->Ntot == 0) return 0;
+    for (Shard* S : {&h->F, &h->H}) {
+        if (S->N == 0) continue;
+        h->require(i >= 1 && i <= (int)S->Tp.size(), "extend: column out of range");
+        Col c = S->Tp[i - 1];          // counts (and the ragged offsets, which follow the counts) are shared with column i
+        c.slab.reset();
+        S->Tp.push_back(c);
+        S->Tp.push_back(c);
+    }
     BLG_LEAVE(h)
 }
 int blg_shrink(blg_handle* h, int i) {
     BLG_ENTER(h)
-    if (h->N == 0) return 0;
-    h->require(i >= 1 && i + 1 <= (int)h->Tp.size(), "shrink: column out of range");
-    h->Tp.erase(h->Tp.begin() + (i - 1), h->Tp.begin() + (i + 1));
+    if (h->Ntot == 0) return 0;
+    for (Shard* S : {&h->F, &h->H}) {
+        if (S->N == 0) continue;
+        h->require(i >= 1 && i + 1 <= (int)S->Tp.size(), "shrink: column out of range");
+        S->Tp.erase(S->Tp.begin() + (i - 1), S->Tp.begin() + (i + 1));
+    }
     BLG_LEAVE(h)
 }
 
 int blg_get_column(blg_handle* h, int pattern, int node, int which, double* out, int cap, int* rows) {
     BLG_ENTER(h)
-    std::vector<Col>& T = which ? h->Tp : h->Tc;
-    h->require(pattern >= 0 && pattern < h->N, "get_column: pattern out of range");
+    h->require(pattern >= 0 && pattern < h->Ntot, "get_column: pattern out of range");
+    const int l = h->loc[pattern];
+    Shard& S = l >= 0 ? h->F : h->H;
+    const int slot = l >= 0 ? l : -1 - l;
+    std::vector<Col>& T = which ? S.Tp : S.Tc;
     h->require(node >= 1 && node <= (int)T.size(), "get_column: node out of range");
     Col& c = T[node - 1];
     CK(cudaStreamSynchronize(h->stream));
-    pattern = h->inv[pattern];
     uint16_t x;
-    CK(cudaMemcpy(&x, c.cnt + pattern, sizeof(uint16_t), cudaMemcpyDeviceToHost));
-    if (rows) *rows = c.xmax + 1;
+    CK(cudaMemcpy(&x, c.cnt + slot, sizeof(uint16_t), cudaMemcpyDeviceToHost));
+    // rows of the column as the reference holds it: count bound of this node over ALL patterns + 1
+    int xm = 0;
+    if (h->F.N > 0) xm = std::max(xm, (which ? h->F.Tp : h->F.Tc)[node - 1].xmax);
+    if (h->H.N > 0) xm = std::max(xm, (which ? h->H.Tp : h->H.Tc)[node - 1].xmax);
+    if (rows) *rows = xm + 1;
     for (int n = 0; n < cap; ++n) out[n] = -INFINITY;
     bool leaf = h->have_topology && node - 1 < h->ncols_model && h->present(node - 1) && h->children[node - 1].empty();
     if (leaf) { if (x < cap) out[x] = 0.0; return 0; }     // model.jl:409-410
     if (!c.slab) return 0;
     int sc;
-    CK(cudaMemcpy(&sc, c.slab->scl + pattern, sizeof(int), cudaMemcpyDeviceToHost));
+    CK(cudaMemcpy(&sc, c.slab->scl + slot, sizeof(int), cudaMemcpyDeviceToHost));
+    size_t base = (size_t)slot, stride = S.ld;
+    if (S.ragged) {
+        h->require(c.off != nullptr, "get_column: column has no offsets");
+        uint32_t o;
+        CK(cudaMemcpy(&o, c.off + slot, sizeof(uint32_t), cudaMemcpyDeviceToHost));
+        base = o;
+        stride = 1;
+    }
     for (int n = 0; n <= (int)x && n < cap; ++n) {
         double v;
-        CK(cudaMemcpy(&v, c.slab->ell + (size_t)n * h->ld + pattern, sizeof(double), cudaMemcpyDeviceToHost));
+        CK(cudaMemcpy(&v, c.slab->ell + base + (size_t)n * stride, sizeof(double), cudaMemcpyDeviceToHost));
         out[n] = std::log(v) + (double)sc * 0.6931471805599453;
     }
     BLG_LEAVE(h)
 }
 int blg_get_family_logpdf(blg_handle* h, double* out, int n) {
     BLG_ENTER(h)
-    h->require(n <= h->N, "get_family_logpdf: n exceeds the pattern count");
+    h->require(n <= h->Ntot, "get_family_logpdf: n exceeds the pattern count");
     CK(cudaStreamSynchronize(h->stream));
     if (n > 0) {
-        std::vector<double> tmp(h->N);
-        CK(cudaMemcpy(tmp.data(), h->fam_ll.p, (size_t)h->N * sizeof(double), cudaMemcpyDeviceToHost));
-        for (int f = 0; f < n; ++f) out[f] = tmp[h->inv[f]];
+        std::vector<double> tf(h->F.N), th(h->H.N);
+        if (h->F.N) CK(cudaMemcpy(tf.data(), h->F.fam_ll.p, (size_t)h->F.N * sizeof(double), cudaMemcpyDeviceToHost));
+        if (h->H.N) CK(cudaMemcpy(th.data(), h->H.fam_ll.p, (size_t)h->H.N * sizeof(double), cudaMemcpyDeviceToHost));
+        for (int f = 0; f < n; ++f) { const int l = h->loc[f]; out[f] = l >= 0 ? tf[l] : th[-1 - l]; }
     }
     BLG_LEAVE(h)
 }
@@ -2390,13 +2619,18 @@ int blg_get_W(blg_handle* h, int node, double* out, int cap, int* dim) {
         for (int j = 0; j < tb.wdim; ++j) out[(size_t)n * tb.wdim + j] = wt[(size_t)j * tb.wdp + n];
     BLG_LEAVE(h)
 }
-int blg_ncols(blg_handle* h, int which) { return h ? (int)(which ? h->Tp.size() : h->Tc.size()) : -1; }
-int blg_npatterns(blg_handle* h) { return h ? h->N : -1; }
+int blg_ncols(blg_handle* h, int which) {
+    if (!h) return -1;
+    const Shard& S = h->F.N > 0 ? h->F : h->H;
+    return (int)(which ? S.Tp.size() : S.Tc.size());
+}
+int blg_npatterns(blg_handle* h) { return h ? h->Ntot : -1; }
 int blg_family_order(const int32_t* X, int ncols, int npatterns, int32_t* perm_out) {
     if (!X || !perm_out || ncols < 0 || npatterns < 0) return 1;
     try {
-        std::vector<int> perm;
-        family_order(X, ncols, npatterns, perm);
+        std::vector<int> perm(npatterns);
+        for (int f = 0; f < npatterns; ++f) perm[f] = f;
+        family_order(X, ncols, perm);
         for (int f = 0; f < npatterns; ++f) perm_out[f] = perm[f];
     } catch (...) { return 1; }
     return 0;
@@ -2407,6 +2641,22 @@ int blg_last_algorithmic(blg_handle* h, double* bytes_total, double* bytes_prune
     if (bytes_prune) *bytes_prune = h->last_prune_bytes;
     if (launches) *launches = h->last_launches;
     return 0;
+}
+// how many launches of the table-free sweep kernel / of the general kernel have done the work so far (cumulative; both
+// kernels decide on the device, from the range flag of the last ε/W build, which of them runs), and how the patterns
+// are split between the fast (SoA, 32 families per warp) and the heavy (ragged, one warp per family) family sets
+int blg_kernel_runs(blg_handle* h, unsigned int* sweep_runs, unsigned int* general_runs, int* nfast, int* nheavy) {
+    BLG_ENTER(h)
+    unsigned int r[4] = {0, 0, 0, 0};
+    if (h->d_ran.p) {
+        CK(cudaStreamSynchronize(h->stream));
+        CK(cudaMemcpy(r, h->d_ran.p, sizeof(r), cudaMemcpyDeviceToHost));
+    }
+    if (sweep_runs) *sweep_runs = r[0];
+    if (general_runs) *general_runs = r[1];
+    if (nfast) *nfast = h->F.N;
+    if (nheavy) *nheavy = h->H.N;
+    BLG_LEAVE(h)
 }
 int blg_set_timing(blg_handle* h, int on) {
     if (!h) return 1;

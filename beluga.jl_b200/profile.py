@@ -213,7 +213,7 @@ class PArray:
 
     # ---- inspection ---------------------------------------------------------------------------------------
     def column(self, pattern, node, proposal=True):
-        cap = 1024
+        cap = 4200
         out = np.full(cap, np.nan)
         rows = C.c_int()
         self._ck(self.L.blg_get_column(self.h, int(pattern), int(node), 1 if proposal else 0, _dp(out), cap, C.byref(rows)))
@@ -245,6 +245,13 @@ class PArray:
         b, bp, l = C.c_double(), C.c_double(), C.c_int()
         self.L.blg_last_algorithmic(self.h, C.byref(b), C.byref(bp), C.byref(l))
         return b.value, bp.value, l.value
+
+    def kernel_runs(self):
+        """-> (sweep_runs, general_runs, nfast, nheavy): cumulative launches of each pruning kernel that did the work,
+        and the split of the patterns between the fast and the heavy family set (diagnostic)."""
+        a, b, nf, nh = C.c_uint(), C.c_uint(), C.c_int(), C.c_int()
+        self._ck(self.L.blg_kernel_runs(self.h, C.byref(a), C.byref(b), C.byref(nf), C.byref(nh)))
+        return a.value, b.value, nf.value, nh.value
 
     def set_timing(self, on=True):
         self._ck(self.L.blg_set_timing(self.h, 1 if on else 0))

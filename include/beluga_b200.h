@@ -123,6 +123,10 @@ int blg_family_order(const int32_t* X, int ncols, int npatterns, int32_t* perm_o
  * its parent, 2 B per leaf count, 4 B per stored scale exponent, 8 B per family result) — in total and
  * for the pruning launches alone — and the number of kernels the last likelihood call launched */
 int blg_last_algorithmic(blg_handle* h, double* bytes_total, double* bytes_prune, int* launches);
+/* diagnostic: launches of the table-free sweep kernel / of the general kernel that did the work so far (the choice is made
+ * on the device from the range flags of the last ε/W build), and the split of the patterns between the fast family set
+ * (root count <= 100: SoA slabs, 32 families per warp) and the heavy one (ragged slabs, one warp per family) */
+int blg_kernel_runs(blg_handle* h, unsigned int* sweep_runs, unsigned int* general_runs, int* nfast, int* nheavy);
 int blg_sync(blg_handle* h);
 /* measurement: when on, every likelihood call records CUDA events on the handle's stream around its
  * pruning launches and around its root/reduction launches; blg_last_timing waits for them and returns

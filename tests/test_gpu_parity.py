@@ -330,11 +330,110 @@ def test_short_branches_tiny_extinction_probabilities():
         want, pf = orc.logpdf(per_family=True)
         assert close(got, want, 1e-10), (tshort, got, want)
         np.testing.assert_allclose(data.family_logpdf(), pf, rtol=1e-10)
-        launches = data.last_algorithmic()[2]
-        assert (launches == 2) == fast, (tshort, launches)       # 2 = sweep_kernel + root_kernel
+        sweep_runs, general_runs, nfast, nheavy = data.kernel_runs()
+        assert nheavy == 0 and nfast == len(data)
+        # which kernel did the work is decided on the device from the range flags of the ε/W build
+        assert (sweep_runs, general_runs) == ((1, 0) if fast else (0, 1)), (tshort, sweep_runs, general_runs)
         B.set_(data); orc.set()
         B.update_(model[3], λ=1.4, μ=0.6); orc.update(3, lam=1.4, mu=0.6)
         assert close(B.logpdf_(model[3], data), orc.logpdf_from(3), 1e-10), tshort
+
+
+def test_heavy_families_go_to_the_general_kernel_the_rest_stays_on_the_sweep_kernel():
+    # the reference has no count bound (m = max(M)+1 is data-determined, model.jl:25,48).  Families whose root count is
+    # above the table-free kernel's bound form their own family set (ragged slabs, one warp per family, probability-form
+    # recursion); one heavy family must not push the others off the sweep kernel.
+    nw = "((A:0.4,B:0.5):0.3,(C:0.6,(D:0.2,E:0.3):0.2):0.25);"
+    names = list("ABCDE")
+    rng = np.random.default_rng(5)
+    counts = rng.integers(0, 12, size=(90, 5)).astype(np.int64)
+    counts[3] = [60, 70, 5, 40, 30]            # root 205
+    counts[17] = [0, 0, 300, 0, 1]             # lopsided, root 301
+    counts[40] = [120, 130, 110, 125, 115]     # root 600: every merge beyond the 4-register tiles
+    counts[41] = [33, 33, 33, 1, 1]            # root 101: just above the bound
+    counts[42] = [20, 20, 20, 20, 20]          # root 100: just inside
+    counts[77] = [1, 0, 0, 0, 400]             # one leaf with 400 copies
+    model, data, orc = pair(nw, (names, counts), 0.9, 1.0, 0.8, B.BRANCH)
+    got = B.logpdf_(model, data)
+    want, pf = orc.logpdf(per_family=True)
+    g = data.family_logpdf()
+    np.testing.assert_allclose(g, pf, rtol=RTOL)
+    assert close(got, want, RTOL)
+    sweep_runs, general_runs, nfast, nheavy = data.kernel_runs()
+    assert nheavy == 5 and nfast == len(data) - 5
+    assert sweep_runs == 1 and general_runs >= 1                 # both kernels worked, each on its own family set
+    # columns of a heavy family, as the reference would hold them
+    ow, ox = orc.profile()
+    heavy = [f for f in range(len(data)) if ox[f].max() > 100]
+    assert len(heavy) == 5
+    # (a column is held in linear fp64 with ONE exponent per (family, node): entries more than ≈ 700 log units below the
+    # column maximum flush to zero.  The reference keeps the column in log space but passes it through exp.(L) in every
+    # contraction (model.jl:426), so ITS entries below ≈ -700 in absolute terms are inexact.  Compare what both hold.)
+    for f in heavy:
+        for i in [1, 2, 3, 7]:
+            gcol, wcol = data.column(f, i), orc.column(f, i)
+            n = min(len(gcol), len(wcol))
+            gcol, wcol = gcol[:n], wcol[:n]
+            top = wcol[np.isfinite(wcol)].max()
+            near = np.isfinite(wcol) & (wcol > max(top - 150.0, -650.0))
+            assert np.all(np.isfinite(gcol[near])), (f, i)
+            np.testing.assert_allclose(gcol[near], wcol[near], rtol=1e-9, atol=1e-9)
+    # partial recompute, commit / revert, root only
+    B.set_(data); orc.set()
+    B.update_(model[4], λ=1.3, μ=0.7); orc.update(4, lam=1.3, mu=0.7)
+    want4, pf4 = orc.logpdf_from(4, per_family=True)
+    assert close(B.logpdf_(model[4], data), want4, RTOL)
+    np.testing.assert_allclose(data.family_logpdf(), pf4, rtol=RTOL)
+    B.rev_(data); orc.rev()
+    B.update_(model[4], λ=0.9, μ=1.0); orc.update(4, lam=0.9, mu=1.0)
+    assert close(B.logpdf_(model[4], data), want, RTOL)
+    B.update_(model[1], "η", 0.6); orc.update(1, eta=0.6)
+    assert close(B.logpdfroot(model[1], data), orc.logpdfroot(), RTOL)
+    # a WGD above a clade with heavy counts: extend!, evaluate, remove, shrink!
+    wgd = B.addwgd_(model, model[6], 0.1, 0.3)
+    B.extend_(data, 6)
+    orc.addwgd(6, 0.1, 0.3); orc.extend(6)
+    wantw, pfw = orc.logpdf(per_family=True)
+    assert close(B.logpdf_(model, data), wantw, RTOL)
+    np.testing.assert_allclose(data.family_logpdf(), pfw, rtol=RTOL)
+
+
+def test_heavy_leaf_beyond_the_reference_linear_W_range():
+    # 900 copies in one leaf: the reference builds W in LINEAR space (node.jl:181-192) and takes log.(W·exp.(L))
+    # (model.jl:425-426); w*(s|900) underflows and the family ends at -Inf although its likelihood is representable in
+    # log space.  The general kernel's probability-form recursion keeps it finite.  This is a documented deviation
+    # (DESIGN.md): pinned here so that it cannot change silently — the oracle, literal like the reference, gives -Inf.
+    nw = "((A:0.4,B:0.5):0.3,(C:0.6,(D:0.2,E:0.3):0.2):0.25);"
+    names = list("ABCDE")
+    counts = np.array([[1, 0, 0, 0, 900], [1, 0, 0, 0, 400], [2, 1, 0, 1, 3]], dtype=np.int64)
+    model, data, orc = pair(nw, (names, counts), 0.9, 1.0, 0.8, B.BRANCH)
+    got = B.logpdf_(model, data)
+    want, pf = orc.logpdf(per_family=True)
+    g = data.family_logpdf()
+    assert pf[0] == -np.inf and want == -np.inf
+    np.testing.assert_allclose(g[1:], pf[1:], rtol=RTOL)
+    # the value follows the trend of the same family with fewer copies (≈ -1.46 per extra copy at these rates)
+    assert np.isfinite(g[0]) and -1500.0 < g[0] < -1250.0 and np.isfinite(got)
+
+
+def test_heavy_only_batch_and_node_model_with_wgt():
+    # every family above the bound (no fast family set at all), Node model, a WGT (table form) and a WGD (polynomial form)
+    nw = "((A:0.4,B:0.5):0.3,(C:0.6,(D:0.2,E:0.3):0.2):0.25);"
+    names = list("ABCDE")
+    rng = np.random.default_rng(6)
+    counts = rng.integers(15, 60, size=(12, 5)).astype(np.int64)
+    counts[0] = [150, 2, 3, 100, 1]
+    model, data, orc = pair(nw, (names, counts), 0.7, 0.9, 0.75, B.NODE)
+    B.addwgd_(model, model[3], 0.15, 0.4); B.extend_(data, 3)
+    orc.addwgd(3, 0.15, 0.4); orc.extend(3)
+    B.addwgt_(model, model[8], 0.1, 0.2); B.extend_(data, 8)
+    orc.addwgt(8, 0.1, 0.2); orc.extend(8)
+    want, pf = orc.logpdf(per_family=True)
+    got = B.logpdf_(model, data)
+    np.testing.assert_allclose(data.family_logpdf(), pf, rtol=RTOL)
+    assert close(got, want, RTOL)
+    sweep_runs, general_runs, nfast, nheavy = data.kernel_runs()
+    assert nfast == 0 and nheavy == len(data) and sweep_runs == 0
 
 
 def test_sparse_profiles_empty_subtrees_and_partial_paths():
@@ -523,13 +622,67 @@ def test_mcmc_and_rjmcmc_keep_device_state_consistent(monocots):
 
 
 # ---- benchmark-shaped workload (C5: 100 taxa + 10 WGDs): oracle on a sample + size-independent properties --------
-def _c5(nfam, seed=20261019):
+def _c5(nfam, seed=20261019, leaf50=False):
     from beluga_b200.sim import add_random_wgds, rand_profiles, random_tree_newick
     nw = random_tree_newick(100, seed=seed)
     model, t, l = build_model(nw, 1.0, 1.2, 0.8, B.BRANCH)
     ext = add_random_wgds(model, 10, seed=seed)
-    names, counts = rand_profiles(model, nfam, seed=seed, max_rootsum=50)
+    if leaf50:      # SURVEY §8(d) C5, primary reading: only families with a LEAF count above 50 are rejected
+        names, counts = rand_profiles(model, nfam, seed=seed, max_leaf=50)
+    else:           # bounded reading: root sum <= 50
+        names, counts = rand_profiles(model, nfam, seed=seed, max_rootsum=50)
     return nw, model, ext, t, l, names, counts
+
+
+def _c5_oracle(nw, names, rows, threads=8):
+    """the oracle on `rows` (leaf counts, columns in `names` order) with add_random_wgds replayed (same seed)"""
+    orc = OracleDLWGD(nw, names, rows, 1.0, 1.2, 0.8, OBRANCH, threads=threads)
+    m2, _, _ = build_model(nw, 1.0, 1.2, 0.8, B.BRANCH)
+    rng = np.random.default_rng(20261019)
+    for _ in range(10):
+        ids = sorted(m2.nodes)
+        ww = np.array([m2.nodes[i]["t"] for i in ids], dtype=np.float64)
+        i = int(rng.choice(ids, p=ww / ww.sum()))
+        n = m2.nodes[i]
+        tt = rng.random() * n["t"]
+        if not (n["t"] - tt > 0.0):
+            tt = 0.5 * n["t"]
+        q = float(rng.beta(1.0, 3.0))
+        m2.addwgd_(n, tt, q)
+        orc.addwgd(i, tt, q)
+        orc.extend(i)
+    return orc
+
+
+def test_c5_leaf50_reading_against_oracle():
+    # the north star's C5 in its primary reading: leaf counts <= 50, m data-determined (root sums in the hundreds).
+    # Most families are above the table-free kernel's bound: they run on the general kernel, the others on the sweep kernel.
+    nw, model, ext, t, l, names, counts = _c5(160, leaf50=True)
+    X, w, _ = B.profile(t, l, (names, counts))
+    assert X[:, 0].max() > 400 and X[:, 0].min() <= 100, (X[:, 0].min(), X[:, 0].max())
+    data = B.PArray(X, w, device=0)
+    for i in ext:
+        B.extend_(data, i)
+    B.set_(data)
+    total = B.logpdf_(model, data)
+    pf = data.family_logpdf()
+    sweep_runs, general_runs, nfast, nheavy = data.kernel_runs()
+    assert nfast > 0 and nheavy > nfast and sweep_runs == 1 and general_runs >= 1
+    leaf_ids = sorted(l)
+    rows = X[:, [i - 1 for i in leaf_ids]]
+    orc = _c5_oracle(nw, [l[i] for i in leaf_ids], rows)
+    want, opf = orc.logpdf(per_family=True)
+    ow, ox = orc.profile()
+    key = {tuple(r[[i - 1 for i in leaf_ids]]): k for k, r in enumerate(ox)}
+    wantpf = np.array([opf[key[tuple(r)]] for r in rows])
+    np.testing.assert_allclose(pf, wantpf, rtol=RTOL)
+    assert close(total, float((w * wantpf).sum()), RTOL)
+    # node-local recompute on the mixed batch
+    B.update_(model[29], λ=1.3, μ=0.9); orc.update(29, lam=1.3, mu=0.9)
+    lp = B.logpdf_(model[29], data)
+    _, opf2 = orc.logpdf_from(29, per_family=True)
+    np.testing.assert_allclose(data.family_logpdf(), np.array([opf2[key[tuple(r)]] for r in rows]), rtol=RTOL)
+    assert close(lp, B.logpdf_(model, data), 1e-12)
 
 
 def test_c5_workload_sample_against_oracle_and_properties():
