@@ -25,6 +25,7 @@
 #include <memory>
 #include <stdexcept>
 #include <string>
+#include <unordered_map>
 #include <vector>
 
 #include "beluga_b200.h"
@@ -1017,7 +1018,8 @@ __global__ void __launch_bounds__(256) root_kernel(const double* __restrict__ el
                                                    const uint16_t* __restrict__ cnt, const double* __restrict__ rootw,
                                                    const double* __restrict__ weight, double* __restrict__ fam_ll,
                                                    double* __restrict__ partial, int N, size_t ld,
-                                                   unsigned int* __restrict__ ticket, unsigned int nblocks_total, double* __restrict__ out) {
+                                                   unsigned int* __restrict__ ticket, unsigned int nblocks_total,
+                                                   const int* __restrict__ flags, double* __restrict__ marker, double* __restrict__ out) {
     __shared__ double red[256];
     __shared__ bool last_block;
     int f = blockIdx.x * blockDim.x + threadIdx.x;
@@ -1054,7 +1056,7 @@ __global__ void __launch_bounds__(256) root_kernel(const double* __restrict__ el
             if ((int)threadIdx.x < k) red[threadIdx.x] += red[threadIdx.x + k];
             __syncthreads();
         }
-        if (threadIdx.x == 0) { out[0] = red[0]; *ticket = 0u; }
+        if (threadIdx.x == 0) { out[0] = red[0]; marker[0] = flags[0] ? 0.0 : 1.0; *ticket = 0u; }
     }
 }
 
@@ -1066,6 +1068,7 @@ __global__ void zero_slab_kernel(double* ell, int* scl, size_t nell, int N) {
 }
 
 #include "general.cuh"
+#include "pattern.cuh"
 #include "gradient.cuh"
 #include "adjoint.cuh"
 
@@ -1076,6 +1079,7 @@ struct Slab {
     double* ell = nullptr;
     int* scl = nullptr;
     size_t nd = 0;                   // doubles in ell
+    bool pat = false;                // columns are node patterns (pattern.cuh), not families
 };
 struct Col {
     const uint16_t* cnt = nullptr;   // device counts of this column (shared between aliases)
@@ -1115,8 +1119,32 @@ template <class T> struct DevBuf {
 // BLG_FAST_MAXCOUNT: node-major SoA slabs ell[n][family] padded to the shard's per-node bound, k-d family order, walked by
 // sweep_kernel (32 families per warp).  The HEAVY shard holds the rest: ragged slabs (family f's column starts at
 // off[f], exactly x_f+1 doubles, no padding), heaviest family first, walked by gsweep_kernel (one warp per family).
+// The distinct sub-patterns of one profile column (pattern.cuh): families with the same leaf counts below the node share
+// one pattern.  Keyed by the column's device count array, so the alias columns extend! creates (a WGD above node i sees
+// exactly node i's sub-patterns) share it.
+struct Pat {
+    int U = 0;                       // distinct patterns
+    size_t ld = 0;                   // column stride, U rounded up to 32
+    int xmax = 0;
+    double colsum = 0.0;             // Σ_p (x_p + 1)
+    uint16_t* d_cnt = nullptr;       // [ld] count of the column per pattern (sorted descending: heaviest tiles first)
+    int* d_fam2pat = nullptr;        // [N] family → pattern, on the device only for the root
+    std::vector<int> fam2pat;        // host
+    std::vector<int> rep;            // a family of each pattern
+    std::vector<uint16_t> h_cnt;
+    ~Pat() { if (d_cnt) cudaFree(d_cnt); if (d_fam2pat) cudaFree(d_fam2pat); }
+};
+// pattern of a node → pattern of each child, for one (node column, ordered child columns) combination
+struct Link {
+    int* d_pidx[BLG_MAXK] = {nullptr};   // nullptr: identity (single child sharing the node's patterns)
+    ~Link() { for (int* q : d_pidx) if (q) cudaFree(q); }
+};
+
 struct Shard {
     bool ragged = false;
+    std::vector<uint16_t> h_counts;  // host copy of the count rows [column][ld] (fast family set: pattern construction)
+    std::map<const uint16_t*, std::shared_ptr<Pat>> pats;
+    std::map<std::vector<const void*>, std::shared_ptr<Link>> links;
     int N = 0;               // families
     size_t ld = 0;           // stride of the count rows (and of the SoA slabs), N rounded up to 128
     std::vector<Col> Tc, Tp; // committed / proposal column tables (by id-1)
@@ -1141,6 +1169,7 @@ struct Shard {
         for (auto* c : count_allocs) cudaFree(c);
         count_allocs.clear();
         N = 0; ld = 0; perm.clear(); classes.clear(); weight_total = 0.0;
+        pats.clear(); links.clear(); h_counts.clear(); h_counts.shrink_to_fit();
     }
 };
 
@@ -1203,6 +1232,14 @@ struct blg_handle {
     int rootw_rows = 0;
     DevBuf<unsigned int> d_ticket;       // last-block-done counter of the root kernels (self-resetting)
 
+    // node patterns (pattern.cuh): the fast family set is evaluated once per distinct sub-pattern of every node.
+    // pat_mode == false: one column per family (the layout the gradient kernels work on; BLG_DEDUP=0 forces it).
+    bool pat_mode = true, pat_default = true;
+    int flag_cache = -1;                      // host copy of the device-side range flag: -1 unknown (since the last ε/W build)
+    std::unique_ptr<PList> plist{new PList()};
+    double last_pattern_bytes = 0.0;          // column bytes the last call actually wrote + read (pattern columns)
+    double last_pattern_cols = 0.0, last_family_cols = 0.0;   // node steps × patterns / × families of the last call
+
     // sweep-kernel plumbing
     int kernel_version = 2;
     bool order_resident = true;
@@ -1216,7 +1253,7 @@ struct blg_handle {
     DevBuf<unsigned int> d_tilectr, d_gctr;
     int sm_count = 148;
     DevBuf<double> gscratch;
-    size_t sweep_smem_set = 0, g4_smem_set = 0, g16_smem_set = 0;
+    size_t sweep_smem_set = 0, g4_smem_set = 0, g16_smem_set = 0, ptile_smem_set = 0;
 
     // accounting of the last likelihood call
     double last_bytes = 0.0, last_prune_bytes = 0.0;
@@ -1250,8 +1287,16 @@ struct blg_handle {
     }
 
     // ---- slabs ---------------------------------------------------------------------------------
-    static size_t slab_doubles(const Shard& S, const Col& col) {
-        return S.ragged ? (size_t)col.colsum + 8 : (size_t)(col.xmax + 1) * S.ld;
+    bool pattern_layout(const Shard& S) const { return pat_mode && !S.ragged; }
+    Pat* pat_of(Shard& S, const Col& col) {
+        auto it = S.pats.find(col.cnt);
+        require(it != S.pats.end(), "internal: column without node patterns");
+        return it->second.get();
+    }
+    size_t slab_doubles(Shard& S, const Col& col) {
+        if (S.ragged) return (size_t)col.colsum + 8;
+        if (pat_mode) { Pat* P = pat_of(S, col); return (size_t)(P->xmax + 1) * P->ld; }
+        return (size_t)(col.xmax + 1) * S.ld;
     }
     std::shared_ptr<Slab> new_slab(Shard& S, size_t nd) {
         Slab* s = nullptr;
@@ -1265,6 +1310,7 @@ struct blg_handle {
             if (e != cudaSuccess) { cudaFree(s->ell); delete s; throw CudaError(std::string("cudaMalloc: ") + cudaGetErrorString(e)); }
             S.all_slabs.push_back(s);
         }
+        s->pat = pattern_layout(S);
         Shard* sp = &S;
         return std::shared_ptr<Slab>(s, [sp](Slab* p) { sp->pool[p->nd].push_back(p); });
     }
@@ -1272,7 +1318,7 @@ struct blg_handle {
     // rewrites the whole column for every family)
     Slab* writable(Shard& S, int c) {
         Col& col = S.Tp[c];
-        if (!col.slab || col.slab.use_count() > 1) col.slab = new_slab(S, slab_doubles(S, col));
+        if (!col.slab || col.slab.use_count() > 1 || col.slab->pat != pattern_layout(S)) col.slab = new_slab(S, slab_doubles(S, col));
         return col.slab.get();
     }
     Slab* readable(Shard& S, int c) {
@@ -1282,6 +1328,7 @@ struct blg_handle {
             zero_slab_kernel<<<296, 256, 0, stream>>>(col.slab->ell, col.slab->scl, col.slab->nd, (int)S.ld);
             CK(cudaGetLastError());
         }
+        require(col.slab->pat == pattern_layout(S), "internal: column layout (node patterns / families) does not match the evaluation mode");
         return col.slab.get();
     }
     Slab* writable(int c) { return writable(F, c); }
@@ -1492,6 +1539,7 @@ struct blg_handle {
         tables_kernel<<<(unsigned)tlist.size(), 128, tsm, stream>>>(m, d_list_p, (int)tlist.size());
         CK(cudaGetLastError());
         if (full) tabs_valid = true;
+        flag_cache = -1;
     }
 
     // ---- pruning -----------------------------------------------------------------------------------
@@ -1654,6 +1702,7 @@ struct blg_handle {
                         Slab* sl = readable(S, c);
                         gc.ell = sl->ell; gc.scl = sl->scl;
                         gc.off = S.ragged ? S.Tp[c].off : nullptr;
+                        gc.ld = (int)S.ld;
                         if (count_bytes) last_bytes += 8.0 * S.Tp[c].colsum + 4.0 * S.N;
                     }
                     gc.cnt = S.Tp[c].cnt;
@@ -1671,6 +1720,7 @@ struct blg_handle {
                 Slab* o = writable(S, u);
                 gs.out = o->ell; gs.out_scl = o->scl; gs.cnt = S.Tp[u].cnt;
                 gs.out_off = S.ragged ? S.Tp[u].off : nullptr;
+                gs.out_ld = S.ld;
                 if (count_bytes) last_bytes += 8.0 * S.Tp[u].colsum + 4.0 * S.N;
                 prev_node = u;
                 ++pos;
@@ -1679,34 +1729,301 @@ struct blg_handle {
             // launch groups: the fast shard is one group; the heavy shard one per root-count class
             std::vector<Shard::Class> groups = S.classes;
             if (groups.empty()) groups.push_back({0, S.N, xmax_of(S, 0)});
-            d_gctr.ensure(16);
             require(groups.size() <= 16, "general_sweep: too many launch groups");
-            CK(cudaMemsetAsync(d_gctr.p, 0, 16 * sizeof(unsigned int), stream));
             int gi = 0;
-            for (const auto& g : groups) {
-                const int nfam = g.f1 - g.f0;
-                if (nfam <= 0) { ++gi; continue; }
-                const int cap = round_up(g.maxroot + 4, 2);
-                const bool small = g.maxroot < 128;                // every merge fits 4 registers per lane
-                const int cmax = small ? 4 : 16;
-                const int nbuf = (g.maxroot >= 32 * cmax) ? 3 : 2;
-                int wpb = 4;
-                while (wpb > 1 && (size_t)wpb * nbuf * cap * sizeof(double) > 200 * 1024) wpb >>= 1;
-                const size_t smem = (size_t)wpb * nbuf * cap * sizeof(double);
-                require(smem <= 227 * 1024, "general_sweep: count bound too large for the shared-memory columns");
-                int blocks = std::min((nfam + wpb - 1) / wpb, sm_count * 16);
-                if (small) {
-                    if (smem > g4_smem_set) { CK(cudaFuncSetAttribute(gsweep_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); g4_smem_set = smem; }
-                    gsweep_kernel<4><<<blocks, 32 * wpb, smem, stream>>>(L, d_nk.p, d_flags.p, when, d_ran.p, g.f0, g.f1, S.ld, cap, nbuf, d_gctr.p + gi);
-                } else {
-                    if (smem > g16_smem_set) { CK(cudaFuncSetAttribute(gsweep_kernel<16>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); g16_smem_set = smem; }
-                    gsweep_kernel<16><<<blocks, 32 * wpb, smem, stream>>>(L, d_nk.p, d_flags.p, when, d_ran.p, g.f0, g.f1, S.ld, cap, nbuf, d_gctr.p + gi);
+            for (const auto& g : groups) { launch_general(L, g.f0, g.f1, g.maxroot, 1, when, gi); ++gi; }
+        }
+    }
+
+    // ---- node patterns (pattern.cuh) -----------------------------------------------------------------------------------
+    const uint16_t* host_counts(const Shard& S, const Col& col) const {
+        return S.h_counts.data() + (col.cnt - S.count_allocs[0]);
+    }
+    void upload_pat(Pat& P) {
+        P.ld = ((size_t)P.U + 31) / 32 * 32;
+        std::vector<uint16_t> st(P.ld, P.h_cnt.empty() ? 0 : P.h_cnt.back());
+        std::copy(P.h_cnt.begin(), P.h_cnt.end(), st.begin());
+        CK(cudaMalloc(&P.d_cnt, P.ld * sizeof(uint16_t)));
+        CK(cudaMemcpy(P.d_cnt, st.data(), P.ld * sizeof(uint16_t), cudaMemcpyHostToDevice));
+    }
+    // distinct sub-patterns of every column of the current topology, bottom-up: a leaf's patterns are its distinct counts,
+    // a single child hands its patterns up unchanged, otherwise the distinct tuples of the children's patterns
+    void ensure_pats(Shard& S) {
+        const int N = S.N;
+        for (int u : postorder) {
+            require(u < (int)S.Tp.size(), "logpdf: model has more node ids than the profile has columns (call blg_extend)");
+            const Col& cu = S.Tp[u];
+            if (S.pats.count(cu.cnt)) continue;
+            const int k = (int)children[u].size();
+            if (k == 1) {
+                const int c = children[u][0];
+                require(c < (int)S.Tp.size(), "logpdf: child id beyond the profile columns");
+                S.pats[cu.cnt] = S.pats.at(S.Tp[c].cnt);
+                continue;
+            }
+            auto P = std::make_shared<Pat>();
+            const uint16_t* hx = host_counts(S, cu);
+            std::vector<int> id(N);
+            int U = 0;
+            std::vector<Pat*> cp;
+            if (k == 0) {
+                std::vector<int> tab(cu.xmax + 1, -1);
+                for (int f = 0; f < N; ++f) tab[hx[f]] = 0;
+                for (int v = cu.xmax; v >= 0; --v) if (tab[v] == 0) tab[v] = U++;      // descending counts
+                for (int f = 0; f < N; ++f) id[f] = tab[hx[f]];
+            } else {
+                for (int c : children[u]) {
+                    require(c < (int)S.Tp.size(), "logpdf: child id beyond the profile columns");
+                    cp.push_back(S.pats.at(S.Tp[c].cnt).get());
                 }
+                id = cp[0]->fam2pat;
+                U = cp[0]->U;
+                for (int j = 1; j < k; ++j) {
+                    const std::vector<int>& b = cp[j]->fam2pat;
+                    const uint64_t Ub = (uint64_t)cp[j]->U, space = (uint64_t)U * Ub;
+                    int next = 0;
+                    if (space <= std::max<uint64_t>(8ull * (uint64_t)N, 1ull << 16)) {
+                        std::vector<int> tab((size_t)space, -1);
+                        for (int f = 0; f < N; ++f) {
+                            int& t_ = tab[(size_t)((uint64_t)id[f] * Ub + (uint64_t)b[f])];
+                            if (t_ < 0) t_ = next++;
+                            id[f] = t_;
+                        }
+                    } else {
+                        std::unordered_map<uint64_t, int> mp;
+                        mp.reserve((size_t)N * 2);
+                        for (int f = 0; f < N; ++f) {
+                            auto ins = mp.emplace((uint64_t)id[f] * Ub + (uint64_t)b[f], next);
+                            if (ins.second) ++next;
+                            id[f] = ins.first->second;
+                        }
+                    }
+                    U = next;
+                }
+            }
+            // a family of each pattern, then the patterns in descending order of (own count, children's counts): the 32
+            // patterns of a tile get (nearly) the same loop bounds, and the heaviest tiles start first
+            std::vector<int> rep(U, -1);
+            for (int f = 0; f < N; ++f) if (rep[id[f]] < 0) rep[id[f]] = f;
+            std::vector<int> ord(U);
+            for (int i = 0; i < U; ++i) ord[i] = i;
+            if (k >= 2) {
+                std::vector<uint64_t> key(U);
+                for (int i = 0; i < U; ++i) {
+                    const int r = rep[i];
+                    uint64_t kk = (uint64_t)hx[r];
+                    for (int j = 0; j < std::min(k, 3); ++j) kk = (kk << 16) | (uint64_t)cp[j]->h_cnt[cp[j]->fam2pat[r]];
+                    key[i] = kk;
+                }
+                std::stable_sort(ord.begin(), ord.end(), [&](int a, int b) { return key[a] > key[b]; });
+            }
+            std::vector<int> newidx(U);
+            for (int i = 0; i < U; ++i) newidx[ord[i]] = i;
+            P->U = U;
+            P->rep.resize(U);
+            P->h_cnt.resize(U);
+            for (int i = 0; i < U; ++i) { P->rep[i] = rep[ord[i]]; P->h_cnt[i] = hx[rep[ord[i]]]; }
+            for (int f = 0; f < N; ++f) id[f] = newidx[id[f]];
+            P->fam2pat.swap(id);
+            P->xmax = cu.xmax;
+            P->colsum = 0.0;
+            for (int i = 0; i < U; ++i) P->colsum += (double)P->h_cnt[i] + 1.0;
+            upload_pat(*P);
+            S.pats[cu.cnt] = P;
+        }
+    }
+    // node pattern → child pattern maps for node u with its children in the order `ord`
+    Link* get_link(Shard& S, int u, const std::vector<int>& ord) {
+        std::vector<const void*> key;
+        key.push_back(S.Tp[u].cnt);
+        for (int c : ord) key.push_back(S.Tp[c].cnt);
+        auto it = S.links.find(key);
+        if (it != S.links.end()) return it->second.get();
+        Pat* Pu = pat_of(S, S.Tp[u]);
+        auto L = std::make_shared<Link>();
+        for (size_t j = 0; j < ord.size(); ++j) {
+            Pat* Pc = pat_of(S, S.Tp[ord[j]]);
+            if (Pc == Pu) {                       // (a single child: the node's patterns ARE the child's)
+                require(ord.size() == 1, "internal: a node with several children shares a child's patterns");
+                continue;
+            }
+            std::vector<int> px(Pu->ld, 0);
+            for (int q = 0; q < Pu->U; ++q) px[q] = Pc->fam2pat[Pu->rep[q]];
+            for (size_t q = Pu->U; q < Pu->ld; ++q) px[q] = Pu->U > 0 ? px[Pu->U - 1] : 0;
+            // the node's pattern must determine the child's for EVERY family (it does when the patterns were built for
+            // this tree; a different tree over the same columns needs new patterns)
+            for (int f = 0; f < S.N; ++f)
+                if (px[Pu->fam2pat[f]] != Pc->fam2pat[f]) throw std::runtime_error("logpdf: node patterns do not match the topology (call blg_set_profiles again after changing the species tree)");
+            CK(cudaMalloc(&L->d_pidx[j], Pu->ld * sizeof(int)));
+            CK(cudaMemcpy(L->d_pidx[j], px.data(), Pu->ld * sizeof(int), cudaMemcpyHostToDevice));
+        }
+        S.links[key] = L;
+        return L.get();
+    }
+    // algorithmic bytes of one node step in SURVEY §8(d)'s per-FAMILY accounting (whatever layout does the work)
+    void count_step_bytes(Shard& S, int u) {
+        for (int c : children[u]) {
+            if (children[c].empty()) last_bytes += 2.0 * S.N;
+            else last_bytes += 8.0 * S.Tp[c].colsum + 4.0 * S.N;
+        }
+        last_bytes += 8.0 * S.Tp[u].colsum + 4.0 * S.N;
+        last_family_cols += (double)S.N;
+    }
+    // the fast family set over node patterns: the nodes of the list level by level (children in earlier launches), a
+    // warp per tile of 32 patterns of one node.  general == true: the general kernel (any parameters), one launch per node.
+    void psweep(const std::vector<int>& nodes, bool general) {
+        Shard& S = F;
+        ensure_pats(S);
+        std::vector<int> level(ncols_model, -1);
+        int nlev = 0;
+        for (int u : nodes) {
+            int lv = 0;
+            for (int c : children[u]) if (level[c] >= 0) lv = std::max(lv, level[c] + 1);
+            level[u] = lv;
+            nlev = std::max(nlev, lv + 1);
+        }
+        bool first = true;
+        for (int lv = 0; lv < nlev; ++lv) {
+            std::vector<int> todo;
+            for (int u : nodes) if (level[u] == lv) todo.push_back(u);
+            // heaviest nodes first inside a level
+            std::stable_sort(todo.begin(), todo.end(), [&](int a, int b) { return pat_of(S, S.Tp[a])->colsum > pat_of(S, S.Tp[b])->colsum; });
+            size_t pos = 0;
+            while (pos < todo.size()) {
+                PList& L = *plist;
+                memset(&L, 0, sizeof(int) * 4);
+                int nch = 0, worst = 1, ntiles = 0;
+                while (pos < todo.size() && L.nsteps < BLG_P_MAXSTEPS) {
+                    const int u = todo[pos];
+                    const int k = (int)children[u].size();
+                    require(k >= 1, "prune_node: leaf");
+                    if (nch + k > BLG_P_MAXCHILD) break;
+                    require(tabs_valid && tabs[u].built && tabs[u].k == k, "logpdf: ε/W tables are stale (call blg_rebuild)");
+                    std::vector<int> ord(tabs[u].mo, tabs[u].mo + k);
+                    Pat* Pu = pat_of(S, S.Tp[u]);
+                    Link* lk = get_link(S, u, ord);
+                    if (general) {
+                        general_pstep(S, u, ord, Pu, lk, first);
+                        first = false;
+                        count_step_bytes(S, u);
+                        ++pos;
+                        continue;
+                    }
+                    PStep& ps = L.step[L.nsteps++];
+                    ps.k = k; ps.first = nch; ps.node = u; ps.U = Pu->U; ps.tile0 = ntiles; ps.ld = (int)Pu->ld;
+                    ps.cnt = Pu->d_cnt;
+                    int sum = 0;
+                    bool tiled = false;
+                    for (int j = 0; j < k; ++j) {
+                        const int c = ord[j];
+                        require(tabs[c].built && tabs[c].wdim >= S.Tp[c].xmax + 1 && tabs[c].xfast == S.Tp[c].xmax,
+                                "logpdf: W table of a child does not match the profile (call blg_rebuild)");
+                        Pat* Pc = pat_of(S, S.Tp[c]);
+                        PChild& pc = L.child[nch++];
+                        memset(&pc, 0, sizeof(pc));
+                        if (!children[c].empty()) { Slab* sl = readable(S, c); pc.ell = sl->ell; pc.scl = sl->scl; }
+                        pc.cnt = Pc->d_cnt;
+                        pc.pidx = lk->d_pidx[j];
+                        pc.Wt = tabs[c].Wt; pc.wdp = tabs[c].wdp; pc.table = (kind[c] == BLG_WGDAFTER) ? 1 : 0;
+                        pc.node = c; pc.ld = (int)Pc->ld;
+                        sum += Pc->xmax;
+                        if (j >= 1 && Pc->xmax >= 20) tiled = true;
+                        last_pattern_bytes += children[c].empty() ? 0.0 : 8.0 * Pc->colsum;   // (each child column is read at least once)
+                    }
+                    if (k == 2 && std::min(pat_of(S, S.Tp[ord[0]])->xmax, pat_of(S, S.Tp[ord[1]])->xmax) < 20) tiled = false;
+                    sum = std::min(sum, k * Pu->xmax);             // (per tile the children's maxima are taken separately)
+                    worst = std::max(worst, tiled ? 3 * (sum + 1) : sum + k + 1);
+                    Slab* o = writable(S, u);
+                    ps.out = o->ell; ps.out_scl = o->scl;
+                    ntiles += (Pu->U + 31) / 32;
+                    last_pattern_bytes += 8.0 * Pu->colsum + 4.0 * Pu->U;
+                    last_pattern_cols += (double)Pu->U;
+                    count_step_bytes(S, u);
+                    ++pos;
+                }
+                if (general) continue;
+                require(L.nsteps > 0, "sweep: a node has more children than one launch can describe");
+                L.ntiles = ntiles;
+                L.first_of_call = first ? 1 : 0;
+                first = false;
+                int cap = std::min(worst, std::max(slice_cap, 56));   // doubles per lane of a warp's shared slice; rare larger tiles use global scratch
+                int wpb = 4;
+                double* gs = nullptr;
+                size_t gstride = 0;
+                if (worst > cap) {
+                    gstride = (size_t)worst * 32;
+                    gscratch.ensure(gstride * (size_t)ntiles);
+                    gs = gscratch.p;
+                }
+                const size_t smem = (size_t)cap * 32 * wpb * sizeof(double);
+                if (smem > ptile_smem_set) {
+                    CK(cudaFuncSetAttribute(ptile_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+                    ptile_smem_set = smem;
+                }
+                ptile_kernel<<<(ntiles + wpb - 1) / wpb, 32 * wpb, smem, stream>>>(L, d_nk.p, d_flags.p, d_ran.p, cap, gs, gstride);
                 CK(cudaGetLastError());
                 last_launches++;
-                ++gi;
             }
         }
+    }
+    // one node over its patterns with the general kernel (one warp per pattern)
+    void general_pstep(Shard& S, int u, const std::vector<int>& ord, Pat* Pu, Link* lk, bool first) {
+        GList& L = *glist;
+        memset(&L, 0, sizeof(int) * 4);
+        L.nsteps = 1;
+        GStep& gs = L.step[0];
+        memset(&gs, 0, sizeof(gs));
+        gs.k = (int)ord.size(); gs.first = 0; gs.node = u; gs.resident = 0;
+        for (size_t j = 0; j < ord.size(); ++j) {
+            const int c = ord[j];
+            Pat* Pc = pat_of(S, S.Tp[c]);
+            GChild& gc = L.child[j];
+            memset(&gc, 0, sizeof(gc));
+            if (!children[c].empty()) { Slab* sl = readable(S, c); gc.ell = sl->ell; gc.scl = sl->scl; }
+            gc.cnt = Pc->d_cnt;
+            gc.pidx = lk->d_pidx[j];
+            gc.node = c;
+            gc.ld = (int)Pc->ld;
+            gc.mode = 0;
+            if (kind[c] == BLG_WGDAFTER) {
+                if (kind[u] == BLG_WGD) gc.mode = 1;
+                else {
+                    gc.mode = 2;
+                    require(tabs[c].built && tabs[c].Wt && tabs[c].wdim >= S.Tp[c].xmax + 1, "logpdf: W table below a WGT does not match the profile (call blg_rebuild)");
+                    gc.Wt = tabs[c].Wt; gc.wdp = tabs[c].wdp;
+                }
+            }
+        }
+        Slab* o = writable(S, u);
+        gs.out = o->ell; gs.out_scl = o->scl; gs.cnt = Pu->d_cnt; gs.out_off = nullptr; gs.out_ld = Pu->ld;
+        launch_general(L, 0, Pu->U, Pu->xmax, first ? 1 : 0, 0, 0);
+        last_pattern_bytes += 8.0 * Pu->colsum + 4.0 * Pu->U;
+        last_pattern_cols += (double)Pu->U;
+    }
+    // gsweep_kernel over items f0..f1-1 whose largest count is maxroot
+    void launch_general(const GList& L, int f0, int f1, int maxroot, int count_run, int when, int counter_slot) {
+        const int nfam = f1 - f0;
+        if (nfam <= 0) return;
+        d_gctr.ensure(16);
+        CK(cudaMemsetAsync(d_gctr.p + counter_slot, 0, sizeof(unsigned int), stream));
+        const int cap = round_up(maxroot + 4, 2);
+        const bool small = maxroot < 128;                // every merge fits 4 registers per lane
+        const int cmax = small ? 4 : 16;
+        const int nbuf = (maxroot >= 32 * cmax) ? 3 : 2;
+        int wpb = 4;
+        while (wpb > 1 && (size_t)wpb * nbuf * cap * sizeof(double) > 200 * 1024) wpb >>= 1;
+        const size_t smem = (size_t)wpb * nbuf * cap * sizeof(double);
+        require(smem <= 227 * 1024, "general_sweep: count bound too large for the shared-memory columns");
+        int blocks = std::min((nfam + wpb - 1) / wpb, sm_count * 16);
+        if (small) {
+            if (smem > g4_smem_set) { CK(cudaFuncSetAttribute(gsweep_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); g4_smem_set = smem; }
+            gsweep_kernel<4><<<blocks, 32 * wpb, smem, stream>>>(L, d_nk.p, d_flags.p, when, d_ran.p, f0, f1, count_run, cap, nbuf, d_gctr.p + counter_slot);
+        } else {
+            if (smem > g16_smem_set) { CK(cudaFuncSetAttribute(gsweep_kernel<16>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); g16_smem_set = smem; }
+            gsweep_kernel<16><<<blocks, 32 * wpb, smem, stream>>>(L, d_nk.p, d_flags.p, when, d_ran.p, f0, f1, count_run, cap, nbuf, d_gctr.p + counter_slot);
+        }
+        CK(cudaGetLastError());
+        last_launches++;
     }
 
     // ---- gradient (forward-mode, path-sparse) ---------------------------------------------------------------
@@ -2026,7 +2343,10 @@ struct blg_handle {
         require(H.N == 0, "gradient: families with a root count above the fast bound are not supported by the gradient kernels "
                           "(raise BLG_HEAVY_MIN up to 256 to keep them in the table-based shard)");
         // fresh evaluation that leaves the committed/proposal state alone (the reference uses a fresh L, model.jl:395)
+        // (the gradient kernels work on one column per FAMILY: the evaluation below is a private per-family sweep)
         std::vector<Col> saved = Tp;
+        const bool pm = pat_mode;
+        pat_mode = false;
         try {
             logpdf(0, 1, result.p);
             double ll;
@@ -2066,8 +2386,9 @@ struct blg_handle {
                 if (dest[i].first >= 0) g[dest[i].first] = res[2 * i];
                 if (dest[i].second >= 0) g[dest[i].second] = res[2 * i + 1];
             }
-        } catch (...) { Tp = saved; throw; }
+        } catch (...) { Tp = saved; pat_mode = pm; throw; }
         Tp = saved;
+        pat_mode = pm;
     }
 
     void root_reduce(double* d_out) {
@@ -2086,10 +2407,23 @@ struct blg_handle {
         const int bF = (F.N + 255) / 256, bH = (H.N + 7) / 8;
         partial.ensure((size_t)(bF + bH));
         if (!d_ticket.p) { d_ticket.ensure(1); CK(cudaMemsetAsync(d_ticket.p, 0, sizeof(unsigned int), stream)); }
+        double* marker = result.p + 8;
         if (F.N > 0) {
             Slab* s = readable(F, 0);
-            root_kernel<<<bF, 256, 0, stream>>>(s->ell, s->scl, F.Tp[0].cnt, rootw.p, F.weight.p, F.fam_ll.p, partial.p, F.N, F.ld, d_ticket.p,
-                                                (unsigned)(bF + bH), d_out);
+            if (pat_mode) {
+                ensure_pats(F);
+                Pat* P0 = pat_of(F, F.Tp[0]);
+                if (!P0->d_fam2pat) {
+                    CK(cudaMalloc(&P0->d_fam2pat, F.ld * sizeof(int)));
+                    CK(cudaMemcpy(P0->d_fam2pat, P0->fam2pat.data(), (size_t)F.N * sizeof(int), cudaMemcpyHostToDevice));
+                }
+                root_pattern_kernel<<<bF, 256, 0, stream>>>(s->ell, s->scl, P0->d_cnt, P0->d_fam2pat, rootw.p, F.weight.p, F.fam_ll.p, partial.p, F.N,
+                                                            P0->ld, d_ticket.p, (unsigned)(bF + bH), d_flags.p, marker, d_out);
+                last_pattern_bytes += 8.0 * P0->colsum + 4.0 * P0->U + 12.0 * F.N;
+            } else {
+                root_kernel<<<bF, 256, 0, stream>>>(s->ell, s->scl, F.Tp[0].cnt, rootw.p, F.weight.p, F.fam_ll.p, partial.p, F.N, F.ld, d_ticket.p,
+                                                    (unsigned)(bF + bH), d_flags.p, marker, d_out);
+            }
             CK(cudaGetLastError());
             last_bytes += 8.0 * F.Tp[0].colsum + 4.0 * F.N + 8.0 * F.N;
             last_launches += 1;
@@ -2097,7 +2431,7 @@ struct blg_handle {
         if (H.N > 0) {
             Slab* s = readable(H, 0);
             root_ragged_kernel<<<bH, 256, 0, stream>>>(s->ell, s->scl, H.Tp[0].cnt, H.Tp[0].off, rootw.p + nrow + 1, rootw.p, H.weight.p, H.fam_ll.p,
-                                                       partial.p, bF, H.N, d_ticket.p, (unsigned)(bF + bH), d_out);
+                                                       partial.p, bF, H.N, d_ticket.p, (unsigned)(bF + bH), d_flags.p, marker, d_out);
             CK(cudaGetLastError());
             last_bytes += 8.0 * H.Tp[0].colsum + 4.0 * H.N + 8.0 * H.N;
             last_launches += 1;
@@ -2121,11 +2455,13 @@ struct blg_handle {
         }
         return nodes;
     }
-    void logpdf(int mode, int node, double* d_out) {
+    // force_general: run the general kernel on the fast family set whatever the range flag says (the caller has seen the flag)
+    void logpdf(int mode, int node, double* d_out, bool force_general = false) {
         // mode 0 full, 1 from node, 2 root only
         require(have_topology, "logpdf: no topology");
         last_bytes = 0.0;
         last_launches = 0;
+        last_pattern_bytes = last_pattern_cols = last_family_cols = 0.0;
         if (Ntot == 0) { CK(cudaMemsetAsync(d_out, 0, sizeof(double), stream)); return; }   // profile.jl:56
         require(have_params && tabs_valid, "logpdf: ε/W tables are stale (call blg_rebuild)");
         if (timing) { for (auto& e : ev) if (!e) CK(cudaEventCreate(&e)); CK(cudaEventRecord(ev[0], stream)); }
@@ -2133,7 +2469,7 @@ struct blg_handle {
             if (S->N == 0) continue;
             require((int)S->Tp.size() >= 1, "logpdf: no profile columns");
             std::vector<int> nodes;
-            if (mode == 0 && !order_resident) {
+            if (mode == 0 && (!order_resident || pattern_layout(*S))) {
                 for (int u : postorder) if (!children[u].empty()) nodes.push_back(u);
             } else if (mode == 0) {
                 nodes = resident_order(*S);
@@ -2143,7 +2479,8 @@ struct blg_handle {
                 while (u >= 0) { if (!children[u].empty()) nodes.push_back(u); u = parent[u]; }
             }
             if (nodes.empty()) continue;
-            if (S == &H) general_sweep(H, nodes, 0, true);
+            if (S == &H) { general_sweep(H, nodes, 0, true); last_family_cols += (double)H.N * nodes.size(); }
+            else if (pat_mode) psweep(nodes, force_general || kernel_version == 1 || flag_cache == 0);
             else if (kernel_version == 1) general_sweep(F, nodes, 0, true);
             else {
                 // the table-free kernel, and right behind it the general one, which only works when the device-side
@@ -2156,6 +2493,15 @@ struct blg_handle {
         last_prune_bytes = last_bytes;
         root_reduce(d_out);
         if (timing) { CK(cudaEventRecord(ev[2], stream)); ev_valid = true; }
+    }
+    // the pattern path runs OPTIMISTICALLY on the table-free kernel: the kernels leave at once when the device-side range
+    // flag of the last ε/W build says no, and the root kernel hands the flag back next to the result.
+    bool pattern_fast_path() const { return pat_mode && F.N > 0 && kernel_version != 1; }
+    void fetch_flag() {
+        int fl = 1;
+        CK(cudaMemcpyAsync(&fl, d_flags.p, sizeof(int), cudaMemcpyDeviceToHost, stream));
+        CK(cudaStreamSynchronize(stream));
+        flag_cache = fl ? 1 : 0;
     }
 };
 
@@ -2211,6 +2557,7 @@ int blg_create(int device, void* stream, blg_handle** out) {
         if (const char* sc = getenv("BLG_SLICE")) h->slice_cap = std::max(8, std::min(224, atoi(sc)));
         // families whose root count reaches this go to the heavy shard; above BLG_FAST_MAXCOUNT+1 the fast shard leaves the
         // table-free kernel's range (general kernel on SoA slabs) but stays inside the table-based gradient kernels' (<= 256)
+        if (const char* dd = getenv("BLG_DEDUP")) h->pat_mode = h->pat_default = atoi(dd) != 0;
         if (const char* hm = getenv("BLG_HEAVY_MIN")) h->heavy_min = std::max(1, std::min(256, atoi(hm)));
         *out = h;
     } catch (const std::exception& e) { g_create_error = e.what(); return 2; }
@@ -2314,6 +2661,7 @@ static void upload_shard(blg_handle* h, Shard& S, const int32_t* X, const int64_
     S.count_allocs.push_back(dcnt);
     CK(cudaMemcpyAsync(dcnt, stage.data(), stage.size() * sizeof(uint16_t), cudaMemcpyHostToDevice, h->stream));
     for (int c = 0; c < ncols; ++c) cols[c].cnt = dcnt + (size_t)c * ld;
+    if (!S.ragged) S.h_counts = stage;
     if (S.ragged) {
         // ragged slabs: family f's column starts at off[f] and holds exactly count+1 doubles
         std::vector<uint32_t> ostage((size_t)ncols * ld, 0);
@@ -2470,13 +2818,25 @@ static int logpdf_sync(blg_handle* h, int mode, int node, double* out) {
     BLG_ENTER(h)
     h->require(out != nullptr, "logpdf: null output");
     h->logpdf(mode, node, h->result.p);
-    CK(cudaMemcpyAsync(out, h->result.p, sizeof(double), cudaMemcpyDeviceToHost, h->stream));
+    double r[9] = {0};
+    CK(cudaMemcpyAsync(r, h->result.p, sizeof(r), cudaMemcpyDeviceToHost, h->stream));
     CK(cudaStreamSynchronize(h->stream));
+    if (h->Ntot > 0 && h->pattern_fast_path() && h->flag_cache != 0) {
+        h->flag_cache = (r[8] != 0.0) ? 0 : 1;
+        if (h->flag_cache == 0) {            // outside the table-free kernel's range: once more, with the general kernel
+            h->logpdf(mode, node, h->result.p, true);
+            CK(cudaMemcpyAsync(r, h->result.p, sizeof(double), cudaMemcpyDeviceToHost, h->stream));
+            CK(cudaStreamSynchronize(h->stream));
+        }
+    }
+    *out = r[0];
     BLG_LEAVE(h)
 }
 static int logpdf_async(blg_handle* h, int mode, int node, double* d_out) {
     BLG_ENTER(h)
     h->require(d_out != nullptr, "logpdf: null output");
+    // nobody looks at the result on the host here: the range flag must be known before the kernels are chosen
+    if (h->Ntot > 0 && h->pattern_fast_path() && h->flag_cache < 0 && h->tabs_valid) h->fetch_flag();
     h->logpdf(mode, node, d_out);
     BLG_LEAVE(h)
 }
@@ -2571,6 +2931,13 @@ int blg_get_column(blg_handle* h, int pattern, int node, int which, double* out,
     int sc;
     CK(cudaMemcpy(&sc, c.slab->scl + slot, sizeof(int), cudaMemcpyDeviceToHost));
     size_t base = (size_t)slot, stride = S.ld;
+    if (c.slab->pat) {                   // node patterns: the column of this family's sub-pattern at the node
+        h->ensure_pats(S);
+        Pat* P = h->pat_of(S, c);
+        base = (size_t)P->fam2pat[slot];
+        stride = P->ld;
+        CK(cudaMemcpy(&sc, c.slab->scl + base, sizeof(int), cudaMemcpyDeviceToHost));
+    }
     if (S.ragged) {
         h->require(c.off != nullptr, "get_column: column has no offsets");
         uint32_t o;
@@ -2657,6 +3024,16 @@ int blg_kernel_runs(blg_handle* h, unsigned int* sweep_runs, unsigned int* gener
     if (nfast) *nfast = h->F.N;
     if (nheavy) *nheavy = h->H.N;
     BLG_LEAVE(h)
+}
+// what the last likelihood call did on the fast family set: bytes of pattern columns actually written + read, node steps ×
+// distinct patterns evaluated, node steps × families they stand for (diagnostic; the algorithmic figure of
+// blg_last_algorithmic stays SURVEY §8(d)'s per-family definition)
+int blg_pattern_stats(blg_handle* h, double* bytes_moved, double* pattern_columns, double* family_columns) {
+    if (!h) return 1;
+    if (bytes_moved) *bytes_moved = h->last_pattern_bytes;
+    if (pattern_columns) *pattern_columns = h->last_pattern_cols;
+    if (family_columns) *family_columns = h->last_family_cols;
+    return 0;
 }
 int blg_set_timing(blg_handle* h, int on) {
     if (!h) return 1;

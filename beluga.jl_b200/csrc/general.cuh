@@ -31,11 +31,13 @@ struct GChild {
     const double* ell;      // nullptr: leaf (one-hot at its count)
     const int* scl;
     const uint16_t* cnt;
-    const uint32_t* off;    // ragged layout: per-family offset into ell (nullptr: SoA)
+    const uint32_t* off;    // ragged layout: per-family offset into ell (nullptr: SoA with stride ld)
+    const int* pidx;        // pattern layout: item of the step → column of the child (nullptr: the same index)
     const double* Wt;       // transposed w* table (branch below a WGT only)
     int wdp;
     int node;               // node index of the child (NodeK)
     int mode;               // 0 ordinary branch, 1 below a WGD (polynomial form), 2 table
+    int ld;                 // SoA stride of the child's columns
 };
 struct GStep {
     int k, first, resident, node;
@@ -43,9 +45,10 @@ struct GStep {
     int* out_scl;
     const uint16_t* cnt;
     const uint32_t* out_off;
+    size_t out_ld;          // SoA stride of the output columns
 };
 #define BLG_G_MAXSTEPS 160
-#define BLG_G_MAXCHILD 280
+#define BLG_G_MAXCHILD 240
 struct GList {
     int nsteps;
     int pad_[3];
@@ -266,12 +269,12 @@ __device__ __forceinline__ int g_cpad(int M) {           // lanes × C register 
 template <int CMAX>
 __global__ void __launch_bounds__(128, (CMAX <= 4) ? 3 : 2)
 gsweep_kernel(const __grid_constant__ GList L, const NodeK* __restrict__ nk, const int* __restrict__ flags, int when,
-              unsigned int* __restrict__ ran, int f0, int f1, size_t ld, int cap, int nbuf, unsigned int* __restrict__ counter) {
+              unsigned int* __restrict__ ran, int f0, int f1, int count_run, int cap, int nbuf, unsigned int* __restrict__ counter) {
     extern __shared__ double gsm[];
     if (when == 1 && flags[0] != 0) return;
     const int lane = threadIdx.x & 31;
     const int warp = threadIdx.x >> 5;
-    if (blockIdx.x == 0 && threadIdx.x == 0) atomicAdd(&ran[1], 1u);
+    if (count_run && blockIdx.x == 0 && threadIdx.x == 0) atomicAdd(&ran[1], 1u);
     double* buf0 = gsm + (size_t)warp * nbuf * cap;
     const double NaN = __longlong_as_double(0x7ff8000000000000LL);
 #pragma unroll 1
@@ -293,7 +296,7 @@ gsweep_kernel(const __grid_constant__ GList L, const NodeK* __restrict__ nk, con
             const int X = st.cnt[f];
             const double ip0 = nk[st.node].ip0;                    // 1, or NaN where the reference's column is NaN
             double* outp = st.out + (st.out_off ? (size_t)st.out_off[f] : (size_t)f);
-            const size_t ostride = st.out_off ? 1 : ld;
+            const size_t ostride = st.out_off ? 1 : st.out_ld;
             if (X == 0) {
                 // no gene below the node: ℓ = [1] (n = 0 lineages leave no descendants with probability 1), or the NaN
                 if (lane == 0) { outp[0] = ip0; st.out_scl[f] = 0; pA[0] = ip0; }
@@ -308,7 +311,8 @@ gsweep_kernel(const __grid_constant__ GList L, const NodeK* __restrict__ nk, con
             for (int i = 0; i < k; ++i) {
                 const GChild& c = ch[i];
                 const NodeK ck = nk[c.node];
-                const int M = c.cnt[f];
+                const int cf = c.pidx ? c.pidx[f] : f;            // the child's column of this item
+                const int M = c.cnt[cf];
                 // ---- the child's column → b̂ (normalised), into `dst` -------------------------------------------
                 double* dst = (i == 0) ? pA : pB;
                 const bool resident = (i == 0) && st.resident && prevNode == c.node;
@@ -317,10 +321,10 @@ gsweep_kernel(const __grid_constant__ GList L, const NodeK* __restrict__ nk, con
                 } else if (resident) {
                     sclsum += prevScl;
                 } else {
-                    const double* src = c.ell + (c.off ? (size_t)c.off[f] : (size_t)f);
-                    const size_t sstride = c.off ? 1 : ld;
+                    const double* src = c.ell + (c.off ? (size_t)c.off[cf] : (size_t)cf);
+                    const size_t sstride = c.off ? 1 : (size_t)c.ld;
                     for (int n = lane; n <= M; n += 32) dst[n] = src[(size_t)n * sstride];
-                    sclsum += c.scl[f];
+                    sclsum += c.scl[cf];
                 }
                 __syncwarp();
                 double* bcol = dst;
@@ -419,7 +423,7 @@ __global__ void __launch_bounds__(256) root_ragged_kernel(const double* __restri
                                                           const double* __restrict__ rootw0, const double* __restrict__ weight,
                                                           double* __restrict__ fam_ll, double* __restrict__ partial, int part0,
                                                           int N, unsigned int* __restrict__ ticket, unsigned int nblocks_total,
-                                                          double* __restrict__ out) {
+                                                          const int* __restrict__ flags, double* __restrict__ marker, double* __restrict__ out) {
     __shared__ double red[8];
     __shared__ bool last_block;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
@@ -470,6 +474,6 @@ __global__ void __launch_bounds__(256) root_ragged_kernel(const double* __restri
             if ((int)threadIdx.x < k) red2[threadIdx.x] += red2[threadIdx.x + k];
             __syncthreads();
         }
-        if (threadIdx.x == 0) { out[0] = red2[0]; *ticket = 0u; }
+        if (threadIdx.x == 0) { out[0] = red2[0]; marker[0] = flags[0] ? 0.0 : 1.0; *ticket = 0u; }
     }
 }

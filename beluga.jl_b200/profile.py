@@ -253,6 +253,12 @@ class PArray:
         self._ck(self.L.blg_kernel_runs(self.h, C.byref(a), C.byref(b), C.byref(nf), C.byref(nh)))
         return a.value, b.value, nf.value, nh.value
 
+    def pattern_stats(self):
+        """-> (bytes_moved, pattern_columns, family_columns) of the last likelihood call (diagnostic)."""
+        a, b, c = C.c_double(), C.c_double(), C.c_double()
+        self.L.blg_pattern_stats(self.h, C.byref(a), C.byref(b), C.byref(c))
+        return a.value, b.value, c.value
+
     def set_timing(self, on=True):
         self._ck(self.L.blg_set_timing(self.h, 1 if on else 0))
 

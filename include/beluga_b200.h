@@ -127,6 +127,9 @@ int blg_last_algorithmic(blg_handle* h, double* bytes_total, double* bytes_prune
  * on the device from the range flags of the last ε/W build), and the split of the patterns between the fast family set
  * (root count <= 100: SoA slabs, 32 families per warp) and the heavy one (ragged slabs, one warp per family) */
 int blg_kernel_runs(blg_handle* h, unsigned int* sweep_runs, unsigned int* general_runs, int* nfast, int* nheavy);
+/* diagnostic: node patterns (families are deduplicated per node by the counts below it, csrc/pattern.cuh) — bytes of
+ * pattern columns the last likelihood call wrote + read, node steps × distinct patterns evaluated, node steps × families */
+int blg_pattern_stats(blg_handle* h, double* bytes_moved, double* pattern_columns, double* family_columns);
 int blg_sync(blg_handle* h);
 /* measurement: when on, every likelihood call records CUDA events on the handle's stream around its
  * pruning launches and around its root/reduction launches; blg_last_timing waits for them and returns
