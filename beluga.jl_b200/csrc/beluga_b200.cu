@@ -1127,6 +1127,7 @@ struct Pat {
     size_t ld = 0;                   // column stride, U rounded up to 32
     int xmax = 0;
     double colsum = 0.0;             // Σ_p (x_p + 1)
+    int nboth = 0;                   // patterns at the front of the order whose second-largest child count is >= 20
     uint16_t* d_cnt = nullptr;       // [ld] count of the column per pattern (sorted descending: heaviest tiles first)
     int* d_fam2pat = nullptr;        // [N] family → pattern, on the device only for the root
     std::vector<int> fam2pat;        // host
@@ -1235,6 +1236,8 @@ struct blg_handle {
     // node patterns (pattern.cuh): the fast family set is evaluated once per distinct sub-pattern of every node.
     // pat_mode == false: one column per family (the layout the gradient kernels work on; BLG_DEDUP=0 forces it).
     bool pat_mode = true, pat_default = true;
+    int gslot = 0;
+    int pdebug = 0;                           // BLG_PDEBUG: time and describe every pattern launch (stderr)
     int flag_cache = -1;                      // host copy of the device-side range flag: -1 unknown (since the last ε/W build)
     std::unique_ptr<PList> plist{new PList()};
     double last_pattern_bytes = 0.0;          // column bytes the last call actually wrote + read (pattern columns)
@@ -1807,16 +1810,24 @@ struct blg_handle {
             for (int f = 0; f < N; ++f) if (rep[id[f]] < 0) rep[id[f]] = f;
             std::vector<int> ord(U);
             for (int i = 0; i < U; ++i) ord[i] = i;
+            int nboth = 0;
             if (k >= 2) {
                 std::vector<uint64_t> key(U);
                 for (int i = 0; i < U; ++i) {
                     const int r = rep[i];
                     uint64_t kk = (uint64_t)hx[r];
-                    for (int j = 0; j < std::min(k, 3); ++j) kk = (kk << 16) | (uint64_t)cp[j]->h_cnt[cp[j]->fam2pat[r]];
+                    int m1 = 0, m2 = 0;                     // largest and second-largest child count
+                    for (int j = 0; j < k; ++j) {
+                        const int mj = cp[j]->h_cnt[cp[j]->fam2pat[r]];
+                        if (j < 2) kk = (kk << 16) | (uint64_t)mj;
+                        if (mj > m1) { m2 = m1; m1 = mj; } else if (mj > m2) m2 = mj;
+                    }
+                    if (m2 >= 20) { kk |= 1ull << 63; ++nboth; }
                     key[i] = kk;
                 }
                 std::stable_sort(ord.begin(), ord.end(), [&](int a, int b) { return key[a] > key[b]; });
             }
+            P->nboth = nboth;
             std::vector<int> newidx(U);
             for (int i = 0; i < U; ++i) newidx[ord[i]] = i;
             P->U = U;
@@ -1869,100 +1880,231 @@ struct blg_handle {
         last_bytes += 8.0 * S.Tp[u].colsum + 4.0 * S.N;
         last_family_cols += (double)S.N;
     }
-    // the fast family set over node patterns: the nodes of the list level by level (children in earlier launches), a
-    // warp per tile of 32 patterns of one node.  general == true: the general kernel (any parameters), one launch per node.
+    // the fast family set over node patterns: the nodes of the list level by level (children in earlier launches).
+    // Per level two launches: the patterns at the front of each node's order — those whose two children both have >= 20
+    // counts (beyond the register tiles of the table-free merge), and, when the level is too small to fill the GPU, every
+    // pattern with more than a few counts — run on the general kernel, one WARP per pattern (short latency); the rest on
+    // the table-free tile kernel, one THREAD per pattern, 32 patterns of (nearly) the same shape per warp (high
+    // throughput).  Single-child nodes on the same patterns (WGD-type nodes) are chained behind the node below them.
+    // general == true: everything on the general kernel (parameters outside the table-free forms' range).
     void psweep(const std::vector<int>& nodes, bool general) {
         Shard& S = F;
         ensure_pats(S);
-        std::vector<int> level(ncols_model, -1);
+        std::vector<int> level(ncols_model, -1), head(ncols_model, -1);
+        std::vector<std::vector<int>> chain(ncols_model);
         int nlev = 0;
         for (int u : nodes) {
+            const int k = (int)children[u].size();
+            require(k >= 1, "prune_node: leaf");
+            if (k == 1 && !general) {
+                const int c = children[u][0];
+                if (level[c] >= 0 && !children[c].empty() && pat_of(S, S.Tp[u]) == pat_of(S, S.Tp[c])) {
+                    head[u] = head[c] >= 0 ? head[c] : c;
+                    level[u] = level[c];
+                    chain[head[u]].push_back(u);
+                    continue;
+                }
+            }
             int lv = 0;
             for (int c : children[u]) if (level[c] >= 0) lv = std::max(lv, level[c] + 1);
             level[u] = lv;
             nlev = std::max(nlev, lv + 1);
         }
         bool first = true;
+        gslot = 0;
         for (int lv = 0; lv < nlev; ++lv) {
             std::vector<int> todo;
-            for (int u : nodes) if (level[u] == lv) todo.push_back(u);
+            for (int u : nodes) if (level[u] == lv && head[u] < 0) todo.push_back(u);
             // heaviest nodes first inside a level
             std::stable_sort(todo.begin(), todo.end(), [&](int a, int b) { return pat_of(S, S.Tp[a])->colsum > pat_of(S, S.Tp[b])->colsum; });
+            if (general) {
+                for (int u : todo) {
+                    const int k = (int)children[u].size();
+                    require(tabs_valid && tabs[u].built && tabs[u].k == k, "logpdf: ε/W tables are stale (call blg_rebuild)");
+                    std::vector<int> ord(tabs[u].mo, tabs[u].mo + k);
+                    general_pstep(S, u, ord, pat_of(S, S.Tp[u]), get_link(S, u, ord), first);
+                    first = false;
+                    count_step_bytes(S, u);
+                }
+                continue;
+            }
+            // a level that cannot fill the GPU with tiles is latency-bound: give every pattern above a few counts a warp
+            long total_tiles = 0;
+            for (int u : todo) total_tiles += (pat_of(S, S.Tp[u])->U + 31) / 32;
+            const int xg = (total_tiles <= (long)sm_count * 8) ? 6 : 0x7fffffff;
             size_t pos = 0;
             while (pos < todo.size()) {
                 PList& L = *plist;
+                GList& G = *glist;
                 memset(&L, 0, sizeof(int) * 4);
-                int nch = 0, worst = 1, ntiles = 0;
-                while (pos < todo.size() && L.nsteps < BLG_P_MAXSTEPS) {
+                memset(&G, 0, sizeof(int) * 4);
+                int nch = 0, gch = 0, worst = 1, ntiles = 0, nitems = 0, gmax = 0;
+                std::vector<PStep> pchain;
+                while (pos < todo.size()) {
                     const int u = todo[pos];
                     const int k = (int)children[u].size();
-                    require(k >= 1, "prune_node: leaf");
-                    if (nch + k > BLG_P_MAXCHILD) break;
+                    const int nc = (int)chain[u].size();
+                    if (L.nsteps + (int)pchain.size() + 1 + nc > BLG_P_MAXSTEPS || nch + k + nc > BLG_P_MAXCHILD) break;
+                    if (G.nsteps + 1 + nc > BLG_G_MAXSTEPS || gch + k + nc > BLG_G_MAXCHILD) break;
                     require(tabs_valid && tabs[u].built && tabs[u].k == k, "logpdf: ε/W tables are stale (call blg_rebuild)");
                     std::vector<int> ord(tabs[u].mo, tabs[u].mo + k);
                     Pat* Pu = pat_of(S, S.Tp[u]);
                     Link* lk = get_link(S, u, ord);
-                    if (general) {
-                        general_pstep(S, u, ord, Pu, lk, first);
-                        first = false;
-                        count_step_bytes(S, u);
-                        ++pos;
-                        continue;
+                    // split of the node's patterns: [0, ug) one warp each, [ug, U) in tiles
+                    int ug = Pu->nboth;
+                    if (xg < 0x7fffffff) {
+                        int lo = ug, hi = Pu->U;           // h_cnt is descending on [nboth, U)
+                        while (lo < hi) { const int mid = (lo + hi) / 2; if ((int)Pu->h_cnt[mid] >= xg) lo = mid + 1; else hi = mid; }
+                        ug = lo;
                     }
-                    PStep& ps = L.step[L.nsteps++];
-                    ps.k = k; ps.first = nch; ps.node = u; ps.U = Pu->U; ps.tile0 = ntiles; ps.ld = (int)Pu->ld;
-                    ps.cnt = Pu->d_cnt;
+                    Slab* o = writable(S, u);
+                    std::vector<Slab*> co;
+                    for (int v : chain[u]) co.push_back(writable(S, v));
                     int sum = 0;
                     bool tiled = false;
+                    const int nch0 = nch, gch0 = gch;
                     for (int j = 0; j < k; ++j) {
                         const int c = ord[j];
                         require(tabs[c].built && tabs[c].wdim >= S.Tp[c].xmax + 1 && tabs[c].xfast == S.Tp[c].xmax,
                                 "logpdf: W table of a child does not match the profile (call blg_rebuild)");
                         Pat* Pc = pat_of(S, S.Tp[c]);
-                        PChild& pc = L.child[nch++];
-                        memset(&pc, 0, sizeof(pc));
-                        if (!children[c].empty()) { Slab* sl = readable(S, c); pc.ell = sl->ell; pc.scl = sl->scl; }
-                        pc.cnt = Pc->d_cnt;
-                        pc.pidx = lk->d_pidx[j];
-                        pc.Wt = tabs[c].Wt; pc.wdp = tabs[c].wdp; pc.table = (kind[c] == BLG_WGDAFTER) ? 1 : 0;
-                        pc.node = c; pc.ld = (int)Pc->ld;
+                        Slab* sl = children[c].empty() ? nullptr : readable(S, c);
+                        if (ug < Pu->U) {
+                            PChild& pc = L.child[nch++];
+                            memset(&pc, 0, sizeof(pc));
+                            if (sl) { pc.ell = sl->ell; pc.scl = sl->scl; }
+                            pc.cnt = Pc->d_cnt;
+                            pc.pidx = lk->d_pidx[j];
+                            pc.Wt = tabs[c].Wt; pc.wdp = tabs[c].wdp; pc.table = (kind[c] == BLG_WGDAFTER) ? 1 : 0;
+                            pc.node = c; pc.ld = (int)Pc->ld;
+                        }
+                        if (ug > 0) fill_gchild(S, G.child[gch++], u, c, Pc, sl, lk->d_pidx[j]);
                         sum += Pc->xmax;
                         if (j >= 1 && Pc->xmax >= 20) tiled = true;
-                        last_pattern_bytes += children[c].empty() ? 0.0 : 8.0 * Pc->colsum;   // (each child column is read at least once)
+                        last_pattern_bytes += sl ? 8.0 * Pc->colsum : 0.0;   // (each child column is read at least once)
                     }
                     if (k == 2 && std::min(pat_of(S, S.Tp[ord[0]])->xmax, pat_of(S, S.Tp[ord[1]])->xmax) < 20) tiled = false;
                     sum = std::min(sum, k * Pu->xmax);             // (per tile the children's maxima are taken separately)
-                    worst = std::max(worst, tiled ? 3 * (sum + 1) : sum + k + 1);
-                    Slab* o = writable(S, u);
-                    ps.out = o->ell; ps.out_scl = o->scl;
-                    ntiles += (Pu->U + 31) / 32;
-                    last_pattern_bytes += 8.0 * Pu->colsum + 4.0 * Pu->U;
-                    last_pattern_cols += (double)Pu->U;
+                    if (ug < Pu->U) {
+                        worst = std::max(worst, tiled ? 3 * (sum + 1) : sum + k + 1);
+                        PStep& ps = L.step[L.nsteps++];
+                        memset(&ps, 0, sizeof(ps));
+                        ps.k = k; ps.first = nch0; ps.node = u; ps.U = Pu->U; ps.tile0 = ntiles; ps.ld = (int)Pu->ld; ps.p0 = ug;
+                        ps.cnt = Pu->d_cnt; ps.out = o->ell; ps.out_scl = o->scl;
+                        ps.chain_first = (int)pchain.size(); ps.nchain = nc;
+                        int below = u;
+                        for (int ci = 0; ci < nc; ++ci) {
+                            const int v = chain[u][ci];
+                            PStep cs;
+                            memset(&cs, 0, sizeof(cs));
+                            cs.k = 1; cs.first = nch; cs.node = v; cs.U = Pu->U; cs.ld = (int)Pu->ld;
+                            cs.cnt = Pu->d_cnt; cs.out = co[ci]->ell; cs.out_scl = co[ci]->scl;
+                            PChild& pc = L.child[nch++];
+                            memset(&pc, 0, sizeof(pc));
+                            pc.cnt = Pu->d_cnt;
+                            pc.ell = (below == u ? o : co[ci - 1])->ell;      // (resident: never read from memory, but not a leaf)
+                            pc.scl = (below == u ? o : co[ci - 1])->scl;
+                            pc.Wt = tabs[below].Wt; pc.wdp = tabs[below].wdp; pc.table = (kind[below] == BLG_WGDAFTER) ? 1 : 0;
+                            pc.node = below; pc.ld = (int)Pu->ld;
+                            pchain.push_back(cs);
+                            below = v;
+                        }
+                        ntiles += (Pu->U - ug + 31) / 32;
+                    }
+                    if (ug > 0) {
+                        GStep& gs = G.step[G.nsteps++];
+                        memset(&gs, 0, sizeof(gs));
+                        gs.k = k; gs.first = gch0; gs.node = u; gs.resident = 0; gs.item0 = nitems; gs.nchain = nc; gs.is_chain = 0;
+                        gs.out = o->ell; gs.out_scl = o->scl; gs.cnt = Pu->d_cnt; gs.out_off = nullptr; gs.out_ld = Pu->ld;
+                        int below = u;
+                        for (int ci = 0; ci < nc; ++ci) {
+                            const int v = chain[u][ci];
+                            GStep& cs = G.step[G.nsteps++];
+                            memset(&cs, 0, sizeof(cs));
+                            cs.k = 1; cs.first = gch; cs.node = v; cs.resident = 1; cs.item0 = nitems; cs.nchain = 0; cs.is_chain = 1;
+                            cs.out = co[ci]->ell; cs.out_scl = co[ci]->scl; cs.cnt = Pu->d_cnt; cs.out_off = nullptr; cs.out_ld = Pu->ld;
+                            fill_gchild(S, G.child[gch++], v, below, Pu, nullptr, nullptr);
+                            G.child[gch - 1].ell = (below == u ? o : co[ci - 1])->ell;      // (resident: never read from memory)
+                            G.child[gch - 1].scl = (below == u ? o : co[ci - 1])->scl;
+                            below = v;
+                        }
+                        nitems += ug;
+                        gmax = std::max(gmax, Pu->xmax);
+                    }
+                    last_pattern_bytes += (8.0 * Pu->colsum + 4.0 * Pu->U) * (1 + nc);
+                    last_pattern_cols += (double)Pu->U * (1 + nc);
                     count_step_bytes(S, u);
+                    for (int v : chain[u]) count_step_bytes(S, v);
                     ++pos;
                 }
-                if (general) continue;
-                require(L.nsteps > 0, "sweep: a node has more children than one launch can describe");
-                L.ntiles = ntiles;
-                L.first_of_call = first ? 1 : 0;
-                first = false;
-                int cap = std::min(worst, std::max(slice_cap, 56));   // doubles per lane of a warp's shared slice; rare larger tiles use global scratch
-                int wpb = 4;
-                double* gs = nullptr;
-                size_t gstride = 0;
-                if (worst > cap) {
-                    gstride = (size_t)worst * 32;
-                    gscratch.ensure(gstride * (size_t)ntiles);
-                    gs = gscratch.p;
+                require(L.nsteps + G.nsteps > 0, "sweep: a node has more children than one launch can describe");
+                cudaEvent_t dbg0 = nullptr, dbg1 = nullptr, dbg2 = nullptr;
+                if (pdebug) { CK(cudaEventCreate(&dbg0)); CK(cudaEventCreate(&dbg1)); CK(cudaEventCreate(&dbg2)); CK(cudaEventRecord(dbg0, stream)); }
+                if (G.nsteps > 0) {
+                    // (work counters of the item launches: 240 slots zeroed in one go, one slot per launch)
+                    if (gslot == 0) { d_gctr.ensure(256); CK(cudaMemsetAsync(d_gctr.p + 16, 0, 240 * sizeof(unsigned int), stream)); }
+                    launch_general(G, 0, nitems, gmax, 0, 0, 16 + gslot, 1);
+                    gslot = (gslot + 1) % 240;
                 }
-                const size_t smem = (size_t)cap * 32 * wpb * sizeof(double);
-                if (smem > ptile_smem_set) {
-                    CK(cudaFuncSetAttribute(ptile_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-                    ptile_smem_set = smem;
+                if (pdebug) CK(cudaEventRecord(dbg1, stream));
+                int cap = 0;
+                if (L.nsteps > 0) {
+                    for (size_t q = 0; q < pchain.size(); ++q) L.step[L.nsteps + q] = pchain[q];
+                    L.ntiles = ntiles;
+                    L.first_of_call = first ? 1 : 0;
+                    first = false;
+                    cap = std::min(worst, std::max(slice_cap, 56));   // doubles per lane of a warp's shared slice; rare larger tiles use global scratch
+                    const int wpb = 4;
+                    double* gs = nullptr;
+                    size_t gstride = 0;
+                    if (worst > cap) {
+                        gstride = (size_t)worst * 32;
+                        gscratch.ensure(gstride * (size_t)ntiles);
+                        gs = gscratch.p;
+                    }
+                    const size_t smem = (size_t)cap * 32 * wpb * sizeof(double);
+                    if (smem > ptile_smem_set) {
+                        CK(cudaFuncSetAttribute(ptile_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+                        ptile_smem_set = smem;
+                    }
+                    ptile_kernel<<<(ntiles + wpb - 1) / wpb, 32 * wpb, smem, stream>>>(L, d_nk.p, d_flags.p, d_ran.p, cap, gs, gstride);
+                    CK(cudaGetLastError());
+                    last_launches++;
                 }
-                ptile_kernel<<<(ntiles + wpb - 1) / wpb, 32 * wpb, smem, stream>>>(L, d_nk.p, d_flags.p, d_ran.p, cap, gs, gstride);
-                CK(cudaGetLastError());
-                last_launches++;
+                if (pdebug) {
+                    CK(cudaEventRecord(dbg2, stream));
+                    CK(cudaEventSynchronize(dbg2));
+                    float ms1 = 0.f, ms2 = 0.f;
+                    CK(cudaEventElapsedTime(&ms1, dbg0, dbg1));
+                    CK(cudaEventElapsedTime(&ms2, dbg1, dbg2));
+                    cudaEventDestroy(dbg0); cudaEventDestroy(dbg1); cudaEventDestroy(dbg2);
+                    fprintf(stderr, "[blg pattern] level %2d: warp-items %6d (%d steps) %7.1f us | tiles %6d (%d+%d steps, cap %d worst %d) %7.1f us |", lv, nitems, G.nsteps,
+                            ms1 * 1e3, ntiles, L.nsteps, (int)pchain.size(), cap, worst, ms2 * 1e3);
+                    for (int i = 0; i < std::min(L.nsteps, 3); ++i) {
+                        const PStep& q = L.step[i];
+                        fprintf(stderr, " [node %d U %d p0 %d x %d chain %d:", q.node, q.U, q.p0, pat_of(S, S.Tp[q.node])->xmax, q.nchain);
+                        for (int j = 0; j < q.k; ++j) fprintf(stderr, " %d", pat_of(S, S.Tp[L.child[q.first + j].node])->xmax);
+                        fprintf(stderr, "]");
+                    }
+                    fprintf(stderr, "\n");
+                }
+            }
+        }
+    }
+    void fill_gchild(Shard& S, GChild& gc, int u, int c, Pat* Pc, Slab* sl, const int* pidx) {
+        memset(&gc, 0, sizeof(gc));
+        if (sl) { gc.ell = sl->ell; gc.scl = sl->scl; }
+        gc.cnt = Pc->d_cnt;
+        gc.pidx = pidx;
+        gc.node = c;
+        gc.ld = (int)Pc->ld;
+        gc.mode = 0;
+        if (kind[c] == BLG_WGDAFTER) {
+            if (kind[u] == BLG_WGD) gc.mode = 1;
+            else {
+                gc.mode = 2;
+                require(tabs[c].built && tabs[c].Wt && tabs[c].wdim >= S.Tp[c].xmax + 1, "logpdf: W table below a WGT does not match the profile (call blg_rebuild)");
+                gc.Wt = tabs[c].Wt; gc.wdp = tabs[c].wdp;
             }
         }
     }
@@ -1976,36 +2118,20 @@ struct blg_handle {
         gs.k = (int)ord.size(); gs.first = 0; gs.node = u; gs.resident = 0;
         for (size_t j = 0; j < ord.size(); ++j) {
             const int c = ord[j];
-            Pat* Pc = pat_of(S, S.Tp[c]);
-            GChild& gc = L.child[j];
-            memset(&gc, 0, sizeof(gc));
-            if (!children[c].empty()) { Slab* sl = readable(S, c); gc.ell = sl->ell; gc.scl = sl->scl; }
-            gc.cnt = Pc->d_cnt;
-            gc.pidx = lk->d_pidx[j];
-            gc.node = c;
-            gc.ld = (int)Pc->ld;
-            gc.mode = 0;
-            if (kind[c] == BLG_WGDAFTER) {
-                if (kind[u] == BLG_WGD) gc.mode = 1;
-                else {
-                    gc.mode = 2;
-                    require(tabs[c].built && tabs[c].Wt && tabs[c].wdim >= S.Tp[c].xmax + 1, "logpdf: W table below a WGT does not match the profile (call blg_rebuild)");
-                    gc.Wt = tabs[c].Wt; gc.wdp = tabs[c].wdp;
-                }
-            }
+            fill_gchild(S, L.child[j], u, c, pat_of(S, S.Tp[c]), children[c].empty() ? nullptr : readable(S, c), lk->d_pidx[j]);
         }
         Slab* o = writable(S, u);
         gs.out = o->ell; gs.out_scl = o->scl; gs.cnt = Pu->d_cnt; gs.out_off = nullptr; gs.out_ld = Pu->ld;
-        launch_general(L, 0, Pu->U, Pu->xmax, first ? 1 : 0, 0, 0);
+        launch_general(L, 0, Pu->U, Pu->xmax, first ? 1 : 0, 0, 0, 0);
         last_pattern_bytes += 8.0 * Pu->colsum + 4.0 * Pu->U;
         last_pattern_cols += (double)Pu->U;
     }
     // gsweep_kernel over items f0..f1-1 whose largest count is maxroot
-    void launch_general(const GList& L, int f0, int f1, int maxroot, int count_run, int when, int counter_slot) {
+    void launch_general(const GList& L, int f0, int f1, int maxroot, int count_run, int when, int counter_slot, int item_mode = 0) {
         const int nfam = f1 - f0;
         if (nfam <= 0) return;
-        d_gctr.ensure(16);
-        CK(cudaMemsetAsync(d_gctr.p + counter_slot, 0, sizeof(unsigned int), stream));
+        d_gctr.ensure(256);
+        if (!item_mode) CK(cudaMemsetAsync(d_gctr.p + counter_slot, 0, sizeof(unsigned int), stream));
         const int cap = round_up(maxroot + 4, 2);
         const bool small = maxroot < 128;                // every merge fits 4 registers per lane
         const int cmax = small ? 4 : 16;
@@ -2017,10 +2143,10 @@ struct blg_handle {
         int blocks = std::min((nfam + wpb - 1) / wpb, sm_count * 16);
         if (small) {
             if (smem > g4_smem_set) { CK(cudaFuncSetAttribute(gsweep_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); g4_smem_set = smem; }
-            gsweep_kernel<4><<<blocks, 32 * wpb, smem, stream>>>(L, d_nk.p, d_flags.p, when, d_ran.p, f0, f1, count_run, cap, nbuf, d_gctr.p + counter_slot);
+            gsweep_kernel<4><<<blocks, 32 * wpb, smem, stream>>>(L, d_nk.p, d_flags.p, when, d_ran.p, f0, f1, count_run, cap, nbuf, d_gctr.p + counter_slot, item_mode);
         } else {
             if (smem > g16_smem_set) { CK(cudaFuncSetAttribute(gsweep_kernel<16>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); g16_smem_set = smem; }
-            gsweep_kernel<16><<<blocks, 32 * wpb, smem, stream>>>(L, d_nk.p, d_flags.p, when, d_ran.p, f0, f1, count_run, cap, nbuf, d_gctr.p + counter_slot);
+            gsweep_kernel<16><<<blocks, 32 * wpb, smem, stream>>>(L, d_nk.p, d_flags.p, when, d_ran.p, f0, f1, count_run, cap, nbuf, d_gctr.p + counter_slot, item_mode);
         }
         CK(cudaGetLastError());
         last_launches++;
@@ -2418,7 +2544,7 @@ struct blg_handle {
                     CK(cudaMemcpy(P0->d_fam2pat, P0->fam2pat.data(), (size_t)F.N * sizeof(int), cudaMemcpyHostToDevice));
                 }
                 root_pattern_kernel<<<bF, 256, 0, stream>>>(s->ell, s->scl, P0->d_cnt, P0->d_fam2pat, rootw.p, F.weight.p, F.fam_ll.p, partial.p, F.N,
-                                                            P0->ld, d_ticket.p, (unsigned)(bF + bH), d_flags.p, marker, d_out);
+                                                            P0->ld, d_ticket.p, (unsigned)(bF + bH), d_flags.p, d_ran.p, marker, d_out);
                 last_pattern_bytes += 8.0 * P0->colsum + 4.0 * P0->U + 12.0 * F.N;
             } else {
                 root_kernel<<<bF, 256, 0, stream>>>(s->ell, s->scl, F.Tp[0].cnt, rootw.p, F.weight.p, F.fam_ll.p, partial.p, F.N, F.ld, d_ticket.p,
@@ -2557,6 +2683,7 @@ int blg_create(int device, void* stream, blg_handle** out) {
         if (const char* sc = getenv("BLG_SLICE")) h->slice_cap = std::max(8, std::min(224, atoi(sc)));
         // families whose root count reaches this go to the heavy shard; above BLG_FAST_MAXCOUNT+1 the fast shard leaves the
         // table-free kernel's range (general kernel on SoA slabs) but stays inside the table-based gradient kernels' (<= 256)
+        if (const char* pd = getenv("BLG_PDEBUG")) h->pdebug = atoi(pd);
         if (const char* dd = getenv("BLG_DEDUP")) h->pat_mode = h->pat_default = atoi(dd) != 0;
         if (const char* hm = getenv("BLG_HEAVY_MIN")) h->heavy_min = std::max(1, std::min(256, atoi(hm)));
         *out = h;

@@ -41,6 +41,8 @@ struct GChild {
 };
 struct GStep {
     int k, first, resident, node;
+    int item0, nchain, is_chain, pad_;   // item mode (pattern layout): first work item of this step in the launch; single-child steps
+                                         // that follow on the same pattern index (their columns stay in shared memory)
     double* out;
     int* out_scl;
     const uint16_t* cnt;
@@ -48,7 +50,7 @@ struct GStep {
     size_t out_ld;          // SoA stride of the output columns
 };
 #define BLG_G_MAXSTEPS 160
-#define BLG_G_MAXCHILD 240
+#define BLG_G_MAXCHILD 230
 struct GList {
     int nsteps;
     int pad_[3];
@@ -269,7 +271,8 @@ __device__ __forceinline__ int g_cpad(int M) {           // lanes × C register 
 template <int CMAX>
 __global__ void __launch_bounds__(128, (CMAX <= 4) ? 3 : 2)
 gsweep_kernel(const __grid_constant__ GList L, const NodeK* __restrict__ nk, const int* __restrict__ flags, int when,
-              unsigned int* __restrict__ ran, int f0, int f1, int count_run, int cap, int nbuf, unsigned int* __restrict__ counter) {
+              unsigned int* __restrict__ ran, int f0, int f1, int count_run, int cap, int nbuf, unsigned int* __restrict__ counter,
+              int item_mode) {
     extern __shared__ double gsm[];
     if (when == 1 && flags[0] != 0) return;
     const int lane = threadIdx.x & 31;
@@ -288,8 +291,21 @@ gsweep_kernel(const __grid_constant__ GList L, const NodeK* __restrict__ nk, con
         double* pB = buf0 + cap;
         double* pC = (nbuf >= 3) ? buf0 + 2 * (size_t)cap : nullptr;
         int prevNode = -1, prevX = 0, prevScl = 0;   // column left in pA by the previous step (normalised, exponent prevScl)
+        int s_lo = 0, s_hi = L.nsteps - 1;
+        if (item_mode) {
+            // item → (step, pattern): the last step whose first item is not beyond it, then back to the head of its chain
+            int lo = 0, hi = L.nsteps - 1;
+            while (lo < hi) {
+                const int mid = (lo + hi + 1) >> 1;
+                if (L.step[mid].item0 <= f) lo = mid; else hi = mid - 1;
+            }
+            while (L.step[lo].is_chain) --lo;
+            f -= L.step[lo].item0;
+            s_lo = lo;
+            s_hi = lo + L.step[lo].nchain;
+        }
 #pragma unroll 1
-        for (int si = 0; si < L.nsteps; ++si) {
+        for (int si = s_lo; si <= s_hi; ++si) {
             const GStep& st = L.step[si];
             const int k = st.k;
             const GChild* ch = &L.child[st.first];

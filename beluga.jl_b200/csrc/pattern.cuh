@@ -30,12 +30,15 @@ struct PChild {
 struct PStep {
     int k, first, node, U;
     int tile0, ld;         // first tile of this step in the launch; stride of the node's pattern columns
+    int p0;                // first pattern the tiles cover (the patterns before it run on the general kernel, one warp each)
+    int chain_first, nchain, pad_;   // single-child steps on the same patterns (WGD-type nodes above this one): they follow in
+                                     // the same warp, with the column still in shared memory; stored at step[nsteps + chain_first ...]
     double* out;
     int* out_scl;
     const uint16_t* cnt;
 };
-#define BLG_P_MAXSTEPS 160
-#define BLG_P_MAXCHILD 330
+#define BLG_P_MAXSTEPS 150
+#define BLG_P_MAXCHILD 300
 struct PList {
     int nsteps, ntiles, first_of_call, pad_;
     PStep step[BLG_P_MAXSTEPS];
@@ -53,7 +56,6 @@ __global__ void __launch_bounds__(128, 4) ptile_kernel(const __grid_constant__ P
     const int warp = threadIdx.x >> 5;
     const int tile = blockIdx.x * (int)(blockDim.x >> 5) + warp;
     if (tile >= L.ntiles) return;
-    if (L.first_of_call && tile == 0 && lane == 0) atomicAdd(&ran[0], 1u);
     int lo = 0, hi = L.nsteps - 1;
     while (lo < hi) {
         const int mid = (lo + hi + 1) >> 1;
@@ -62,7 +64,7 @@ __global__ void __launch_bounds__(128, 4) ptile_kernel(const __grid_constant__ P
     const PStep& st = L.step[lo];
     const int k = st.k;
     const PChild* ch = &L.child[st.first];
-    int p = (tile - st.tile0) * 32 + (int)lane;
+    int p = st.p0 + (tile - st.tile0) * 32 + (int)lane;
     const bool live = p < st.U;
     if (!live) p = st.U - 1;          // idle lanes shadow the last pattern (loads stay in bounds; they never store)
     const size_t ldo = (size_t)st.ld;
@@ -72,7 +74,14 @@ __global__ void __launch_bounds__(128, 4) ptile_kernel(const __grid_constant__ P
     const double ip0 = nk[st.node].ip0;          // 1, or NaN where the reference's column is NaN (here or below)
     if (Xw == 0) {
         // no pattern of this tile has a gene below the node: ℓ = [1] (n = 0 lineages leave no descendants with probability 1)
-        if (live) { st.out[p] = ip0; st.out_scl[p] = 0; }
+        if (live) {
+            st.out[p] = ip0; st.out_scl[p] = 0;
+#pragma unroll 1
+            for (int cj = 0; cj < st.nchain; ++cj) {
+                const PStep& sv = L.step[L.nsteps + st.chain_first + cj];
+                sv.out[p] = nk[sv.node].ip0; sv.out_scl[p] = 0;
+            }
+        }
         return;
     }
     const int c0 = ch[0].pidx ? ch[0].pidx[p] : p;
@@ -202,6 +211,43 @@ __global__ void __launch_bounds__(128, 4) ptile_kernel(const __grid_constant__ P
         if (n == X) o[(size_t)n * ldo] = R[n * 32] * sc;
         st.out_scl[p] = sclsum + ex;
     }
+    // ---- the chain: single-child nodes above this one, on the same patterns.  The column stays in R (its stored copy
+    // is rescaled, R is not: the pending power of two goes into the contraction, exact) ------------------------------------
+    double prevSc = sc;
+    int prevScl = sclsum + ex;
+#pragma unroll 1
+    for (int cj = 0; cj < st.nchain; ++cj) {
+        const PStep& sv = L.step[L.nsteps + st.chain_first + cj];
+        const PChild& cv = L.child[sv.first];
+        const NodeK kv = nk[cv.node];
+        __syncwarp();
+        sweep_child(child_args(cv, kv.psi, kv.cc), 0, 0, X, Xw, R, 1, prevSc);
+        // ℓ_v[n] = b[n]·(1-e)^(-n)
+        double ip = nk[sv.node].ip0;
+        const double invv = nk[sv.node].inv;
+        double mv = 0.0;
+#pragma unroll 1
+        for (int n = 0; n <= Xw; ++n) {
+            double v = 0.0;
+            if (n <= X) { v = R[n * 32] * ip; mv = fmax(mv, v); }
+            R[n * 32] = v;
+            ip *= invv;
+        }
+        int exv = 0;
+        if (mv > 0.0) {
+            const int be = (__double2hiint(mv) >> 20) & 0x7ff;
+            if (be != 0 && be != 0x7ff) exv = be - 1023;
+        }
+        const double scv = __hiloint2double((1023 - exv) << 20, 0);
+        if (live) {
+            double* o = sv.out + p;
+#pragma unroll 1
+            for (int n = 0; n <= X; ++n) o[(size_t)n * ldo] = R[n * 32] * scv;
+            sv.out_scl[p] = prevScl + exv;
+        }
+        prevSc = scv;
+        prevScl += exv;
+    }
 }
 
 // root integration over pattern columns: family f reads the column of its root pattern fam2pat[f]
@@ -211,11 +257,13 @@ __global__ void __launch_bounds__(256) root_pattern_kernel(const double* __restr
                                                            const double* __restrict__ rootw, const double* __restrict__ weight,
                                                            double* __restrict__ fam_ll, double* __restrict__ partial, int N, size_t ld,
                                                            unsigned int* __restrict__ ticket, unsigned int nblocks_total,
-                                                           const int* __restrict__ flags, double* __restrict__ marker, double* __restrict__ out) {
+                                                           const int* __restrict__ flags, unsigned int* __restrict__ ran,
+                                                           double* __restrict__ marker, double* __restrict__ out) {
     __shared__ double red[256];
     __shared__ bool last_block;
     int f = blockIdx.x * blockDim.x + threadIdx.x;
     double contrib = 0.0;
+    if (f == 0 && flags[0]) atomicAdd(&ran[0], 1u);          // the table-free pattern path did this call's work
     if (f < N) {
         const int p = fam2pat[f];
         const int X = pcnt[p];
@@ -249,6 +297,10 @@ __global__ void __launch_bounds__(256) root_pattern_kernel(const double* __restr
             if ((int)threadIdx.x < k) red[threadIdx.x] += red[threadIdx.x + k];
             __syncthreads();
         }
-        if (threadIdx.x == 0) { out[0] = red[0]; marker[0] = flags[0] ? 0.0 : 1.0; *ticket = 0u; }
+        if (threadIdx.x == 0) {
+            out[0] = red[0];
+            marker[0] = flags[0] ? 0.0 : 1.0;
+            *ticket = 0u;
+        }
     }
 }
