@@ -548,20 +548,28 @@ __device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commi
 __device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_group 0;" ::: "memory"); }
 __device__ __forceinline__ void cp_async_wait_but_one() { asm volatile("cp.async.wait_group 1;" ::: "memory"); }
 
-// in-place table contraction (branch below a WGD/WGT): col[s] ← Σ_{j=s..Mw} Wt[j*wdp+s]·col[j]
+// in-place table contraction (branch below a WGD/WGT): col[s] ← Σ_{j=s..min(Mw, band·s)} Wt[j*wdp+s]·col[j]
+// w*(s|j) of these branches is banded: s lineages above a WGD leave at most 2s below it (3s for a WGT), so rows j > band·s
+// of column s are zero (band = 2 or 3; the literal WGT table of node.jl:205-218 keeps the same support).  Table rows are
+// read 16 bytes at a time (wdp is a multiple of 16 and s0 of TS: aligned).
 template <int TS>
-__device__ __noinline__ void sweep_contract_table(double* col, int Mw, const double* __restrict__ Wt, int wdp, double osc) {
+__device__ __noinline__ void sweep_contract_table(double* col, int Mw, const double* __restrict__ Wt, int wdp, double osc, int band) {
 #pragma unroll 1
     for (int s0 = 0; s0 <= Mw; s0 += TS) {
         double acc[TS];
 #pragma unroll
         for (int k = 0; k < TS; ++k) acc[k] = 0.0;
+        const int jhi = min(Mw, band * (s0 + TS - 1));
 #pragma unroll 1
-        for (int j = s0; j <= Mw; ++j) {
+        for (int j = s0; j <= jhi; ++j) {
             const double x = col[j * 32];
-            const double* __restrict__ w = Wt + (size_t)j * wdp + s0;
+            const double2* __restrict__ w = reinterpret_cast<const double2*>(Wt + (size_t)j * wdp + s0);
 #pragma unroll
-            for (int k = 0; k < TS; ++k) acc[k] = fma(w[k], x, acc[k]);
+            for (int k = 0; k < TS / 2; ++k) {
+                const double2 ww = __ldg(w + k);
+                acc[2 * k] = fma(ww.x, x, acc[2 * k]);
+                acc[2 * k + 1] = fma(ww.y, x, acc[2 * k + 1]);
+            }
         }
 #pragma unroll
         for (int k = 0; k < TS; ++k)
@@ -723,7 +731,7 @@ __device__ __noinline__ void sweep_child(const ChildArgs c, int f, size_t ld, in
         for (int j = 0; j <= Mw; ++j) col[j * 32] = (j <= M) ? src[(size_t)j * ld] : 0.0;
     }
     if (c.table) {
-        sweep_contract_table<16>(col, Mw, c.Wt, c.wdp, osc);
+        sweep_contract_table<16>(col, Mw, c.Wt, c.wdp, osc, c.table);
     } else {
         const double psi = c.psi, cc = c.cc;
         if (have == 1) col[0] *= osc;              // b[0] = ℓ[0]
@@ -1127,7 +1135,9 @@ struct Pat {
     size_t ld = 0;                   // column stride, U rounded up to 32
     int xmax = 0;
     double colsum = 0.0;             // Σ_p (x_p + 1)
-    int nboth = 0;                   // patterns at the front of the order whose second-largest child count is >= 20
+    // the order of the patterns: first those whose second-largest child count m2 is >= 36 (general kernel, one warp each),
+    // then 20 <= m2 < 36 (wide tile kernel), then the rest, grouped by which child is the larger one and sorted by counts
+    int nvery = 0, nwide = 0;
     uint16_t* d_cnt = nullptr;       // [ld] count of the column per pattern (sorted descending: heaviest tiles first)
     int* d_fam2pat = nullptr;        // [N] family → pattern, on the device only for the root
     std::vector<int> fam2pat;        // host
@@ -1237,9 +1247,11 @@ struct blg_handle {
     // pat_mode == false: one column per family (the layout the gradient kernels work on; BLG_DEDUP=0 forces it).
     bool pat_mode = true, pat_default = true;
     int gslot = 0;
+    cudaStream_t stream2 = nullptr;           // the wide tile launches of a level run beside its other launches
+    cudaEvent_t ev_main = nullptr, ev_side = nullptr;
     int pdebug = 0;                           // BLG_PDEBUG: time and describe every pattern launch (stderr)
     int flag_cache = -1;                      // host copy of the device-side range flag: -1 unknown (since the last ε/W build)
-    std::unique_ptr<PList> plist{new PList()};
+    std::unique_ptr<PList> plist{new PList()}, plist_w{new PList()};
     double last_pattern_bytes = 0.0;          // column bytes the last call actually wrote + read (pattern columns)
     double last_pattern_cols = 0.0, last_family_cols = 0.0;   // node steps × patterns / × families of the last call
 
@@ -1255,8 +1267,8 @@ struct blg_handle {
     std::unique_ptr<GList> glist{new GList()};
     DevBuf<unsigned int> d_tilectr, d_gctr;
     int sm_count = 148;
-    DevBuf<double> gscratch;
-    size_t sweep_smem_set = 0, g4_smem_set = 0, g16_smem_set = 0, ptile_smem_set = 0;
+    DevBuf<double> gscratch, gscratch_w;
+    size_t sweep_smem_set = 0, g4_smem_set = 0, g16_smem_set = 0, ptile_smem_set[2] = {0, 0};
 
     // accounting of the last likelihood call
     double last_bytes = 0.0, last_prune_bytes = 0.0;
@@ -1279,7 +1291,10 @@ struct blg_handle {
         d_prof.free_();
         gpool_release();
         for (auto& e : ev) if (e) cudaEventDestroy(e);
-        gscratch.free_(); d_tilectr.free_(); d_gctr.free_(); d_ticket.free_();
+        gscratch.free_(); gscratch_w.free_(); d_tilectr.free_(); d_gctr.free_(); d_ticket.free_();
+        if (stream2) cudaStreamDestroy(stream2);
+        if (ev_main) cudaEventDestroy(ev_main);
+        if (ev_side) cudaEventDestroy(ev_side);
         if (own_stream && stream) cudaStreamDestroy(stream);
     }
     static void free_tab(HostTab& tb) {
@@ -1341,6 +1356,11 @@ struct blg_handle {
 
     // ---- topology helpers ------------------------------------------------------------------------
     bool present(int i) const { return i >= 0 && i < ncols_model && kind[i] != BLG_ABSENT; }
+    // 0: ordinary branch above node c; 2 / 3: the branch below a WGD / WGT (table contraction, band of the table)
+    int table_band(int c) const {
+        if (kind[c] != BLG_WGDAFTER) return 0;
+        return (parent[c] >= 0 && kind[parent[c]] == BLG_WGT) ? 3 : 2;
+    }
     void build_children() {
         children.assign(ncols_model, {});
         std::vector<std::vector<std::pair<int, int>>> tmp(ncols_model);
@@ -1609,7 +1629,7 @@ struct blg_handle {
                     SweepChild& sc = L.child[nch++];
                     const ChildRef& cr = st.child[c];
                     sc.ell = cr.ell; sc.scl = cr.scl; sc.cnt = cr.cnt; sc.Wt = cr.Wt;
-                    sc.wdp = cr.wdp; sc.table = (kind[cr.id] == BLG_WGDAFTER) ? 1 : 0;
+                    sc.wdp = cr.wdp; sc.table = table_band(cr.id);
                     sc.node = cr.id; sc.pad_ = 0;
                     int xm = Tp[cr.id].xmax;
                     sum += xm;
@@ -1810,24 +1830,28 @@ struct blg_handle {
             for (int f = 0; f < N; ++f) if (rep[id[f]] < 0) rep[id[f]] = f;
             std::vector<int> ord(U);
             for (int i = 0; i < U; ++i) ord[i] = i;
-            int nboth = 0;
+            int nvery = 0, nwide = 0;
             if (k >= 2) {
                 std::vector<uint64_t> key(U);
                 for (int i = 0; i < U; ++i) {
                     const int r = rep[i];
-                    uint64_t kk = (uint64_t)hx[r];
                     int m1 = 0, m2 = 0;                     // largest and second-largest child count
+                    int mc[2] = {0, 0};
                     for (int j = 0; j < k; ++j) {
                         const int mj = cp[j]->h_cnt[cp[j]->fam2pat[r]];
-                        if (j < 2) kk = (kk << 16) | (uint64_t)mj;
+                        if (j < 2) mc[j] = mj;
                         if (mj > m1) { m2 = m1; m1 = mj; } else if (mj > m2) m2 = mj;
                     }
-                    if (m2 >= 20) { kk |= 1ull << 63; ++nboth; }
-                    key[i] = kk;
+                    // class, then (own count, the larger child's count) descending: the 32 patterns of a tile get (nearly)
+                    // the same loop bounds AND the same register-tiled side
+                    uint64_t cls = m2 >= 36 ? 3 : m2 >= 20 ? 2 : (mc[0] >= mc[1] ? 1 : 0);
+                    if (cls == 3) ++nvery; else if (cls == 2) ++nwide;
+                    key[i] = (cls << 60) | ((uint64_t)hx[r] << 32) | ((uint64_t)std::max(mc[0], mc[1]) << 16) | (uint64_t)std::min(mc[0], mc[1]);
                 }
                 std::stable_sort(ord.begin(), ord.end(), [&](int a, int b) { return key[a] > key[b]; });
             }
-            P->nboth = nboth;
+            P->nvery = nvery;
+            P->nwide = nwide;
             std::vector<int> newidx(U);
             for (int i = 0; i < U; ++i) newidx[ord[i]] = i;
             P->U = U;
@@ -1928,94 +1952,93 @@ struct blg_handle {
                 }
                 continue;
             }
-            // a level that cannot fill the GPU with tiles is latency-bound: give every pattern above a few counts a warp
-            long total_tiles = 0;
-            for (int u : todo) total_tiles += (pat_of(S, S.Tp[u])->U + 31) / 32;
-            const int xg = (total_tiles <= (long)sm_count * 8) ? 6 : 0x7fffffff;
             size_t pos = 0;
             while (pos < todo.size()) {
-                PList& L = *plist;
+                // three launches per level: [0, nvery) of every node on the general kernel (one warp per pattern),
+                // [nvery, nvery + nwide) on the wide tile kernel, the rest on the tile kernel
+                struct TL { PList* L; std::vector<PStep> chain; int nch = 0, ntiles = 0, worst = 1; };
+                TL tl[2];
+                tl[0].L = plist.get(); tl[1].L = plist_w.get();
+                for (auto& t_ : tl) memset(t_.L, 0, sizeof(int) * 4);
                 GList& G = *glist;
-                memset(&L, 0, sizeof(int) * 4);
                 memset(&G, 0, sizeof(int) * 4);
-                int nch = 0, gch = 0, worst = 1, ntiles = 0, nitems = 0, gmax = 0;
-                std::vector<PStep> pchain;
+                int gch = 0, nitems = 0, gmax = 0;
                 while (pos < todo.size()) {
                     const int u = todo[pos];
                     const int k = (int)children[u].size();
                     const int nc = (int)chain[u].size();
-                    if (L.nsteps + (int)pchain.size() + 1 + nc > BLG_P_MAXSTEPS || nch + k + nc > BLG_P_MAXCHILD) break;
-                    if (G.nsteps + 1 + nc > BLG_G_MAXSTEPS || gch + k + nc > BLG_G_MAXCHILD) break;
+                    bool room = G.nsteps + 1 + nc <= BLG_G_MAXSTEPS && gch + k + nc <= BLG_G_MAXCHILD;
+                    for (auto& t_ : tl) room = room && t_.L->nsteps + (int)t_.chain.size() + 1 + nc <= BLG_P_MAXSTEPS && t_.nch + k + nc <= BLG_P_MAXCHILD;
+                    if (!room) break;
                     require(tabs_valid && tabs[u].built && tabs[u].k == k, "logpdf: ε/W tables are stale (call blg_rebuild)");
                     std::vector<int> ord(tabs[u].mo, tabs[u].mo + k);
                     Pat* Pu = pat_of(S, S.Tp[u]);
                     Link* lk = get_link(S, u, ord);
-                    // split of the node's patterns: [0, ug) one warp each, [ug, U) in tiles
-                    int ug = Pu->nboth;
-                    if (xg < 0x7fffffff) {
-                        int lo = ug, hi = Pu->U;           // h_cnt is descending on [nboth, U)
-                        while (lo < hi) { const int mid = (lo + hi) / 2; if ((int)Pu->h_cnt[mid] >= xg) lo = mid + 1; else hi = mid; }
-                        ug = lo;
-                    }
+                    const int ng = Pu->nvery, nw = Pu->nvery + Pu->nwide;
                     Slab* o = writable(S, u);
                     std::vector<Slab*> co;
                     for (int v : chain[u]) co.push_back(writable(S, v));
+                    std::vector<Slab*> csl(k, nullptr);
                     int sum = 0;
-                    bool tiled = false;
-                    const int nch0 = nch, gch0 = gch;
                     for (int j = 0; j < k; ++j) {
                         const int c = ord[j];
                         require(tabs[c].built && tabs[c].wdim >= S.Tp[c].xmax + 1 && tabs[c].xfast == S.Tp[c].xmax,
                                 "logpdf: W table of a child does not match the profile (call blg_rebuild)");
                         Pat* Pc = pat_of(S, S.Tp[c]);
-                        Slab* sl = children[c].empty() ? nullptr : readable(S, c);
-                        if (ug < Pu->U) {
-                            PChild& pc = L.child[nch++];
-                            memset(&pc, 0, sizeof(pc));
-                            if (sl) { pc.ell = sl->ell; pc.scl = sl->scl; }
-                            pc.cnt = Pc->d_cnt;
-                            pc.pidx = lk->d_pidx[j];
-                            pc.Wt = tabs[c].Wt; pc.wdp = tabs[c].wdp; pc.table = (kind[c] == BLG_WGDAFTER) ? 1 : 0;
-                            pc.node = c; pc.ld = (int)Pc->ld;
-                        }
-                        if (ug > 0) fill_gchild(S, G.child[gch++], u, c, Pc, sl, lk->d_pidx[j]);
+                        csl[j] = children[c].empty() ? nullptr : readable(S, c);
                         sum += Pc->xmax;
-                        if (j >= 1 && Pc->xmax >= 20) tiled = true;
-                        last_pattern_bytes += sl ? 8.0 * Pc->colsum : 0.0;   // (each child column is read at least once)
+                        last_pattern_bytes += csl[j] ? 8.0 * Pc->colsum : 0.0;   // (each child column is read at least once)
                     }
-                    if (k == 2 && std::min(pat_of(S, S.Tp[ord[0]])->xmax, pat_of(S, S.Tp[ord[1]])->xmax) < 20) tiled = false;
                     sum = std::min(sum, k * Pu->xmax);             // (per tile the children's maxima are taken separately)
-                    if (ug < Pu->U) {
-                        worst = std::max(worst, tiled ? 3 * (sum + 1) : sum + k + 1);
+                    for (int w = 0; w < 2; ++w) {                  // w = 0: tile kernel, w = 1: wide tile kernel
+                        const int lo = w ? ng : nw, hi = w ? nw : Pu->U;
+                        if (hi <= lo) continue;
+                        TL& T = tl[w];
+                        PList& L = *T.L;
+                        // a tile whose two largest children both reach the widest register merge takes the chained-tile
+                        // merge, which needs three columns (rare: the pattern order keeps such tiles apart)
+                        T.worst = std::max(T.worst, std::max(3 * (sum + 1), sum + k + 1));
                         PStep& ps = L.step[L.nsteps++];
                         memset(&ps, 0, sizeof(ps));
-                        ps.k = k; ps.first = nch0; ps.node = u; ps.U = Pu->U; ps.tile0 = ntiles; ps.ld = (int)Pu->ld; ps.p0 = ug;
+                        ps.k = k; ps.first = T.nch; ps.node = u; ps.U = hi; ps.tile0 = T.ntiles; ps.ld = (int)Pu->ld; ps.p0 = lo;
                         ps.cnt = Pu->d_cnt; ps.out = o->ell; ps.out_scl = o->scl;
-                        ps.chain_first = (int)pchain.size(); ps.nchain = nc;
+                        ps.chain_first = (int)T.chain.size(); ps.nchain = nc;
+                        for (int j = 0; j < k; ++j) {
+                            const int c = ord[j];
+                            Pat* Pc = pat_of(S, S.Tp[c]);
+                            PChild& pc = L.child[T.nch++];
+                            memset(&pc, 0, sizeof(pc));
+                            if (csl[j]) { pc.ell = csl[j]->ell; pc.scl = csl[j]->scl; }
+                            pc.cnt = Pc->d_cnt;
+                            pc.pidx = lk->d_pidx[j];
+                            pc.Wt = tabs[c].Wt; pc.wdp = tabs[c].wdp; pc.table = table_band(c);
+                            pc.node = c; pc.ld = (int)Pc->ld;
+                        }
                         int below = u;
                         for (int ci = 0; ci < nc; ++ci) {
                             const int v = chain[u][ci];
                             PStep cs;
                             memset(&cs, 0, sizeof(cs));
-                            cs.k = 1; cs.first = nch; cs.node = v; cs.U = Pu->U; cs.ld = (int)Pu->ld;
+                            cs.k = 1; cs.first = T.nch; cs.node = v; cs.U = hi; cs.ld = (int)Pu->ld;
                             cs.cnt = Pu->d_cnt; cs.out = co[ci]->ell; cs.out_scl = co[ci]->scl;
-                            PChild& pc = L.child[nch++];
+                            PChild& pc = L.child[T.nch++];
                             memset(&pc, 0, sizeof(pc));
                             pc.cnt = Pu->d_cnt;
                             pc.ell = (below == u ? o : co[ci - 1])->ell;      // (resident: never read from memory, but not a leaf)
                             pc.scl = (below == u ? o : co[ci - 1])->scl;
-                            pc.Wt = tabs[below].Wt; pc.wdp = tabs[below].wdp; pc.table = (kind[below] == BLG_WGDAFTER) ? 1 : 0;
+                            pc.Wt = tabs[below].Wt; pc.wdp = tabs[below].wdp; pc.table = table_band(below);
                             pc.node = below; pc.ld = (int)Pu->ld;
-                            pchain.push_back(cs);
+                            T.chain.push_back(cs);
                             below = v;
                         }
-                        ntiles += (Pu->U - ug + 31) / 32;
+                        T.ntiles += (hi - lo + 31) / 32;
                     }
-                    if (ug > 0) {
+                    if (ng > 0) {
                         GStep& gs = G.step[G.nsteps++];
                         memset(&gs, 0, sizeof(gs));
-                        gs.k = k; gs.first = gch0; gs.node = u; gs.resident = 0; gs.item0 = nitems; gs.nchain = nc; gs.is_chain = 0;
+                        gs.k = k; gs.first = gch; gs.node = u; gs.resident = 0; gs.item0 = nitems; gs.nchain = nc; gs.is_chain = 0;
                         gs.out = o->ell; gs.out_scl = o->scl; gs.cnt = Pu->d_cnt; gs.out_off = nullptr; gs.out_ld = Pu->ld;
+                        for (int j = 0; j < k; ++j) fill_gchild(S, G.child[gch++], u, ord[j], pat_of(S, S.Tp[ord[j]]), csl[j], lk->d_pidx[j]);
                         int below = u;
                         for (int ci = 0; ci < nc; ++ci) {
                             const int v = chain[u][ci];
@@ -2028,7 +2051,7 @@ struct blg_handle {
                             G.child[gch - 1].scl = (below == u ? o : co[ci - 1])->scl;
                             below = v;
                         }
-                        nitems += ug;
+                        nitems += ng;
                         gmax = std::max(gmax, Pu->xmax);
                     }
                     last_pattern_bytes += (8.0 * Pu->colsum + 4.0 * Pu->U) * (1 + nc);
@@ -2037,53 +2060,79 @@ struct blg_handle {
                     for (int v : chain[u]) count_step_bytes(S, v);
                     ++pos;
                 }
-                require(L.nsteps + G.nsteps > 0, "sweep: a node has more children than one launch can describe");
-                cudaEvent_t dbg0 = nullptr, dbg1 = nullptr, dbg2 = nullptr;
-                if (pdebug) { CK(cudaEventCreate(&dbg0)); CK(cudaEventCreate(&dbg1)); CK(cudaEventCreate(&dbg2)); CK(cudaEventRecord(dbg0, stream)); }
+                require(tl[0].L->nsteps + tl[1].L->nsteps + G.nsteps > 0, "sweep: a node has more children than one launch can describe");
+                cudaEvent_t dbg[4] = {nullptr, nullptr, nullptr, nullptr};
+                if (pdebug) { for (auto& e : dbg) CK(cudaEventCreate(&e)); CK(cudaEventRecord(dbg[0], stream)); }
                 if (G.nsteps > 0) {
                     // (work counters of the item launches: 240 slots zeroed in one go, one slot per launch)
                     if (gslot == 0) { d_gctr.ensure(256); CK(cudaMemsetAsync(d_gctr.p + 16, 0, 240 * sizeof(unsigned int), stream)); }
                     launch_general(G, 0, nitems, gmax, 0, 0, 16 + gslot, 1);
                     gslot = (gslot + 1) % 240;
                 }
-                if (pdebug) CK(cudaEventRecord(dbg1, stream));
-                int cap = 0;
-                if (L.nsteps > 0) {
-                    for (size_t q = 0; q < pchain.size(); ++q) L.step[L.nsteps + q] = pchain[q];
-                    L.ntiles = ntiles;
-                    L.first_of_call = first ? 1 : 0;
-                    first = false;
-                    cap = std::min(worst, std::max(slice_cap, 56));   // doubles per lane of a warp's shared slice; rare larger tiles use global scratch
-                    const int wpb = 4;
-                    double* gs = nullptr;
-                    size_t gstride = 0;
-                    if (worst > cap) {
-                        gstride = (size_t)worst * 32;
-                        gscratch.ensure(gstride * (size_t)ntiles);
-                        gs = gscratch.p;
+                if (pdebug) CK(cudaEventRecord(dbg[1], stream));
+                int caps[2] = {0, 0};
+                // the wide launch goes to a second (high-priority) stream: it usually holds a few long tiles, which then run
+                // beside the level's other launches instead of in front of them
+                const bool side = tl[1].L->nsteps > 0 && !pdebug;
+                if (side) {
+                    if (!stream2) {
+                        int lo_ = 0, hi_ = 0;
+                        CK(cudaDeviceGetStreamPriorityRange(&lo_, &hi_));
+                        CK(cudaStreamCreateWithPriority(&stream2, cudaStreamNonBlocking, hi_));
+                        CK(cudaEventCreateWithFlags(&ev_main, cudaEventDisableTiming));
+                        CK(cudaEventCreateWithFlags(&ev_side, cudaEventDisableTiming));
                     }
-                    const size_t smem = (size_t)cap * 32 * wpb * sizeof(double);
-                    if (smem > ptile_smem_set) {
-                        CK(cudaFuncSetAttribute(ptile_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-                        ptile_smem_set = smem;
+                    CK(cudaEventRecord(ev_main, stream));          // everything below this level is in `stream` up to here
+                    CK(cudaStreamWaitEvent(stream2, ev_main, 0));
+                }
+                for (int w = 1; w >= 0; --w) {                     // the wide tiles first: they are the long ones
+                    TL& T = tl[w];
+                    PList& L = *T.L;
+                    cudaStream_t stream = (w == 1 && side) ? stream2 : this->stream;
+                    if (L.nsteps > 0) {
+                        for (size_t q = 0; q < T.chain.size(); ++q) L.step[L.nsteps + q] = T.chain[q];
+                        L.ntiles = T.ntiles;
+                        // doubles per lane of a warp's shared slice; rare larger tiles use global scratch
+                        const int cap = std::min(T.worst, w ? 104 : std::max(slice_cap, 56));
+                        caps[w] = cap;
+                        const int wpb = 4;
+                        double* gs = nullptr;
+                        size_t gstride = 0;
+                        if (T.worst > cap) {
+                            gstride = (size_t)T.worst * 32;
+                            DevBuf<double>& sb = w ? gscratch_w : gscratch;
+                            sb.ensure(gstride * (size_t)T.ntiles);
+                            gs = sb.p;
+                        }
+                        const size_t smem = (size_t)cap * 32 * wpb * sizeof(double);
+                        if (smem > ptile_smem_set[w]) {
+                            if (w) CK(cudaFuncSetAttribute(ptile_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+                            else CK(cudaFuncSetAttribute(ptile_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+                            ptile_smem_set[w] = smem;
+                        }
+                        if (w) ptile_kernel<true><<<(T.ntiles + wpb - 1) / wpb, 32 * wpb, smem, stream>>>(L, d_nk.p, d_flags.p, d_ran.p, cap, gs, gstride);
+                        else ptile_kernel<false><<<(T.ntiles + wpb - 1) / wpb, 32 * wpb, smem, stream>>>(L, d_nk.p, d_flags.p, d_ran.p, cap, gs, gstride);
+                        CK(cudaGetLastError());
+                        last_launches++;
                     }
-                    ptile_kernel<<<(ntiles + wpb - 1) / wpb, 32 * wpb, smem, stream>>>(L, d_nk.p, d_flags.p, d_ran.p, cap, gs, gstride);
-                    CK(cudaGetLastError());
-                    last_launches++;
+                    if (pdebug) CK(cudaEventRecord(dbg[3 - w], stream));
+                }
+                if (side) {                                        // join: the next level reads what the wide launch wrote
+                    CK(cudaEventRecord(ev_side, stream2));
+                    CK(cudaStreamWaitEvent(stream, ev_side, 0));
                 }
                 if (pdebug) {
-                    CK(cudaEventRecord(dbg2, stream));
-                    CK(cudaEventSynchronize(dbg2));
-                    float ms1 = 0.f, ms2 = 0.f;
-                    CK(cudaEventElapsedTime(&ms1, dbg0, dbg1));
-                    CK(cudaEventElapsedTime(&ms2, dbg1, dbg2));
-                    cudaEventDestroy(dbg0); cudaEventDestroy(dbg1); cudaEventDestroy(dbg2);
-                    fprintf(stderr, "[blg pattern] level %2d: warp-items %6d (%d steps) %7.1f us | tiles %6d (%d+%d steps, cap %d worst %d) %7.1f us |", lv, nitems, G.nsteps,
-                            ms1 * 1e3, ntiles, L.nsteps, (int)pchain.size(), cap, worst, ms2 * 1e3);
-                    for (int i = 0; i < std::min(L.nsteps, 3); ++i) {
-                        const PStep& q = L.step[i];
+                    CK(cudaEventSynchronize(dbg[3]));
+                    float ms[3] = {0.f, 0.f, 0.f};
+                    for (int q = 0; q < 3; ++q) CK(cudaEventElapsedTime(&ms[q], dbg[q], dbg[q + 1]));
+                    for (auto& e : dbg) cudaEventDestroy(e);
+                    fprintf(stderr, "[blg pattern] level %2d: warp-items %6d (%d steps) %6.1f us | wide tiles %5d (%d steps, cap %d) %6.1f us | tiles %6d (%d+%d steps, cap %d worst %d) %6.1f us |",
+                            lv, nitems, G.nsteps, ms[0] * 1e3, tl[1].ntiles, tl[1].L->nsteps, caps[1], ms[1] * 1e3, tl[0].ntiles, tl[0].L->nsteps, (int)tl[0].chain.size(),
+                            caps[0], tl[0].worst, ms[2] * 1e3);
+                    for (int i = 0; i < std::min(tl[0].L->nsteps, 3); ++i) {
+                        const PStep& q = tl[0].L->step[i];
                         fprintf(stderr, " [node %d U %d p0 %d x %d chain %d:", q.node, q.U, q.p0, pat_of(S, S.Tp[q.node])->xmax, q.nchain);
-                        for (int j = 0; j < q.k; ++j) fprintf(stderr, " %d", pat_of(S, S.Tp[L.child[q.first + j].node])->xmax);
+                        for (int j = 0; j < q.k; ++j) fprintf(stderr, " %d", pat_of(S, S.Tp[tl[0].L->child[q.first + j].node])->xmax);
                         fprintf(stderr, "]");
                     }
                     fprintf(stderr, "\n");

@@ -47,7 +47,10 @@ struct PList {
 static_assert(sizeof(PList) <= 32000, "kernel parameter space");
 __device__ __forceinline__ ChildArgs child_args(const PChild& c, double psi, double cc) { return ChildArgs{c.ell, c.Wt, c.wdp, c.table, psi, cc}; }
 
-__global__ void __launch_bounds__(128, 4) ptile_kernel(const __grid_constant__ PList L, const NodeK* __restrict__ nk,
+// WIDE: the instantiation for patterns whose smaller child has 20..35 counts — register-tiled merges 28 and 36 wide, which
+// need more than 128 registers (2 blocks per SM instead of 4); such patterns sit at the front of a node's order.
+template <bool WIDE>
+__global__ void __launch_bounds__(128, WIDE ? 2 : 4) ptile_kernel(const __grid_constant__ PList L, const NodeK* __restrict__ nk,
                                                        const int* __restrict__ flags, unsigned int* __restrict__ ran,
                                                        int slice_cap, double* gscratch, size_t gs_stride) {
     extern __shared__ double smem[];
@@ -94,20 +97,35 @@ __global__ void __launch_bounds__(128, 4) ptile_kernel(const __grid_constant__ P
     int sumw = M0w + M1w;
     // which side of a binary merge is register-tiled: the child with the smaller bound in THIS tile
     const bool swap = (k == 2) && (M0w < M1w);
-    bool tiled = (k == 2) ? (min(M0w, M1w) >= 20) : (M1w >= 20);
+    constexpr int TMAX = WIDE ? 36 : 20;      // widest register-tiled merge of this instantiation
+    bool tiled = (k == 2) ? (min(M0w, M1w) >= TMAX) : (M1w >= TMAX);
 #pragma unroll 1
     for (int i = 2; i < k; ++i) {
         const int ci = ch[i].pidx ? ch[i].pidx[p] : p;
         const int Miw = warp_max((int)ch[i].cnt[ci]);
         sumw += Miw;
-        if (Miw >= 20) tiled = true;
+        if (Miw >= TMAX) tiled = true;
         if (ch[i].scl) sclsum += ch[i].scl[ci];
     }
     const int need = tiled ? 3 * (sumw + 1) : sumw + k + 1;
     double* R = (need <= slice_cap) ? sl : gscratch + (size_t)tile * gs_stride + lane;
     const NodeK k0 = nk[ch[0].node];
-    // child 1's input column is copied asynchronously while child 0 is being contracted
+    // the input columns of the first two children are gathers (every lane reads another pattern's column): all requests
+    // are issued at once as asynchronous copies — a loop of dependent loads would pay one L2 round trip per element
+    const bool async0 = R == sl;
     const bool async1 = (k >= 2) && !tiled && R == sl;
+    if (async0) {
+        if (ch[0].ell == nullptr) {
+            const double* row = ch[0].Wt + (size_t)M0 * ch[0].wdp;
+#pragma unroll 1
+            for (int s = 0; s <= M0w; ++s) cp_async_f64(R + s * 32, (s <= M0) ? row + s : row, s <= M0);
+        } else {
+            const double* src = ch[0].ell + c0;
+            const size_t ld0 = (size_t)ch[0].ld;
+#pragma unroll 1
+            for (int j = 0; j <= M0w; ++j) cp_async_f64(R + j * 32, (j <= M0) ? src + (size_t)j * ld0 : src, j <= M0);
+        }
+    }
     if (async1) {
         double* dst = R + (size_t)(M0w + 1) * 32;
         if (ch[1].ell == nullptr) {
@@ -120,10 +138,9 @@ __global__ void __launch_bounds__(128, 4) ptile_kernel(const __grid_constant__ P
 #pragma unroll 1
             for (int j = 0; j <= M1w; ++j) cp_async_f64(dst + j * 32, (j <= M1) ? src + (size_t)j * ld1 : src, j <= M1);
         }
-        cp_async_commit();
     }
-    sweep_child(child_args(ch[0], k0.psi, k0.cc), c0, (size_t)ch[0].ld, M0, M0w, R, 0, 1.0);
-    if (async1) cp_async_wait_all();
+    if (async0) { cp_async_commit(); cp_async_wait_all(); }
+    sweep_child(child_args(ch[0], k0.psi, k0.cc), c0, (size_t)ch[0].ld, M0, M0w, R, async0 ? 2 : 0, 1.0);
     int Sw = M0w;
     double mxv = 0.0;
     bool scaled = false;        // has the (1-E_k)^(-n) normalisation already been applied (and mxv taken)?
@@ -151,10 +168,16 @@ __global__ void __launch_bounds__(128, 4) ptile_kernel(const __grid_constant__ P
             const double inve = swap ? k0.inve : ki.inve;
             Eraw *= ki.e;
             double mx;
-            if (sW < 4) mx = sweep_merge_fast<4>(R, tA, tW, sB, sW, E, invE, e, inve, em0, emg, Xm);
-            else if (sW < 8) mx = sweep_merge_fast<8>(R, tA, tW, sB, sW, E, invE, e, inve, em0, emg, Xm);
-            else if (sW < 12) mx = sweep_merge_fast<12>(R, tA, tW, sB, sW, E, invE, e, inve, em0, emg, Xm);
-            else mx = sweep_merge_fast<20>(R, tA, tW, sB, sW, E, invE, e, inve, em0, emg, Xm);
+            if (WIDE) {
+                if (sW < 20) mx = sweep_merge_fast<20>(R, tA, tW, sB, sW, E, invE, e, inve, em0, emg, Xm);
+                else if (sW < 28) mx = sweep_merge_fast<28>(R, tA, tW, sB, sW, E, invE, e, inve, em0, emg, Xm);
+                else mx = sweep_merge_fast<36>(R, tA, tW, sB, sW, E, invE, e, inve, em0, emg, Xm);
+            } else {
+                if (sW < 4) mx = sweep_merge_fast<4>(R, tA, tW, sB, sW, E, invE, e, inve, em0, emg, Xm);
+                else if (sW < 8) mx = sweep_merge_fast<8>(R, tA, tW, sB, sW, E, invE, e, inve, em0, emg, Xm);
+                else if (sW < 12) mx = sweep_merge_fast<12>(R, tA, tW, sB, sW, E, invE, e, inve, em0, emg, Xm);
+                else mx = sweep_merge_fast<20>(R, tA, tW, sB, sW, E, invE, e, inve, em0, emg, Xm);
+            }
             Sw += Miw;
             if (last) { mxv = mx; scaled = true; }
         }
