@@ -32,6 +32,7 @@
 
 #define BLG_MAXK 8          // max children of one node (polytomies)
 #define BLG_MAXCOUNT 4095   // largest extended count supported (general kernel: probability-form recursion, no tables)
+#define BLG_MMA_MIN 12         // count bound of a warp from which a contraction runs as a DMMA table product
 #define BLG_FAST_MAXCOUNT 100   // largest count bound the table-free sweep kernel handles (families above it: heavy shard)
 
 namespace {
@@ -576,6 +577,48 @@ __device__ __noinline__ void sweep_contract_table(double* col, int Mw, const dou
             if (s0 + k <= Mw) col[(s0 + k) * 32] = acc[k] * osc;
     }
 }
+// in-place contraction of the 32 columns of a warp with the w* TABLE of the branch on the fp64 tensor pipe:
+//     out[s][pattern] = Σ_{j >= s} w*(s|j)·col[j][pattern]      — a triangular (Mw+1)×(Mw+1) by (Mw+1)×32 product,
+// mma.sync.m8n8k4.f64: A = w* (row s, column j; the table is stored transposed, Wt[j·wdp + s]), B = the warp's slice
+// (row j, column = lane/pattern), C = 8 output rows × 8 patterns per instruction (256 FMA).  Output rows are produced in
+// ascending blocks of 8, so the product can overwrite its input: block s0 only reads rows >= s0.  One DMMA replaces 8
+// DFMA warp instructions and their loop/shared-memory traffic; for columns of a few dozen counts the contraction is the
+// densest part of a pruning step.  band: 0 for an ordinary branch (dense upper triangle), 2/3 below a WGD/WGT (rows
+// j > band·s of column s are zero).
+__device__ __forceinline__ void dmma_m8n8k4(double& c0, double& c1, double a, double b) {
+    asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};" : "+d"(c0), "+d"(c1) : "d"(a), "d"(b));
+}
+__device__ __noinline__ void sweep_contract_mma(double* col, int Mw, const double* __restrict__ Wt, int wdp, int band) {
+    const unsigned lane = threadIdx.x & 31u;
+    double* cb = col - lane;                       // the warp's slice: element (j, pattern) at cb[j*32 + pattern]
+    const int g = (int)(lane >> 2), t = (int)(lane & 3u);
+#pragma unroll 1
+    for (int s0 = 0; s0 <= Mw; s0 += 8) {
+        double c[4][2];
+#pragma unroll
+        for (int nb = 0; nb < 4; ++nb) { c[nb][0] = 0.0; c[nb][1] = 0.0; }
+        const int jhi = band ? min(Mw, band * (s0 + 7)) : Mw;
+#pragma unroll 1
+        for (int j0 = s0; j0 <= jhi; j0 += 4) {
+            const int j = j0 + t;
+            const bool in = j <= Mw;
+            const double a = in ? __ldg(Wt + (size_t)j * wdp + s0 + g) : 0.0;
+            const double* row = cb + (size_t)(in ? j : Mw) * 32 + g;
+#pragma unroll
+            for (int nb = 0; nb < 4; ++nb) {
+                const double b = in ? row[nb * 8] : 0.0;
+                dmma_m8n8k4(c[nb][0], c[nb][1], a, b);
+            }
+        }
+        __syncwarp();                              // every lane has read rows s0..s0+7 before they are overwritten
+        const int s = s0 + g;
+        if (s <= Mw) {
+#pragma unroll
+            for (int nb = 0; nb < 4; ++nb) *reinterpret_cast<double2*>(cb + (size_t)s * 32 + nb * 8 + 2 * t) = make_double2(c[nb][0], c[nb][1]);
+        }
+        __syncwarp();
+    }
+}
 // in-place contraction over an ordinary branch, col[j] = ℓ[j] → col[n] = b[n] (j, n = 0..Mw; b[0] = ℓ[0]).
 // The columns of w* obey v_j = T·v_{j-1}, (T v)[n] = ψ'·v[n] + c·v[n-1], v_1 = c·δ_{n1} (wstar!, node.jl:181-192), so
 // b = Σ_j ℓ[j]·T^(j-1)·v_1 is evaluated by Horner's rule from j = Mw down to 1.  With r[n] = (partial b[n])/c^n a stage is
@@ -730,7 +773,14 @@ __device__ __noinline__ void sweep_child(const ChildArgs c, int f, size_t ld, in
 #pragma unroll 1
         for (int j = 0; j <= Mw; ++j) col[j * 32] = (j <= M) ? src[(size_t)j * ld] : 0.0;
     }
-    if (c.table) {
+    if (Mw >= BLG_MMA_MIN && c.Wt != nullptr) {   // a few dozen counts: the table product on the tensor pipe
+        if (have == 1) {                           // (the pending power of two of a resident column: exact)
+#pragma unroll 1
+            for (int j = 0; j <= Mw; ++j) col[j * 32] *= osc;
+        }
+        __syncwarp();
+        sweep_contract_mma(col, Mw, c.Wt, c.wdp, c.table);
+    } else if (c.table) {
         sweep_contract_table<16>(col, Mw, c.Wt, c.wdp, osc, c.table);
     } else {
         const double psi = c.psi, cc = c.cc;
