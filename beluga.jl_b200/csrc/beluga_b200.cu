@@ -598,7 +598,7 @@ __device__ __noinline__ void sweep_contract_mma(double* col, int Mw, const doubl
 #pragma unroll
         for (int nb = 0; nb < 4; ++nb) { c[nb][0] = 0.0; c[nb][1] = 0.0; }
         const int jhi = band ? min(Mw, band * (s0 + 7)) : Mw;
-#pragma unroll 1
+#pragma unroll 2
         for (int j0 = s0; j0 <= jhi; j0 += 4) {
             const int j = j0 + t;
             const bool in = j <= Mw;
@@ -1297,6 +1297,8 @@ struct blg_handle {
     // pat_mode == false: one column per family (the layout the gradient kernels work on; BLG_DEDUP=0 forces it).
     bool pat_mode = true, pat_default = true;
     int gslot = 0;
+    DevBuf<double> pat_ll;                    // per root pattern: the integrated log-likelihood (written by the root's tiles)
+    bool root_fused = false;
     cudaStream_t stream2 = nullptr;           // the wide tile launches of a level run beside its other launches
     cudaEvent_t ev_main = nullptr, ev_side = nullptr;
     int pdebug = 0;                           // BLG_PDEBUG: time and describe every pattern launch (stderr)
@@ -1341,7 +1343,7 @@ struct blg_handle {
         d_prof.free_();
         gpool_release();
         for (auto& e : ev) if (e) cudaEventDestroy(e);
-        gscratch.free_(); gscratch_w.free_(); d_tilectr.free_(); d_gctr.free_(); d_ticket.free_();
+        gscratch.free_(); gscratch_w.free_(); pat_ll.free_(); d_tilectr.free_(); d_gctr.free_(); d_ticket.free_();
         if (stream2) cudaStreamDestroy(stream2);
         if (ev_main) cudaEventDestroy(ev_main);
         if (ev_side) cudaEventDestroy(ev_side);
@@ -2053,6 +2055,11 @@ struct blg_handle {
                         ps.k = k; ps.first = T.nch; ps.node = u; ps.U = hi; ps.tile0 = T.ntiles; ps.ld = (int)Pu->ld; ps.p0 = lo;
                         ps.cnt = Pu->d_cnt; ps.out = o->ell; ps.out_scl = o->scl;
                         ps.chain_first = (int)T.chain.size(); ps.nchain = nc;
+                        if (u == 0 && rootw_valid && rootw_rows == root_rows()) {      // the root: integrate on the spot
+                            pat_ll.ensure(Pu->ld);
+                            ps.rootw = rootw.p; ps.pat_ll = pat_ll.p;
+                            root_fused = true;
+                        }
                         for (int j = 0; j < k; ++j) {
                             const int c = ord[j];
                             Pat* Pc = pat_of(S, S.Tp[c]);
@@ -2643,7 +2650,8 @@ struct blg_handle {
                     CK(cudaMemcpy(P0->d_fam2pat, P0->fam2pat.data(), (size_t)F.N * sizeof(int), cudaMemcpyHostToDevice));
                 }
                 root_pattern_kernel<<<bF, 256, 0, stream>>>(s->ell, s->scl, P0->d_cnt, P0->d_fam2pat, rootw.p, F.weight.p, F.fam_ll.p, partial.p, F.N,
-                                                            P0->ld, d_ticket.p, (unsigned)(bF + bH), d_flags.p, d_ran.p, marker, d_out);
+                                                            P0->ld, d_ticket.p, (unsigned)(bF + bH), d_flags.p, d_ran.p,
+                                                            root_fused ? pat_ll.p : nullptr, P0->nvery, marker, d_out);
                 last_pattern_bytes += 8.0 * P0->colsum + 4.0 * P0->U + 12.0 * F.N;
             } else {
                 root_kernel<<<bF, 256, 0, stream>>>(s->ell, s->scl, F.Tp[0].cnt, rootw.p, F.weight.p, F.fam_ll.p, partial.p, F.N, F.ld, d_ticket.p,
@@ -2687,6 +2695,7 @@ struct blg_handle {
         last_bytes = 0.0;
         last_launches = 0;
         last_pattern_bytes = last_pattern_cols = last_family_cols = 0.0;
+        root_fused = false;
         if (Ntot == 0) { CK(cudaMemsetAsync(d_out, 0, sizeof(double), stream)); return; }   // profile.jl:56
         require(have_params && tabs_valid, "logpdf: ε/W tables are stale (call blg_rebuild)");
         if (timing) { for (auto& e : ev) if (!e) CK(cudaEventCreate(&e)); CK(cudaEventRecord(ev[0], stream)); }

@@ -36,8 +36,12 @@ struct PStep {
     double* out;
     int* out_scl;
     const uint16_t* cnt;
+    // the root's step integrates its column on the spot (integrate_root / condition_oib, model.jl:465-501):
+    // pat_ll[p] = log Σ_n ℓ[n]·rootw[n] - rootw[0], the value every family of the pattern gets
+    const double* rootw;
+    double* pat_ll;
 };
-#define BLG_P_MAXSTEPS 150
+#define BLG_P_MAXSTEPS 120
 #define BLG_P_MAXCHILD 300
 struct PList {
     int nsteps, ntiles, first_of_call, pad_;
@@ -222,21 +226,37 @@ __global__ void __launch_bounds__(128, WIDE ? 2 : 4) ptile_kernel(const __grid_c
         if (be != 0 && be != 0x7ff) ex = be - 1023;
     }
     const double sc = __hiloint2double((1023 - ex) << 20, 0);         // 2^-ex, exact (|ex| <= 1022)
-    if (live) {
+    const bool keep = st.nchain > 0;               // a chain follows: the resident copy is rescaled too (same bits as the stored one)
+    {
         double* o = st.out + p;
         int n = 0;
 #pragma unroll 1
         for (; n < X; n += 2) {                    // two loads in flight
-            const double v0 = R[n * 32], v1 = R[(n + 1) * 32];
-            o[(size_t)n * ldo] = v0 * sc;
-            o[(size_t)(n + 1) * ldo] = v1 * sc;
+            const double v0 = R[n * 32] * sc, v1 = R[(n + 1) * 32] * sc;
+            if (live) { o[(size_t)n * ldo] = v0; o[(size_t)(n + 1) * ldo] = v1; }
+            if (keep) { R[n * 32] = v0; R[(n + 1) * 32] = v1; }
         }
-        if (n == X) o[(size_t)n * ldo] = R[n * 32] * sc;
-        st.out_scl[p] = sclsum + ex;
+        if (n == X) {
+            const double v0 = R[n * 32] * sc;
+            if (live) o[(size_t)n * ldo] = v0;
+            if (keep) R[n * 32] = v0;
+        }
+        if (live) st.out_scl[p] = sclsum + ex;
     }
-    // ---- the chain: single-child nodes above this one, on the same patterns.  The column stays in R (its stored copy
-    // is rescaled, R is not: the pending power of two goes into the contraction, exact) ------------------------------------
-    double prevSc = sc;
+    if (st.pat_ll != nullptr) {                    // same arithmetic, in the same order, as root_pattern_kernel on the stored column
+        const double* __restrict__ rw = st.rootw;
+        double acc = 0.0;
+#pragma unroll 1
+        for (int n = 1; n <= Xw; ++n) {
+            const double w = rw[n];
+            if (n <= X) acc = fma(R[n * 32] * sc, w, acc);
+        }
+        double l = log(acc) + (double)(sclsum + ex) * 0.6931471805599453 - rw[0];
+        if (!isfinite(l)) l = -INFINITY;                                        // model.jl:366
+        if (live) st.pat_ll[p] = l;
+    }
+    // ---- the chain: single-child nodes above this one, on the same patterns.  The column stays in R, rescaled like its
+    // stored copy (so a partial recompute that starts from the stored copy sees the same bits) ------------------------------
     int prevScl = sclsum + ex;
 #pragma unroll 1
     for (int cj = 0; cj < st.nchain; ++cj) {
@@ -244,17 +264,21 @@ __global__ void __launch_bounds__(128, WIDE ? 2 : 4) ptile_kernel(const __grid_c
         const PChild& cv = L.child[sv.first];
         const NodeK kv = nk[cv.node];
         __syncwarp();
-        sweep_child(child_args(cv, kv.psi, kv.cc), 0, 0, X, Xw, R, 1, prevSc);
-        // ℓ_v[n] = b[n]·(1-e)^(-n)
+        sweep_child(child_args(cv, kv.psi, kv.cc), 0, 0, X, Xw, R, 2, 1.0);
+        // ℓ_v[n] = b[n]·(1-e)^(-n): first pass the values and their maximum, second pass the rescaled column out
         double ip = nk[sv.node].ip0;
         const double invv = nk[sv.node].inv;
         double mv = 0.0;
+        {
+            int n = 0;
 #pragma unroll 1
-        for (int n = 0; n <= Xw; ++n) {
-            double v = 0.0;
-            if (n <= X) { v = R[n * 32] * ip; mv = fmax(mv, v); }
-            R[n * 32] = v;
-            ip *= invv;
+            for (; n < X; n += 2) {
+                const double v0 = R[n * 32] * ip, v1 = R[(n + 1) * 32] * (ip * invv);
+                mv = fmax(mv, fmax(v0, v1));
+                R[n * 32] = v0; R[(n + 1) * 32] = v1;
+                ip *= invv * invv;
+            }
+            if (n == X) { const double v0 = R[n * 32] * ip; mv = fmax(mv, v0); R[n * 32] = v0; }
         }
         int exv = 0;
         if (mv > 0.0) {
@@ -262,13 +286,22 @@ __global__ void __launch_bounds__(128, WIDE ? 2 : 4) ptile_kernel(const __grid_c
             if (be != 0 && be != 0x7ff) exv = be - 1023;
         }
         const double scv = __hiloint2double((1023 - exv) << 20, 0);
-        if (live) {
+        {
             double* o = sv.out + p;
+            int n = 0;
 #pragma unroll 1
-            for (int n = 0; n <= X; ++n) o[(size_t)n * ldo] = R[n * 32] * scv;
-            sv.out_scl[p] = prevScl + exv;
+            for (; n < X; n += 2) {
+                const double v0 = R[n * 32] * scv, v1 = R[(n + 1) * 32] * scv;
+                if (live) { o[(size_t)n * ldo] = v0; o[(size_t)(n + 1) * ldo] = v1; }
+                R[n * 32] = v0; R[(n + 1) * 32] = v1;
+            }
+            if (n == X) {
+                const double v0 = R[n * 32] * scv;
+                if (live) o[(size_t)n * ldo] = v0;
+                R[n * 32] = v0;
+            }
+            if (live) sv.out_scl[p] = prevScl + exv;
         }
-        prevSc = scv;
         prevScl += exv;
     }
 }
@@ -281,6 +314,7 @@ __global__ void __launch_bounds__(256) root_pattern_kernel(const double* __restr
                                                            double* __restrict__ fam_ll, double* __restrict__ partial, int N, size_t ld,
                                                            unsigned int* __restrict__ ticket, unsigned int nblocks_total,
                                                            const int* __restrict__ flags, unsigned int* __restrict__ ran,
+                                                           const double* __restrict__ pat_ll, int pat_lo,
                                                            double* __restrict__ marker, double* __restrict__ out) {
     __shared__ double red[256];
     __shared__ bool last_block;
@@ -289,11 +323,16 @@ __global__ void __launch_bounds__(256) root_pattern_kernel(const double* __restr
     if (f == 0 && flags[0]) atomicAdd(&ran[0], 1u);          // the table-free pattern path did this call's work
     if (f < N) {
         const int p = fam2pat[f];
-        const int X = pcnt[p];
-        double acc = 0.0;
-        for (int n = 1; n <= X; ++n) acc = fma(ell[(size_t)n * ld + p], rootw[n], acc);
-        double l = log(acc) + (double)scl[p] * 0.6931471805599453 - rootw[0];
-        if (!isfinite(l)) l = -INFINITY;                                        // model.jl:366
+        double l;
+        if (pat_ll != nullptr && p >= pat_lo) {
+            l = pat_ll[p];                       // integrated by the tile that computed the root's column
+        } else {
+            const int X = pcnt[p];
+            double acc = 0.0;
+            for (int n = 1; n <= X; ++n) acc = fma(ell[(size_t)n * ld + p], rootw[n], acc);
+            l = log(acc) + (double)scl[p] * 0.6931471805599453 - rootw[0];
+            if (!isfinite(l)) l = -INFINITY;                                        // model.jl:366
+        }
         fam_ll[f] = l;
         contrib = weight[f] * l;
     }
