@@ -12,7 +12,7 @@ _lib = None
 SYMBOLS = [
     "blg_create", "blg_destroy", "blg_last_error", "blg_set_profiles", "blg_set_topology", "blg_set_params",
     "blg_rebuild", "blg_logpdf_full", "blg_logpdf_from", "blg_logpdf_root", "blg_logpdf_full_async",
-    "blg_logpdf_from_async", "blg_logpdf_root_async", "blg_gradient", "blg_gradient_cr", "blg_gradient_async",
+    "blg_logpdf_from_async", "blg_logpdf_root_async", "blg_gradient", "blg_gradient_cr", "blg_comm_unique_id", "blg_comm_init", "blg_comm_size",
     "blg_commit", "blg_revert", "blg_extend", "blg_shrink", "blg_get_column", "blg_get_family_logpdf",
     "blg_get_eps", "blg_get_W", "blg_ncols", "blg_npatterns", "blg_last_algorithmic", "blg_sync",
     "blg_set_timing", "blg_last_timing", "blg_family_order", "blg_fp64_peak", "blg_kernel_runs", "blg_pattern_stats",
@@ -51,7 +51,9 @@ def lib():
     L.blg_logpdf_root_async.argtypes = [vp, vp]
     L.blg_gradient.argtypes = [vp, dp, C.c_int, dp]
     L.blg_gradient_cr.argtypes = [vp, dp, dp]
-    L.blg_gradient_async.argtypes = [vp, vp, C.c_int]
+    L.blg_comm_unique_id.argtypes = [C.POINTER(C.c_uint8)]
+    L.blg_comm_init.argtypes = [vp, C.c_int, C.c_int, C.POINTER(C.c_uint8)]
+    L.blg_comm_size.argtypes = [vp]
     for f in ("blg_commit", "blg_revert", "blg_sync", "blg_npatterns"):
         getattr(L, f).argtypes = [vp]
     L.blg_extend.argtypes = [vp, C.c_int]

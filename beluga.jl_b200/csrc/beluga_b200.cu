@@ -14,6 +14,7 @@
 // accesses coalesced along the family axis).  No CPU fallback: every entry fails loudly when
 // CUDA is unavailable.
 #include <cuda_runtime.h>
+#include <dlfcn.h>
 
 #include <algorithm>
 #include <cmath>
@@ -47,6 +48,49 @@ struct CudaError : std::runtime_error { using std::runtime_error::runtime_error;
     } while (0)
 
 thread_local std::string g_create_error;
+
+// ------------------------------------------------------------------------------------------------
+// NCCL, bound at run time (dlopen): the library owns the communicator of a multi-GPU run (one process per GPU, one
+// handle per process) and every likelihood / gradient entry returns the all-reduced value (src/profile.jl:56-75 is a
+// mapreduce over worker processes).  Binding at run time keeps a single copy of NCCL in a process that has already loaded
+// one (a PyTorch host), and lets single-GPU users run without NCCL installed.
+// ------------------------------------------------------------------------------------------------
+struct NcclApi {
+    typedef struct { char internal[128]; } UniqueId;
+    typedef void* Comm;
+    int (*GetUniqueId)(UniqueId*) = nullptr;
+    int (*CommInitRank)(Comm*, int, UniqueId, int) = nullptr;
+    int (*AllReduce)(const void*, void*, size_t, int, int, Comm, cudaStream_t) = nullptr;
+    int (*CommDestroy)(Comm) = nullptr;
+    const char* (*GetErrorString)(int) = nullptr;
+    void* lib = nullptr;
+    std::string why;
+    bool load() {
+        if (lib) return true;
+        const char* names[] = {getenv("BLG_NCCL_LIB"), "libnccl.so.2", "libnccl.so"};
+        for (const char* n : names) {
+            if (!n || !*n) continue;
+            lib = dlopen(n, RTLD_NOW | RTLD_GLOBAL);
+            if (lib) break;
+            why = dlerror();
+        }
+        if (!lib) return false;
+        GetUniqueId = (int (*)(UniqueId*))dlsym(lib, "ncclGetUniqueId");
+        CommInitRank = (int (*)(Comm*, int, UniqueId, int))dlsym(lib, "ncclCommInitRank");
+        AllReduce = (int (*)(const void*, void*, size_t, int, int, Comm, cudaStream_t))dlsym(lib, "ncclAllReduce");
+        CommDestroy = (int (*)(Comm))dlsym(lib, "ncclCommDestroy");
+        GetErrorString = (const char* (*)(int))dlsym(lib, "ncclGetErrorString");
+        if (!GetUniqueId || !CommInitRank || !AllReduce || !CommDestroy) { why = "NCCL symbols missing"; lib = nullptr; return false; }
+        return true;
+    }
+};
+NcclApi g_nccl;
+#define NCK(call)                                                                                          \
+    do {                                                                                                   \
+        int r_ = (call);                                                                                   \
+        if (r_ != 0)                                                                                       \
+            throw std::runtime_error(std::string(#call) + ": " + (g_nccl.GetErrorString ? g_nccl.GetErrorString(r_) : "NCCL error")); \
+    } while (0)
 
 // ------------------------------------------------------------------------------------------------
 // device-side model description
@@ -402,23 +446,35 @@ __global__ void __launch_bounds__(128) tables_kernel(ModelDev m, const int* __re
     __syncthreads();
     if (last_block) {
         __threadfence();
-        int* pz = reinterpret_cast<int*>(sm);
-        for (int i = tid; i < m.n; i += nt) pz[i] = isnan(__ldcg(&m.nk[i].ip0raw)) ? 1 : 0;
+        // everything the serial fold below touches goes to shared memory first (in parallel): the fold itself is a chain
+        // of dependent reads, one L2 round trip each if left in global memory
+        int* pz = reinterpret_cast<int*>(sm);          // [n] NaN flag of the subtree
+        int* sok = pz + m.n;                           // [n] range flag
+        int* soff = sok + m.n;                         // [n + 1] CSR of the children
+        int* sidx = soff + m.n + 1;                    // [n]
+        int* spost = sidx + m.n;                       // [npost]
+        for (int i = tid; i < m.n; i += nt) {
+            pz[i] = isnan(__ldcg(&m.nk[i].ip0raw)) ? 1 : 0;
+            sok[i] = __ldcg(&m.fast_ok[i]);
+            sidx[i] = m.child_idx[i];                  // (a tree has n - 1 child entries; the array holds at least n)
+        }
+        for (int i = tid; i <= m.n; i += nt) soff[i] = m.child_off[i];
+        for (int i = tid; i < m.npost; i += nt) spost[i] = m.post[i];
         __syncthreads();
         if (tid == 0) {
             int all_ok = 1;
             for (int li = 0; li < m.npost; ++li) {
-                const int u = m.post[li];
-                int p = (m.child_off[u + 1] > m.child_off[u]) ? pz[u] : 0;
-                for (int ci = m.child_off[u]; ci < m.child_off[u + 1]; ++ci) p |= pz[m.child_idx[ci]];
+                const int u = spost[li];
+                int p = (soff[u + 1] > soff[u]) ? pz[u] : 0;
+                for (int ci = soff[u]; ci < soff[u + 1]; ++ci) p |= pz[sidx[ci]];
                 pz[u] = p;
-                if (__ldcg(&m.fast_ok[u]) == 0) all_ok = 0;
+                if (sok[u] == 0) all_ok = 0;
             }
             m.flags[0] = all_ok;
             *m.ticket = 0u;
         }
         __syncthreads();
-        for (int li = tid; li < m.npost; li += nt) { const int u = m.post[li]; m.nk[u].ip0 = pz[u] ? NaN : 1.0; }
+        for (int li = tid; li < m.npost; li += nt) { const int u = spost[li]; m.nk[u].ip0 = pz[u] ? NaN : 1.0; }
     }
 }
 
@@ -1293,6 +1349,14 @@ struct blg_handle {
     int rootw_rows = 0;
     DevBuf<unsigned int> d_ticket;       // last-block-done counter of the root kernels (self-resetting)
 
+    // multi-GPU: this handle's rank in a communicator the library owns (nullptr: single GPU)
+    NcclApi::Comm comm = nullptr;
+    int comm_rank = 0, comm_size = 1;
+    DevBuf<double> d_red;                     // [1 + P] staging of the gradient all-reduce
+    void allreduce_sum(double* d_buf, size_t n) {
+        if (comm) NCK(g_nccl.AllReduce(d_buf, d_buf, n, /*ncclDouble*/ 8, /*ncclSum*/ 0, comm, stream));
+    }
+
     // node patterns (pattern.cuh): the fast family set is evaluated once per distinct sub-pattern of every node.
     // pat_mode == false: one column per family (the layout the gradient kernels work on; BLG_DEDUP=0 forces it).
     bool pat_mode = true, pat_default = true;
@@ -1344,6 +1408,8 @@ struct blg_handle {
         gpool_release();
         for (auto& e : ev) if (e) cudaEventDestroy(e);
         gscratch.free_(); gscratch_w.free_(); pat_ll.free_(); d_tilectr.free_(); d_gctr.free_(); d_ticket.free_();
+        if (comm && g_nccl.CommDestroy) g_nccl.CommDestroy(comm);
+        d_red.free_();
         if (stream2) cudaStreamDestroy(stream2);
         if (ev_main) cudaEventDestroy(ev_main);
         if (ev_side) cudaEventDestroy(ev_side);
@@ -1610,7 +1676,7 @@ struct blg_handle {
         }
         eps_kernel<<<1, 128, 0, stream>>>(m, d_elist_p, d_seg_p, (int)seg.size() - 1);
         CK(cudaGetLastError());
-        const size_t tsm = std::max(2 * (size_t)maxdim * sizeof(double), nn * sizeof(int));
+        const size_t tsm = std::max(2 * (size_t)maxdim * sizeof(double), (5 * nn + 8) * sizeof(int));
         tables_kernel<<<(unsigned)tlist.size(), 128, tsm, stream>>>(m, d_list_p, (int)tlist.size());
         CK(cudaGetLastError());
         if (full) tabs_valid = true;
@@ -2571,7 +2637,16 @@ struct blg_handle {
         const int P = cr ? 2 : 2 * nn + (int)wg.size() + 1;
         require(len >= P, "gradient: output vector too short");
         for (int i = 0; i < P; ++i) g[i] = 0.0;
-        if (Ntot == 0) { if (logpdf_out) *logpdf_out = 0.0; return; }
+        if (Ntot == 0) {
+            double ll = 0.0;
+            if (comm) {                          // an empty shard still takes part in the sums
+                logpdf(0, 1, result.p);
+                CK(cudaMemcpyAsync(&ll, result.p, sizeof(double), cudaMemcpyDeviceToHost, stream));
+                CK(cudaStreamSynchronize(stream));
+            }
+            if (logpdf_out) *logpdf_out = ll;
+            return;
+        }
         require(H.N == 0, "gradient: families with a root count above the fast bound are not supported by the gradient kernels "
                           "(raise BLG_HEAVY_MIN up to 256 to keep them in the table-based shard)");
         // fresh evaluation that leaves the committed/proposal state alone (the reference uses a fresh L, model.jl:395)
@@ -2696,7 +2771,12 @@ struct blg_handle {
         last_launches = 0;
         last_pattern_bytes = last_pattern_cols = last_family_cols = 0.0;
         root_fused = false;
-        if (Ntot == 0) { CK(cudaMemsetAsync(d_out, 0, sizeof(double), stream)); return; }   // profile.jl:56
+        if (Ntot == 0) {                                                                  // profile.jl:56
+            CK(cudaMemsetAsync(d_out, 0, sizeof(double), stream));
+            CK(cudaMemsetAsync(result.p + 8, 0, sizeof(double), stream));
+            allreduce_sum(d_out, 1);             // (an empty shard still takes part in the sum)
+            return;
+        }
         require(have_params && tabs_valid, "logpdf: ε/W tables are stale (call blg_rebuild)");
         if (timing) { for (auto& e : ev) if (!e) CK(cudaEventCreate(&e)); CK(cudaEventRecord(ev[0], stream)); }
         for (Shard* S : {&F, &H}) {
@@ -2726,6 +2806,7 @@ struct blg_handle {
         if (timing) CK(cudaEventRecord(ev[1], stream));
         last_prune_bytes = last_bytes;
         root_reduce(d_out);
+        allreduce_sum(d_out, 1);                 // Σ over the ranks' shards, on the same stream (8 bytes over NVLink)
         if (timing) { CK(cudaEventRecord(ev[2], stream)); ev_valid = true; }
     }
     // the pattern path runs OPTIMISTICALLY on the table-free kernel: the kernels leave at once when the device-side range
@@ -3009,7 +3090,7 @@ int blg_set_topology(blg_handle* h, int ncols, const int32_t* parent, const uint
     size_t n = (size_t)ncols;
     std::vector<int> off(n + 1, 0), idx;
     for (int i = 0; i < ncols; ++i) { off[i + 1] = off[i] + (int)h->children[i].size(); for (int c : h->children[i]) idx.push_back(c); }
-    h->d_kind.ensure(n); h->d_parent.ensure(n); h->d_child_off.ensure(n + 1); h->d_child_idx.ensure(std::max<size_t>(idx.size(), 1));
+    h->d_kind.ensure(n); h->d_parent.ensure(n); h->d_child_off.ensure(n + 1); h->d_child_idx.ensure(std::max<size_t>(idx.size(), n));
     CK(cudaMemcpyAsync(h->d_kind.p, h->kind.data(), n, cudaMemcpyHostToDevice, h->stream));
     CK(cudaMemcpyAsync(h->d_parent.p, h->parent.data(), n * sizeof(int), cudaMemcpyHostToDevice, h->stream));
     CK(cudaMemcpyAsync(h->d_child_off.p, off.data(), (n + 1) * sizeof(int), cudaMemcpyHostToDevice, h->stream));
@@ -3052,11 +3133,14 @@ int blg_rebuild(blg_handle* h, const int32_t* nodes, int n) {
 static int logpdf_sync(blg_handle* h, int mode, int node, double* out) {
     BLG_ENTER(h)
     h->require(out != nullptr, "logpdf: null output");
+    // with a communicator every rank must issue the same number of collectives: no optimistic run + rerun, the range
+    // flag is looked at first (one 4-byte read per ε/W build)
+    if (h->comm && h->Ntot > 0 && h->pattern_fast_path() && h->flag_cache < 0 && h->tabs_valid) h->fetch_flag();
     h->logpdf(mode, node, h->result.p);
     double r[9] = {0};
     CK(cudaMemcpyAsync(r, h->result.p, sizeof(r), cudaMemcpyDeviceToHost, h->stream));
     CK(cudaStreamSynchronize(h->stream));
-    if (h->Ntot > 0 && h->pattern_fast_path() && h->flag_cache != 0) {
+    if (!h->comm && h->Ntot > 0 && h->pattern_fast_path() && h->flag_cache != 0) {
         h->flag_cache = (r[8] != 0.0) ? 0 : 1;
         if (h->flag_cache == 0) {            // outside the table-free kernel's range: once more, with the general kernel
             h->logpdf(mode, node, h->result.p, true);
@@ -3082,29 +3166,54 @@ int blg_logpdf_full_async(blg_handle* h, double* d_out) { return logpdf_async(h,
 int blg_logpdf_from_async(blg_handle* h, int node, double* d_out) { return logpdf_async(h, 1, node, d_out); }
 int blg_logpdf_root_async(blg_handle* h, double* d_out) { return logpdf_async(h, 2, 1, d_out); }
 
+// with a communicator: Σ over the ranks of logL (inside the evaluation) and of the gradient vector (here, P doubles)
+static void gradient_allreduce(blg_handle* h, double* g, int P) {
+    if (!h->comm || P <= 0) return;
+    h->d_red.ensure((size_t)P);
+    CK(cudaMemcpyAsync(h->d_red.p, g, (size_t)P * sizeof(double), cudaMemcpyHostToDevice, h->stream));
+    h->allreduce_sum(h->d_red.p, (size_t)P);
+    CK(cudaMemcpyAsync(g, h->d_red.p, (size_t)P * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
+    CK(cudaStreamSynchronize(h->stream));
+}
 int blg_gradient(blg_handle* h, double* g, int len, double* logpdf_out) {
     BLG_ENTER(h)
     h->require(g != nullptr, "gradient: null output");
     h->gradient(g, len, logpdf_out, false);
+    gradient_allreduce(h, g, len);
     BLG_LEAVE(h)
 }
 int blg_gradient_cr(blg_handle* h, double* g2, double* logpdf_out) {
     BLG_ENTER(h)
     h->require(g2 != nullptr, "gradient_cr: null output");
     h->gradient(g2, 2, logpdf_out, true);
+    gradient_allreduce(h, g2, 2);
     BLG_LEAVE(h)
 }
-// d_g[0] = logL, d_g[1..len] = ∇ in device memory on the handle's stream (for an all-reduce behind it).  The
-// tangent passes synchronise internally; only the final placement is asynchronous.
-int blg_gradient_async(blg_handle* h, double* d_g, int len) {
+
+// ---- multi-GPU: one process per GPU, the library owns the NCCL communicator -------------------------------------------
+int blg_comm_unique_id(uint8_t* id128) {
+    if (!id128) return 1;
+    try {
+        if (!g_nccl.load()) throw std::runtime_error("NCCL not available (" + g_nccl.why + "); set BLG_NCCL_LIB");
+        NcclApi::UniqueId id;
+        NCK(g_nccl.GetUniqueId(&id));
+        memcpy(id128, id.internal, 128);
+    } catch (const std::exception& e) { g_create_error = e.what(); return 2; }
+    return 0;
+}
+int blg_comm_init(blg_handle* h, int nranks, int rank, const uint8_t* id128) {
     BLG_ENTER(h)
-    h->require(d_g != nullptr && len >= 1, "gradient_async: bad arguments");
-    std::vector<double> tmp(len + 1, 0.0);
-    h->gradient(tmp.data() + 1, len, tmp.data(), false);
-    CK(cudaMemcpyAsync(d_g, tmp.data(), (size_t)(len + 1) * sizeof(double), cudaMemcpyHostToDevice, h->stream));
-    CK(cudaStreamSynchronize(h->stream));
+    h->require(id128 != nullptr && nranks >= 1 && rank >= 0 && rank < nranks, "comm_init: bad arguments");
+    h->require(h->comm == nullptr, "comm_init: this handle already has a communicator");
+    if (!g_nccl.load()) throw std::runtime_error("NCCL not available (" + g_nccl.why + "); set BLG_NCCL_LIB");
+    NcclApi::UniqueId id;
+    memcpy(id.internal, id128, 128);
+    NCK(g_nccl.CommInitRank(&h->comm, nranks, id, rank));
+    h->comm_rank = rank;
+    h->comm_size = nranks;
     BLG_LEAVE(h)
 }
+int blg_comm_size(blg_handle* h) { return h ? h->comm_size : -1; }
 
 int blg_commit(blg_handle* h) {
     BLG_ENTER(h)

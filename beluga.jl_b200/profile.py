@@ -33,7 +33,9 @@ class PArray:
     X: (npatterns, ncols) extended counts (``permutedims(M)`` of model.jl:48, one row per site
     pattern), weights: pattern multiplicities.  ``X is None`` is the mock profile ``PArray()``
     (profile.jl:28,31) and needs no GPU.  With ``distributed=True`` the patterns passed in are this
-    rank's shard and every likelihood/gradient is all-reduced over torch.distributed."""
+    rank's shard; the library joins an NCCL communicator (the 128-byte id travels over
+    torch.distributed, nothing else does) and every likelihood / gradient entry returns the sum over
+    the ranks — the all-reduce is issued by the library on its own stream."""
 
     def __init__(self, X=None, weights=None, device=0, distributed=False):
         self.h = None
@@ -67,8 +69,30 @@ class PArray:
             raise _lib.BelugaError(self.L.blg_last_error(None).decode())
         self.h = h
         self.device = int(device)
+        self.world = 1
+        if self.distributed:
+            self._join_communicator()
         self._ck(self.L.blg_set_profiles(self.h, X.ctypes.data_as(C.POINTER(C.c_int32)),
                                          weights.ctypes.data_as(C.POINTER(C.c_int64)), X.shape[1], X.shape[0]))
+
+    def _join_communicator(self):
+        """blg_comm_unique_id on rank 0, broadcast of the 128 bytes over torch.distributed, blg_comm_init everywhere."""
+        import torch
+        import torch.distributed as dist
+        rank, world = dist_info()
+        if world <= 1:
+            return
+        uid = np.zeros(128, dtype=np.uint8)
+        if rank == 0 and self.L.blg_comm_unique_id(uid.ctypes.data_as(C.POINTER(C.c_uint8))) != 0:
+            raise _lib.BelugaError(self.L.blg_last_error(None).decode())
+        backend = dist.get_backend()
+        t = torch.from_numpy(uid)
+        if backend == "nccl":
+            t = t.to("cuda:%d" % self.device)
+        dist.broadcast(t, src=0)
+        uid = t.cpu().numpy().copy()
+        self._ck(self.L.blg_comm_init(self.h, world, rank, uid.ctypes.data_as(C.POINTER(C.c_uint8))))
+        self.world = world
 
     def __del__(self):
         try:
@@ -127,20 +151,7 @@ class PArray:
 
     # ---- likelihood -----------------------------------------------------------------------------------
     def _run(self, mode, node):
-        if self.distributed:
-            import torch
-            with torch.cuda.stream(self.torch_stream):
-                if self._torch_out is None:
-                    self._torch_out = torch.zeros(1, dtype=torch.float64, device="cuda:%d" % self.device)
-                ptr = C.c_void_p(self._torch_out.data_ptr())
-                if mode == 0:
-                    self._ck(self.L.blg_logpdf_full_async(self.h, ptr))
-                elif mode == 1:
-                    self._ck(self.L.blg_logpdf_from_async(self.h, node, ptr))
-                else:
-                    self._ck(self.L.blg_logpdf_root_async(self.h, ptr))
-                allreduce_sum_(self._torch_out)
-                return float(self._torch_out.item())
+        # (with a communicator the library has already summed over the ranks)
         out = C.c_double()
         if mode == 0:
             self._ck(self.L.blg_logpdf_full(self.h, C.byref(out)))
@@ -181,14 +192,7 @@ class PArray:
             self._ck(self.L.blg_gradient_cr(self.h, _dp(g), C.byref(ll)))
         else:
             self._ck(self.L.blg_gradient(self.h, _dp(g), P, C.byref(ll)))
-        llv = ll.value
-        if self.distributed:
-            import torch
-            with torch.cuda.stream(self.torch_stream):
-                t = torch.from_numpy(np.concatenate([[llv], g])).to("cuda:%d" % self.device)
-                allreduce_sum_(t)
-                h = t.cpu().numpy()
-            llv, g = float(h[0]), h[1:].copy()
+        llv = ll.value               # (summed over the ranks by the library when it owns a communicator)
         if not cr and k > 1:
             # the library orders ∂/∂q by ascending wgd id; asvector lists q in getwgds order (descending id)
             g[2 * n:2 * n + k] = g[2 * n:2 * n + k][::-1].copy()

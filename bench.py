@@ -3,10 +3,16 @@
 
 Workload (BASELINE.json configs[4] / SURVEY.md §8d C5): synthetic ultrametric 100-taxon tree
 (Kingman coalescent, height 1, seed 20261019) with 10 WGDs, Branch model λ=1.0 μ=1.2 η=0.8,
-10^6 families drawn from the model (conditioned on both root clades, max count 50 = the reference's
-m-1, i.e. Σ leaves ≤ 50), site-pattern compressed like profile() does.  A "step" is one full
-leaves-to-root sweep over every pattern of the rank's shard.  One process per GPU; each rank draws
-its own 10^6 families (weak scaling); the only cross-rank step is the all-reduce of the scalar.
+10^6 families drawn from the model, conditioned on both root clades, site-pattern compressed like
+profile() does.  "max count 50" has two readings; both are measured and labelled:
+  * headline (`value`): ROOT-SUM <= 50, i.e. m = 51 — the reference's m is the maximum of the extended
+    profile, which is the root count (src/model.jl:25,48);
+  * `c5_leaf50`: only families with a LEAF count above 50 are rejected, m is data-determined (root
+    sums in the hundreds to thousands) — a smaller draw, most of it on the general kernel.
+A "step" is one full leaves-to-root sweep over every pattern of the rank's shard.  One process per
+GPU; each rank draws its own 10^6 families (weak scaling); the only cross-rank step is the all-reduce
+of the scalar, issued by the library on its own NCCL communicator.  With more than one GPU a
+`strong_scaling` block is added: ONE 10^6-family draw, compressed globally, sharded contiguously.
 
   python bench.py [--gpus N] [--steps K] [--warmup W]            # the CUDA path
   python bench.py --impl reference [...]                         # the reference algorithm on host cores
@@ -44,6 +50,7 @@ def parse():
     ap.add_argument("--no-mcmc", action="store_true", help="skip the rjMCMC iterations/s leg")
     ap.add_argument("--mcmc-families", type=int, default=100_000)
     ap.add_argument("--mcmc-generations", type=int, default=40)
+    ap.add_argument("--leaf50-families", type=int, default=100_000, help="families of the 'leaf count <= 50' reading (0: skip)")
     return ap.parse_args()
 
 
@@ -104,20 +111,37 @@ class ClockSampler(threading.Thread):
                 "reasons": reasons, "samples": len(self.rows)}
 
 
-def cpu_baseline(args, threads, target_seconds, steps=None, warmup=1):
-    """The reference algorithm (oracle/, literal log-space restatement) on host cores, on a bounded
+def sample_pattern_rows(args, device=None, nsample=20000):
+    """Leaf-count rows of `nsample` patterns drawn uniformly (seeded) from the compressed 10^6-family set of rank 0 — the
+    same pattern mix the CUDA arm evaluates.  Without a GPU to draw the 10^6 families with, a 4000-family CPU draw."""
+    import beluga_b200 as B
+    if device is None:
+        nw, model, ext, t, l, names, counts = build_workload(args, 0, device=None, families=4000)
+        return nw, names, counts, "4000-family CPU draw (no GPU to draw the full set)", False
+    nw, model, ext, t, l, names, counts = build_workload(args, 0, device=device)
+    X, w, m = B.profile(t, l, (names, counts))
+    leaf_ids = sorted(l)
+    rng = np.random.default_rng(SEED)
+    sel = np.sort(rng.choice(X.shape[0], size=min(nsample, X.shape[0]), replace=False))
+    rows = X[sel][:, [i - 1 for i in leaf_ids]].astype(np.int64)
+    return nw, [l[i] for i in leaf_ids], rows, "uniform sample of the %d patterns of the compressed %d-family set" % (X.shape[0], args.families), True
+
+
+def cpu_baseline(args, threads, target_seconds, steps=None, warmup=1, sample=None):
+    """The reference algorithm (oracle/, literal log-space restatement, built -O3) on host cores, on a bounded
     sample of the same workload.  Test infrastructure used as a yard-stick, never as the product."""
     from oracle.oracle import BRANCH as OBRANCH, OracleDLWGD, max_threads
 
     # all the host cores this process may use — not OMP_NUM_THREADS, which torchrun pins to 1
     threads = threads or max(max_threads(), len(os.sched_getaffinity(0)))
-    nw, model, ext, t, l, names, counts = build_workload(args, 0, device=None, families=4000)
+    if sample is None:
+        sample = sample_pattern_rows(args, None)
+    nw, names, counts, what, same_mix = sample
 
     # the oracle API inserts a WGD at distance t above a node; replay in insertion order
     def replay(o):
         import beluga_b200 as B
         from beluga_b200.model import build_model
-        from beluga_b200.sim import add_random_wgds
         m2, _, _ = build_model(nw, 1.0, 1.2, 0.8, B.BRANCH)
         rng = np.random.default_rng(SEED)
         for _ in range(args.wgds):
@@ -142,6 +166,7 @@ def cpu_baseline(args, threads, target_seconds, steps=None, warmup=1):
     per = dt / max(o.npatterns, 1)
     reps = steps if steps else 5
     n = int(min(len(counts), max(64, target_seconds / max(per, 1e-9) / (reps + warmup))))
+    # (rows are in random order already when they come from the GPU arm's pattern set: a prefix is a uniform sample)
     o = OracleDLWGD(nw, names, counts[:n], 1.0, 1.2, 0.8, OBRANCH, threads=threads)
     replay(o)
     for _ in range(warmup):
@@ -151,9 +176,9 @@ def cpu_baseline(args, threads, target_seconds, steps=None, warmup=1):
         val = o.logpdf()
     dt = (time.perf_counter() - t0) / reps
     return {"value": o.npatterns / dt, "unit": UNIT, "cores": threads, "kind": "port",
-            "sample": "%d patterns (%d families) of the same workload, %d full sweeps, literal log-space C++ restatement of "
-                      "src/model.jl:402-463 with OpenMP over families; Julia is not installed in this image" % (o.npatterns, n, reps),
-            "ms_per_step": dt * 1e3, "logpdf": val}
+            "sample": "%d patterns: %s; %d full sweeps; literal log-space C++ restatement of src/model.jl:402-463 (gcc -O3, OpenMP over "
+                      "families); Julia is not installed in this image" % (o.npatterns, what, reps),
+            "same_pattern_mix": same_mix, "ms_per_step": dt * 1e3, "logpdf": val}
 
 
 def run_reference(args):
@@ -162,19 +187,29 @@ def run_reference(args):
         return
     from oracle.oracle import max_threads
     threads = max(max_threads(), len(os.sched_getaffinity(0)))
-    cb = cpu_baseline(args, threads, target_seconds=max(30.0, args.cpu_seconds), steps=args.steps, warmup=args.warmup)
+    sample = None
+    try:                                   # the same pattern mix as the CUDA arm when there is a GPU to draw the 10^6 families with
+        import torch
+        if torch.cuda.is_available():
+            local = int(os.environ.get("LOCAL_RANK", "0"))
+            sample = sample_pattern_rows(args, "cuda:%d" % local)
+            rng = np.random.default_rng(SEED + 1)
+            sample = (sample[0], sample[1], sample[2][rng.permutation(sample[2].shape[0])], sample[3], sample[4])
+    except Exception:
+        sample = None
+    cb = cpu_baseline(args, threads, target_seconds=max(30.0, args.cpu_seconds), steps=args.steps, warmup=args.warmup, sample=sample)
     line = {
         "impl": "reference", "metric": METRIC, "value": cb["value"], "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": cb["ms_per_step"], "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": "f64", "data": "synthetic",
         "config": workload_config(args, None, None),
-        "cpu_baseline": {k: cb[k] for k in ("value", "unit", "cores", "kind", "sample")},
+        "cpu_baseline": {k: cb[k] for k in ("value", "unit", "cores", "kind", "sample", "same_pattern_mix")},
         "e2e": {"value": cb["value"], "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     }
     print(json.dumps(line))
 
 
-def mcmc_leg(args, local):
+def mcmc_leg(args, local, distributed=False):
     """rjMCMC iterations/s (second half of BASELINE.json's metric), config C4: 12monocots tree, 10^5 synthetic
     families from the model, one GPU, `rjmcmc!` generations (one add/remove jump + one MWG sweep each) replayed
     through the public API by beluga_b200.mcmc (flat prior, fixed-width proposals)."""
@@ -186,7 +221,9 @@ def mcmc_leg(args, local):
     nw = open(os.path.join(ROOT, "tests", "data", "12monocots.nw")).readline().strip()
     m0, _, _ = build_model(nw, 0.004, 0.003, 0.9, B.BRANCH)
     names, counts = rand_profiles_torch(m0, args.mcmc_families, seed=SEED, device="cuda:%d" % local, max_rootsum=60, chunk=1 << 19)
-    model, data = B.DLWGD(nw, (names, counts), 0.004, 0.003, 0.9, B.BRANCH, device=local)
+    # distributed: every rank draws the same table (same seed), the patterns are compressed globally and sharded contiguously;
+    # every rank runs the same chain (same seed, same all-reduced log-likelihoods, hence the same decisions)
+    model, data = B.DLWGD(nw, (names, counts), 0.004, 0.003, 0.9, B.BRANCH, device=local, distributed=distributed)
     chain = RevJumpChain(data, model, seed=SEED, step=0.02).init_()
     chain.rjmcmc_(5, trace=0)                      # warm-up
     data.synchronize()
@@ -196,6 +233,8 @@ def mcmc_leg(args, local):
     data.synchronize()
     dt = time.perf_counter() - t0
     try:                                           # BASELINE.json's "gradient-based" wording: one gradient(model, data) on the chain's state
+        if distributed:
+            raise RuntimeError("skipped on sharded data")
         data.gradient(model)
         t1 = time.perf_counter()
         gg, _ = data.gradient(model)
@@ -203,7 +242,8 @@ def mcmc_leg(args, local):
     except Exception:
         grad_ms, grad_p = None, None
     return {"metric": "rjMCMC iters/sec", "value": args.mcmc_generations / dt, "unit": "generations/s", "gradient_ms": grad_ms, "gradient_P": grad_p,
-            "config": {"workload": "C4: 12monocots, %d synthetic families (%d patterns), rjmcmc! generations on 1 GPU" % (args.mcmc_families, len(data)),
+            "config": {"workload": "C4: 12monocots, %d synthetic families (%d patterns on this rank), rjmcmc! generations, %s" % (
+                args.mcmc_families, len(data), "families sharded over the ranks, every proposal all-reduced" if distributed else "1 GPU"),
                        "nodes": len(model), "wgds_at_end": model.nwgd()},
             "likelihood_calls_per_s": (chain.evals - e0) / dt, "proposals_per_s": (chain.proposed - p0) / dt,
             "acceptance": chain.accepted / max(chain.proposed, 1), "generations": args.mcmc_generations}
@@ -309,26 +349,115 @@ def gradient_leg(args, local):
 
 
 def ncu_traffic():
-    """dram read+write bytes of one sweep_kernel launch from the committed ncu --set full capture of this
-    workload (profiles/r01_sweep_kernel_ncu.csv); None if the file is missing."""
-    path = os.path.join(ROOT, "profiles", "r01_sweep_kernel_ncu.csv")
+    """dram read+write bytes of the pruning launches of ONE sweep of this workload, summed over the launches, from the
+    committed ncu capture (profiles/r02_sweep_traffic.json, which names the commit it was taken at); None if missing."""
+    path = os.path.join(ROOT, "profiles", "r02_sweep_traffic.json")
     try:
-        tot = 0.0
-        for line in open(path):
-            parts = line.strip().split(",")
-            if parts[0] in ("dram__bytes_read.sum", "dram__bytes_write.sum"):
-                mult = {"byte": 1.0, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9}[parts[1]]
-                tot += float(parts[2]) * mult
-        return tot if tot > 0 else None
-    except OSError:
+        d = json.load(open(path))
+        return {"bytes": d["dram_bytes_per_sweep"], "commit": d.get("commit"), "launches": d.get("launches")}
+    except (OSError, ValueError, KeyError):
         return None
 
 
 def workload_config(args, npat, nfam):
-    return {"workload": "C5: %d-taxon coalescent tree + %d WGDs, %s families/GPU drawn from the model (max count %d), pattern-compressed; "
-                        "full logpdf! sweep" % (args.taxa, args.wgds, args.families, args.max_count),
+    return {"workload": "C5, reading 'root-sum <= %d' (m = %d, the reference's m = max of the extended profile = root count, src/model.jl:25,48): "
+                        "%d-taxon coalescent tree + %d WGDs, %s families/GPU drawn from the model (rand(model, N), condition = rootclades), "
+                        "pattern-compressed; full logpdf! sweep.  The other reading ('leaf count <= %d', m data-determined) is the c5_leaf50 block."
+                        % (args.max_count, args.max_count + 1, args.taxa, args.wgds, args.families, args.max_count),
+            "unit_note": "a 'family' of the metric is one pattern-compressed family (a unique profile row, what logpdf! evaluates); "
+                         "weighted_families_per_s counts the multiplicities",
             "patterns_per_gpu": npat, "families_per_gpu": nfam, "tree_seed": SEED, "lambda": 1.0, "mu": 1.2, "eta": 0.8,
-            "model": "Branch", "l2": "inputs larger than L2 (partial-likelihood slabs of one sweep exceed 126 MB)"}
+            "model": "Branch", "l2": "inputs larger than L2: a sweep writes and re-reads ~0.3 GB of partial-likelihood columns (126 MB L2)"}
+
+
+def leaf50_leg(args, local):
+    """C5 in the north star's primary reading: families are rejected only when a LEAF count exceeds 50; m is
+    data-determined (root sums in the hundreds to thousands).  Families above the table-free kernel's count bound run on the
+    general kernel (one warp per family, fp64-bound); the others on the pattern path."""
+    import beluga_b200 as B
+    from beluga_b200.model import build_model, nonwgdchild
+    from beluga_b200.sim import add_random_wgds, rand_profiles_torch, random_tree_newick
+    import torch
+    nw = random_tree_newick(args.taxa, seed=SEED)
+    model, t, l = build_model(nw, 1.0, 1.2, 0.8, B.BRANCH)
+    ext = add_random_wgds(model, args.wgds, seed=SEED)
+    names, counts = rand_profiles_torch(model, args.leaf50_families, seed=SEED, device="cuda:%d" % local, max_leaf=args.max_count)
+    X, w, m = B.profile(t, l, (names, counts))
+    X = np.ascontiguousarray(X, dtype=np.int32)
+    fma = algorithmic_fma(model, X)
+    data = B.PArray(X, w, device=local)
+    for i in ext:
+        B.extend_(data, i)
+    B.set_(data)
+    B.logpdf_(model, data)
+    data.set_timing(True)
+    reps = 3
+    data.synchronize()
+    t0 = time.perf_counter()
+    for _ in range(reps):
+        ll = B.logpdf_(model, data)
+    dt = (time.perf_counter() - t0) / reps
+    pm, rm = data.last_timing()
+    _, _, nfast, nheavy = data.kernel_runs()
+    alg_bytes, prune_bytes, launches = data.last_algorithmic()
+    peak = data.fp64_peak()
+    root = X[:, 0]
+    return {"workload": "C5, reading 'leaf count <= %d' (m = %d data-determined): %d families drawn from the model, %d patterns" % (args.max_count, m, args.leaf50_families, X.shape[0]),
+            "value": X.shape[0] / dt, "unit": UNIT, "ms_per_step": dt * 1e3, "prune_ms": pm, "logpdf": ll,
+            "root_count_quantiles": {"min": int(root.min()), "median": float(np.median(root)), "q99": float(np.quantile(root, 0.99)), "max": int(root.max())},
+            "patterns_on_pattern_path": int(nfast), "patterns_on_general_kernel": int(nheavy),
+            "roofline_fp64": {"bound": "fp64", "achieved": 2.0 * fma / (pm / 1e3) / 1e12, "peak": peak, "unit": "TFLOP/s",
+                              "frac": 2.0 * fma / (pm / 1e3) / 1e12 / peak, "algorithmic_fma_per_step": fma},
+            "roofline_hbm": {"achieved": prune_bytes / 1e9 / (pm / 1e3), "unit": "GB/s", "algorithmic_bytes": prune_bytes}}
+
+
+def strong_scaling_leg(args, rank, world, local):
+    """ONE draw of `--families` families (rank 0's seed), compressed globally, sharded contiguously over the ranks by the
+    product's own path (DLWGD_(distributed=True) semantics: profile() then shard_range), evaluated with the library's own
+    communicator.  Reports ms per full sweep, resident and end to end."""
+    import torch
+    import torch.distributed as dist
+    import beluga_b200 as B
+    nw, model, ext, t, l, names, counts = build_workload(args, 0, device="cuda:%d" % local)
+    X, w, m = B.profile(t, l, (names, counts))
+    lo, hi = B.shard_range(X.shape[0], rank, world)
+    Xs = np.ascontiguousarray(X[lo:hi], dtype=np.int32)
+    data = B.PArray(Xs, w[lo:hi], device=local, distributed=True)
+    for i in ext:
+        B.extend_(data, i)
+    B.set_(data)
+    total = B.logpdf_(model, data)
+    stream = data.torch_stream
+    import ctypes as C
+    out = torch.zeros(1, dtype=torch.float64, device="cuda:%d" % local)
+    ptr = C.c_void_p(out.data_ptr())
+    with torch.cuda.stream(stream):
+        for _ in range(3):
+            data._ck(data.L.blg_logpdf_full_async(data.h, ptr))
+        dist.barrier(); torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record(stream)
+        for _ in range(args.steps):
+            data._ck(data.L.blg_logpdf_full_async(data.h, ptr))
+        e1.record(stream)
+        dist.barrier(); torch.cuda.synchronize()
+    ms = e0.elapsed_time(e1) / args.steps
+    rates = model.getrates()
+    rng = np.random.default_rng(SEED)
+    dist.barrier(); torch.cuda.synchronize()
+    t0 = time.perf_counter()
+    esteps = max(3, args.steps // 2)
+    for _ in range(esteps):
+        model.setrates_(rates * np.exp(rng.normal(0, 1e-3, size=rates.shape)))
+        B.logpdf_(model, data)
+    dist.barrier(); torch.cuda.synchronize()
+    e2e_ms = (time.perf_counter() - t0) * 1e3 / esteps
+    tt = torch.tensor([ms, e2e_ms], dtype=torch.float64, device="cuda:%d" % local)
+    dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+    ms, e2e_ms = [float(x) for x in tt.tolist()]
+    return {"workload": "ONE %d-family draw, %d patterns after global compression, sharded contiguously over %d GPUs by the library's path" % (args.families, X.shape[0], world),
+            "scaling": "strong", "patterns_total": int(X.shape[0]), "patterns_this_rank": int(hi - lo), "ms_per_step": ms, "value": X.shape[0] / (ms / 1e3), "unit": UNIT,
+            "e2e_ms_per_step": e2e_ms, "e2e_value": X.shape[0] / (e2e_ms / 1e3), "logpdf": total}
 
 
 def main():
@@ -365,6 +494,11 @@ def main():
     for i in ext:                 # extend!(data, i) for every inserted WGD (src/profile.jl:108), then set!(data)
         B.extend_(data, i)
     B.set_(data)
+    # the CPU baseline gets a uniform sample of THIS pattern set (same pattern mix as the CUDA arm)
+    leaf_ids = sorted(l)
+    sel = np.random.default_rng(SEED).permutation(X.shape[0])[:20000]
+    cpu_sample = (nw, [l[i] for i in leaf_ids], X[sel][:, [i - 1 for i in leaf_ids]].astype(np.int64),
+                  "uniform sample of the %d patterns of rank 0's compressed %d-family set" % (X.shape[0], args.families), True)
     del X, counts
 
     stream = data.torch_stream
@@ -382,8 +516,7 @@ def main():
     ptr = C.c_void_p(out.data_ptr())
 
     def step_resident():
-        data._ck(data.L.blg_logpdf_full_async(data.h, ptr))
-        B.allreduce_sum_(out)
+        data._ck(data.L.blg_logpdf_full_async(data.h, ptr))      # (sweep, root, and the library's own all-reduce of the scalar)
 
     sampler = ClockSampler(local)          # samples clocks from the warm-up through both timed regions
     sampler.start()
@@ -403,6 +536,7 @@ def main():
     # per-launch-group durations of the LAST step (events recorded inside the timed region)
     pm, rm = data.last_timing()
     alg_bytes, prune_bytes, launches = data.last_algorithmic()
+    moved_bytes, pattern_cols, family_cols = data.pattern_stats()
     data.set_timing(False)
 
     # ---- end to end through the public API: host θ in, host scalar out, every step -------------------------
@@ -438,6 +572,22 @@ def main():
     ms, e2e_ms, pm, rm = [float(x) for x in tt.tolist()]
     tot_pat, tot_fam, tot_bytes = [float(x) for x in cnt.tolist()]
 
+    # ---- legs every rank takes part in: the sharded 10^6-family problem (strong scaling), rjMCMC on sharded data ----------
+    strong = None
+    mcmc_n = None
+    if world > 1:
+        torch.cuda.set_stream(torch.cuda.default_stream())
+        try:
+            strong = strong_scaling_leg(args, rank, world, local)
+        except Exception as e:
+            strong = {"error": repr(e)}
+        if not args.no_mcmc:
+            try:
+                mcmc_n = mcmc_leg(args, local, distributed=True)
+            except Exception as e:
+                mcmc_n = {"metric": "rjMCMC iters/sec", "value": None, "error": repr(e)}
+        dist.barrier()
+
     if rank == 0:
         peak, peak_src = peaks()
         # dominant kernel: sweep_kernel (one launch per likelihood call; the other launch is root_kernel).  Its algorithmic
@@ -450,9 +600,15 @@ def main():
             "weighted_families_per_s": tot_fam / (ms / 1e3),
             "logpdf": total_ll,
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                         "traffic": ncu_traffic(), "kernel": "sweep_kernel (%d launch/step, event-bracketed)" % (launches - 1),
+                         "traffic": (ncu_traffic() or {}).get("bytes"), "traffic_source": ncu_traffic(),
+                         "kernel": "the pruning launches of one sweep (ptile_kernel per tree level, %d launches/step, event-bracketed as one group)" % (launches - 1),
                          "algorithmic_bytes_per_launch_group": prune_bytes, "algorithmic_bytes_per_step": alg_bytes, "phase_ms": {"prune": pm, "root+reduce": rm},
-                         "peak_source": peak_src},
+                         "peak_source": peak_src,
+                         "note": "achieved = SURVEY 8(d)'s algorithmic bytes (one column per FAMILY per node, written once and read once) / time. "
+                                 "The kernels evaluate one column per distinct NODE PATTERN (families deduplicated per node by the counts below it), so the "
+                                 "bytes actually moved (pattern_path.bytes_moved_model, and `traffic` = measured DRAM bytes) are far below the algorithmic figure"},
+            "pattern_path": {"node_steps_x_families": family_cols, "node_steps_x_patterns": pattern_cols,
+                             "dedup_factor": (family_cols / pattern_cols) if pattern_cols else None, "bytes_moved_model": moved_bytes},
             "e2e": {"value": tot_pat / (e2e_ms / 1e3), "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": 8,
                     "ms_per_step": e2e_ms, "what": "setrates!(model, X) on host + logpdf!(model, profile): θ upload, on-device ε/W build, full sweep, scalar back"},
             "gpu_launches": int(launches * args.steps),
@@ -483,7 +639,16 @@ def main():
                     line[key] = {"error": repr(e)}
             if c5_grad is not None and isinstance(line.get("gradient"), dict):
                 line["gradient"]["C5"] = c5_grad
-        if not args.no_mcmc:
+        if strong is not None:
+            line["strong_scaling"] = strong
+        if world == 1 and args.leaf50_families > 0:
+            try:
+                line["c5_leaf50"] = leaf50_leg(args, local)
+            except Exception as e:
+                line["c5_leaf50"] = {"error": repr(e)}
+        if mcmc_n is not None:
+            line["mcmc"] = mcmc_n
+        elif not args.no_mcmc:
             try:
                 del data
                 torch.cuda.empty_cache()
@@ -492,8 +657,8 @@ def main():
                 line["mcmc"] = {"metric": "rjMCMC iters/sec", "value": None, "error": repr(e)}
         if not args.no_cpu_baseline:
             try:
-                line["cpu_baseline"] = {k: v for k, v in cpu_baseline(args, None, args.cpu_seconds).items()
-                                        if k in ("value", "unit", "cores", "kind", "sample")}
+                line["cpu_baseline"] = {k: v for k, v in cpu_baseline(args, None, args.cpu_seconds, sample=cpu_sample).items()
+                                        if k in ("value", "unit", "cores", "kind", "sample", "same_pattern_mix")}
             except Exception as e:  # the baseline must not take the measurement down with it
                 line["cpu_baseline"] = {"value": None, "unit": UNIT, "cores": 0, "kind": "port", "sample": "failed: %r" % (e,)}
         print(json.dumps(line))

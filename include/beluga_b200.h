@@ -17,7 +17,8 @@
  *     indexed id-1 and have `ncols` entries (ncols = largest id in use).
  *   - one handle drives ONE GPU on ONE stream.  Families shard across GPUs by giving each
  *     process/handle a contiguous block of patterns (profile.jl:27,34-37 is the same DP); the
- *     only cross-GPU step is the sum of the returned scalars / gradient vectors.
+ *     only cross-GPU step is the sum of the scalars / gradient vectors, which the library does
+ *     itself once the handles share a communicator (blg_comm_init).
  *   - host pointers are borrowed for the duration of the call only.  `d_*` pointers are device
  *     pointers on the handle's device.
  *   - not re-entrant per handle; independent handles are independent.
@@ -94,7 +95,17 @@ int blg_logpdf_root_async(blg_handle* h, double* d_out);
  * Does not disturb the committed or proposal state (the reference uses a fresh L, model.jl:395). */
 int blg_gradient(blg_handle* h, double* g, int len, double* logpdf_out);
 int blg_gradient_cr(blg_handle* h, double* g2, double* logpdf_out);
-int blg_gradient_async(blg_handle* h, double* d_g, int len);   /* d_g[0] = logL, d_g[1..] = ∇ */
+
+/* --- multi-GPU: families shard across GPUs, one process and one handle per GPU (profile.jl:27-37,56-75 is a mapreduce
+ * over worker processes holding contiguous blocks of families).  The library owns the NCCL communicator: rank 0 asks for
+ * a unique id (128 bytes), the host program hands it to every rank by its own means (MPI / Distributed / torch.distributed)
+ * and each rank joins with blg_comm_init.  From then on every likelihood and gradient entry of the handle returns the SUM
+ * over all ranks (one ncclAllReduce of 8 bytes — 8·P for a gradient — on the handle's stream, over NVLink); each rank
+ * passes its own contiguous block of patterns to blg_set_profiles (an empty block is fine).  All ranks must make the same
+ * sequence of likelihood / gradient calls.  NCCL is bound at run time (libnccl.so.2, or $BLG_NCCL_LIB). */
+int blg_comm_unique_id(uint8_t* id128);
+int blg_comm_init(blg_handle* h, int nranks, int rank, const uint8_t* id128);
+int blg_comm_size(blg_handle* h);
 
 /* --- accept / reject / reversible jump: set!, rev!, extend!, shrink! (profile.jl:79-121) --------
  * commit: proposal becomes committed (Lp→L, xp→x); revert: the reverse.  Both are O(#nodes)

@@ -263,8 +263,12 @@ def test_larger_counts_and_long_branches(monocots):      # 12monocots: t up to 1
 
 
 def test_stress_extreme_rates_do_not_fail():             # test/tests.jl:113-128
+    # rates over ten orders of magnitude.  Every draw is compared with the oracle; the disagreement set is recorded and
+    # must stay inside the one documented class: the GPU may return a FINITE value where the literal log-space reference
+    # ends at -Inf (its linear-space W underflows; DESIGN.md "deviations"), never the other way round, and where both are
+    # finite they agree at the north star's 1e-10.
     rng = np.random.default_rng(333)
-    agree = 0
+    worse, gpu_inf_only, ref_inf_only = [], [], []
     for i in range(60):
         lam = float(np.exp(rng.normal(0, 5)))
         mu = lam if i >= 30 else float(np.exp(rng.normal(0, 5)))
@@ -272,12 +276,20 @@ def test_stress_extreme_rates_do_not_fail():             # test/tests.jl:113-128
         model, data, orc = pair(S1, DF1, lam, mu, eta, B.NODE)
         got = B.logpdf_(model, data)
         want = orc.logpdf()
-        assert not np.isnan(got)
-        if close(got, want, 1e-8):
-            agree += 1
-    # linear-space fp64 with per-column exponents and the log-space reference agree except where
-    # intermediate quantities leave the fp64 range; require the bulk to agree
-    assert agree >= 50, agree
+        assert not np.isnan(got), (i, lam, mu, eta)
+        rec = (i, lam, mu, eta, got, want)
+        if np.isfinite(got) and np.isfinite(want):
+            if not close(got, want, RTOL):
+                worse.append(rec)
+        elif np.isfinite(want):
+            gpu_inf_only.append(rec)
+        elif np.isfinite(got):
+            ref_inf_only.append(rec)
+    print("stress: finite on both sides but apart:", worse)
+    print("stress: GPU -Inf, oracle finite:", gpu_inf_only)
+    print("stress: oracle -Inf, GPU finite:", ref_inf_only)
+    assert not gpu_inf_only, gpu_inf_only
+    assert not worse, worse
 
 
 def test_synthetic_large_batch_vs_oracle():
@@ -566,6 +578,67 @@ def test_gradient_heterogeneous_rates_with_wgd(plants1, nt):
     n = model.ne() + 1
     want[2 * n:2 * n + 2] = want[2 * n:2 * n + 2][::-1]
     assert_grad_close(g, want)
+
+
+@pytest.mark.parametrize("nt", [B.BRANCH, B.NODE])
+def test_gradient_c5_shaped_tree_with_stacked_wgds(nt):
+    # the headline configuration's shape (BASELINE.json configs[4]): 100 taxa, 10 WGDs — two of them stacked on one
+    # branch —, P = 409 parameters, heterogeneous rates; a small family sample so that the oracle's dual-number
+    # gradient (src/model.jl:517-522 through ForwardDiff in the reference) stays affordable
+    from beluga_b200.sim import add_random_wgds, rand_profiles, random_tree_newick
+    nw = random_tree_newick(100, seed=20261019)
+    m0, _, _ = build_model(nw, 1.0, 1.2, 0.8, nt)
+    names, counts = rand_profiles(m0, 24, seed=5, max_rootsum=50)
+    model, data, orc = pair(nw, (names, counts), 1.0, 1.2, 0.8, nt)
+    rng = np.random.default_rng(20261019)
+    placed = []
+    for _ in range(10):                                   # add_random_wgds, replayed on both sides
+        ids = sorted(model.nodes)
+        ww = np.array([model.nodes[i]["t"] for i in ids], dtype=np.float64)
+        i = int(rng.choice(ids, p=ww / ww.sum()))
+        n = model.nodes[i]
+        tt = rng.random() * n["t"]
+        if not (n["t"] - tt > 0.0):
+            tt = 0.5 * n["t"]
+        q = float(rng.beta(1.0, 3.0))
+        B.addwgd_(model, n, tt, q); B.extend_(data, i)
+        orc.addwgd(i, tt, q); orc.extend(i)
+        placed.append(i)
+    assert len(set(placed)) < len(placed)                 # a stacked pair: two WGDs above the same node
+    X = np.exp(np.random.default_rng(3).normal(0, 0.25, size=(2, model.ne() + 1))) * np.array([[1.0], [1.2]])
+    model.setrates_(X); orc.setrates(X)
+    g, ll = data.gradient(model)
+    assert len(g) == 409
+    assert ll == pytest.approx(orc.logpdf(), rel=1e-12)
+    n = model.ne() + 1
+    # the oracle's dual numbers (like ForwardDiff on the reference's log-space code) turn NaN on this tree: a -Inf entry
+    # meets a -Inf entry in logaddexp (Inf - Inf in the partials) wherever a clade is empty, and the NaN spreads.  The
+    # independent check is therefore the central difference of the ORACLE's log-likelihood, parameter by parameter
+    # (asvector layout, src/model.jl:541-546: λ_1..λ_n, μ_1..μ_n, q by descending wgd id, η); entries the duals do give
+    # are held to the gradient tolerance as usual.
+    dual = np.asarray(orc.gradient(literal=False))
+    dual[2 * n:2 * n + 10] = dual[2 * n:2 * n + 10][::-1]
+    params = [(i, "lam", "λ") for i in range(1, n + 1)] + [(i, "mu", "μ") for i in range(1, n + 1)]
+    params += [(w, "q", "q") for w in model.getwgds()] + [(1, "eta", "η")]
+    assert len(params) == 409
+    fd = np.zeros(409)
+    for j, (i, field, key) in enumerate(params):
+        if nt == B.BRANCH and i == 1 and field in ("lam", "mu"):
+            continue                                      # root rates are unused by Branch models
+        v0 = model[i][key]
+        h = 1e-6 * max(abs(v0), 1e-2)
+        vals = []
+        for v in (v0 + h, v0 - h):
+            orc.setfield(i, field, v); orc.setall()
+            vals.append(orc.logpdf())
+        orc.setfield(i, field, v0)
+        fd[j] = (vals[0] - vals[1]) / (2 * h)
+    orc.setall()
+    scale = np.abs(fd).max()
+    np.testing.assert_allclose(g, fd, rtol=2e-5, atol=2e-6 * scale)
+    ok = np.isfinite(dual)
+    if ok.any():
+        np.testing.assert_allclose(g[ok], dual[ok], rtol=GRTOL, atol=GRTOL * scale)
 
 
 def test_gradient_cr(dicots):
