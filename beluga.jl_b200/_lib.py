@@ -32,6 +32,19 @@ def lib():
             "libbeluga_b200.so is not built (%s). Run `python -c 'import __graft_entry__ as g; g.build()'`; "
             "there is no CPU fallback." % SO
         )
+    # the library binds NCCL at run time (multi-GPU only).  In a Python process PyTorch may be imported later and brings its
+    # own libnccl.so.2: point the library at that copy, so that one process never holds two different NCCLs
+    if "BLG_NCCL_LIB" not in os.environ:
+        try:
+            import importlib.util
+            spec = importlib.util.find_spec("nvidia.nccl")
+            for base in (list(spec.submodule_search_locations) if spec and spec.submodule_search_locations else []):
+                cand = os.path.join(base, "lib", "libnccl.so.2")
+                if os.path.exists(cand):
+                    os.environ["BLG_NCCL_LIB"] = cand
+                    break
+        except Exception:
+            pass
     L = C.CDLL(SO)
     vp, dp, ip = C.c_void_p, C.POINTER(C.c_double), C.POINTER(C.c_int)
     i32p, i64p, u8p = C.POINTER(C.c_int32), C.POINTER(C.c_int64), C.POINTER(C.c_uint8)
