@@ -245,12 +245,28 @@ __global__ void __launch_bounds__(128, WIDE ? 2 : 4) ptile_kernel(const __grid_c
     }
     if (st.pat_ll != nullptr) {                    // same arithmetic, in the same order, as root_pattern_kernel on the stored column
         const double* __restrict__ rw = st.rootw;
-        double acc = 0.0;
+        // four interleaved partial sums (n ≡ 1, 2, 3, 0 mod 4), added pairwise: four loads in flight per trip
+        double a0 = 0.0, a1 = 0.0, a2 = 0.0, a3 = 0.0;
+        int n = 1;
 #pragma unroll 1
-        for (int n = 1; n <= Xw; ++n) {
-            const double w = rw[n];
-            if (n <= X) acc = fma(R[n * 32] * sc, w, acc);
+        for (; n + 3 <= Xw; n += 4) {
+            const double w0 = rw[n], w1 = rw[n + 1], w2 = rw[n + 2], w3 = rw[n + 3];
+            const double r0 = R[n * 32], r1 = R[(n + 1) * 32], r2 = R[(n + 2) * 32], r3 = R[(n + 3) * 32];
+            if (n <= X) a0 = fma(r0 * sc, w0, a0);
+            if (n + 1 <= X) a1 = fma(r1 * sc, w1, a1);
+            if (n + 2 <= X) a2 = fma(r2 * sc, w2, a2);
+            if (n + 3 <= X) a3 = fma(r3 * sc, w3, a3);
         }
+#pragma unroll 1
+        for (; n <= Xw; ++n) {
+            const double w = rw[n];
+            const int k = (n - 1) & 3;
+            if (n <= X) {
+                const double v = R[n * 32] * sc;
+                if (k == 0) a0 = fma(v, w, a0); else if (k == 1) a1 = fma(v, w, a1); else if (k == 2) a2 = fma(v, w, a2); else a3 = fma(v, w, a3);
+            }
+        }
+        const double acc = (a0 + a1) + (a2 + a3);
         double l = log(acc) + (double)(sclsum + ex) * 0.6931471805599453 - rw[0];
         if (!isfinite(l)) l = -INFINITY;                                        // model.jl:366
         if (live) st.pat_ll[p] = l;
@@ -328,8 +344,10 @@ __global__ void __launch_bounds__(256) root_pattern_kernel(const double* __restr
             l = pat_ll[p];                       // integrated by the tile that computed the root's column
         } else {
             const int X = pcnt[p];
-            double acc = 0.0;
-            for (int n = 1; n <= X; ++n) acc = fma(ell[(size_t)n * ld + p], rootw[n], acc);
+            // (the same four interleaved partial sums as the root's tiles: both routes give the same bits)
+            double a[4] = {0.0, 0.0, 0.0, 0.0};
+            for (int n = 1; n <= X; ++n) a[(n - 1) & 3] = fma(ell[(size_t)n * ld + p], rootw[n], a[(n - 1) & 3]);
+            const double acc = (a[0] + a[1]) + (a[2] + a[3]);
             l = log(acc) + (double)scl[p] * 0.6931471805599453 - rootw[0];
             if (!isfinite(l)) l = -INFINITY;                                        // model.jl:366
         }
