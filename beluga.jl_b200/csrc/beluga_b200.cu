@@ -1365,6 +1365,8 @@ struct blg_handle {
     bool root_fused = false;
     cudaStream_t stream2 = nullptr;           // the wide tile launches of a level run beside its other launches
     cudaEvent_t ev_main = nullptr, ev_side = nullptr;
+    cudaStream_t gstreams[8] = {nullptr}, lstream = nullptr;   // general-kernel launches of independent family ranges
+    cudaEvent_t ev_fork = nullptr, ev_join[8] = {nullptr};
     int pdebug = 0;                           // BLG_PDEBUG: time and describe every pattern launch (stderr)
     int flag_cache = -1;                      // host copy of the device-side range flag: -1 unknown (since the last ε/W build)
     std::unique_ptr<PList> plist{new PList()}, plist_w{new PList()};
@@ -1410,6 +1412,9 @@ struct blg_handle {
         gscratch.free_(); gscratch_w.free_(); pat_ll.free_(); d_tilectr.free_(); d_gctr.free_(); d_ticket.free_();
         if (comm && g_nccl.CommDestroy) g_nccl.CommDestroy(comm);
         d_red.free_();
+        for (auto& st_ : gstreams) if (st_) cudaStreamDestroy(st_);
+        if (ev_fork) cudaEventDestroy(ev_fork);
+        for (auto& e : ev_join) if (e) cudaEventDestroy(e);
         if (stream2) cudaStreamDestroy(stream2);
         if (ev_main) cudaEventDestroy(ev_main);
         if (ev_side) cudaEventDestroy(ev_side);
@@ -1871,8 +1876,28 @@ struct blg_handle {
             std::vector<Shard::Class> groups = S.classes;
             if (groups.empty()) groups.push_back({0, S.N, xmax_of(S, 0)});
             require(groups.size() <= 16, "general_sweep: too many launch groups");
+            // the classes are independent family ranges: each on its own stream (the top classes hold a handful of
+            // families whose columns take milliseconds — they run beside the wide classes instead of in front of them)
+            const bool fan = groups.size() > 1;
+            if (fan && !ev_fork) {
+                CK(cudaEventCreateWithFlags(&ev_fork, cudaEventDisableTiming));
+                for (auto& e : ev_join) CK(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+                for (auto& st_ : gstreams) CK(cudaStreamCreateWithFlags(&st_, cudaStreamNonBlocking));
+            }
+            if (fan) CK(cudaEventRecord(ev_fork, stream));
             int gi = 0;
-            for (const auto& g : groups) { launch_general(L, g.f0, g.f1, g.maxroot, 1, when, gi); ++gi; }
+            for (const auto& g : groups) {
+                if (fan) { CK(cudaStreamWaitEvent(gstreams[gi % 8], ev_fork, 0)); lstream = gstreams[gi % 8]; }
+                launch_general(L, g.f0, g.f1, g.maxroot, 1, when, gi);
+                lstream = nullptr;
+                ++gi;
+            }
+            if (fan) {
+                for (int q = 0; q < std::min<int>(8, (int)groups.size()); ++q) {
+                    CK(cudaEventRecord(ev_join[q], gstreams[q]));
+                    CK(cudaStreamWaitEvent(stream, ev_join[q], 0));
+                }
+            }
         }
     }
 
@@ -2302,6 +2327,7 @@ struct blg_handle {
     void launch_general(const GList& L, int f0, int f1, int maxroot, int count_run, int when, int counter_slot, int item_mode = 0) {
         const int nfam = f1 - f0;
         if (nfam <= 0) return;
+        cudaStream_t stream = lstream ? lstream : this->stream;
         d_gctr.ensure(256);
         if (!item_mode) CK(cudaMemsetAsync(d_gctr.p + counter_slot, 0, sizeof(unsigned int), stream));
         const int cap = round_up(maxroot + 4, 2);

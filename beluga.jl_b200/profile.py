@@ -177,11 +177,30 @@ class PArray:
         return self._run(2, 1)
 
     # ---- gradient (src/profile.jl:71-75) -----------------------------------------------------------------------
-    def gradient(self, model, cr=False):
+    def gradient(self, model, cr=False, literal=False):
         """-> (g, logpdf).  g is laid out like asvector(model) (src/model.jl:541-546): [λ…, μ…, q in getwgds
-        order, η]; ``cr=True`` gives gradient_cr's [∂λ, ∂μ] with the rates tied across nodes."""
+        order, η]; ``cr=True`` gives gradient_cr's [∂λ, ∂μ] with the rates tied across nodes.
+
+        With two or more WGDs the reference's own ``gradient`` differentiates a model whose q's are permuted:
+        asvector lists them by descending wgd id, model(θ) (src/model.jl:320-322) reads them by ascending id.  The
+        default here is the gradient AT the model's parameters; ``literal=True`` reproduces the reference's
+        evaluation (q's reversed among the WGDs, entry j of the q block = ∂/∂q of the j-th WGD by ascending id)."""
         n = model.ne() + 1
         k = model.nwgd()
+        if literal and not cr and k > 1:
+            wg = model.getwgds()                                    # descending ids
+            qs = [model[w]["q"] for w in wg]
+            for j, w in enumerate(wg[::-1]):                         # the j-th ascending WGD gets the j-th descending q
+                model[w]["q"] = qs[j]
+            model.set_()
+            try:
+                g, llv = self.gradient(model, cr=False, literal=False)
+            finally:
+                for w, q in zip(wg, qs):
+                    model[w]["q"] = q
+                model.set_()
+            g[2 * n:2 * n + k] = g[2 * n:2 * n + k][::-1].copy()   # back to the library's ascending order = θ's positions
+            return g, llv
         P = 2 if cr else 2 * n + k + 1
         g = np.zeros(P)
         if self.N == 0 and not self.distributed:

@@ -578,6 +578,12 @@ def test_gradient_heterogeneous_rates_with_wgd(plants1, nt):
     n = model.ne() + 1
     want[2 * n:2 * n + 2] = want[2 * n:2 * n + 2][::-1]
     assert_grad_close(g, want)
+    # ... and the reference's literal evaluation (asvector / model(θ) disagree on the q order, src/model.jl:320-322,541-546):
+    # pinned against the oracle's literal mode, so that the difference between the two is explicit, not implied
+    gl, _ = data.gradient(model, literal=True)
+    assert_grad_close(gl, orc.gradient(literal=True))
+    assert np.abs(gl - g).max() > 1e-6
+    assert_grad_close(B.gradient(model, data), want)                         # the model is left as it was
 
 
 @pytest.mark.parametrize("nt", [B.BRANCH, B.NODE])
