@@ -1185,6 +1185,7 @@ __global__ void zero_slab_kernel(double* ell, int* scl, size_t nell, int N) {
 #include "pattern.cuh"
 #include "gradient.cuh"
 #include "adjoint.cuh"
+#include "ingest.cuh"
 
 // ------------------------------------------------------------------------------------------------
 // host-side state
@@ -3403,6 +3404,53 @@ int blg_pattern_stats(blg_handle* h, double* bytes_moved, double* pattern_column
     if (bytes_moved) *bytes_moved = h->last_pattern_bytes;
     if (pattern_columns) *pattern_columns = h->last_pattern_cols;
     if (family_columns) *family_columns = h->last_family_cols;
+    return 0;
+}
+// profile(t, l, df), first half (src/model.jl:40-41): the site patterns of a count table and their multiplicities, in
+// order of first appearance.  counts: N × T, row-major (one row per family, one column per taxon), host memory.
+// rep_out[k] = index of the first family with pattern k, weight_out[k] = how many families share it, k < *npatterns.
+// Runs on the given device (hash grouping, csrc/ingest.cuh); the host only sorts the representatives.
+int blg_site_patterns(int device, const int32_t* counts, int N, int T, int32_t* rep_out, int64_t* weight_out, int* npatterns) {
+    if (!counts || !rep_out || !weight_out || !npatterns || N < 0 || T < 1) return 1;
+    try {
+        *npatterns = 0;
+        if (N == 0) return 0;
+        CK(cudaSetDevice(device));
+        unsigned int nslots = 1024;
+        while (nslots < 2u * (unsigned int)N) nslots <<= 1;
+        DevBuf<int32_t> d_counts;
+        DevBuf<unsigned int> d_u;           // [slot_rep | slot_min | slot_cnt] (nslots each), fam_slot (N), out_rep, out_cnt (N each), counter
+        d_counts.ensure((size_t)N * T);
+        d_u.ensure((size_t)3 * nslots + (size_t)3 * N + 16);
+        unsigned int* slot_rep = d_u.p;
+        unsigned int* slot_min = slot_rep + nslots;
+        unsigned int* slot_cnt = slot_min + nslots;
+        unsigned int* fam_slot = slot_cnt + nslots;
+        unsigned int* out_rep = fam_slot + N;
+        unsigned int* out_cnt = out_rep + N;
+        unsigned int* counter = out_cnt + N;
+        CK(cudaMemcpy(d_counts.p, counts, (size_t)N * T * sizeof(int32_t), cudaMemcpyHostToDevice));
+        CK(cudaMemset(slot_rep, 0xff, (size_t)2 * nslots * sizeof(unsigned int)));      // rep and min: 0xffffffff
+        CK(cudaMemset(slot_cnt, 0, (size_t)nslots * sizeof(unsigned int)));
+        CK(cudaMemset(counter, 0, sizeof(unsigned int)));
+        const int nb = (N + 255) / 256;
+        ingest_insert_kernel<<<nb, 256>>>(d_counts.p, N, T, slot_rep, fam_slot, nslots - 1);
+        ingest_group_kernel<<<nb, 256>>>(N, fam_slot, slot_min, slot_cnt);
+        ingest_compact_kernel<<<(nslots + 255) / 256, 256>>>(nslots, slot_min, slot_cnt, out_rep, out_cnt, counter);
+        CK(cudaGetLastError());
+        unsigned int U = 0;
+        CK(cudaMemcpy(&U, counter, sizeof(unsigned int), cudaMemcpyDeviceToHost));
+        std::vector<unsigned int> rep(U), cnt(U);
+        CK(cudaMemcpy(rep.data(), out_rep, (size_t)U * sizeof(unsigned int), cudaMemcpyDeviceToHost));
+        CK(cudaMemcpy(cnt.data(), out_cnt, (size_t)U * sizeof(unsigned int), cudaMemcpyDeviceToHost));
+        d_counts.free_();
+        d_u.free_();
+        std::vector<unsigned int> ord(U);
+        for (unsigned int i = 0; i < U; ++i) ord[i] = i;
+        std::sort(ord.begin(), ord.end(), [&](unsigned int a, unsigned int b) { return rep[a] < rep[b]; });
+        for (unsigned int i = 0; i < U; ++i) { rep_out[i] = (int32_t)rep[ord[i]]; weight_out[i] = (int64_t)cnt[ord[i]]; }
+        *npatterns = (int)U;
+    } catch (const std::exception& e) { g_create_error = e.what(); return 2; }
     return 0;
 }
 int blg_set_timing(blg_handle* h, int on) {

@@ -13,6 +13,7 @@ entries launch the sm_100a kernels.  Method-for-method:
     extend!, shrink!               profile.jl:108-109 -> extend_(p, i), shrink_(p, i)
 """
 import ctypes as C
+import os
 
 import numpy as np
 
@@ -313,7 +314,38 @@ def _as_table(df):
     return list(names), np.asarray(counts, dtype=np.int64)
 
 
-def profile(t, leaves, df):
+def site_patterns(counts, device=None):
+    """Unique rows of the count table and their multiplicities, in order of first appearance (what the reference's
+    `by(df, names(df), x->size(x)[1])` returns, src/model.jl:41).  On a CUDA device the grouping runs there
+    (blg_site_patterns: content-keyed hash table); `device=None` uses it when a device and the library are present
+    and the table is large, otherwise numpy."""
+    counts = np.asarray(counts)
+    N = counts.shape[0]
+    use = device is not None
+    if device is None and N >= 50_000 and os.path.exists(_lib.SO):
+        try:
+            import torch
+            use = torch.cuda.is_available()
+            device = torch.cuda.current_device() if use else None
+        except ImportError:
+            use = False
+    if use and int(counts.max(initial=0)) < 2 ** 31:
+        c32 = np.ascontiguousarray(counts, dtype=np.int32)
+        rep = np.zeros(N, dtype=np.int32)
+        wgt = np.zeros(N, dtype=np.int64)
+        n = C.c_int()
+        rc = _lib.lib().blg_site_patterns(int(device), c32.ctypes.data_as(C.POINTER(C.c_int32)), N, c32.shape[1],
+                                          rep.ctypes.data_as(C.POINTER(C.c_int32)), wgt.ctypes.data_as(C.POINTER(C.c_int64)), C.byref(n))
+        if rc != 0:
+            raise _lib.BelugaError(_lib.lib().blg_last_error(None).decode())
+        rep = rep[: n.value]
+        return counts[rep], wgt[: n.value].copy()
+    uniq, first, mult = np.unique(counts, axis=0, return_index=True, return_counts=True)
+    order = np.argsort(first, kind="stable")
+    return uniq[order], mult[order]
+
+
+def profile(t, leaves, df, device=None):
     """profile(t, l, df): site-pattern compression (unique rows + multiplicity, first-appearance
     order) and extended counts (leaf = observed count, internal = Σ children).
     -> (X [npatterns × nnodes], weights, m)."""
@@ -321,9 +353,7 @@ def profile(t, leaves, df):
     col = {nm: j for j, nm in enumerate(names)}
     if counts.shape[0] == 0:
         raise ValueError("empty count table")
-    uniq, first, mult = np.unique(counts, axis=0, return_index=True, return_counts=True)
-    order = np.argsort(first, kind="stable")
-    uniq, mult = uniq[order], mult[order]
+    uniq, mult = site_patterns(counts, device)
     nn = max(leaves) if leaves else 1
     nodes = []
     stack = [t]

@@ -56,6 +56,12 @@ const char* blg_last_error(blg_handle* h);
  * (profile.jl:28,31): every likelihood entry then returns 0. */
 int blg_set_profiles(blg_handle* h, const int32_t* X, const int64_t* weight, int ncols, int npatterns);
 
+/* --- profile(t, l, df), first half (model.jl:40-41): the site patterns of a count table (N families × T taxa, row-major,
+ * host memory) and their multiplicities, in order of first appearance, grouped on the device by a content-keyed hash
+ * table.  rep_out[k] = first family with pattern k, weight_out[k] = its multiplicity (both with room for N entries). */
+int blg_site_patterns(int device, const int32_t* counts, int N, int T, int32_t* rep_out, int64_t* weight_out,
+                      int* npatterns);
+
 /* --- model graph: initmodel (model.jl:227-244), addwgd!/addwgt!/removewgd!/reindex!
  * (model.jl:106-183) -----------------------------------------------------------------------------
  * parent[i]: id of the parent (0 for the root); kind[i]: BLG_*; child_pos[i]: position of node

@@ -832,3 +832,30 @@ def test_c5_workload_sample_against_oracle_and_properties():
         del os.environ["BLG_KERNEL"]
     assert l3 == pytest.approx(lf, rel=1e-12)
     np.testing.assert_allclose(data3.family_logpdf(), data.family_logpdf(), rtol=1e-11)
+
+
+# ---- ingestion: site patterns grouped on the device (src/model.jl:40-41) ------------------------------------------------
+def test_site_patterns_on_device_match_the_host_grouping():
+    from beluga_b200.profile import site_patterns
+    rng = np.random.default_rng(17)
+    for N, T, hi in ((1, 3, 2), (257, 5, 2), (20000, 9, 3), (120000, 40, 2)):
+        counts = rng.integers(0, hi, size=(N, T)).astype(np.int64)
+        counts[N // 2] = counts[0]                            # at least one repeat of the very first row
+        u0, w0 = site_patterns(counts, device=None if N < 50000 else 0) if N >= 50000 else (None, None)
+        ud, wd = site_patterns(counts, device=0)
+        uniq, first, mult = np.unique(counts, axis=0, return_index=True, return_counts=True)
+        order = np.argsort(first, kind="stable")
+        assert np.array_equal(ud, uniq[order])                # same patterns, in order of first appearance
+        assert np.array_equal(wd, mult[order])
+        assert wd.sum() == N
+        if u0 is not None:
+            assert np.array_equal(u0, ud) and np.array_equal(w0, wd)
+    # and through profile(): extended counts of the compressed table
+    nw = "((A:0.4,B:0.5):0.3,(C:0.6,(D:0.2,E:0.3):0.2):0.25);"
+    model, t, l = build_model(nw, 1.0, 1.0, 0.8, B.BRANCH)
+    counts = rng.integers(0, 3, size=(60000, 5)).astype(np.int64)
+    Xd, wdv, md = B.profile(t, l, (list("ABCDE"), counts), device=0)
+    import beluga_b200.profile as P
+    uniq, first, mult = np.unique(counts, axis=0, return_index=True, return_counts=True)
+    assert Xd.shape[0] == uniq.shape[0] and wdv.sum() == 60000
+    assert np.array_equal(Xd[:, 0], Xd[:, [i - 1 for i in sorted(l)]].sum(axis=1))     # root = Σ leaves
