@@ -14,6 +14,7 @@
 // accesses coalesced along the family axis).  No CPU fallback: every entry fails loudly when
 // CUDA is unavailable.
 #include <cuda_runtime.h>
+#include <curand_kernel.h>
 #include <dlfcn.h>
 
 #include <algorithm>
@@ -1186,6 +1187,7 @@ __global__ void zero_slab_kernel(double* ell, int* scl, size_t nell, int N) {
 #include "gradient.cuh"
 #include "adjoint.cuh"
 #include "ingest.cuh"
+#include "sampler.cuh"
 
 // ------------------------------------------------------------------------------------------------
 // host-side state
@@ -3406,6 +3408,99 @@ int blg_pattern_stats(blg_handle* h, double* bytes_moved, double* pattern_column
     if (family_columns) *family_columns = h->last_family_cols;
     return 0;
 }
+// rand(model, N; condition) (src/sim.jl:17-27) at the count level, on the device (csrc/sampler.cuh), for the handle's current
+// topology and parameters (blg_set_topology + blg_set_params; no profiles needed).  condition: 0 none, 1 at least one gene
+// (the reference's default), 2 at least one gene in every clade below the root (rootclades); max_leaf / max_rootsum: also
+// reject families with a larger leaf count / total count (-1: no bound).  counts_out: N × nleaves, row-major, leaf columns
+// by ascending leaf id (leaf_ids_out).  draws_out: how many families were drawn to accept N.
+int blg_rand_profiles(blg_handle* h, int N, unsigned long long seed, int condition, int max_leaf, int max_rootsum,
+                      int32_t* leaf_ids_out, int* nleaves_out, uint16_t* counts_out, long long* draws_out) {
+    BLG_ENTER(h)
+    h->require(h->have_topology && h->have_params, "rand_profiles: set the topology and the parameters first");
+    h->require(N >= 0 && counts_out && leaf_ids_out && nleaves_out, "rand_profiles: bad arguments");
+    // pre-order over the model, children in the reference's iteration order
+    std::vector<int> pre, pos(h->ncols_model, -1);
+    {
+        std::vector<int> stk{0};
+        while (!stk.empty()) {
+            const int u = stk.back(); stk.pop_back();
+            pos[u] = (int)pre.size(); pre.push_back(u);
+            for (auto it = h->children[u].rbegin(); it != h->children[u].rend(); ++it) stk.push_back(*it);
+        }
+    }
+    std::vector<int> leaf_ids;
+    for (int i = 0; i < h->ncols_model; ++i) if (h->present(i) && h->children[i].empty()) leaf_ids.push_back(i);
+    const int nleaves = (int)leaf_ids.size();
+    std::vector<int> leafcol(h->ncols_model, -1);
+    for (int k = 0; k < nleaves; ++k) { leafcol[leaf_ids[k]] = k; leaf_ids_out[k] = leaf_ids[k] + 1; }
+    *nleaves_out = nleaves;
+    const int nclades = (int)h->children[0].size();
+    h->require(nclades <= 30, "rand_profiles: too many clades below the root");
+    std::vector<SimNode> sn(pre.size());
+    for (size_t k = 0; k < pre.size(); ++k) {
+        const int u = pre[k];
+        SimNode& s_ = sn[k];
+        memset(&s_, 0, sizeof(s_));
+        s_.leaf = leafcol[u];
+        if (u == 0) { s_.parent = -1; s_.clade = -1; continue; }
+        const int p = h->parent[u];
+        s_.parent = pos[p];
+        s_.clade = (p == 0) ? (int)(std::find(h->children[0].begin(), h->children[0].end(), u) - h->children[0].begin()) : sn[pos[p]].clade;
+        s_.ret = h->kind[p] == BLG_WGD ? 2 : h->kind[p] == BLG_WGT ? 3 : 0;
+        s_.q = s_.ret ? h->q[p] : 0.0;
+        const double t = h->t[u];
+        if (t > 0.0) {
+            // getλμ(nonwgdparent(node), nonwgdchild(c)) as sim.jl:108 calls it (node.jl:220-230); ϕ, ψ of utils.jl:8-9
+            const int a = h->nonwgdparent_h(p), b = h->nonwgdchild_h(u);
+            double l = h->lam[b], m = h->mu[b];
+            if (h->model_kind == BLG_NODE_MODEL) { l = 0.5 * (h->lam[a] + h->lam[b]); m = 0.5 * (h->mu[a] + h->mu[b]); }
+            if (std::fabs(l - m) <= 1.4901161193847656e-8 * std::max(std::fabs(l), std::fabs(m))) {
+                s_.phi = s_.psi = l * t / (1.0 + l * t);
+            } else {
+                const double e = std::exp(t * (l - m));
+                s_.phi = m * (e - 1.0) / (l * e - m);
+                s_.psi = (l / m) * s_.phi;
+            }
+        }
+    }
+    long long draws = 0;
+    if (N > 0) {
+        const int chunk = 1 << 19;
+        DevBuf<SimNode> d_nodes;
+        DevBuf<int> d_cnt;
+        DevBuf<uint16_t> d_leaves, d_out;
+        DevBuf<unsigned int> d_keep, d_bsum;
+        d_nodes.ensure(sn.size());
+        d_cnt.ensure(sn.size() * (size_t)chunk);
+        d_leaves.ensure((size_t)chunk * nleaves);
+        d_out.ensure((size_t)N * nleaves);
+        const int nb = (chunk + 1023) / 1024;
+        d_keep.ensure((size_t)chunk);
+        d_bsum.ensure((size_t)nb + 4);
+        CK(cudaMemcpyAsync(d_nodes.p, sn.data(), sn.size() * sizeof(SimNode), cudaMemcpyHostToDevice, h->stream));
+        long long have = 0;
+        int rounds = 0;
+        while (have < N) {
+            h->require(++rounds <= 100000, "rand_profiles: the condition is (almost) never met");
+            rand_counts_kernel<<<(chunk + 255) / 256, 256, 0, h->stream>>>(d_nodes.p, (int)sn.size(), nleaves, nclades, h->eta, seed, (unsigned long long)draws, chunk,
+                                                                         condition, max_leaf, max_rootsum, d_cnt.p, d_leaves.p, d_keep.p);
+            sim_block_sums<<<nb, 256, 0, h->stream>>>(d_keep.p, chunk, d_bsum.p);
+            sim_scan_sums<<<1, 32, 0, h->stream>>>(d_bsum.p, nb, d_bsum.p + nb);
+            sim_compact<<<nb, 256, 0, h->stream>>>(d_keep.p, chunk, d_bsum.p, d_leaves.p, nleaves, d_out.p, have, (long long)N);
+            CK(cudaGetLastError());
+            unsigned int got = 0;
+            CK(cudaMemcpyAsync(&got, d_bsum.p + nb, sizeof(unsigned int), cudaMemcpyDeviceToHost, h->stream));
+            CK(cudaStreamSynchronize(h->stream));
+            have += got;
+            draws += chunk;
+        }
+        CK(cudaMemcpy(counts_out, d_out.p, (size_t)N * nleaves * sizeof(uint16_t), cudaMemcpyDeviceToHost));
+        d_nodes.free_(); d_cnt.free_(); d_leaves.free_(); d_out.free_(); d_keep.free_(); d_bsum.free_();
+    }
+    if (draws_out) *draws_out = draws;
+    BLG_LEAVE(h)
+}
+
 // profile(t, l, df), first half (src/model.jl:40-41): the site patterns of a count table and their multiplicities, in
 // order of first appearance.  counts: N × T, row-major (one row per family, one column per taxon), host memory.
 // rep_out[k] = index of the first family with pattern k, weight_out[k] = how many families share it, k < *npatterns.

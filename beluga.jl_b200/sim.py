@@ -198,6 +198,45 @@ def rand_profiles_torch(model, N, seed=20261019, device="cuda", condition="rootc
     return [names[k] for k in order_], np.ascontiguousarray(counts[:, order_])
 
 
+def rand_profiles_device(model, N, seed=20261019, device=0, condition="rootclades", max_leaf=None, max_rootsum=None):
+    """rand(model, N, condition=…) drawn by the library's own sampler kernel (csrc/sampler.cuh: one thread and one Philox
+    stream per family, rejection with ordered compaction): equal in distribution to ``rand_profiles``, reproducible
+    for a given seed, WGT nodes supported.  Returns (names sorted alphabetically, counts[N × ntaxa] uint16)."""
+    import ctypes as C
+    from . import _lib
+    L = _lib.lib()
+    h = C.c_void_p()
+    if L.blg_create(int(device), None, C.byref(h)) != 0:
+        raise _lib.BelugaError(L.blg_last_error(None).decode())
+    try:
+        def ck(rc):
+            if rc != 0:
+                raise _lib.BelugaError(L.blg_last_error(h).decode())
+        n, parent, kind, cpos = model.flat_topology()
+        ck(L.blg_set_topology(h, n, parent.ctypes.data_as(C.POINTER(C.c_int32)), kind.ctypes.data_as(C.POINTER(C.c_uint8)),
+                              cpos.ctypes.data_as(C.POINTER(C.c_int32))))
+        lam, mu, q, t, eta = model.flat_params()
+        dp = C.POINTER(C.c_double)
+        ck(L.blg_set_params(h, 0 if model.nt == "Node" else 1, lam.ctypes.data_as(dp), mu.ctypes.data_as(dp), q.ctypes.data_as(dp),
+                            t.ctypes.data_as(dp), float(eta)))
+        nleaf = sum(1 for nd in model.nodes.values() if isleaf(nd))
+        leaf_ids = np.zeros(n, dtype=np.int32)
+        nl = C.c_int()
+        out = np.zeros((int(N), nleaf), dtype=np.uint16)
+        draws = C.c_longlong()
+        cond = {None: 0, "nonextinct": 1, "rootclades": 2}[condition]
+        ck(L.blg_rand_profiles(h, int(N), C.c_ulonglong(int(seed)), cond, -1 if max_leaf is None else int(max_leaf),
+                               -1 if max_rootsum is None else int(max_rootsum), leaf_ids.ctypes.data_as(C.POINTER(C.c_int32)), C.byref(nl),
+                               out.ctypes.data_as(C.POINTER(C.c_uint16)), C.byref(draws)))
+        assert nl.value == nleaf
+    finally:
+        L.blg_destroy(h)
+    names = [model.leaves[int(i)] for i in leaf_ids[:nleaf]]
+    order = np.argsort(names)
+    rand_profiles_device.last_draws = draws.value
+    return [names[k] for k in order], np.ascontiguousarray(out[:, order])
+
+
 def add_random_wgds(model, k, seed=20261019, qa=1.0, qb=3.0):
     """k WGDs placed with the reference's randpos semantics (src/model.jl:197-206: branch ∝ length,
     uniform position along it), retention q ~ Beta(qa, qb).  Returns the ids extend! must be

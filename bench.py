@@ -65,14 +65,14 @@ def build_workload(args, rank, device=None, families=None):
     """-> (newick, model with WGDs, ext ids, names, counts) for this rank."""
     import beluga_b200 as B
     from beluga_b200.model import build_model
-    from beluga_b200.sim import add_random_wgds, rand_profiles, rand_profiles_torch, random_tree_newick
+    from beluga_b200.sim import add_random_wgds, rand_profiles, rand_profiles_device, random_tree_newick
 
     nw = random_tree_newick(args.taxa, seed=SEED)
     model, t, l = build_model(nw, 1.0, 1.2, 0.8, B.BRANCH)
     ext = add_random_wgds(model, args.wgds, seed=SEED)
     nfam = families if families is not None else args.families
-    if device is not None:
-        names, counts = rand_profiles_torch(model, nfam, seed=SEED + rank, device=device, max_rootsum=args.max_count)
+    if device is not None:         # rand(model, N, condition = rootclades) by the library's own sampler kernel (csrc/sampler.cuh)
+        names, counts = rand_profiles_device(model, nfam, seed=SEED + rank, device=int(str(device).split(":")[-1]), max_rootsum=args.max_count)
     else:
         names, counts = rand_profiles(model, nfam, seed=SEED + rank, max_rootsum=args.max_count)
     return nw, model, ext, t, l, names, counts
@@ -216,11 +216,11 @@ def mcmc_leg(args, local, distributed=False):
     import beluga_b200 as B
     from beluga_b200.mcmc import RevJumpChain
     from beluga_b200.model import build_model
-    from beluga_b200.sim import rand_profiles_torch
+    from beluga_b200.sim import rand_profiles_device
 
     nw = open(os.path.join(ROOT, "tests", "data", "12monocots.nw")).readline().strip()
     m0, _, _ = build_model(nw, 0.004, 0.003, 0.9, B.BRANCH)
-    names, counts = rand_profiles_torch(m0, args.mcmc_families, seed=SEED, device="cuda:%d" % local, max_rootsum=60, chunk=1 << 19)
+    names, counts = rand_profiles_device(m0, args.mcmc_families, seed=SEED, device=local, max_rootsum=60)
     # distributed: every rank draws the same table (same seed), the patterns are compressed globally and sharded contiguously;
     # every rank runs the same chain (same seed, same all-reduced log-likelihoods, hence the same decisions)
     model, data = B.DLWGD(nw, (names, counts), 0.004, 0.003, 0.9, B.BRANCH, device=local, distributed=distributed)
@@ -282,13 +282,13 @@ def node_local_leg(args, local):
     then `rev!`; reports the mean over nodes and the time of `set!`/`rev!`."""
     import beluga_b200 as B
     from beluga_b200.model import build_model, update_
-    from beluga_b200.sim import rand_profiles_torch
+    from beluga_b200.sim import rand_profiles_device
 
     nw = open(os.path.join(ROOT, "tests", "data", "9dicots.nw")).readline().strip()
     m0, _, _ = build_model(nw, 1.0, 0.92, 0.66, B.BRANCH)
     for i, t, q in ((6, 0.01, 0.25), (14, 0.02, 0.5), (10, 0.05, 0.3)):
         m0.addwgd_(m0[i], t, q)
-    names, counts = rand_profiles_torch(m0, 100_000, seed=SEED, device="cuda:%d" % local, max_rootsum=60, chunk=1 << 19)
+    names, counts = rand_profiles_device(m0, 100_000, seed=SEED, device=local, max_rootsum=60)
     model, data = B.DLWGD(nw, (names, counts), 1.0, 0.92, 0.66, B.BRANCH, device=local)
     for i, t, q in ((6, 0.01, 0.25), (14, 0.02, 0.5), (10, 0.05, 0.3)):
         model.addwgd_(model[i], t, q)
@@ -326,7 +326,7 @@ def gradient_leg(args, local):
     """`gradient(model, data)`: C1 (README example, 9dicots × 25 families, P = 35) and the C4 tree with 10^4 families."""
     import beluga_b200 as B
     from beluga_b200.model import build_model
-    from beluga_b200.sim import rand_profiles_torch
+    from beluga_b200.sim import rand_profiles_device
     out = {}
     nw = open(os.path.join(ROOT, "tests", "data", "9dicots.nw")).readline().strip()
     rows = [ln.strip().split(",") for ln in open(os.path.join(ROOT, "tests", "data", "9dicots-f01-25.csv"))]
@@ -339,7 +339,7 @@ def gradient_leg(args, local):
     out["C1"] = {"ms": (time.perf_counter() - t0) / 3 * 1e3, "P": int(len(g)), "patterns": len(data)}
     nw = open(os.path.join(ROOT, "tests", "data", "12monocots.nw")).readline().strip()
     m0, _, _ = build_model(nw, 0.004, 0.003, 0.9, B.BRANCH)
-    names, counts = rand_profiles_torch(m0, 10_000, seed=SEED, device="cuda:%d" % local, max_rootsum=60, chunk=1 << 19)
+    names, counts = rand_profiles_device(m0, 10_000, seed=SEED, device=local, max_rootsum=60)
     model, data = B.DLWGD(nw, (names, counts), 0.004, 0.003, 0.9, B.BRANCH, device=local)
     B.gradient(model, data)
     t0 = time.perf_counter()
@@ -376,12 +376,11 @@ def leaf50_leg(args, local):
     general kernel (one warp per family, fp64-bound); the others on the pattern path."""
     import beluga_b200 as B
     from beluga_b200.model import build_model, nonwgdchild
-    from beluga_b200.sim import add_random_wgds, rand_profiles_torch, random_tree_newick
-    import torch
+    from beluga_b200.sim import add_random_wgds, rand_profiles_device, random_tree_newick
     nw = random_tree_newick(args.taxa, seed=SEED)
     model, t, l = build_model(nw, 1.0, 1.2, 0.8, B.BRANCH)
     ext = add_random_wgds(model, args.wgds, seed=SEED)
-    names, counts = rand_profiles_torch(model, args.leaf50_families, seed=SEED, device="cuda:%d" % local, max_leaf=args.max_count)
+    names, counts = rand_profiles_device(model, args.leaf50_families, seed=SEED, device=local, max_leaf=args.max_count)
     X, w, m = B.profile(t, l, (names, counts))
     X = np.ascontiguousarray(X, dtype=np.int32)
     fma = algorithmic_fma(model, X)

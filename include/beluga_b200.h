@@ -56,6 +56,13 @@ const char* blg_last_error(blg_handle* h);
  * (profile.jl:28,31): every likelihood entry then returns 0. */
 int blg_set_profiles(blg_handle* h, const int32_t* X, const int64_t* weight, int ncols, int npatterns);
 
+/* --- rand(model, N; condition) (sim.jl:17-27), count level, on the device: families are drawn from the handle's current
+ * topology and parameters (no profiles needed) until N are accepted.  condition: 0 none, 1 non-extinct (the reference's
+ * default), 2 rootclades (sim.jl:51); max_leaf / max_rootsum: extra rejection bounds (-1: none).  counts_out: N × nleaves
+ * uint16, row-major, columns by ascending leaf id (leaf_ids_out, room for ncols entries).  Reproducible for a given seed. */
+int blg_rand_profiles(blg_handle* h, int N, unsigned long long seed, int condition, int max_leaf, int max_rootsum,
+                      int32_t* leaf_ids_out, int* nleaves_out, uint16_t* counts_out, long long* draws_out);
+
 /* --- profile(t, l, df), first half (model.jl:40-41): the site patterns of a count table (N families × T taxa, row-major,
  * host memory) and their multiplicities, in order of first appearance, grouped on the device by a content-keyed hash
  * table.  rep_out[k] = first family with pattern k, weight_out[k] = its multiplicity (both with room for N entries). */

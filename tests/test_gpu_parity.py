@@ -859,3 +859,45 @@ def test_site_patterns_on_device_match_the_host_grouping():
     uniq, first, mult = np.unique(counts, axis=0, return_index=True, return_counts=True)
     assert Xd.shape[0] == uniq.shape[0] and wdv.sum() == 60000
     assert np.array_equal(Xd[:, 0], Xd[:, [i - 1 for i in sorted(l)]].sum(axis=1))     # root = Σ leaves
+
+
+# ---- rand(model, N) on the device (src/sim.jl:17-145 at the count level) ------------------------------------------------
+def test_device_sampler_follows_the_count_law():
+    # the library's sampler kernel against the numpy restatement of the same law (sim.py::rand_counts, which mirrors
+    # sim.jl's lineage-by-lineage birth-death simulation at the count level): per-leaf means, variances, zero
+    # fractions and the pairwise covariances of a cherry, unconditioned and conditioned, with a WGD in the tree
+    from beluga_b200.sim import rand_counts, rand_profiles, rand_profiles_device
+    nw = "((A:0.4,B:0.5):0.3,(C:0.6,(D:0.2,E:0.3):0.2):0.25);"
+    for nt in (B.BRANCH, B.NODE):
+        model, t, l = build_model(nw, 0.9, 1.1, 0.7, nt)
+        model.addwgd_(model[6], 0.1, 0.4)
+        X = np.exp(np.random.default_rng(8).normal(0, 0.3, size=(2, model.ne() + 1)))
+        model.setrates_(X)
+        N = 400_000
+        names, dev = rand_profiles_device(model, N, seed=11, device=0, condition=None)
+        leaf_ids, ref = rand_counts(model, N, np.random.default_rng(12))
+        ref = ref[:, np.argsort([model.leaves[i] for i in leaf_ids])]
+        dev = dev.astype(np.float64); ref = ref.astype(np.float64)
+        se = np.sqrt((dev.var(axis=0) + ref.var(axis=0)) / N)
+        assert np.all(np.abs(dev.mean(axis=0) - ref.mean(axis=0)) < 5 * se), (dev.mean(axis=0), ref.mean(axis=0))
+        assert np.allclose(dev.var(axis=0), ref.var(axis=0), rtol=0.05)
+        assert np.allclose((dev == 0).mean(axis=0), (ref == 0).mean(axis=0), atol=0.005)
+        assert np.allclose(np.cov(dev.T), np.cov(ref.T), rtol=0.08, atol=0.02)
+        # conditioned on both root clades, with a bound on the total: every family obeys the condition, the law of the
+        # accepted families is the same
+        names, devc = rand_profiles_device(model, 100_000, seed=5, device=0, condition="rootclades", max_rootsum=12)
+        _, refc = rand_profiles(model, 100_000, seed=6, condition="rootclades", max_rootsum=12)
+        assert devc.sum(axis=1).max() <= 12
+        col = {nm: k for k, nm in enumerate(names)}
+        assert np.all(devc[:, [col["A"], col["B"]]].sum(axis=1) > 0) and np.all(devc[:, [col["C"], col["D"], col["E"]]].sum(axis=1) > 0)
+        assert np.allclose(devc.mean(axis=0), refc.mean(axis=0), atol=0.02)
+        # reproducible: same seed, same families
+        _, again = rand_profiles_device(model, 100_000, seed=5, device=0, condition="rootclades", max_rootsum=12)
+        assert np.array_equal(again, devc)
+    # a WGT: each of the two extra copies is kept with probability q: 1, 2 or 3 copies w.p. (1-q)², 2q(1-q), q²
+    model, t, l = build_model("(A:0.0000001,B:1.0);", 1e-9, 1e-9, 1.0, B.BRANCH)    # η = 1: one lineage at the root, no birth-death
+    model.addwgt_(model[2], 0.00000005, 0.3)
+    names, dev = rand_profiles_device(model, 300_000, seed=3, device=0, condition=None)
+    a = dev[:, names.index("A")]
+    p = np.array([(a == k).mean() for k in (1, 2, 3)])
+    assert np.allclose(p, [0.49, 0.42, 0.09], atol=0.004), p
