@@ -9,6 +9,7 @@ from .model import (BRANCH, NODE, DLWGD as DLWGDModel, ModelNode, closestnode, i
                     postwalk, prewalk, update_)
 from .newick import readnw
 from .parallel import allreduce_sum_, dist_info, shard_range
+from .priors import BMRevJumpPrior, CRRevJumpPrior, IRRevJumpPrior
 from .profile import (DLWGD_ as DLWGD, PArray, extend_, gradient, gradient_cr, logpdf_, logpdfroot, profile, rev_, set_,
                       shrink_)
 

@@ -20,9 +20,10 @@ from .model import (isawgd, isroot, iswgm, iswgmafter, nonwgdchild, postwalk, up
 class RevJumpChain:
     """RevJumpChain (src/rjmcmc.jl:127-137): data, model, state (logp, logπ, k)."""
 
-    def __init__(self, data, model, seed=20261019, step=0.05, max_wgds=20, rate_bounds=(1e-4, 50.0)):
+    def __init__(self, data, model, seed=20261019, step=0.05, max_wgds=20, rate_bounds=(1e-4, 50.0), prior=None):
         self.data = data
         self.model = model
+        self.prior = prior              # an object with logpdf(model) (priors.py: IRRevJumpPrior, …); None: flat within the bounds
         self.rng = np.random.default_rng(seed)
         self.step = float(step)
         self.max_wgds = int(max_wgds)
@@ -35,6 +36,7 @@ class RevJumpChain:
 
     # init!(chain) (rjmcmc.jl:148-155)
     def init_(self):
+        self.state["logπ"] = self.logprior()
         self.state["logp"] = self.data.logpdf_(self.model)
         self.evals += 1
         self.data.set_()
@@ -48,7 +50,9 @@ class RevJumpChain:
             if "q" in th and not (0.0 < th["q"] < 1.0):
                 return -math.inf
         eta = self.model.nodes[1]["η"]
-        return 0.0 if 0.0 < eta <= 1.0 else -math.inf
+        if not (0.0 < eta <= 1.0):
+            return -math.inf
+        return self.prior.logpdf(self.model) if self.prior is not None else 0.0   # logpdf(chain.prior, model), rjmcmc.jl:150
 
     # acceptreject_da (rjmcmc.jl:311-320): prior first, the likelihood closure only if that stage accepts
     def _acceptreject(self, f, q=0.0):

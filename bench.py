@@ -224,7 +224,9 @@ def mcmc_leg(args, local, distributed=False):
     # distributed: every rank draws the same table (same seed), the patterns are compressed globally and sharded contiguously;
     # every rank runs the same chain (same seed, same all-reduced log-likelihoods, hence the same decisions)
     model, data = B.DLWGD(nw, (names, counts), 0.004, 0.003, 0.9, B.BRANCH, device=local, distributed=distributed)
-    chain = RevJumpChain(data, model, seed=SEED, step=0.02).init_()
+    from beluga_b200.priors import IRRevJumpPrior
+    # C2/C4: the chain runs under IRRevJumpPrior(Tl = treelength(model)) (README.md:75-88 of the reference)
+    chain = RevJumpChain(data, model, seed=SEED, step=0.02, prior=IRRevJumpPrior(Tl=model.treelength())).init_()
     chain.rjmcmc_(5, trace=0)                      # warm-up
     data.synchronize()
     e0, p0 = chain.evals, chain.proposed
