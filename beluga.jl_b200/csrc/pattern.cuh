@@ -129,6 +129,7 @@ __global__ void __launch_bounds__(128, WIDE ? 2 : 4) ptile_kernel(const __grid_c
 #pragma unroll 1
             for (int j = 0; j <= M0w; ++j) cp_async_f64(R + j * 32, (j <= M0) ? src + (size_t)j * ld0 : src, j <= M0);
         }
+        cp_async_commit();
     }
     if (async1) {
         double* dst = R + (size_t)(M0w + 1) * 32;
@@ -142,9 +143,12 @@ __global__ void __launch_bounds__(128, WIDE ? 2 : 4) ptile_kernel(const __grid_c
 #pragma unroll 1
             for (int j = 0; j <= M1w; ++j) cp_async_f64(dst + j * 32, (j <= M1) ? src + (size_t)j * ld1 : src, j <= M1);
         }
+        cp_async_commit();
     }
-    if (async0) { cp_async_commit(); cp_async_wait_all(); }
+    // child 0's column is waited for now, child 1's only after child 0 has been contracted
+    if (async0) { if (async1) cp_async_wait_but_one(); else cp_async_wait_all(); }
     sweep_child(child_args(ch[0], k0.psi, k0.cc), c0, (size_t)ch[0].ld, M0, M0w, R, async0 ? 2 : 0, 1.0);
+    if (async1) cp_async_wait_all();
     int Sw = M0w;
     double mxv = 0.0;
     bool scaled = false;        // has the (1-E_k)^(-n) normalisation already been applied (and mxv taken)?
