@@ -606,12 +606,32 @@ __device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commi
 __device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_group 0;" ::: "memory"); }
 __device__ __forceinline__ void cp_async_wait_but_one() { asm volatile("cp.async.wait_group 1;" ::: "memory"); }
 
+// How the helpers below address a working column.  GCol: a generic pointer (the per-family sweep kernel, whose column may
+// live in shared memory or in global scratch).  SCol: an index into the kernel's dynamic shared memory — the compiler then
+// knows the address space and emits LDS/STS with 32-bit address arithmetic instead of generic LD/ST (the tile kernel, whose
+// tiles are cut on the host so that they always fit their shared slice).
+extern __shared__ double blg_smem[];
+struct GCol {
+    double* p;
+    __device__ __forceinline__ double& operator[](int i) const { return p[i]; }
+    __device__ __forceinline__ GCol operator+(int k) const { return GCol{p + k}; }
+    __device__ __forceinline__ double* ptr(int i) const { return p + i; }
+    __device__ __forceinline__ bool same(const GCol& o) const { return p == o.p; }
+};
+struct SCol {
+    int off;
+    __device__ __forceinline__ double& operator[](int i) const { return blg_smem[off + i]; }
+    __device__ __forceinline__ SCol operator+(int k) const { return SCol{off + k}; }
+    __device__ __forceinline__ double* ptr(int i) const { return &blg_smem[off + i]; }
+    __device__ __forceinline__ bool same(const SCol& o) const { return off == o.off; }
+};
+
 // in-place table contraction (branch below a WGD/WGT): col[s] ← Σ_{j=s..min(Mw, band·s)} Wt[j*wdp+s]·col[j]
 // w*(s|j) of these branches is banded: s lineages above a WGD leave at most 2s below it (3s for a WGT), so rows j > band·s
 // of column s are zero (band = 2 or 3; the literal WGT table of node.jl:205-218 keeps the same support).  Table rows are
 // read 16 bytes at a time (wdp is a multiple of 16 and s0 of TS: aligned).
-template <int TS>
-__device__ __noinline__ void sweep_contract_table(double* col, int Mw, const double* __restrict__ Wt, int wdp, double osc, int band) {
+template <int TS, class C>
+__device__ __noinline__ void sweep_contract_table(C col, int Mw, const double* __restrict__ Wt, int wdp, double osc, int band) {
 #pragma unroll 1
     for (int s0 = 0; s0 <= Mw; s0 += TS) {
         double acc[TS];
@@ -645,9 +665,10 @@ __device__ __noinline__ void sweep_contract_table(double* col, int Mw, const dou
 __device__ __forceinline__ void dmma_m8n8k4(double& c0, double& c1, double a, double b) {
     asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};" : "+d"(c0), "+d"(c1) : "d"(a), "d"(b));
 }
-__device__ __noinline__ void sweep_contract_mma(double* col, int Mw, const double* __restrict__ Wt, int wdp, int band) {
+template <class C>
+__device__ __noinline__ void sweep_contract_mma(C col, int Mw, const double* __restrict__ Wt, int wdp, int band) {
     const unsigned lane = threadIdx.x & 31u;
-    double* cb = col - lane;                       // the warp's slice: element (j, pattern) at cb[j*32 + pattern]
+    const C cb = col + (-(int)lane);               // the warp's slice: element (j, pattern) at cb[j*32 + pattern]
     const int g = (int)(lane >> 2), t = (int)(lane & 3u);
 #pragma unroll 1
     for (int s0 = 0; s0 <= Mw; s0 += 8) {
@@ -660,7 +681,7 @@ __device__ __noinline__ void sweep_contract_mma(double* col, int Mw, const doubl
             const int j = j0 + t;
             const bool in = j <= Mw;
             const double a = in ? __ldg(Wt + (size_t)j * wdp + s0 + g) : 0.0;
-            const double* row = cb + (size_t)(in ? j : Mw) * 32 + g;
+            const C row = cb + ((in ? j : Mw) * 32 + g);
 #pragma unroll
             for (int nb = 0; nb < 4; ++nb) {
                 const double b = in ? row[nb * 8] : 0.0;
@@ -671,7 +692,7 @@ __device__ __noinline__ void sweep_contract_mma(double* col, int Mw, const doubl
         const int s = s0 + g;
         if (s <= Mw) {
 #pragma unroll
-            for (int nb = 0; nb < 4; ++nb) *reinterpret_cast<double2*>(cb + (size_t)s * 32 + nb * 8 + 2 * t) = make_double2(c[nb][0], c[nb][1]);
+            for (int nb = 0; nb < 4; ++nb) *reinterpret_cast<double2*>(cb.ptr(s * 32 + nb * 8 + 2 * t)) = make_double2(c[nb][0], c[nb][1]);
         }
         __syncwarp();
     }
@@ -684,8 +705,8 @@ __device__ __noinline__ void sweep_contract_mma(double* col, int Mw, const doubl
 // scaling (r is bounded by 2^Mw·max ℓ whatever the parameters are).  TS consecutive n live in registers; a tile hands the
 // old value of its top element to the tile above through the column itself: at stage j tile `base` reads col[base+j]
 // (ℓ[j] for the first tile) and leaves its top element in col[base+TS+j], a slot it has already consumed.
-template <int TS>
-__device__ __noinline__ void sweep_contract_horner(double* col, int Mw, double psi, double cc, double osc) {
+template <int TS, class C>
+__device__ __noinline__ void sweep_contract_horner(C col, int Mw, double psi, double cc, double osc) {
     double cpow = cc * osc;                            // c^n (times the pending power-of-two rescale of a resident column) at the tile's first output
 #pragma unroll 1
     for (int base = 0; base < Mw; base += TS) {        // outputs n = base+1 .. base+TS
@@ -713,8 +734,8 @@ __device__ __noinline__ void sweep_contract_horner(double* col, int Mw, double p
 // single-tile in-place merge (M2w < TS).  A[0..Sw] is the "t" side, B0[0..M2w] the "s" side (both inside the
 // warp's slice); the result Σ_{t+s=n} C(n,s)·E^s·A[t]·B[t,s], n = 0..Sw+M2w, is written to O[n] at step n.
 // O may alias the slice as long as O+n never passes an unread A[t] (O == A, or O below A).
-template <int TS>
-__device__ __noinline__ double sweep_merge_fast(double* O, const double* A, int Sw, const double* B0, int M2w, double E, double invE,
+template <int TS, class C>
+__device__ __noinline__ double sweep_merge_fast(C O, C A, int Sw, C B0, int M2w, double E, double invE,
                                                 double e, double inve, double em0, double emg, int X) {
     // em0/emg: the emitted value is acc·n!·E^n·(extra factor em0·emg^n): the last merge of a node passes
     // the (1-E_k)^(-n) normalisation (and the NaN poison) through them.  Returns max_{n<=X} of the result.
@@ -765,7 +786,8 @@ __device__ __noinline__ double sweep_merge_fast(double* O, const double* A, int 
 }
 // general merge for a smaller child with >= 20 counts: 16-wide tiles from high s to low s chained
 // through the history column H.  A[0..Sw]; O[0..M2w] = B[0,·], O[M2w+1..Sw+M2w] = 0 on entry; result in O.
-__device__ __noinline__ void sweep_merge_tiled(const double* A, int Sw, double* O, int M2w, double* H, double E, double e) {
+template <class C>
+__device__ __noinline__ void sweep_merge_tiled(C A, int Sw, C O, int M2w, C H, double E, double e) {
     constexpr int TS = 16;
     const int ntile = M2w / TS + 1;
     const int nmax = Sw + M2w;
@@ -816,7 +838,8 @@ __device__ __noinline__ void sweep_merge_tiled(const double* A, int Sw, double* 
 // from the parameter bank that missed the carved-down L1 — a long-scoreboard stall at the top of every call)
 struct ChildArgs { const double* ell; const double* Wt; int wdp, table; double psi, cc; };
 __device__ __forceinline__ ChildArgs child_args(const SweepChild& c, double psi, double cc) { return ChildArgs{c.ell, c.Wt, c.wdp, c.table, psi, cc}; }
-__device__ __noinline__ void sweep_child(const ChildArgs c, int f, size_t ld, int M, int Mw, double* col, int have, double osc) {
+template <class C>
+__device__ __noinline__ void sweep_child(const ChildArgs c, int f, size_t ld, int M, int Mw, C col, int have, double osc) {
     const bool resident = have != 0;
     if (c.ell == nullptr) {                        // leaf: column x_c of w* (one-hot likelihood)
         if (have) return;
@@ -838,13 +861,13 @@ __device__ __noinline__ void sweep_child(const ChildArgs c, int f, size_t ld, in
         __syncwarp();
         sweep_contract_mma(col, Mw, c.Wt, c.wdp, c.table);
     } else if (c.table) {
-        sweep_contract_table<16>(col, Mw, c.Wt, c.wdp, osc, c.table);
+        sweep_contract_table<16, C>(col, Mw, c.Wt, c.wdp, osc, c.table);
     } else {
         const double psi = c.psi, cc = c.cc;
         if (have == 1) col[0] *= osc;              // b[0] = ℓ[0]
-        if (Mw <= 4) sweep_contract_horner<4>(col, Mw, psi, cc, osc);
-        else if (Mw <= 8) sweep_contract_horner<8>(col, Mw, psi, cc, osc);
-        else sweep_contract_horner<16>(col, Mw, psi, cc, osc);
+        if (Mw <= 4) sweep_contract_horner<4, C>(col, Mw, psi, cc, osc);
+        else if (Mw <= 8) sweep_contract_horner<8, C>(col, Mw, psi, cc, osc);
+        else sweep_contract_horner<16, C>(col, Mw, psi, cc, osc);
     }
 }
 
@@ -996,7 +1019,7 @@ __global__ void __launch_bounds__(128, MINB) sweep_kernel(const __grid_constant_
             }
             cp_async_commit();
         }
-        sweep_child(child_args(ch[0], sc_[2], sc_[3]), f, ld, M0, M0w, R, res0 ? 1 : 0, res0 ? prevSc : 1.0);
+        sweep_child(child_args(ch[0], sc_[2], sc_[3]), f, ld, M0, M0w, GCol{R}, res0 ? 1 : 0, res0 ? prevSc : 1.0);
         if (async1) cp_async_wait_all();
         BLG_TICK(1);
         int Sw = M0w;
@@ -1012,7 +1035,7 @@ __global__ void __launch_bounds__(128, MINB) sweep_kernel(const __grid_constant_
                 // scalars of child i: staged for i == 1, straight from NodeK for the further children of a polytomy
                 const double ei = (i == 1) ? sc_[4] : nk[ch[i].node].e;
                 const double invei = (i == 1) ? sc_[5] : nk[ch[i].node].inve;
-                sweep_child(child_args(ch[i], (i == 1) ? sc_[6] : nk[ch[i].node].psi, (i == 1) ? sc_[7] : nk[ch[i].node].cc), f, ld, Mi, Miw, colB,
+                sweep_child(child_args(ch[i], (i == 1) ? sc_[6] : nk[ch[i].node].psi, (i == 1) ? sc_[7] : nk[ch[i].node].cc), f, ld, Mi, Miw, GCol{colB},
                             (i == 1 && async1) ? 2 : 0, 1.0);
                 BLG_TICK(2);
                 const bool last = (i == k - 1);
@@ -1030,10 +1053,10 @@ __global__ void __launch_bounds__(128, MINB) sweep_kernel(const __grid_constant_
                 const double inve = swap ? sc_[1] : invei;
                 Eraw *= ei;
                 double mx;
-                if (sW < 4) mx = sweep_merge_fast<4>(R, tA, tW, sB, sW, E, invE, e, inve, em0, emg, Xm);
-                else if (sW < 8) mx = sweep_merge_fast<8>(R, tA, tW, sB, sW, E, invE, e, inve, em0, emg, Xm);
-                else if (sW < 12) mx = sweep_merge_fast<12>(R, tA, tW, sB, sW, E, invE, e, inve, em0, emg, Xm);
-                else mx = sweep_merge_fast<20>(R, tA, tW, sB, sW, E, invE, e, inve, em0, emg, Xm);
+                if (sW < 4) mx = sweep_merge_fast<4>(GCol{R}, GCol{const_cast<double*>(tA)}, tW, GCol{const_cast<double*>(sB)}, sW, E, invE, e, inve, em0, emg, Xm);
+                else if (sW < 8) mx = sweep_merge_fast<8>(GCol{R}, GCol{const_cast<double*>(tA)}, tW, GCol{const_cast<double*>(sB)}, sW, E, invE, e, inve, em0, emg, Xm);
+                else if (sW < 12) mx = sweep_merge_fast<12>(GCol{R}, GCol{const_cast<double*>(tA)}, tW, GCol{const_cast<double*>(sB)}, sW, E, invE, e, inve, em0, emg, Xm);
+                else mx = sweep_merge_fast<20>(GCol{R}, GCol{const_cast<double*>(tA)}, tW, GCol{const_cast<double*>(sB)}, sW, E, invE, e, inve, em0, emg, Xm);
                 Sw += Miw;
                 if (last) { mxv = mx; scaled = true; }
                 BLG_TICK(3);
@@ -1048,10 +1071,10 @@ __global__ void __launch_bounds__(128, MINB) sweep_kernel(const __grid_constant_
                 const int Mi = (i == 1) ? M1 : (int)ch[i].cnt[f];
                 const int Miw = (i == 1) ? M1w : warp_max(Mi);
                 const double ei = (i == 1) ? sc_[4] : nk[ch[i].node].e;
-                sweep_child(child_args(ch[i], (i == 1) ? sc_[6] : nk[ch[i].node].psi, (i == 1) ? sc_[7] : nk[ch[i].node].cc), f, ld, Mi, Miw, rO, 0, 1.0);
+                sweep_child(child_args(ch[i], (i == 1) ? sc_[6] : nk[ch[i].node].psi, (i == 1) ? sc_[7] : nk[ch[i].node].cc), f, ld, Mi, Miw, GCol{rO}, 0, 1.0);
 #pragma unroll 1
                 for (int n = Miw + 1; n <= Sw + Miw; ++n) rO[n * 32] = 0.0;
-                sweep_merge_tiled(rA, Sw, rO, Miw, rH, fmin(Eraw, 1.0), ei);
+                sweep_merge_tiled(GCol{rA}, Sw, GCol{rO}, Miw, GCol{rH}, fmin(Eraw, 1.0), ei);
                 Eraw *= ei;
                 Sw += Miw;
 #pragma unroll 1
@@ -1257,7 +1280,14 @@ struct Pat {
 // pattern of a node → pattern of each child, for one (node column, ordered child columns) combination
 struct Link {
     int* d_pidx[BLG_MAXK] = {nullptr};   // nullptr: identity (single child sharing the node's patterns)
-    ~Link() { for (int* q : d_pidx) if (q) cudaFree(q); }
+    // tiles cut on the host for the tile kernels (w = 0: normal range, w = 1: wide range of the node's pattern order): at most
+    // 32 patterns, children's maxima summing to at most the slice, the smaller maximum below the kernel's widest register
+    // merge — so that every tile runs out of shared memory on the register-tiled merge.  nullptr: fixed tiles of 32.
+    int* d_tiles[2] = {nullptr, nullptr};
+    int ntiles[2] = {0, 0};
+    int maxneed[2] = {0, 0};             // largest slice need (doubles per lane) over the tiles
+    bool cut = false;                    // tiles were cut (binary merges); otherwise the generic instantiation runs
+    ~Link() { for (int* q : d_pidx) if (q) cudaFree(q); for (int* q : d_tiles) if (q) cudaFree(q); }
 };
 
 struct Shard {
@@ -1372,7 +1402,7 @@ struct blg_handle {
     cudaEvent_t ev_fork = nullptr, ev_join[8] = {nullptr};
     int pdebug = 0;                           // BLG_PDEBUG: time and describe every pattern launch (stderr)
     int flag_cache = -1;                      // host copy of the device-side range flag: -1 unknown (since the last ε/W build)
-    std::unique_ptr<PList> plist{new PList()}, plist_w{new PList()};
+    std::unique_ptr<PList> plist{new PList()}, plist_w{new PList()}, plist_g{new PList()};
     double last_pattern_bytes = 0.0;          // column bytes the last call actually wrote + read (pattern columns)
     double last_pattern_cols = 0.0, last_family_cols = 0.0;   // node steps × patterns / × families of the last call
 
@@ -1388,8 +1418,8 @@ struct blg_handle {
     std::unique_ptr<GList> glist{new GList()};
     DevBuf<unsigned int> d_tilectr, d_gctr;
     int sm_count = 148;
-    DevBuf<double> gscratch, gscratch_w;
-    size_t sweep_smem_set = 0, g4_smem_set = 0, g16_smem_set = 0, ptile_smem_set[2] = {0, 0};
+    DevBuf<double> gscratch;
+    size_t sweep_smem_set = 0, g4_smem_set = 0, g16_smem_set = 0, ptile_smem_set[3] = {0, 0, 0};
 
     // accounting of the last likelihood call
     double last_bytes = 0.0, last_prune_bytes = 0.0;
@@ -1412,7 +1442,7 @@ struct blg_handle {
         d_prof.free_();
         gpool_release();
         for (auto& e : ev) if (e) cudaEventDestroy(e);
-        gscratch.free_(); gscratch_w.free_(); pat_ll.free_(); d_tilectr.free_(); d_gctr.free_(); d_ticket.free_();
+        gscratch.free_(); pat_ll.free_(); d_tilectr.free_(); d_gctr.free_(); d_ticket.free_();
         if (comm && g_nccl.CommDestroy) g_nccl.CommDestroy(comm);
         d_red.free_();
         for (auto& st_ : gstreams) if (st_) cudaStreamDestroy(st_);
@@ -1990,7 +2020,9 @@ struct blg_handle {
                     }
                     // class, then (own count, the larger child's count) descending: the 32 patterns of a tile get (nearly)
                     // the same loop bounds AND the same register-tiled side
-                    uint64_t cls = m2 >= 36 ? 3 : m2 >= 20 ? 2 : (mc[0] >= mc[1] ? 1 : 0);
+                    // (polytomies: no wide class — their tiles run on the generic instantiation, anything beyond its register
+                    // merges on the general kernel)
+                    uint64_t cls = (m2 >= 36 || (k > 2 && m2 >= 20)) ? 3 : m2 >= 20 ? 2 : (mc[0] >= mc[1] ? 1 : 0);
                     if (cls == 3) ++nvery; else if (cls == 2) ++nwide;
                     key[i] = (cls << 60) | ((uint64_t)hx[r] << 32) | ((uint64_t)std::max(mc[0], mc[1]) << 16) | (uint64_t)std::min(mc[0], mc[1]);
                 }
@@ -2037,6 +2069,39 @@ struct blg_handle {
                 if (px[Pu->fam2pat[f]] != Pc->fam2pat[f]) throw std::runtime_error("logpdf: node patterns do not match the topology (call blg_set_profiles again after changing the species tree)");
             CK(cudaMalloc(&L->d_pidx[j], Pu->ld * sizeof(int)));
             CK(cudaMemcpy(L->d_pidx[j], px.data(), Pu->ld * sizeof(int), cudaMemcpyHostToDevice));
+        }
+        // ---- cut the tiles -------------------------------------------------------------------------------------------
+        const int k = (int)ord.size();
+        if (k <= 2) {
+            Pat* P0 = pat_of(S, S.Tp[ord[0]]);
+            Pat* P1 = k == 2 ? pat_of(S, S.Tp[ord[1]]) : nullptr;
+            L->cut = true;
+            for (int w = 0; w < 2; ++w) {
+                const int lo = w ? Pu->nvery : Pu->nvery + Pu->nwide, hi = w ? Pu->nvery + Pu->nwide : Pu->U;
+                if (hi <= lo) continue;
+                const int tmax = w ? 36 : 20;                                   // widest register merge of the instantiation
+                const int lim = w ? 104 : std::max(56, std::min(104, Pu->xmax + 6));
+                std::vector<int> tb;
+                int m0 = 0, m1 = 0, cnt = 0, need = 0;
+                for (int q = lo; q < hi; ++q) {
+                    const int r = Pu->rep[q];
+                    const int a = P0->h_cnt[P0->fam2pat[r]], b = P1 ? (int)P1->h_cnt[P1->fam2pat[r]] : 0;
+                    const int n0 = std::max(m0, a), n1 = std::max(m1, b);
+                    const bool fits = cnt < 32 && n0 + n1 + k + 1 <= lim && (k == 1 || std::min(n0, n1) < tmax);
+                    if (cnt == 0 || !fits) {                                    // (a single pattern always fits: its class says so)
+                        tb.push_back(q);
+                        m0 = a; m1 = b; cnt = 1;
+                    } else { m0 = n0; m1 = n1; ++cnt; }
+                    need = std::max(need, m0 + m1 + k + 1);
+                }
+                tb.push_back(hi);
+                L->ntiles[w] = (int)tb.size() - 1;
+                L->maxneed[w] = need;
+                CK(cudaMalloc(&L->d_tiles[w], tb.size() * sizeof(int)));
+                CK(cudaMemcpy(L->d_tiles[w], tb.data(), tb.size() * sizeof(int), cudaMemcpyHostToDevice));
+            }
+            if (pdebug) fprintf(stderr, "[blg link] node %d U %d x %d: tiles %d (need %d) | wide tiles %d (need %d)\n", u, Pu->U, Pu->xmax,
+                                L->ntiles[0], L->maxneed[0], L->ntiles[1], L->maxneed[1]);
         }
         S.links[key] = L;
         return L.get();
@@ -2102,9 +2167,11 @@ struct blg_handle {
             while (pos < todo.size()) {
                 // three launches per level: [0, nvery) of every node on the general kernel (one warp per pattern),
                 // [nvery, nvery + nwide) on the wide tile kernel, the rest on the tile kernel
+                // tile lists: 0 = tile kernel, 1 = wide tile kernel (both over host-cut tiles, shared-memory addressing),
+                // 2 = the generic instantiation (polytomies: fixed tiles, the column may spill to global scratch)
                 struct TL { PList* L; std::vector<PStep> chain; int nch = 0, ntiles = 0, worst = 1; };
-                TL tl[2];
-                tl[0].L = plist.get(); tl[1].L = plist_w.get();
+                TL tl[3];
+                tl[0].L = plist.get(); tl[1].L = plist_w.get(); tl[2].L = plist_g.get();
                 for (auto& t_ : tl) memset(t_.L, 0, sizeof(int) * 4);
                 GList& G = *glist;
                 memset(&G, 0, sizeof(int) * 4);
@@ -2139,14 +2206,15 @@ struct blg_handle {
                     for (int w = 0; w < 2; ++w) {                  // w = 0: tile kernel, w = 1: wide tile kernel
                         const int lo = w ? ng : nw, hi = w ? nw : Pu->U;
                         if (hi <= lo) continue;
-                        TL& T = tl[w];
+                        TL& T = tl[lk->cut ? w : 2];
+                        require(lk->cut || w == 0, "internal: a polytomy with a wide pattern class");
                         PList& L = *T.L;
-                        // a tile whose two largest children both reach the widest register merge takes the chained-tile
-                        // merge, which needs three columns (rare: the pattern order keeps such tiles apart)
-                        T.worst = std::max(T.worst, std::max(3 * (sum + 1), sum + k + 1));
+                        if (lk->cut) T.worst = std::max(T.worst, lk->maxneed[w]);                      // exact: the host cut the tiles
+                        else T.worst = std::max(T.worst, std::max(3 * (sum + 1), sum + k + 1));       // a bound: chained-tile merge, 3 columns
                         PStep& ps = L.step[L.nsteps++];
                         memset(&ps, 0, sizeof(ps));
                         ps.k = k; ps.first = T.nch; ps.node = u; ps.U = hi; ps.tile0 = T.ntiles; ps.ld = (int)Pu->ld; ps.p0 = lo;
+                        ps.tstart = lk->cut ? lk->d_tiles[w] : nullptr;
                         ps.cnt = Pu->d_cnt; ps.out = o->ell; ps.out_scl = o->scl;
                         ps.chain_first = (int)T.chain.size(); ps.nchain = nc;
                         if (u == 0 && rootw_valid && rootw_rows == root_rows()) {      // the root: integrate on the spot
@@ -2182,7 +2250,7 @@ struct blg_handle {
                             T.chain.push_back(cs);
                             below = v;
                         }
-                        T.ntiles += (hi - lo + 31) / 32;
+                        T.ntiles += lk->cut ? lk->ntiles[w] : (hi - lo + 31) / 32;
                     }
                     if (ng > 0) {
                         GStep& gs = G.step[G.nsteps++];
@@ -2211,7 +2279,7 @@ struct blg_handle {
                     for (int v : chain[u]) count_step_bytes(S, v);
                     ++pos;
                 }
-                require(tl[0].L->nsteps + tl[1].L->nsteps + G.nsteps > 0, "sweep: a node has more children than one launch can describe");
+                require(tl[0].L->nsteps + tl[1].L->nsteps + tl[2].L->nsteps + G.nsteps > 0, "sweep: a node has more children than one launch can describe");
                 cudaEvent_t dbg[4] = {nullptr, nullptr, nullptr, nullptr};
                 if (pdebug) { for (auto& e : dbg) CK(cudaEventCreate(&e)); CK(cudaEventRecord(dbg[0], stream)); }
                 if (G.nsteps > 0) {
@@ -2236,37 +2304,40 @@ struct blg_handle {
                     CK(cudaEventRecord(ev_main, stream));          // everything below this level is in `stream` up to here
                     CK(cudaStreamWaitEvent(stream2, ev_main, 0));
                 }
-                for (int w = 1; w >= 0; --w) {                     // the wide tiles first: they are the long ones
+                for (int w : {1, 2, 0}) {                          // the wide tiles first: they are the long ones
                     TL& T = tl[w];
                     PList& L = *T.L;
                     cudaStream_t stream = (w == 1 && side) ? stream2 : this->stream;
                     if (L.nsteps > 0) {
                         for (size_t q = 0; q < T.chain.size(); ++q) L.step[L.nsteps + q] = T.chain[q];
                         L.ntiles = T.ntiles;
-                        // doubles per lane of a warp's shared slice; rare larger tiles use global scratch
-                        const int cap = std::min(T.worst, w ? 104 : std::max(slice_cap, 56));
-                        caps[w] = cap;
+                        // doubles per lane of a warp's shared slice: exactly what the launch's tiles need (w < 2); the generic
+                        // instantiation sends larger tiles to global scratch
+                        const int cap = w == 2 ? std::min(T.worst, std::max(slice_cap, 56)) : T.worst;
+                        caps[w == 1 ? 1 : 0] = std::max(caps[w == 1 ? 1 : 0], cap);
                         const int wpb = 4;
                         double* gs = nullptr;
                         size_t gstride = 0;
                         if (T.worst > cap) {
                             gstride = (size_t)T.worst * 32;
-                            DevBuf<double>& sb = w ? gscratch_w : gscratch;
-                            sb.ensure(gstride * (size_t)T.ntiles);
-                            gs = sb.p;
+                            gscratch.ensure(gstride * (size_t)T.ntiles);
+                            gs = gscratch.p;
                         }
                         const size_t smem = (size_t)cap * 32 * wpb * sizeof(double);
                         if (smem > ptile_smem_set[w]) {
-                            if (w) CK(cudaFuncSetAttribute(ptile_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-                            else CK(cudaFuncSetAttribute(ptile_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+                            if (w == 1) CK(cudaFuncSetAttribute(ptile_kernel<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+                            else if (w == 0) CK(cudaFuncSetAttribute(ptile_kernel<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+                            else CK(cudaFuncSetAttribute(ptile_kernel<false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
                             ptile_smem_set[w] = smem;
                         }
-                        if (w) ptile_kernel<true><<<(T.ntiles + wpb - 1) / wpb, 32 * wpb, smem, stream>>>(L, d_nk.p, d_flags.p, d_ran.p, cap, gs, gstride);
-                        else ptile_kernel<false><<<(T.ntiles + wpb - 1) / wpb, 32 * wpb, smem, stream>>>(L, d_nk.p, d_flags.p, d_ran.p, cap, gs, gstride);
+                        const int nb = (T.ntiles + wpb - 1) / wpb;
+                        if (w == 1) ptile_kernel<true, true><<<nb, 32 * wpb, smem, stream>>>(L, d_nk.p, d_flags.p, d_ran.p, cap, gs, gstride);
+                        else if (w == 0) ptile_kernel<false, true><<<nb, 32 * wpb, smem, stream>>>(L, d_nk.p, d_flags.p, d_ran.p, cap, gs, gstride);
+                        else ptile_kernel<false, false><<<nb, 32 * wpb, smem, stream>>>(L, d_nk.p, d_flags.p, d_ran.p, cap, gs, gstride);
                         CK(cudaGetLastError());
                         last_launches++;
                     }
-                    if (pdebug) CK(cudaEventRecord(dbg[3 - w], stream));
+                    if (pdebug && w != 2) CK(cudaEventRecord(dbg[3 - w], stream));
                 }
                 if (side) {                                        // join: the next level reads what the wide launch wrote
                     CK(cudaEventRecord(ev_side, stream2));

@@ -31,6 +31,8 @@ struct PStep {
     int k, first, node, U;
     int tile0, ld;         // first tile of this step in the launch; stride of the node's pattern columns
     int p0;                // first pattern the tiles cover (the patterns before it run on the general kernel, one warp each)
+    const int* tstart;     // host-cut tiles: tile t of this step covers patterns tstart[t] .. tstart[t+1]-1 (at most 32, and few
+                           // enough that the tile fits the shared slice); nullptr: fixed tiles of 32 from p0
     int chain_first, nchain, pad_;   // single-child steps on the same patterns (WGD-type nodes above this one): they follow in
                                      // the same warp, with the column still in shared memory; stored at step[nsteps + chain_first ...]
     double* out;
@@ -41,7 +43,7 @@ struct PStep {
     const double* rootw;
     double* pat_ll;
 };
-#define BLG_P_MAXSTEPS 120
+#define BLG_P_MAXSTEPS 110
 #define BLG_P_MAXCHILD 300
 struct PList {
     int nsteps, ntiles, first_of_call, pad_;
@@ -53,11 +55,15 @@ __device__ __forceinline__ ChildArgs child_args(const PChild& c, double psi, dou
 
 // WIDE: the instantiation for patterns whose smaller child has 20..35 counts — register-tiled merges 28 and 36 wide, which
 // need more than 128 registers (2 blocks per SM instead of 4); such patterns sit at the front of a node's order.
-template <bool WIDE>
+// SH: every tile of the launch fits its shared slice (the host cut the tiles that way): the working column is addressed as
+// an offset into shared memory (SCol: LDS/STS).  !SH: the column may live in global scratch (GCol, generic accesses) —
+// polytomies and anything else the host could not bound.
+template <bool WIDE, bool SH>
 __global__ void __launch_bounds__(128, WIDE ? 2 : 4) ptile_kernel(const __grid_constant__ PList L, const NodeK* __restrict__ nk,
                                                        const int* __restrict__ flags, unsigned int* __restrict__ ran,
                                                        int slice_cap, double* gscratch, size_t gs_stride) {
     extern __shared__ double smem[];
+    typedef typename std::conditional<SH, SCol, GCol>::type C;
     if (flags[0] == 0) return;        // some node is outside the table-free forms' range: the caller re-runs the general kernel
     const unsigned lane = threadIdx.x & 31u;
     const int warp = threadIdx.x >> 5;
@@ -71,11 +77,13 @@ __global__ void __launch_bounds__(128, WIDE ? 2 : 4) ptile_kernel(const __grid_c
     const PStep& st = L.step[lo];
     const int k = st.k;
     const PChild* ch = &L.child[st.first];
-    int p = st.p0 + (tile - st.tile0) * 32 + (int)lane;
-    const bool live = p < st.U;
-    if (!live) p = st.U - 1;          // idle lanes shadow the last pattern (loads stay in bounds; they never store)
+    int p, pend;
+    if (st.tstart != nullptr) { p = st.tstart[tile - st.tile0] + (int)lane; pend = st.tstart[tile - st.tile0 + 1]; }
+    else { p = st.p0 + (tile - st.tile0) * 32 + (int)lane; pend = st.U; }
+    const bool live = p < pend;
+    if (!live) p = pend - 1;          // idle lanes shadow the tile's last pattern (loads stay in bounds; they never store)
     const size_t ldo = (size_t)st.ld;
-    double* sl = smem + (size_t)warp * slice_cap * 32 + lane;
+    const int sloff = warp * slice_cap * 32 + (int)lane;
     const int X = st.cnt[p];
     const int Xw = warp_max(X);
     const double ip0 = nk[st.node].ip0;          // 1, or NaN where the reference's column is NaN (here or below)
@@ -102,46 +110,50 @@ __global__ void __launch_bounds__(128, WIDE ? 2 : 4) ptile_kernel(const __grid_c
     // which side of a binary merge is register-tiled: the child with the smaller bound in THIS tile
     const bool swap = (k == 2) && (M0w < M1w);
     constexpr int TMAX = WIDE ? 36 : 20;      // widest register-tiled merge of this instantiation
-    bool tiled = (k == 2) ? (min(M0w, M1w) >= TMAX) : (M1w >= TMAX);
+    // (host-cut tiles never need the chained-tile merge: the smaller maximum stays below TMAX by construction)
+    bool tiled = SH ? false : ((k == 2) ? (min(M0w, M1w) >= TMAX) : (M1w >= TMAX));
 #pragma unroll 1
     for (int i = 2; i < k; ++i) {
         const int ci = ch[i].pidx ? ch[i].pidx[p] : p;
         const int Miw = warp_max((int)ch[i].cnt[ci]);
         sumw += Miw;
-        if (Miw >= TMAX) tiled = true;
+        if (!SH && Miw >= TMAX) tiled = true;
         if (ch[i].scl) sclsum += ch[i].scl[ci];
     }
     const int need = tiled ? 3 * (sumw + 1) : sumw + k + 1;
-    double* R = (need <= slice_cap) ? sl : gscratch + (size_t)tile * gs_stride + lane;
+    C R;
+    bool insl = true;
+    if constexpr (SH) { R = SCol{sloff}; (void)need; }
+    else { insl = need <= slice_cap; R = GCol{insl ? smem + sloff : gscratch + (size_t)tile * gs_stride + lane}; }
     const NodeK k0 = nk[ch[0].node];
     // the input columns of the first two children are gathers (every lane reads another pattern's column): all requests
     // are issued at once as asynchronous copies — a loop of dependent loads would pay one L2 round trip per element
-    const bool async0 = R == sl;
-    const bool async1 = (k >= 2) && !tiled && R == sl;
+    const bool async0 = insl;
+    const bool async1 = (k >= 2) && !tiled && insl;
     if (async0) {
         if (ch[0].ell == nullptr) {
             const double* row = ch[0].Wt + (size_t)M0 * ch[0].wdp;
 #pragma unroll 1
-            for (int s = 0; s <= M0w; ++s) cp_async_f64(R + s * 32, (s <= M0) ? row + s : row, s <= M0);
+            for (int s = 0; s <= M0w; ++s) cp_async_f64(R.ptr(s * 32), (s <= M0) ? row + s : row, s <= M0);
         } else {
             const double* src = ch[0].ell + c0;
             const size_t ld0 = (size_t)ch[0].ld;
 #pragma unroll 1
-            for (int j = 0; j <= M0w; ++j) cp_async_f64(R + j * 32, (j <= M0) ? src + (size_t)j * ld0 : src, j <= M0);
+            for (int j = 0; j <= M0w; ++j) cp_async_f64(R.ptr(j * 32), (j <= M0) ? src + (size_t)j * ld0 : src, j <= M0);
         }
         cp_async_commit();
     }
     if (async1) {
-        double* dst = R + (size_t)(M0w + 1) * 32;
+        const C dst = R + (M0w + 1) * 32;
         if (ch[1].ell == nullptr) {
             const double* row = ch[1].Wt + (size_t)M1 * ch[1].wdp;
 #pragma unroll 1
-            for (int s = 0; s <= M1w; ++s) cp_async_f64(dst + s * 32, (s <= M1) ? row + s : row, s <= M1);
+            for (int s = 0; s <= M1w; ++s) cp_async_f64(dst.ptr(s * 32), (s <= M1) ? row + s : row, s <= M1);
         } else {
             const double* src = ch[1].ell + c1;
             const size_t ld1 = (size_t)ch[1].ld;
 #pragma unroll 1
-            for (int j = 0; j <= M1w; ++j) cp_async_f64(dst + j * 32, (j <= M1) ? src + (size_t)j * ld1 : src, j <= M1);
+            for (int j = 0; j <= M1w; ++j) cp_async_f64(dst.ptr(j * 32), (j <= M1) ? src + (size_t)j * ld1 : src, j <= M1);
         }
         cp_async_commit();
     }
@@ -160,14 +172,14 @@ __global__ void __launch_bounds__(128, WIDE ? 2 : 4) ptile_kernel(const __grid_c
             const int ci = (i == 1) ? c1 : (ch[i].pidx ? ch[i].pidx[p] : p);
             const int Mi = (i == 1) ? M1 : (int)ch[i].cnt[ci];
             const int Miw = (i == 1) ? M1w : warp_max(Mi);
-            double* colB = R + (size_t)(Sw + 1) * 32;
+            const C colB = R + (Sw + 1) * 32;
             const NodeK ki = nk[ch[i].node];
             sweep_child(child_args(ch[i], ki.psi, ki.cc), ci, (size_t)ch[i].ld, Mi, Miw, colB, (i == 1 && async1) ? 2 : 0, 1.0);
             const bool last = (i == k - 1);
             const double em0 = last ? ip0 : 1.0, emg = last ? inv : 1.0;
             const int Xm = last ? X : 0x7fffffff;
-            const double* tA = swap ? colB : R;
-            const double* sB = swap ? R : colB;
+            const C tA = swap ? colB : R;
+            const C sB = swap ? R : colB;
             const int tW = swap ? Miw : Sw, sW = swap ? Sw : Miw;
             const double Epre = fmin(Eraw, 1.0);              // clamped prefix of the children merged before this one
             const double E = swap ? fmin(ki.e, 1.0) : Epre;
@@ -189,11 +201,11 @@ __global__ void __launch_bounds__(128, WIDE ? 2 : 4) ptile_kernel(const __grid_c
             Sw += Miw;
             if (last) { mxv = mx; scaled = true; }
         }
-    } else {
+    } else if constexpr (!SH) {
         const int cap = sumw + 1;
-        double* rA = R;
-        double* rH = R + (size_t)cap * 32;
-        double* rO = R + (size_t)2 * cap * 32;
+        const C rA = R;
+        const C rH = R + cap * 32;
+        const C rO = R + 2 * cap * 32;
 #pragma unroll 1
         for (int i = 1; i < k; ++i) {
             const int ci = (i == 1) ? c1 : (ch[i].pidx ? ch[i].pidx[p] : p);
