@@ -616,14 +616,12 @@ struct GCol {
     __device__ __forceinline__ double& operator[](int i) const { return p[i]; }
     __device__ __forceinline__ GCol operator+(int k) const { return GCol{p + k}; }
     __device__ __forceinline__ double* ptr(int i) const { return p + i; }
-    __device__ __forceinline__ bool same(const GCol& o) const { return p == o.p; }
 };
 struct SCol {
     int off;
     __device__ __forceinline__ double& operator[](int i) const { return blg_smem[off + i]; }
     __device__ __forceinline__ SCol operator+(int k) const { return SCol{off + k}; }
     __device__ __forceinline__ double* ptr(int i) const { return &blg_smem[off + i]; }
-    __device__ __forceinline__ bool same(const SCol& o) const { return off == o.off; }
 };
 
 // in-place table contraction (branch below a WGD/WGT): col[s] ← Σ_{j=s..min(Mw, band·s)} Wt[j*wdp+s]·col[j]
@@ -1280,6 +1278,7 @@ struct Pat {
 // pattern of a node → pattern of each child, for one (node column, ordered child columns) combination
 struct Link {
     int* d_pidx[BLG_MAXK] = {nullptr};   // nullptr: identity (single child sharing the node's patterns)
+    uint16_t* d_xcnt[BLG_MAXK] = {nullptr};   // the child's count per NODE pattern (saves the dependent load cnt_child[pidx[p]])
     // tiles cut on the host for the tile kernels (w = 0: normal range, w = 1: wide range of the node's pattern order): at most
     // 32 patterns, children's maxima summing to at most the slice, the smaller maximum below the kernel's widest register
     // merge — so that every tile runs out of shared memory on the register-tiled merge.  nullptr: fixed tiles of 32.
@@ -1287,7 +1286,7 @@ struct Link {
     int ntiles[2] = {0, 0};
     int maxneed[2] = {0, 0};             // largest slice need (doubles per lane) over the tiles
     bool cut = false;                    // tiles were cut (binary merges); otherwise the generic instantiation runs
-    ~Link() { for (int* q : d_pidx) if (q) cudaFree(q); for (int* q : d_tiles) if (q) cudaFree(q); }
+    ~Link() { for (int* q : d_pidx) if (q) cudaFree(q); for (int* q : d_tiles) if (q) cudaFree(q); for (uint16_t* q : d_xcnt) if (q) cudaFree(q); }
 };
 
 struct Shard {
@@ -2069,6 +2068,10 @@ struct blg_handle {
                 if (px[Pu->fam2pat[f]] != Pc->fam2pat[f]) throw std::runtime_error("logpdf: node patterns do not match the topology (call blg_set_profiles again after changing the species tree)");
             CK(cudaMalloc(&L->d_pidx[j], Pu->ld * sizeof(int)));
             CK(cudaMemcpy(L->d_pidx[j], px.data(), Pu->ld * sizeof(int), cudaMemcpyHostToDevice));
+            std::vector<uint16_t> xc(Pu->ld, 0);
+            for (size_t q = 0; q < Pu->ld; ++q) xc[q] = Pc->h_cnt[px[q]];
+            CK(cudaMalloc(&L->d_xcnt[j], Pu->ld * sizeof(uint16_t)));
+            CK(cudaMemcpy(L->d_xcnt[j], xc.data(), Pu->ld * sizeof(uint16_t), cudaMemcpyHostToDevice));
         }
         // ---- cut the tiles -------------------------------------------------------------------------------------------
         const int k = (int)ord.size();
@@ -2230,6 +2233,7 @@ struct blg_handle {
                             if (csl[j]) { pc.ell = csl[j]->ell; pc.scl = csl[j]->scl; }
                             pc.cnt = Pc->d_cnt;
                             pc.pidx = lk->d_pidx[j];
+                            pc.xcnt = lk->d_xcnt[j];
                             pc.Wt = tabs[c].Wt; pc.wdp = tabs[c].wdp; pc.table = table_band(c);
                             pc.node = c; pc.ld = (int)Pc->ld;
                         }

@@ -23,6 +23,7 @@ struct PChild {
     const int* scl;
     const uint16_t* cnt;   // child's count per pattern
     const int* pidx;       // node pattern → child pattern (nullptr: identity, the single child of a WGD-type node)
+    const uint16_t* xcnt;  // the child's count per NODE pattern (nullptr: read cnt[child pattern])
     const double* Wt;      // transposed w* of the child's branch (leaf gather, WGD/WGT-after contraction)
     int wdp, table;
     int node, ld;          // node index of the child (NodeK); stride of its pattern columns
@@ -44,7 +45,7 @@ struct PStep {
     double* pat_ll;
 };
 #define BLG_P_MAXSTEPS 110
-#define BLG_P_MAXCHILD 300
+#define BLG_P_MAXCHILD 270
 struct PList {
     int nsteps, ntiles, first_of_call, pad_;
     PStep step[BLG_P_MAXSTEPS];
@@ -100,9 +101,9 @@ __global__ void __launch_bounds__(128, WIDE ? 2 : 4) ptile_kernel(const __grid_c
         return;
     }
     const int c0 = ch[0].pidx ? ch[0].pidx[p] : p;
-    const int M0 = ch[0].cnt[c0];
+    const int M0 = ch[0].xcnt ? ch[0].xcnt[p] : ch[0].cnt[c0];
     int c1 = 0, M1 = 0;
-    if (k >= 2) { c1 = ch[1].pidx ? ch[1].pidx[p] : p; M1 = ch[1].cnt[c1]; }
+    if (k >= 2) { c1 = ch[1].pidx ? ch[1].pidx[p] : p; M1 = ch[1].xcnt ? ch[1].xcnt[p] : ch[1].cnt[c1]; }
     int sclsum = (ch[0].scl ? ch[0].scl[c0] : 0) + ((k >= 2 && ch[1].scl) ? ch[1].scl[c1] : 0);
     const int M0w = warp_max(M0);
     const int M1w = warp_max(M1);
