@@ -1224,6 +1224,7 @@ struct Col {
     int xmax = 0;
     double colsum = 0.0;             // Σ_f (x_f + 1): the algorithmic byte count, and the size of a ragged slab
     std::shared_ptr<Slab> slab;      // null: never computed ("-Inf")
+    int lmax = 0x7fffffff;           // fast set: entries above this count are left to the heavy family set (see set_profiles)
     const uint32_t* off = nullptr;   // ragged (heavy) shard: per-family offsets of the column, prefix sums of (count+1); shared between aliases
 };
 struct HostTab {                     // host mirror of NodeTab allocations
@@ -1340,7 +1341,10 @@ struct blg_handle {
     DevBuf<double>& fam_ll = F.fam_ll;
     double& weight_total = F.weight_total;
     int Ntot = 0;                            // patterns of this handle (both shards)
-    std::vector<int> loc;                    // caller's pattern index -> device index (fast) or -1 - index (heavy)
+    std::vector<int> loc;                    // caller's pattern index -> index in the fast set (which holds every family)
+    std::vector<int> hloc;                   // caller's pattern index -> index in the heavy set, -1 for families below the heavy bound
+    std::vector<int> H2F;                    // heavy index -> fast index
+    std::map<const uint16_t*, int*> hpat;    // per column (fast set's count array): device [H.N] node pattern of every heavy family, -1 where the entry is heavy
     int heavy_min = BLG_FAST_MAXCOUNT + 1;   // families whose root count reaches this go to the heavy shard (BLG_HEAVY_MIN)
     DevBuf<double> partial, result, rootw;
     int maxcount = 0;
@@ -1430,6 +1434,7 @@ struct blg_handle {
     ~blg_handle() {
         cudaSetDevice(device);
         if (stream) cudaStreamSynchronize(stream);
+        for (auto& kv : hpat) cudaFree(kv.second);
         F.release();
         H.release();
         F.weight.free_(); F.fam_ll.free_(); H.weight.free_(); H.fam_ll.free_();
@@ -1468,7 +1473,7 @@ struct blg_handle {
     }
     size_t slab_doubles(Shard& S, const Col& col) {
         if (S.ragged) return (size_t)col.colsum + 8;
-        if (pat_mode) { Pat* P = pat_of(S, col); return (size_t)(P->xmax + 1) * P->ld; }
+        if (pat_mode) { Pat* P = pat_of(S, col); return std::max<size_t>((size_t)(P->xmax + 1) * P->ld, 32); }
         return (size_t)(col.xmax + 1) * S.ld;
     }
     std::shared_ptr<Slab> new_slab(Shard& S, size_t nd) {
@@ -1850,6 +1855,22 @@ struct blg_handle {
         }
     }
 
+    // node pattern of every heavy family at column c (-1 where its entry is heavy), on the device
+    const int* hpat_of(int c) {
+        require(pat_mode, "heavy families need the node-pattern evaluation (BLG_DEDUP=0 and the gradient do not support them)");
+        const uint16_t* key = F.Tp[c].cnt;
+        auto it = hpat.find(key);
+        if (it != hpat.end()) return it->second;
+        Pat* P = pat_of(F, F.Tp[c]);
+        std::vector<int> v(std::max(H.N, 1), -1);
+        for (int i = 0; i < H.N; ++i) v[i] = P->fam2pat[H2F[i]];
+        int* d = nullptr;
+        CK(cudaMalloc(&d, v.size() * sizeof(int)));
+        CK(cudaMemcpy(d, v.data(), v.size() * sizeof(int), cudaMemcpyHostToDevice));
+        hpat[key] = d;
+        return d;
+    }
+
     // the general kernel over a shard: one warp per family, any counts, any parameters.
     // when = 0: always; when = 1: only if the device-side range flag says the sweep kernel could not run (fast shard).
     void general_sweep(Shard& S, const std::vector<int>& nodes, int when, bool count_bytes) {
@@ -1882,6 +1903,12 @@ struct blg_handle {
                         gc.off = S.ragged ? S.Tp[c].off : nullptr;
                         gc.ld = (int)S.ld;
                         if (count_bytes) last_bytes += 8.0 * S.Tp[c].colsum + 4.0 * S.N;
+                        if (S.ragged) {              // light entries of this child: the fast set's pattern columns (computed just before)
+                            Pat* Pc = pat_of(F, F.Tp[c]);
+                            Slab* ps = readable(F, c);
+                            gc.fpat = hpat_of(c);
+                            gc.pell = ps->ell; gc.pscl = ps->scl; gc.pld = (int)Pc->ld;
+                        }
                     }
                     gc.cnt = S.Tp[c].cnt;
                     gc.node = c;
@@ -1899,6 +1926,7 @@ struct blg_handle {
                 gs.out = o->ell; gs.out_scl = o->scl; gs.cnt = S.Tp[u].cnt;
                 gs.out_off = S.ragged ? S.Tp[u].off : nullptr;
                 gs.out_ld = S.ld;
+                gs.fpat = S.ragged ? hpat_of(u) : nullptr;
                 if (count_bytes) last_bytes += 8.0 * S.Tp[u].colsum + 4.0 * S.N;
                 prev_node = u;
                 ++pos;
@@ -1938,7 +1966,7 @@ struct blg_handle {
         return S.h_counts.data() + (col.cnt - S.count_allocs[0]);
     }
     void upload_pat(Pat& P) {
-        P.ld = ((size_t)P.U + 31) / 32 * 32;
+        P.ld = std::max<size_t>(((size_t)P.U + 31) / 32 * 32, 32);
         std::vector<uint16_t> st(P.ld, P.h_cnt.empty() ? 0 : P.h_cnt.back());
         std::copy(P.h_cnt.begin(), P.h_cnt.end(), st.begin());
         CK(cudaMalloc(&P.d_cnt, P.ld * sizeof(uint16_t)));
@@ -1961,20 +1989,27 @@ struct blg_handle {
             }
             auto P = std::make_shared<Pat>();
             const uint16_t* hx = host_counts(S, cu);
-            std::vector<int> id(N);
+            // entries above the column's bound belong to the heavy family set: pattern -1; so does every entry with such a child
+            const int hm = cu.lmax + 1;
+            std::vector<int> id(N, -1);
             int U = 0;
             std::vector<Pat*> cp;
             if (k == 0) {
                 std::vector<int> tab(cu.xmax + 1, -1);
-                for (int f = 0; f < N; ++f) tab[hx[f]] = 0;
+                for (int f = 0; f < N; ++f) if (hx[f] < hm) tab[hx[f]] = 0;
                 for (int v = cu.xmax; v >= 0; --v) if (tab[v] == 0) tab[v] = U++;      // descending counts
-                for (int f = 0; f < N; ++f) id[f] = tab[hx[f]];
+                for (int f = 0; f < N; ++f) if (hx[f] < hm) id[f] = tab[hx[f]];
             } else {
                 for (int c : children[u]) {
                     require(c < (int)S.Tp.size(), "logpdf: child id beyond the profile columns");
                     cp.push_back(S.pats.at(S.Tp[c].cnt).get());
                 }
-                id = cp[0]->fam2pat;
+                for (int f = 0; f < N; ++f) {
+                    if (hx[f] >= hm) continue;
+                    bool ok = true;
+                    for (int j = 0; j < k; ++j) ok = ok && cp[j]->fam2pat[f] >= 0;
+                    if (ok) id[f] = cp[0]->fam2pat[f];
+                }
                 U = cp[0]->U;
                 for (int j = 1; j < k; ++j) {
                     const std::vector<int>& b = cp[j]->fam2pat;
@@ -1983,6 +2018,7 @@ struct blg_handle {
                     if (space <= std::max<uint64_t>(8ull * (uint64_t)N, 1ull << 16)) {
                         std::vector<int> tab((size_t)space, -1);
                         for (int f = 0; f < N; ++f) {
+                            if (id[f] < 0) continue;
                             int& t_ = tab[(size_t)((uint64_t)id[f] * Ub + (uint64_t)b[f])];
                             if (t_ < 0) t_ = next++;
                             id[f] = t_;
@@ -1991,6 +2027,7 @@ struct blg_handle {
                         std::unordered_map<uint64_t, int> mp;
                         mp.reserve((size_t)N * 2);
                         for (int f = 0; f < N; ++f) {
+                            if (id[f] < 0) continue;
                             auto ins = mp.emplace((uint64_t)id[f] * Ub + (uint64_t)b[f], next);
                             if (ins.second) ++next;
                             id[f] = ins.first->second;
@@ -2001,8 +2038,15 @@ struct blg_handle {
             }
             // a family of each pattern, then the patterns in descending order of (own count, children's counts): the 32
             // patterns of a tile get (nearly) the same loop bounds, and the heaviest tiles start first
+            {   // ids may have gaps (patterns of a child that only heavy entries of this node use): make them dense
+                std::vector<int> dense(std::max(U, 1), -1);
+                int nu = 0;
+                for (int f = 0; f < N; ++f) if (id[f] >= 0 && dense[id[f]] < 0) dense[id[f]] = nu++;
+                for (int f = 0; f < N; ++f) if (id[f] >= 0) id[f] = dense[id[f]];
+                U = nu;
+            }
             std::vector<int> rep(U, -1);
-            for (int f = 0; f < N; ++f) if (rep[id[f]] < 0) rep[id[f]] = f;
+            for (int f = 0; f < N; ++f) if (id[f] >= 0 && rep[id[f]] < 0) rep[id[f]] = f;
             std::vector<int> ord(U);
             for (int i = 0; i < U; ++i) ord[i] = i;
             int nvery = 0, nwide = 0;
@@ -2035,11 +2079,11 @@ struct blg_handle {
             P->rep.resize(U);
             P->h_cnt.resize(U);
             for (int i = 0; i < U; ++i) { P->rep[i] = rep[ord[i]]; P->h_cnt[i] = hx[rep[ord[i]]]; }
-            for (int f = 0; f < N; ++f) id[f] = newidx[id[f]];
+            for (int f = 0; f < N; ++f) if (id[f] >= 0) id[f] = newidx[id[f]];
             P->fam2pat.swap(id);
-            P->xmax = cu.xmax;
+            P->xmax = 0;
             P->colsum = 0.0;
-            for (int i = 0; i < U; ++i) P->colsum += (double)P->h_cnt[i] + 1.0;
+            for (int i = 0; i < U; ++i) { P->colsum += (double)P->h_cnt[i] + 1.0; P->xmax = std::max(P->xmax, (int)P->h_cnt[i]); }
             upload_pat(*P);
             S.pats[cu.cnt] = P;
         }
@@ -2065,11 +2109,11 @@ struct blg_handle {
             // the node's pattern must determine the child's for EVERY family (it does when the patterns were built for
             // this tree; a different tree over the same columns needs new patterns)
             for (int f = 0; f < S.N; ++f)
-                if (px[Pu->fam2pat[f]] != Pc->fam2pat[f]) throw std::runtime_error("logpdf: node patterns do not match the topology (call blg_set_profiles again after changing the species tree)");
+                if (Pu->fam2pat[f] >= 0 && px[Pu->fam2pat[f]] != Pc->fam2pat[f]) throw std::runtime_error("logpdf: node patterns do not match the topology (call blg_set_profiles again after changing the species tree)");
             CK(cudaMalloc(&L->d_pidx[j], Pu->ld * sizeof(int)));
             CK(cudaMemcpy(L->d_pidx[j], px.data(), Pu->ld * sizeof(int), cudaMemcpyHostToDevice));
             std::vector<uint16_t> xc(Pu->ld, 0);
-            for (size_t q = 0; q < Pu->ld; ++q) xc[q] = Pc->h_cnt[px[q]];
+            for (size_t q = 0; q < Pu->ld; ++q) xc[q] = px[q] < Pc->U ? Pc->h_cnt[px[q]] : 0;     // (a node without light patterns: U = 0)
             CK(cudaMalloc(&L->d_xcnt[j], Pu->ld * sizeof(uint16_t)));
             CK(cudaMemcpy(L->d_xcnt[j], xc.data(), Pu->ld * sizeof(uint16_t), cudaMemcpyHostToDevice));
         }
@@ -2179,6 +2223,7 @@ struct blg_handle {
                 GList& G = *glist;
                 memset(&G, 0, sizeof(int) * 4);
                 int gch = 0, nitems = 0, gmax = 0;
+                const size_t pos_before = pos;
                 while (pos < todo.size()) {
                     const int u = todo[pos];
                     const int k = (int)children[u].size();
@@ -2283,7 +2328,8 @@ struct blg_handle {
                     for (int v : chain[u]) count_step_bytes(S, v);
                     ++pos;
                 }
-                require(tl[0].L->nsteps + tl[1].L->nsteps + tl[2].L->nsteps + G.nsteps > 0, "sweep: a node has more children than one launch can describe");
+                require(pos > pos_before, "sweep: a node has more children than one launch can describe");
+                if (tl[0].L->nsteps + tl[1].L->nsteps + tl[2].L->nsteps + G.nsteps == 0) continue;   // (nodes whose entries are all heavy)
                 cudaEvent_t dbg[4] = {nullptr, nullptr, nullptr, nullptr};
                 if (pdebug) { for (auto& e : dbg) CK(cudaEventCreate(&e)); CK(cudaEventRecord(dbg[0], stream)); }
                 if (G.nsteps > 0) {
@@ -2845,7 +2891,6 @@ struct blg_handle {
             root_ragged_kernel<<<bH, 256, 0, stream>>>(s->ell, s->scl, H.Tp[0].cnt, H.Tp[0].off, rootw.p + nrow + 1, rootw.p, H.weight.p, H.fam_ll.p,
                                                        partial.p, bF, H.N, d_ticket.p, (unsigned)(bF + bH), d_flags.p, marker, d_out);
             CK(cudaGetLastError());
-            last_bytes += 8.0 * H.Tp[0].colsum + 4.0 * H.N + 8.0 * H.N;
             last_launches += 1;
         }
     }
@@ -2883,6 +2928,8 @@ struct blg_handle {
         }
         require(have_params && tabs_valid, "logpdf: ε/W tables are stale (call blg_rebuild)");
         if (timing) { for (auto& e : ev) if (!e) CK(cudaEventCreate(&e)); CK(cudaEventRecord(ev[0], stream)); }
+        require(pat_mode || H.N == 0, "families at or above the heavy bound need the node-pattern evaluation (BLG_DEDUP=0 and the gradient do not support them)");
+        if (H.N > 0) ensure_pats(F);
         for (Shard* S : {&F, &H}) {
             if (S->N == 0) continue;
             require((int)S->Tp.size() >= 1, "logpdf: no profile columns");
@@ -2897,7 +2944,7 @@ struct blg_handle {
                 while (u >= 0) { if (!children[u].empty()) nodes.push_back(u); u = parent[u]; }
             }
             if (nodes.empty()) continue;
-            if (S == &H) { general_sweep(H, nodes, 0, true); last_family_cols += (double)H.N * nodes.size(); }
+            if (S == &H) general_sweep(H, nodes, 0, false);     // (the fast set's accounting already covers every family)
             else if (pat_mode) psweep(nodes, force_general || kernel_version == 1 || flag_cache == 0);
             else if (kernel_version == 1) general_sweep(F, nodes, 0, true);
             else {
@@ -3056,7 +3103,7 @@ static void family_order(const int32_t* X, int ncols, std::vector<int>& perm) {
 }
 
 // upload one family set: counts [column][family] (uint16), weights, column tables
-static void upload_shard(blg_handle* h, Shard& S, const int32_t* X, const int64_t* weight, int ncols) {
+static void upload_shard(blg_handle* h, Shard& S, const int32_t* X, const int64_t* weight, int ncols, const std::vector<char>& isheavy) {
     S.N = (int)S.perm.size();
     S.ld = ((size_t)S.N + 127) / 128 * 128;
     if (S.N == 0) return;
@@ -3067,11 +3114,22 @@ static void upload_shard(blg_handle* h, Shard& S, const int32_t* X, const int64_
         int mx = 0;
         double cs = 0.0;
         uint16_t* dst = stage.data() + (size_t)c * ld;
+        int fastmax = 0;                 // largest count of this column among the families below the heavy bound
         for (int f = 0; f < S.N; ++f) {
             const int32_t v = X[(size_t)S.perm[f] * ncols + c];
             dst[f] = (uint16_t)v;
+            if (!isheavy[S.perm[f]]) fastmax = std::max(fastmax, (int)v);
             mx = std::max(mx, (int)v);
             cs += (double)v + 1.0;
+        }
+        if (!S.ragged) {
+            // the fast set holds every family, but a heavy family's entries are evaluated there (as node patterns) only up to
+            // the count the other families reach at this column (at least 32): the column's bound — and with it the
+            // range of the table-free merge, whose scalings grow with the bound — stays what the fast families need
+            const int lmax = std::min(h->heavy_min - 1, std::max(fastmax, 32));
+            cols[c].lmax = lmax;
+            mx = 0;
+            for (int f = 0; f < S.N; ++f) if ((int)dst[f] <= lmax) mx = std::max(mx, (int)dst[f]);
         }
         cols[c].xmax = mx;
         cols[c].colsum = cs;
@@ -3135,7 +3193,8 @@ int blg_set_profiles(blg_handle* h, const int32_t* X, const int64_t* weight, int
             mx = std::max(mx, (int)x[c]);
         }
         rootc[f] = mx;
-        (mx >= h->heavy_min ? h->H.perm : h->F.perm).push_back(f);
+        h->F.perm.push_back(f);                                    // the fast set holds EVERY family (its entries below the heavy bound)
+        if (mx >= h->heavy_min) h->H.perm.push_back(f);            // the heavy set: the families with an entry at or above it
     }
     family_order(X, ncols, h->F.perm);
     // heavy shard: heaviest first (the general kernel hands families out one per warp), launch groups by root count
@@ -3151,11 +3210,17 @@ int blg_set_profiles(blg_handle* h, const int32_t* X, const int64_t* weight, int
             pos = end;
         }
     }
-    upload_shard(h, h->F, X, weight, ncols);
-    upload_shard(h, h->H, X, weight, ncols);
+    std::vector<char> isheavy(npatterns, 0);
+    for (int f : h->H.perm) isheavy[f] = 1;
+    upload_shard(h, h->F, X, weight, ncols, isheavy);
+    upload_shard(h, h->H, X, weight, ncols, isheavy);
     h->loc.assign(npatterns, 0);
+    h->hloc.assign(npatterns, -1);
     for (int i = 0; i < h->F.N; ++i) h->loc[h->F.perm[i]] = i;
-    for (int i = 0; i < h->H.N; ++i) h->loc[h->H.perm[i]] = -1 - i;
+    h->H2F.assign(h->H.N, 0);
+    for (int i = 0; i < h->H.N; ++i) { h->hloc[h->H.perm[i]] = i; h->H2F[i] = h->loc[h->H.perm[i]]; }
+    for (auto& kv : h->hpat) cudaFree(kv.second);
+    h->hpat.clear();
     // Pascal triangle for the merge tables of the gradient kernels (fast shard bounds only)
     int gmax = 0;
     for (const Col& c : h->F.Tp) gmax = std::max(gmax, c.xmax);
@@ -3358,15 +3423,20 @@ int blg_shrink(blg_handle* h, int i) {
 int blg_get_column(blg_handle* h, int pattern, int node, int which, double* out, int cap, int* rows) {
     BLG_ENTER(h)
     h->require(pattern >= 0 && pattern < h->Ntot, "get_column: pattern out of range");
-    const int l = h->loc[pattern];
-    Shard& S = l >= 0 ? h->F : h->H;
-    const int slot = l >= 0 ? l : -1 - l;
-    std::vector<Col>& T = which ? S.Tp : S.Tc;
-    h->require(node >= 1 && node <= (int)T.size(), "get_column: node out of range");
-    Col& c = T[node - 1];
+    // every family lives in the fast set; its entries at or above the heavy bound are held by the heavy set
+    h->require(node >= 1 && node <= (int)(which ? h->F.Tp : h->F.Tc).size(), "get_column: node out of range");
     CK(cudaStreamSynchronize(h->stream));
     uint16_t x;
-    CK(cudaMemcpy(&x, c.cnt + slot, sizeof(uint16_t), cudaMemcpyDeviceToHost));
+    CK(cudaMemcpy(&x, (which ? h->F.Tp : h->F.Tc)[node - 1].cnt + h->loc[pattern], sizeof(uint16_t), cudaMemcpyDeviceToHost));
+    bool heavy = false;
+    if (h->hloc[pattern] >= 0) {          // a family of the heavy set: is THIS entry one the fast set's patterns cover?
+        h->ensure_pats(h->F);
+        heavy = h->pat_of(h->F, (which ? h->F.Tp : h->F.Tc)[node - 1])->fam2pat[h->loc[pattern]] < 0;
+    }
+    Shard& S = heavy ? h->H : h->F;
+    const int slot = heavy ? h->hloc[pattern] : h->loc[pattern];
+    std::vector<Col>& T = which ? S.Tp : S.Tc;
+    Col& c = T[node - 1];
     // rows of the column as the reference holds it: count bound of this node over ALL patterns + 1
     int xm = 0;
     if (h->F.N > 0) xm = std::max(xm, (which ? h->F.Tp : h->F.Tc)[node - 1].xmax);
@@ -3408,7 +3478,7 @@ int blg_get_family_logpdf(blg_handle* h, double* out, int n) {
         std::vector<double> tf(h->F.N), th(h->H.N);
         if (h->F.N) CK(cudaMemcpy(tf.data(), h->F.fam_ll.p, (size_t)h->F.N * sizeof(double), cudaMemcpyDeviceToHost));
         if (h->H.N) CK(cudaMemcpy(th.data(), h->H.fam_ll.p, (size_t)h->H.N * sizeof(double), cudaMemcpyDeviceToHost));
-        for (int f = 0; f < n; ++f) { const int l = h->loc[f]; out[f] = l >= 0 ? tf[l] : th[-1 - l]; }
+        for (int f = 0; f < n; ++f) out[f] = h->hloc[f] >= 0 ? th[h->hloc[f]] : tf[h->loc[f]];
     }
     BLG_LEAVE(h)
 }
@@ -3469,7 +3539,7 @@ int blg_kernel_runs(blg_handle* h, unsigned int* sweep_runs, unsigned int* gener
     }
     if (sweep_runs) *sweep_runs = r[0];
     if (general_runs) *general_runs = r[1];
-    if (nfast) *nfast = h->F.N;
+    if (nfast) *nfast = h->F.N - h->H.N;      // (the fast set holds every family; these are the ones entirely inside it)
     if (nheavy) *nheavy = h->H.N;
     BLG_LEAVE(h)
 }

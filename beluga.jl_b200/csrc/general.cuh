@@ -38,6 +38,12 @@ struct GChild {
     int node;               // node index of the child (NodeK)
     int mode;               // 0 ordinary branch, 1 below a WGD (polynomial form), 2 table
     int ld;                 // SoA stride of the child's columns
+    // heavy family set: where the family's entry at this child is below the heavy bound, the column is the node pattern
+    // fpat[f] of the fast set (SoA pattern columns pell/pscl, stride pld), not a ragged per-family column
+    const int* fpat;
+    const double* pell;
+    const int* pscl;
+    int pld, pad_;
 };
 struct GStep {
     int k, first, resident, node;
@@ -48,9 +54,11 @@ struct GStep {
     const uint16_t* cnt;
     const uint32_t* out_off;
     size_t out_ld;          // SoA stride of the output columns
+    const int* fpat;        // heavy family set: fpat[f] >= 0 — the entry is below the heavy bound, the fast set's pattern path
+                            // computes it: skip the step for this family
 };
-#define BLG_G_MAXSTEPS 160
-#define BLG_G_MAXCHILD 230
+#define BLG_G_MAXSTEPS 128
+#define BLG_G_MAXCHILD 200
 struct GList {
     int nsteps;
     int pad_[3];
@@ -309,6 +317,7 @@ gsweep_kernel(const __grid_constant__ GList L, const NodeK* __restrict__ nk, con
             const GStep& st = L.step[si];
             const int k = st.k;
             const GChild* ch = &L.child[st.first];
+            if (st.fpat != nullptr && st.fpat[f] >= 0) { prevNode = -1; continue; }   // light entry: the pattern path has it
             const int X = st.cnt[f];
             const double ip0 = nk[st.node].ip0;                    // 1, or NaN where the reference's column is NaN
             double* outp = st.out + (st.out_off ? (size_t)st.out_off[f] : (size_t)f);
@@ -337,10 +346,17 @@ gsweep_kernel(const __grid_constant__ GList L, const NodeK* __restrict__ nk, con
                 } else if (resident) {
                     sclsum += prevScl;
                 } else {
-                    const double* src = c.ell + (c.off ? (size_t)c.off[cf] : (size_t)cf);
-                    const size_t sstride = c.off ? 1 : (size_t)c.ld;
-                    for (int n = lane; n <= M; n += 32) dst[n] = src[(size_t)n * sstride];
-                    sclsum += c.scl[cf];
+                    const int pc = c.fpat ? c.fpat[f] : -1;
+                    if (pc >= 0) {                                 // the child's entry is light: its node pattern's column
+                        const double* src = c.pell + pc;
+                        for (int n = lane; n <= M; n += 32) dst[n] = src[(size_t)n * c.pld];
+                        sclsum += c.pscl[pc];
+                    } else {
+                        const double* src = c.ell + (c.off ? (size_t)c.off[cf] : (size_t)cf);
+                        const size_t sstride = c.off ? 1 : (size_t)c.ld;
+                        for (int n = lane; n <= M; n += 32) dst[n] = src[(size_t)n * sstride];
+                        sclsum += c.scl[cf];
+                    }
                 }
                 __syncwarp();
                 double* bcol = dst;

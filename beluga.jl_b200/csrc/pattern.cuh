@@ -357,7 +357,9 @@ __global__ void __launch_bounds__(256) root_pattern_kernel(const double* __restr
     if (f < N) {
         const int p = fam2pat[f];
         double l;
-        if (pat_ll != nullptr && p >= pat_lo) {
+        if (p < 0) {
+            l = 0.0;                             // a family of the heavy set: its value comes from root_ragged_kernel
+        } else if (pat_ll != nullptr && p >= pat_lo) {
             l = pat_ll[p];                       // integrated by the tile that computed the root's column
         } else {
             const int X = pcnt[p];
@@ -369,7 +371,7 @@ __global__ void __launch_bounds__(256) root_pattern_kernel(const double* __restr
             if (!isfinite(l)) l = -INFINITY;                                        // model.jl:366
         }
         fam_ll[f] = l;
-        contrib = weight[f] * l;
+        contrib = p < 0 ? 0.0 : weight[f] * l;
     }
     red[threadIdx.x] = contrib;
     __syncthreads();
