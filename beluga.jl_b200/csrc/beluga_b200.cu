@@ -23,6 +23,7 @@
 #include <cstdint>
 #include <cstdio>
 #include <cstring>
+#include <deque>
 #include <map>
 #include <memory>
 #include <stdexcept>
@@ -1397,6 +1398,8 @@ struct blg_handle {
     // pat_mode == false: one column per family (the layout the gradient kernels work on; BLG_DEDUP=0 forces it).
     bool pat_mode = true, pat_default = true;
     int gslot = 0;
+    int side_min = 0;                         // BLG_SIDE: fewest tiles of a level for which the wide launch goes to the second stream (-1: never)
+    bool fan_classes = true;                  // heavy set: root-count classes on their own streams (BLG_FAN=0: one after the other)
     DevBuf<double> pat_ll;                    // per root pattern: the integrated log-likelihood (written by the root's tiles)
     bool root_fused = false;
     cudaStream_t stream2 = nullptr;           // the wide tile launches of a level run beside its other launches
@@ -1938,7 +1941,7 @@ struct blg_handle {
             require(groups.size() <= 16, "general_sweep: too many launch groups");
             // the classes are independent family ranges: each on its own stream (the top classes hold a handful of
             // families whose columns take milliseconds — they run beside the wide classes instead of in front of them)
-            const bool fan = groups.size() > 1;
+            const bool fan = groups.size() > 1 && fan_classes;
             if (fan && !ev_fork) {
                 CK(cudaEventCreateWithFlags(&ev_fork, cudaEventDisableTiming));
                 for (auto& e : ev_join) CK(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
@@ -2342,7 +2345,7 @@ struct blg_handle {
                 int caps[2] = {0, 0};
                 // the wide launch goes to a second (high-priority) stream: it usually holds a few long tiles, which then run
                 // beside the level's other launches instead of in front of them
-                const bool side = tl[1].L->nsteps > 0 && !pdebug;
+                const bool side = tl[1].L->nsteps > 0 && !pdebug && side_min >= 0 && tl[0].ntiles + tl[1].ntiles >= side_min;
                 if (side) {
                     if (!stream2) {
                         int lo_ = 0, hi_ = 0;
@@ -2694,7 +2697,6 @@ struct blg_handle {
         CK(cudaMemsetAsync(rwbar, 0, (size_t)nrow * sizeof(double), stream));
         // tangent inputs of the dual W tables below a WGD/WGT: lane 0 = ∂/∂q (no ε tangent), lane 1 = ∂/∂ε of the child
         double* dez = (double*)ga((size_t)2 * n * sizeof(double));
-        double* de1c = (double*)ga((size_t)2 * n * sizeof(double));
         CK(cudaMemsetAsync(dez, 0, (size_t)2 * n * sizeof(double), stream));
         // stage 1: root, then every internal node, parents before children
         {
@@ -2709,6 +2711,8 @@ struct blg_handle {
         const int nblk = (N + 127) / 128;
         double* npart = (double*)ga((size_t)6 * nblk * sizeof(double));
         std::vector<std::vector<double>> keep_host;          // staging of the one-hot tangent vectors (must outlive the copies)
+        std::deque<DualTab> keep_dt;                         // (deques: stable addresses for the asynchronous copies)
+        std::deque<int> keep_id;
         for (auto it = postorder.rbegin(); it != postorder.rend(); ++it) {
             const int u = *it;
             if (children[u].empty()) continue;
@@ -2729,19 +2733,22 @@ struct blg_handle {
                     DualTab dt;
                     memset(&dt, 0, sizeof(dt));
                     dt.dWt = dW;
+                    // (every WGD gets its own small staging buffers: nothing is reused, so nothing has to be waited for)
                     DualTab* ddt = (DualTab*)ga(sizeof(DualTab));
                     int* dl = (int*)ga(sizeof(int));
+                    double* de1w = (double*)ga((size_t)2 * n * sizeof(double));
                     keep_host.emplace_back((size_t)2 * n, 0.0);
                     keep_host.back()[(size_t)n + cr.id] = 1.0;
-                    CK(cudaMemcpyAsync(de1c, keep_host.back().data(), (size_t)2 * n * sizeof(double), cudaMemcpyHostToDevice, stream));
-                    CK(cudaMemcpyAsync(ddt, &dt, sizeof(DualTab), cudaMemcpyHostToDevice, stream));
-                    CK(cudaMemcpyAsync(dl, &cr.id, sizeof(int), cudaMemcpyHostToDevice, stream));
+                    keep_dt.push_back(dt);
+                    keep_id.push_back(cr.id);
+                    CK(cudaMemcpyAsync(de1w, keep_host.back().data(), (size_t)2 * n * sizeof(double), cudaMemcpyHostToDevice, stream));
+                    CK(cudaMemcpyAsync(ddt, &keep_dt.back(), sizeof(DualTab), cudaMemcpyHostToDevice, stream));
+                    CK(cudaMemcpyAsync(dl, &keep_id.back(), sizeof(int), cudaMemcpyHostToDevice, stream));
                     Seeds<2> sd;
                     sd.kind[0] = SEED_Q; sd.node[0] = u; sd.kind[1] = SEED_NONE; sd.node[1] = -1;
                     size_t smem = (size_t)2 * std::max(tb.wdim, 1) * 3 * sizeof(double);
-                    tables_dual_kernel<2><<<1, 128, smem, stream>>>(m, sd, dl, ddt, dez, de1c);
+                    tables_dual_kernel<2><<<1, 128, smem, stream>>>(m, sd, dl, ddt, dez, de1w);
                     CK(cudaGetLastError());
-                    CK(cudaStreamSynchronize(stream));       // ddt/dl/de1c are reused by the next WGD
                     c.dW = dW;
                     c.dW_stride = wsz;
                 }
@@ -3024,6 +3031,8 @@ int blg_create(int device, void* stream, blg_handle** out) {
         // families whose root count reaches this go to the heavy shard; above BLG_FAST_MAXCOUNT+1 the fast shard leaves the
         // table-free kernel's range (general kernel on SoA slabs) but stays inside the table-based gradient kernels' (<= 256)
         if (const char* pd = getenv("BLG_PDEBUG")) h->pdebug = atoi(pd);
+        if (const char* fn = getenv("BLG_FAN")) h->fan_classes = atoi(fn) != 0;
+        if (const char* sd = getenv("BLG_SIDE")) h->side_min = atoi(sd);
         if (const char* dd = getenv("BLG_DEDUP")) h->pat_mode = h->pat_default = atoi(dd) != 0;
         if (const char* hm = getenv("BLG_HEAVY_MIN")) h->heavy_min = std::max(1, std::min(256, atoi(hm)));
         *out = h;

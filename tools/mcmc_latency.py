@@ -4,11 +4,11 @@ sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import numpy as np
 import beluga_b200 as B
 from beluga_b200.model import build_model, update_
-from beluga_b200.sim import rand_profiles_torch
+from beluga_b200.sim import rand_profiles_device
 
 nw = open(os.path.join(os.path.dirname(__file__), "..", "tests", "data", "12monocots.nw")).readline().strip()
 m0, _, _ = build_model(nw, 0.004, 0.003, 0.9, B.BRANCH)
-names, counts = rand_profiles_torch(m0, int(sys.argv[1]) if len(sys.argv) > 1 else 100000, seed=1, device="cuda:0", max_rootsum=60, chunk=1 << 19)
+names, counts = rand_profiles_device(m0, int(sys.argv[1]) if len(sys.argv) > 1 else 100000, seed=1, device=0, max_rootsum=60)
 model, data = B.DLWGD(nw, (names, counts), 0.004, 0.003, 0.9, B.BRANCH, device=0)
 print("patterns", len(data))
 B.logpdf_(model, data); B.set_(data)
