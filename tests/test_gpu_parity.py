@@ -904,3 +904,27 @@ def test_device_sampler_follows_the_count_law():
     a = dev[:, names.index("A")]
     p = np.array([(a == k).mean() for k in (1, 2, 3)])
     assert np.allclose(p, [0.49, 0.42, 0.09], atol=0.004), p
+
+
+def test_wide_tree_many_nodes_per_level():
+    # 400 taxa: the lowest level of the tree holds more nodes than one launch describes (the step lists are cut into
+    # several launches), and the sweep is ~800 steps long; full sweep, a partial path and a WGD chain against the oracle
+    from beluga_b200.sim import random_tree_newick, rand_profiles
+    nw = random_tree_newick(400, seed=7)
+    m0, _, _ = build_model(nw, 0.2, 3.0, 0.8, B.BRANCH)
+    names, counts = rand_profiles(m0, 100, seed=3)           # sparse profiles; root counts from a few dozen to a few hundred
+    model, data = B.DLWGD(nw, (names, counts), 0.2, 3.0, 0.8, B.BRANCH, device=0)
+    orc = OracleDLWGD(nw, names, counts, 0.2, 3.0, 0.8, OBRANCH, threads=8)
+    got = B.logpdf_(model, data)
+    want, pf = orc.logpdf(per_family=True)
+    np.testing.assert_allclose(data.family_logpdf(), pf, rtol=RTOL)
+    assert close(got, want, RTOL)
+    B.set_(data); orc.set()
+    leaf = max(i for i, n in model.nodes.items() if not n.c)
+    B.update_(model[leaf], λ=0.9, μ=0.4); orc.update(leaf, lam=0.9, mu=0.4)
+    assert close(B.logpdf_(model[leaf], data), orc.logpdf_from(leaf), RTOL)
+    B.addwgd_(model, model[leaf], 0.001, 0.3); B.extend_(data, leaf)
+    orc.addwgd(leaf, 0.001, 0.3); orc.extend(leaf)
+    assert close(B.logpdf_(model, data), orc.logpdf(), RTOL)
+    moved, pattern_cols, family_cols = data.pattern_stats()
+    assert pattern_cols < 0.5 * family_cols
