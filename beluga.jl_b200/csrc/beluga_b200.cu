@@ -1241,6 +1241,10 @@ inline int round_up(int v, int m) { return (v + m - 1) / m * m; }
 template <class T> struct DevBuf {
     T* p = nullptr;
     size_t cap = 0;
+    DevBuf() = default;
+    DevBuf(const DevBuf&) = delete;
+    DevBuf& operator=(const DevBuf&) = delete;
+    ~DevBuf() { if (p) cudaFree(p); }           // (also on the exception paths of the entries that use local buffers)
     void ensure(size_t n) {
         if (n <= cap) return;
         if (p) cudaFree(p);

@@ -124,6 +124,7 @@ def sample_pattern_rows(args, device=None, nsample=20000):
     rng = np.random.default_rng(SEED)
     sel = np.sort(rng.choice(X.shape[0], size=min(nsample, X.shape[0]), replace=False))
     rows = X[sel][:, [i - 1 for i in leaf_ids]].astype(np.int64)
+    sample_pattern_rows.last = (int(X.shape[0]), int(w.sum()))
     return nw, [l[i] for i in leaf_ids], rows, "uniform sample of the %d patterns of the compressed %d-family set" % (X.shape[0], args.families), True
 
 
@@ -202,7 +203,7 @@ def run_reference(args):
         "impl": "reference", "metric": METRIC, "value": cb["value"], "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": cb["ms_per_step"], "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-        "config": workload_config(args, None, None),
+        "config": workload_config(args, *getattr(sample_pattern_rows, "last", (None, None))),
         "cpu_baseline": {k: cb[k] for k in ("value", "unit", "cores", "kind", "sample", "same_pattern_mix")},
         "e2e": {"value": cb["value"], "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     }
@@ -249,6 +250,32 @@ def mcmc_leg(args, local, distributed=False):
                        "nodes": len(model), "wgds_at_end": model.nwgd()},
             "likelihood_calls_per_s": (chain.evals - e0) / dt, "proposals_per_s": (chain.proposed - p0) / dt,
             "acceptance": chain.accepted / max(chain.proposed, 1), "generations": args.mcmc_generations}
+
+
+def c2_leg(args, local):
+    """Config C2 (BASELINE.json configs[1]): the 12monocots tree with its shipped profile CSV (1000 families), a
+    fixed-dimension `mcmc!` chain under IRRevJumpPrior(Tl = treelength(model)) (README.md:75-88 of the reference), replayed
+    through the public API: generations/s (one generation = one Metropolis-within-Gibbs sweep over the 23 nodes)."""
+    import beluga_b200 as B
+    from beluga_b200.mcmc import RevJumpChain
+    from beluga_b200.priors import IRRevJumpPrior
+    nw = open(os.path.join(ROOT, "tests", "data", "12monocots.nw")).readline().strip()
+    path = os.path.join(ROOT, "tests", "data", "12monocots-f01-1000.csv")
+    names = open(path).readline().strip().split(",")
+    counts = np.loadtxt(path, delimiter=",", skiprows=1, dtype=np.int64, ndmin=2)
+    model, data = B.DLWGD(nw, (names, counts), 0.003, 0.003, 0.9, B.BRANCH, device=local)
+    chain = RevJumpChain(data, model, seed=SEED, step=0.02, prior=IRRevJumpPrior(Tl=model.treelength())).init_()
+    chain.mcmc_(5, trace=0)
+    data.synchronize()
+    p0 = chain.proposed
+    gens = 60
+    t0 = time.perf_counter()
+    chain.mcmc_(gens, trace=0)
+    data.synchronize()
+    dt = time.perf_counter() - t0
+    return {"metric": "mcmc! generations/sec", "value": gens / dt, "unit": "generations/s", "proposals_per_s": (chain.proposed - p0) / dt,
+            "acceptance": chain.accepted / max(chain.proposed, 1), "logp": chain.state["logp"],
+            "config": {"workload": "C2: 12monocots.nw + 12monocots-f01-1000.csv (%d patterns), fixed-dimension mcmc! under IRRevJumpPrior, 1 GPU" % len(data)}}
 
 
 def algorithmic_fma(model, X):
@@ -633,7 +660,7 @@ def main():
             except Exception as e:
                 c5_grad = {"error": repr(e)}
         if not args.no_mcmc:
-            for key, leg in (("node_local", node_local_leg), ("gradient", gradient_leg)):
+            for key, leg in (("node_local", node_local_leg), ("gradient", gradient_leg), ("c2_mcmc", c2_leg)):
                 try:
                     line[key] = leg(args, local)
                 except Exception as e:
