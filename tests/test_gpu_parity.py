@@ -703,6 +703,46 @@ def test_mcmc_and_rjmcmc_keep_device_state_consistent(monocots):
     assert l0 != lfull
 
 
+def test_rjmcmc_with_heavy_families_keeps_both_family_sets_consistent(dicots):
+    # the same chain on a data set where a fifth of the families exceed the table-free bound: partial recomputes,
+    # commits, reverts, extend!/shrink! must keep the pattern columns (fast set) and the ragged per-family columns
+    # (heavy set, which reads its light children from the pattern columns) consistent with each other
+    from beluga_b200.mcmc import RevJumpChain
+    nw, df = dicots
+    names, counts = df
+    rng = np.random.default_rng(21)
+    counts = np.array(counts, dtype=np.int64)
+    extra = rng.integers(0, 40, size=(6, counts.shape[1])).astype(np.int64)      # root counts of a few hundred
+    extra[0, :3] = [90, 80, 1]
+    counts = np.concatenate([counts, extra], axis=0)
+    model, data, _ = pair(nw, (names, counts), 0.9, 1.0, 0.7, B.BRANCH)
+    chain = RevJumpChain(data, model, seed=9, step=0.1).init_()
+    _, _, nfast, nheavy = data.kernel_runs()
+    assert nheavy >= 5 and nfast >= 10
+    l0 = chain.state["logp"]
+    chain.mcmc_(2)
+    chain.rjmcmc_(10)
+    assert chain.accepted > 0 and chain.proposed > chain.accepted
+    assert data.ncols() == data.ncols(proposal=False) == max(model.nodes)
+    lfull = B.logpdf_(model, data)
+    assert chain.state["logp"] == pytest.approx(lfull, rel=1e-11)
+    orc = OracleDLWGD(nw, names, counts, 0.9, 1.0, 0.7, OBRANCH, threads=4)
+    for wid in sorted(i for i, n in model.nodes.items() if n.kind == "wgd"):
+        w = model[wid]
+        below = w.c[0].c[0]
+        orc.addwgd(below.i, below["t"], w["q"])
+        orc.extend(below.i)
+    for i, n in model.nodes.items():
+        for key, field in (("λ", "lam"), ("μ", "mu"), ("q", "q"), ("t", "t")):
+            if key in n.theta:
+                orc.setfield(i, field, n[key])
+    orc.setfield(1, "eta", model[1]["η"])
+    orc.setall()
+    want, pf = orc.logpdf(per_family=True)
+    assert lfull == pytest.approx(want, rel=1e-10)
+    assert l0 != lfull
+
+
 # ---- benchmark-shaped workload (C5: 100 taxa + 10 WGDs): oracle on a sample + size-independent properties --------
 def _c5(nfam, seed=20261019, leaf50=False):
     from beluga_b200.sim import add_random_wgds, rand_profiles, random_tree_newick
