@@ -22,6 +22,7 @@
 #include <limits>
 #include <cstdint>
 #include <cstdio>
+#include <chrono>
 #include <cstring>
 #include <deque>
 #include <map>
@@ -1207,6 +1208,7 @@ __global__ void zero_slab_kernel(double* ell, int* scl, size_t nell, int N) {
 #include "pattern.cuh"
 #include "gradient.cuh"
 #include "adjoint.cuh"
+#include "padjoint.cuh"
 #include "ingest.cuh"
 #include "sampler.cuh"
 
@@ -1275,10 +1277,17 @@ struct Pat {
     int nvery = 0, nwide = 0;
     uint16_t* d_cnt = nullptr;       // [ld] count of the column per pattern (sorted descending: heaviest tiles first)
     int* d_fam2pat = nullptr;        // [N] family → pattern, on the device only for the root
+    double* d_pw = nullptr;          // [ld] weight of the families with the pattern (root, gradient only)
+    std::map<int, std::pair<int*, int>> big;   // T → indices of the patterns with at least T counts (padjoint.cuh)
     std::vector<int> fam2pat;        // host
     std::vector<int> rep;            // a family of each pattern
     std::vector<uint16_t> h_cnt;
-    ~Pat() { if (d_cnt) cudaFree(d_cnt); if (d_fam2pat) cudaFree(d_fam2pat); }
+    ~Pat() {
+        if (d_cnt) cudaFree(d_cnt);
+        if (d_fam2pat) cudaFree(d_fam2pat);
+        if (d_pw) cudaFree(d_pw);
+        for (auto& b : big) if (b.second.first) cudaFree(b.second.first);
+    }
 };
 // pattern of a node → pattern of each child, for one (node column, ordered child columns) combination
 struct Link {
@@ -1291,7 +1300,24 @@ struct Link {
     int ntiles[2] = {0, 0};
     int maxneed[2] = {0, 0};             // largest slice need (doubles per lane) over the tiles
     bool cut = false;                    // tiles were cut (binary merges); otherwise the generic instantiation runs
-    ~Link() { for (int* q : d_pidx) if (q) cudaFree(q); for (int* q : d_tiles) if (q) cudaFree(q); for (uint16_t* q : d_xcnt) if (q) cudaFree(q); }
+    // the inverse maps (padjoint.cuh, built at the first gradient): per child pattern the node patterns that use it, as a
+    // CSR in ascending node-pattern order, and the child patterns with more than BLG_PB_HIT of them
+    int* d_inv_off[BLG_MAXK] = {nullptr};
+    int* d_inv_idx[BLG_MAXK] = {nullptr};    // node pattern → its place in that order
+    int* d_hit[BLG_MAXK] = {nullptr};
+    int* d_mid[BLG_MAXK] = {nullptr};
+    int nhit[BLG_MAXK] = {0};
+    int nmid[BLG_MAXK] = {0};
+    int nmid_many[BLG_MAXK] = {0};
+    ~Link() {
+        for (int* q : d_pidx) if (q) cudaFree(q);
+        for (int* q : d_tiles) if (q) cudaFree(q);
+        for (uint16_t* q : d_xcnt) if (q) cudaFree(q);
+        for (int* q : d_inv_off) if (q) cudaFree(q);
+        for (int* q : d_inv_idx) if (q) cudaFree(q);
+        for (int* q : d_hit) if (q) cudaFree(q);
+        for (int* q : d_mid) if (q) cudaFree(q);
+    }
 };
 
 struct Shard {
@@ -1418,6 +1444,11 @@ struct blg_handle {
     // sweep-kernel plumbing
     int kernel_version = 2;
     bool order_resident = true;
+    bool padj_constants = false;
+    int padj_warp_min = 0;               // BLG_PADJ_WARP: fixed count bound of the warp kernel of the pattern adjoint (0: per depth)
+    int padj_warp_big = 257;             // BLG_PADJ_BIG: the warp path's count bound at depths with many patterns
+    long long padj_warp_level = 32768;   // BLG_PADJ_LEVEL: depths with at most this many patterns use the warp kernel
+    bool grad_pat = true;                // reverse mode over node patterns (padjoint.cuh); BLG_GRAD_PAT=0: over families (adjoint.cuh)
     int grad_mode = 1;                   // 1: reverse-mode sweep where the tree allows it; 0: forward-mode tangent passes (BLG_GRAD=forward)
     int profile_sweep = 0;
     DevBuf<unsigned long long> d_prof;
@@ -2783,6 +2814,312 @@ struct blg_handle {
         for (auto& t : temps) gfree(t.first, t.second);
     }
 
+    // ---- gradient, reverse mode over node patterns (padjoint.cuh) -----------------------------------------------------
+    void ensure_inverse(Shard& S, Link* lk, int j, Pat* Pu, Pat* Pc) {
+        if (lk->d_inv_off[j]) return;
+        std::vector<int> off(Pc->U + 2, 0), idx(std::max(Pu->U, 1)), hit;
+        std::vector<int> px(Pu->U);
+        for (int q = 0; q < Pu->U; ++q) { px[q] = Pc->fam2pat[Pu->rep[q]]; ++off[px[q] + 1]; }
+        for (int c = 0; c < Pc->U; ++c) off[c + 1] += off[c];
+        std::vector<int> fill(off.begin(), off.begin() + Pc->U + 1);
+        for (int q = 0; q < Pu->U; ++q) idx[fill[px[q]]++] = q;
+        // the warp kernel's list: first the child patterns with many node patterns, then those with many counts (which
+        // only go there at tree depths with few patterns)
+        std::vector<int> mid, mid2;
+        for (int c = 0; c < Pc->U; ++c) {
+            const int np = off[c + 1] - off[c];
+            if (Pc->h_cnt[c] == 0) continue;
+            if (np > BLG_PB_BLOCK) hit.push_back(c);
+            else if (np > BLG_PB_HIT) mid.push_back(c);
+            else if (Pc->h_cnt[c] >= BLG_PB_MID) mid2.push_back(c);
+        }
+        lk->nmid_many[j] = (int)mid.size();
+        mid.insert(mid.end(), mid2.begin(), mid2.end());
+        lk->nmid[j] = (int)mid.size();
+        if (!mid.empty()) {
+            CK(cudaMalloc(&lk->d_mid[j], mid.size() * sizeof(int)));
+            CK(cudaMemcpy(lk->d_mid[j], mid.data(), mid.size() * sizeof(int), cudaMemcpyHostToDevice));
+        }
+        CK(cudaMalloc(&lk->d_inv_off[j], (size_t)(Pc->U + 1) * sizeof(int)));
+        CK(cudaMemcpy(lk->d_inv_off[j], off.data(), (size_t)(Pc->U + 1) * sizeof(int), cudaMemcpyHostToDevice));
+        // (uploaded as the inverse permutation: where phase A puts a node pattern's b̄)
+        std::vector<int> pos(std::max(Pu->U, 1), 0);
+        for (int k = 0; k < Pu->U; ++k) pos[idx[k]] = k;
+        CK(cudaMalloc(&lk->d_inv_idx[j], pos.size() * sizeof(int)));
+        CK(cudaMemcpy(lk->d_inv_idx[j], pos.data(), pos.size() * sizeof(int), cudaMemcpyHostToDevice));
+        lk->nhit[j] = (int)hit.size();
+        if (!hit.empty()) {
+            CK(cudaMalloc(&lk->d_hit[j], hit.size() * sizeof(int)));
+            CK(cudaMemcpy(lk->d_hit[j], hit.data(), hit.size() * sizeof(int), cudaMemcpyHostToDevice));
+        }
+        (void)S;
+    }
+    // weight of the families behind every root pattern (summed in family order)
+    double* root_pattern_weights(Shard& S, Pat* P0) {
+        if (P0->d_pw) return P0->d_pw;
+        std::vector<double> w(S.N), pw(P0->ld, 0.0);
+        CK(cudaMemcpyAsync(w.data(), S.weight.p, (size_t)S.N * sizeof(double), cudaMemcpyDeviceToHost, stream));
+        CK(cudaStreamSynchronize(stream));
+        for (int f = 0; f < S.N; ++f) if (P0->fam2pat[f] >= 0) pw[P0->fam2pat[f]] += w[f];
+        CK(cudaMalloc(&P0->d_pw, P0->ld * sizeof(double)));
+        CK(cudaMemcpy(P0->d_pw, pw.data(), P0->ld * sizeof(double), cudaMemcpyHostToDevice));
+        return P0->d_pw;
+    }
+    template <int CAP> void launch_padj(const PAStep* d, int n0, int n, int blocks, double* part, int wblocks, int wcap) {
+        const size_t smem = wblocks > 0 ? (size_t)4 * 8 * wcap * sizeof(double) : 0;
+        if (smem > 48 * 1024) CK(cudaFuncSetAttribute(padj_parent_kernel<CAP>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        padj_parent_kernel<CAP><<<wblocks + blocks, 128, smem, stream>>>(d + n0, n, d_nk.p, pascal.p, pdim, part, wblocks, wcap);
+        CK(cudaGetLastError());
+    }
+    template <int CAP> void launch_pchild(const PBStep* d, int n0, int n, int blocks, int hblocks, int mblocks, int cap) {
+        padj_child_kernel<CAP><<<hblocks + mblocks + blocks, 128, (size_t)4 * cap * sizeof(double), stream>>>(d + n0, n, hblocks, mblocks, cap);
+        CK(cudaGetLastError());
+    }
+    // res[2·i + lane] = ∂logL/∂(parameter of lane `lane` of group i); the caller has just run a full logpdf in the
+    // node-pattern layout
+    void gradient_padjoint(const std::vector<Seeds<2>>& groups, std::vector<double>& res) {
+        const auto t_enter = std::chrono::steady_clock::now();
+        if (!padj_constants) {
+            double r[257];
+            r[0] = 0.0;
+            for (int q = 1; q <= 256; ++q) r[q] = 1.0 / (double)q;
+            CK(cudaMemcpyToSymbol(c_rinv, r, sizeof(r)));
+            padj_constants = true;
+        }
+        Shard& S = F;
+        const int n = ncols_model;
+        ModelDev m = model_dev();
+        ensure_pats(S);
+        std::vector<std::pair<void*, size_t>> temps;
+        auto ga = [&](size_t b) { void* p = galloc(b); temps.push_back({p, b}); return p; };
+        std::vector<double*> adj(n, nullptr);
+        std::vector<int> depth(n, 0);
+        int maxdepth = 0;
+        for (auto it = postorder.rbegin(); it != postorder.rend(); ++it) {
+            const int u = *it;
+            if (children[u].empty()) continue;
+            depth[u] = parent[u] >= 0 ? depth[parent[u]] + 1 : 0;
+            maxdepth = std::max(maxdepth, depth[u]);
+            Pat* Pu = pat_of(S, S.Tp[u]);
+            adj[u] = (double*)ga(std::max<size_t>((size_t)(Pu->xmax + 1) * Pu->ld, 32) * sizeof(double));
+        }
+        double* sadj = (double*)ga((size_t)n * 4 * sizeof(double));
+        CK(cudaMemsetAsync(sadj, 0, (size_t)n * 4 * sizeof(double), stream));
+        const int nrow = S.Tp[0].xmax + 1;
+        double* rwbar = (double*)ga((size_t)nrow * sizeof(double));
+        CK(cudaMemsetAsync(rwbar, 0, (size_t)nrow * sizeof(double), stream));
+        double* dez = (double*)ga((size_t)2 * n * sizeof(double));
+        CK(cudaMemsetAsync(dez, 0, (size_t)2 * n * sizeof(double), stream));
+        // root
+        {
+            Pat* P0 = pat_of(S, S.Tp[0]);
+            Slab* rs = readable(S, 0);
+            const int blocks = (P0->U + 255) / 256;
+            double* rpart = (double*)ga((size_t)nrow * blocks * sizeof(double));
+            root_padjoint_kernel<<<blocks, 256, 0, stream>>>(rs->ell, P0->d_cnt, rootw.p, root_pattern_weights(S, P0), adj[0], rpart, blocks, nrow,
+                                                             P0->U, P0->ld);
+            CK(cudaGetLastError());
+            grad_reduce_kernel<<<1, 256, 0, stream>>>(rpart, blocks, nrow, rwbar);
+            CK(cudaGetLastError());
+        }
+        // the steps of every depth
+        std::vector<std::vector<double>> keep_host;
+        std::deque<DualTab> keep_dt;
+        std::deque<int> keep_id;
+        std::vector<PAStep> sa;
+        std::vector<PBStep> sb;
+        struct Lev { int a0, a1, b0, b1, ablk, bblk, hblk, acap, bcap, wblk, wcap, mblk, midM; };
+        std::vector<Lev> levs;
+        int pblk = 0;
+        for (int d = 0; d <= maxdepth; ++d) {
+            Lev lv;
+            memset(&lv, 0, sizeof(lv));
+            lv.a0 = (int)sa.size(); lv.b0 = (int)sb.size();
+            // a depth is as slow as its longest thread: the patterns with many counts go to the warp path of the same launch
+            // (from 16 counts at a depth with few patterns, where nothing else hides the thread path's latency; from 40
+            // where the thread path's throughput is what counts)
+            int T = 257;
+            {
+                long long total = 0;
+                for (int u : postorder)
+                    if (!children[u].empty() && depth[u] == d) total += pat_of(S, S.Tp[u])->U;
+                T = total <= padj_warp_level ? 16 : padj_warp_big;
+                if (padj_warp_min > 0) T = padj_warp_min;
+                long long ctotal = 0;
+                for (int u : postorder)
+                    if (!children[u].empty() && depth[u] == d && children[u].size() == 2)
+                        for (int c : children[u]) if (!children[c].empty()) ctotal += pat_of(S, S.Tp[c])->U;
+                lv.midM = ctotal <= padj_warp_level ? BLG_PB_MID : 0x7fff;
+            }
+            for (auto it = postorder.rbegin(); it != postorder.rend(); ++it) {
+                const int u = *it;
+                if (children[u].empty() || depth[u] != d) continue;
+                const int k = (int)children[u].size();
+                require(tabs_valid && tabs[u].built && tabs[u].k == k, "gradient: ε/W tables are stale (call blg_rebuild)");
+                std::vector<int> ord(tabs[u].mo, tabs[u].mo + k);
+                Pat* Pu = pat_of(S, S.Tp[u]);
+                if (Pu->U == 0) continue;
+                Link* lk = get_link(S, u, ord);
+                PAStep as;
+                memset(&as, 0, sizeof(as));
+                as.k = k; as.node = u; as.U = Pu->U; as.ld = (int)Pu->ld;
+                as.blk0 = lv.ablk; as.nblk = (Pu->U + 127) / 128; as.pblk0 = pblk;
+                lv.ablk += as.nblk; pblk += as.nblk;
+                as.T = T;
+                if (Pu->xmax >= T) {
+                    auto bi = Pu->big.find(T);
+                    if (bi == Pu->big.end()) {
+                        std::vector<int> bl;
+                        for (int q = 0; q < Pu->U; ++q) if (Pu->h_cnt[q] >= T) bl.push_back(q);
+                        int* dbl = nullptr;
+                        CK(cudaMalloc(&dbl, std::max<size_t>(bl.size(), 1) * sizeof(int)));
+                        CK(cudaMemcpy(dbl, bl.data(), bl.size() * sizeof(int), cudaMemcpyHostToDevice));
+                        bi = Pu->big.emplace(T, std::make_pair(dbl, (int)bl.size())).first;
+                    }
+                    as.big = bi->second.first; as.nbig = bi->second.second;
+                    as.nwblk = (as.nbig + 3) / 4;
+                    as.wblk0 = lv.wblk; as.wpblk0 = pblk;
+                    lv.wblk += as.nwblk; pblk += as.nwblk;
+                    lv.wcap = std::max(lv.wcap, Pu->xmax + 1);
+                    // (the thread kernel's arrays only have to hold what is left to it)
+                    lv.acap = std::max(lv.acap, T);
+                } else {
+                    as.wblk0 = lv.wblk; as.wpblk0 = pblk;
+                    lv.acap = std::max(lv.acap, Pu->xmax + 1);
+                }
+                Slab* su = readable(S, u);
+                as.ell = su->ell; as.scl = su->scl; as.cnt = Pu->d_cnt; as.adj = adj[u]; as.ipow = tabs[u].ipow;
+                for (int j = 0; j < k; ++j) {
+                    const int c = ord[j];
+                    require(tabs[c].built && tabs[c].wdim >= S.Tp[c].xmax + 1 && tabs[c].Wt, "gradient: W table of a child does not match the profile (call blg_rebuild)");
+                    Pat* Pc = pat_of(S, S.Tp[c]);
+                    PAChild& pc = as.child[j];
+                    if (!children[c].empty()) { Slab* sc_ = readable(S, c); pc.ell = sc_->ell; pc.scl = sc_->scl; }
+                    pc.cnt = Pc->d_cnt; pc.pidx = lk->d_pidx[j]; pc.xcnt = lk->d_xcnt[j];
+                    pc.Wt = tabs[c].Wt; pc.wdp = tabs[c].wdp; pc.id = c; pc.ld = (int)Pc->ld;
+                    if (!children[c].empty()) {
+                        if (Pc == Pu) pc.adj = adj[c];
+                        else {
+                            ensure_inverse(S, lk, j, Pu, Pc);
+                            pc.bbar = (double*)ga(std::max<size_t>((size_t)(Pc->xmax + 1) * Pu->ld, 32) * sizeof(double));
+                            PBStep bs;
+                            memset(&bs, 0, sizeof(bs));
+                            bs.Uc = Pc->U; bs.ldc = (int)Pc->ld; bs.ldp = (int)Pu->ld; bs.blk0 = lv.bblk; bs.hblk0 = lv.hblk;
+                            bs.nhit = lk->nhit[j]; bs.wdp = tabs[c].wdp;
+                            pc.pos = lk->d_inv_idx[j];
+                            bs.cnt = Pc->d_cnt; bs.off = lk->d_inv_off[j]; bs.hit = lk->d_hit[j];
+                            bs.bbar = pc.bbar; bs.Wt = tabs[c].Wt; bs.adj = adj[c];
+                            bs.midM = lv.midM;
+                            bs.mblk0 = lv.mblk; bs.nmid = lv.midM < 0x7fff ? lk->nmid[j] : lk->nmid_many[j]; bs.mid = lk->d_mid[j];
+                            lv.mblk += (bs.nmid + 3) / 4;
+                            lv.bblk += (Pc->U + 127) / 128;
+                            lv.hblk += bs.nhit;
+                            lv.bcap = std::max(lv.bcap, Pc->xmax + 1);
+                            sb.push_back(bs);
+                        }
+                    }
+                    if (kind[c] == BLG_WGDAFTER) {
+                        const HostTab& tb = tabs[c];
+                        const size_t wsz = (size_t)tb.wdim * tb.wdp;
+                        double* dW = (double*)ga(2 * wsz * sizeof(double));
+                        DualTab dt;
+                        memset(&dt, 0, sizeof(dt));
+                        dt.dWt = dW;
+                        DualTab* ddt = (DualTab*)ga(sizeof(DualTab));
+                        int* dl = (int*)ga(sizeof(int));
+                        double* de1w = (double*)ga((size_t)2 * n * sizeof(double));
+                        keep_host.emplace_back((size_t)2 * n, 0.0);
+                        keep_host.back()[(size_t)n + c] = 1.0;
+                        keep_dt.push_back(dt);
+                        keep_id.push_back(c);
+                        CK(cudaMemcpyAsync(de1w, keep_host.back().data(), (size_t)2 * n * sizeof(double), cudaMemcpyHostToDevice, stream));
+                        CK(cudaMemcpyAsync(ddt, &keep_dt.back(), sizeof(DualTab), cudaMemcpyHostToDevice, stream));
+                        CK(cudaMemcpyAsync(dl, &keep_id.back(), sizeof(int), cudaMemcpyHostToDevice, stream));
+                        Seeds<2> sd;
+                        sd.kind[0] = SEED_Q; sd.node[0] = u; sd.kind[1] = SEED_NONE; sd.node[1] = -1;
+                        size_t smem = (size_t)2 * std::max(tb.wdim, 1) * 3 * sizeof(double);
+                        tables_dual_kernel<2><<<1, 128, smem, stream>>>(m, sd, dl, ddt, dez, de1w);
+                        CK(cudaGetLastError());
+                        pc.dW = dW;
+                        pc.dW_stride = wsz;
+                    }
+                }
+                sa.push_back(as);
+            }
+            lv.a1 = (int)sa.size(); lv.b1 = (int)sb.size();
+            levs.push_back(lv);
+        }
+        PAStep* dsa = (PAStep*)ga(std::max<size_t>(sa.size(), 1) * sizeof(PAStep));
+        PBStep* dsb = (PBStep*)ga(std::max<size_t>(sb.size(), 1) * sizeof(PBStep));
+        double* part = (double*)ga((size_t)std::max(pblk, 1) * 6 * sizeof(double));
+        if (!sa.empty()) CK(cudaMemcpyAsync(dsa, sa.data(), sa.size() * sizeof(PAStep), cudaMemcpyHostToDevice, stream));
+        if (!sb.empty()) CK(cudaMemcpyAsync(dsb, sb.data(), sb.size() * sizeof(PBStep), cudaMemcpyHostToDevice, stream));
+        const auto t_launch = std::chrono::steady_clock::now();
+        std::vector<std::pair<std::string, cudaEvent_t>> marks;
+        auto mark = [&](const std::string& what) {
+            if (!pdebug) return;
+            cudaEvent_t e;
+            CK(cudaEventCreate(&e));
+            CK(cudaEventRecord(e, stream));
+            marks.push_back({what, e});
+        };
+        mark("start");
+        int lvno = 0;
+        for (const Lev& lv : levs) {
+            const std::string tag = "depth " + std::to_string(lvno++) + " ";
+            if (lv.a1 > lv.a0) {
+                const int na = lv.a1 - lv.a0;
+                const int wcap = round_up(lv.wcap + 1, 2);
+                if (lv.acap <= 8) launch_padj<8>(dsa, lv.a0, na, lv.ablk, part, lv.wblk, wcap);
+                else if (lv.acap <= 16) launch_padj<16>(dsa, lv.a0, na, lv.ablk, part, lv.wblk, wcap);
+                else if (lv.acap <= 32) launch_padj<32>(dsa, lv.a0, na, lv.ablk, part, lv.wblk, wcap);
+                else if (lv.acap <= 64) launch_padj<64>(dsa, lv.a0, na, lv.ablk, part, lv.wblk, wcap);
+                else if (lv.acap <= 128) launch_padj<128>(dsa, lv.a0, na, lv.ablk, part, lv.wblk, wcap);
+                else launch_padj<256>(dsa, lv.a0, na, lv.ablk, part, lv.wblk, wcap);
+                mark(tag + "A: warp blocks " + std::to_string(lv.wblk) + " + thread blocks " + std::to_string(lv.ablk) + ", cap " + std::to_string(lv.acap));
+            }
+            if (lv.b1 > lv.b0) {
+                const int nb = lv.b1 - lv.b0;
+                const int bcap = std::min(lv.bcap, lv.midM);          // (the thread path's columns: below the warp path's bound)
+                const int cap = round_up(lv.bcap + 1, 2);
+                if (bcap <= 16) launch_pchild<16>(dsb, lv.b0, nb, lv.bblk, lv.hblk, lv.mblk, cap);
+                else if (bcap <= 32) launch_pchild<32>(dsb, lv.b0, nb, lv.bblk, lv.hblk, lv.mblk, cap);
+                else if (bcap <= 64) launch_pchild<64>(dsb, lv.b0, nb, lv.bblk, lv.hblk, lv.mblk, cap);
+                else if (bcap <= 128) launch_pchild<128>(dsb, lv.b0, nb, lv.bblk, lv.hblk, lv.mblk, cap);
+                else launch_pchild<256>(dsb, lv.b0, nb, lv.bblk, lv.hblk, lv.mblk, cap);
+                mark(tag + "B: block " + std::to_string(lv.hblk) + " + warp blocks " + std::to_string(lv.mblk) + " + thread blocks " + std::to_string(lv.bblk));
+            }
+        }
+        if (!sa.empty()) {
+            padj_reduce_kernel<<<(unsigned)sa.size(), 256, 0, stream>>>(part, dsa, sadj);
+            CK(cudaGetLastError());
+            mark("reduce");
+        }
+        // stage 2: chain rule per parameter group
+        Seeds<2>* dg = (Seeds<2>*)ga(groups.size() * sizeof(Seeds<2>));
+        int* dpost = (int*)ga(postorder.size() * sizeof(int));
+        double* dout = (double*)ga(groups.size() * 2 * sizeof(double));
+        CK(cudaMemcpyAsync(dg, groups.data(), groups.size() * sizeof(Seeds<2>), cudaMemcpyHostToDevice, stream));
+        CK(cudaMemcpyAsync(dpost, postorder.data(), postorder.size() * sizeof(int), cudaMemcpyHostToDevice, stream));
+        adjoint_params_kernel<<<(unsigned)groups.size(), 32, (size_t)4 * n * sizeof(double), stream>>>(m, dg, dpost, (int)postorder.size(), sadj, rwbar,
+                                                                                                   nrow, weight_total, dout);
+        CK(cudaGetLastError());
+        mark("parameters");
+        CK(cudaMemcpyAsync(res.data(), dout, groups.size() * 2 * sizeof(double), cudaMemcpyDeviceToHost, stream));
+        CK(cudaStreamSynchronize(stream));
+        if (pdebug) {
+            const double host_ms = std::chrono::duration<double, std::milli>(t_launch - t_enter).count();
+            fprintf(stderr, "[blg padjoint] host: steps built in %.3f ms\n", host_ms);
+            for (size_t i = 1; i < marks.size(); ++i) {
+                float ms = 0.f;
+                CK(cudaEventElapsedTime(&ms, marks[i - 1].second, marks[i].second));
+                fprintf(stderr, "[blg padjoint] %-40s %8.1f us\n", marks[i].first.c_str(), ms * 1e3);
+            }
+            for (auto& mk : marks) cudaEventDestroy(mk.second);
+        }
+        for (auto& t : temps) gfree(t.first, t.second);
+    }
+
     // g: [λ_1..λ_n, μ_1..μ_n, q (ascending wgd id), η]  (asvector layout, model.jl:541-546) or [λ, μ] for cr
     void gradient(double* g, int len, double* logpdf_out, bool cr) {
         require(have_topology && have_params && tabs_valid, "gradient: model not set (topology, params, rebuild)");
@@ -2811,19 +3148,25 @@ struct blg_handle {
                           "(raise BLG_HEAVY_MIN up to 256 to keep them in the table-based shard)");
         // fresh evaluation that leaves the committed/proposal state alone (the reference uses a fresh L, model.jl:395)
         // (the gradient kernels work on one column per FAMILY: the evaluation below is a private per-family sweep)
+        // (the reverse-mode sweep runs on the node patterns; the forward-mode passes and BLG_GRAD_PAT=0 work on one column
+        // per FAMILY: their evaluation below is then a private per-family sweep)
         std::vector<Col> saved = Tp;
         const bool pm = pat_mode;
-        pat_mode = false;
+        const bool padj = pat_mode && grad_pat && grad_mode == 1 && adjoint_eligible();
+        if (!padj) pat_mode = false;
         try {
+            if (padj && pattern_fast_path() && flag_cache < 0) fetch_flag();
             logpdf(0, 1, result.p);
             double ll;
             CK(cudaMemcpyAsync(&ll, result.p, sizeof(double), cudaMemcpyDeviceToHost, stream));
             CK(cudaStreamSynchronize(stream));
             if (logpdf_out) *logpdf_out = ll;
             // the per-node scalars live on the device; the gradient's host-side step descriptions need a copy
-            h_nk.resize(ncols_model);
-            CK(cudaMemcpyAsync(h_nk.data(), d_nk.p, (size_t)ncols_model * sizeof(NodeK), cudaMemcpyDeviceToHost, stream));
-            CK(cudaStreamSynchronize(stream));
+            if (!padj) {
+                h_nk.resize(ncols_model);
+                CK(cudaMemcpyAsync(h_nk.data(), d_nk.p, (size_t)ncols_model * sizeof(NodeK), cudaMemcpyDeviceToHost, stream));
+                CK(cudaStreamSynchronize(stream));
+            }
             // parameter groups (two tangent lanes each) and where their results go
             std::vector<Seeds<2>> groups;
             std::vector<std::pair<int, int>> dest;
@@ -2844,7 +3187,9 @@ struct blg_handle {
                 add_group(SEED_ETA, 0, P - 1, SEED_NONE, -1, -1);
             }
             std::vector<double> res(2 * groups.size(), 0.0);
-            if (grad_mode == 1 && adjoint_eligible()) {
+            if (padj) {
+                gradient_padjoint(groups, res);
+            } else if (grad_mode == 1 && adjoint_eligible()) {
                 gradient_adjoint(groups, res);
             } else {
                 for (size_t i = 0; i < groups.size(); ++i) tangent_pass(groups[i], &res[2 * i]);
@@ -3029,6 +3374,10 @@ int blg_create(int device, void* stream, blg_handle** out) {
         if (const char* o = getenv("BLG_ORDER")) h->order_resident = atoi(o) != 0;
         if (const char* o = getenv("BLG_PROF")) h->profile_sweep = atoi(o);
         if (const char* o = getenv("BLG_GRAD")) h->grad_mode = (strcmp(o, "forward") == 0) ? 0 : 1;
+        if (const char* o = getenv("BLG_GRAD_PAT")) h->grad_pat = atoi(o) != 0;
+        if (const char* o = getenv("BLG_PADJ_WARP")) h->padj_warp_min = std::max(0, atoi(o));
+        if (const char* o = getenv("BLG_PADJ_LEVEL")) h->padj_warp_level = atoll(o);
+        if (const char* o = getenv("BLG_PADJ_BIG")) h->padj_warp_big = std::max(1, atoi(o));
         if (const char* w = getenv("BLG_WPB")) { int v = atoi(w); if (v == 1 || v == 2 || v == 4) h->sweep_wpb = v; }
         if (const char* sc = getenv("BLG_SLICE")) h->slice_cap = std::max(8, std::min(224, atoi(sc)));
         // families whose root count reaches this go to the heavy shard; above BLG_FAST_MAXCOUNT+1 the fast shard leaves the
