@@ -1278,7 +1278,6 @@ struct Pat {
     uint16_t* d_cnt = nullptr;       // [ld] count of the column per pattern (sorted descending: heaviest tiles first)
     int* d_fam2pat = nullptr;        // [N] family → pattern, on the device only for the root
     double* d_pw = nullptr;          // [ld] weight of the families with the pattern (root, gradient only)
-    std::map<int, std::pair<int*, int>> big;   // T → indices of the patterns with at least T counts (padjoint.cuh)
     std::vector<int> fam2pat;        // host
     std::vector<int> rep;            // a family of each pattern
     std::vector<uint16_t> h_cnt;
@@ -1286,7 +1285,6 @@ struct Pat {
         if (d_cnt) cudaFree(d_cnt);
         if (d_fam2pat) cudaFree(d_fam2pat);
         if (d_pw) cudaFree(d_pw);
-        for (auto& b : big) if (b.second.first) cudaFree(b.second.first);
     }
 };
 // pattern of a node → pattern of each child, for one (node column, ordered child columns) combination
@@ -1309,6 +1307,7 @@ struct Link {
     int nhit[BLG_MAXK] = {0};
     int nmid[BLG_MAXK] = {0};
     int nmid_many[BLG_MAXK] = {0};
+    std::map<int, std::pair<int*, int>> big;   // (msmin, T) → the node patterns of the adjoint's warp path (padj_is_big)
     ~Link() {
         for (int* q : d_pidx) if (q) cudaFree(q);
         for (int* q : d_tiles) if (q) cudaFree(q);
@@ -1317,6 +1316,7 @@ struct Link {
         for (int* q : d_inv_idx) if (q) cudaFree(q);
         for (int* q : d_hit) if (q) cudaFree(q);
         for (int* q : d_mid) if (q) cudaFree(q);
+        for (auto& b : big) if (b.second.first) cudaFree(b.second.first);
     }
 };
 
@@ -1447,6 +1447,7 @@ struct blg_handle {
     bool padj_constants = false;
     int padj_warp_min = 0;               // BLG_PADJ_WARP: fixed count bound of the warp kernel of the pattern adjoint (0: per depth)
     int padj_warp_big = 257;             // BLG_PADJ_BIG: the warp path's count bound at depths with many patterns
+    int padj_mid_big = 0x7fff;           // BLG_PB_MIDM: phase B's warp path takes child patterns from this many counts at such depths
     long long padj_warp_level = 32768;   // BLG_PADJ_LEVEL: depths with at most this many patterns use the warp kernel
     bool grad_pat = true;                // reverse mode over node patterns (padjoint.cuh); BLG_GRAD_PAT=0: over families (adjoint.cuh)
     int grad_mode = 1;                   // 1: reverse-mode sweep where the tree allows it; 0: forward-mode tangent passes (BLG_GRAD=forward)
@@ -2866,7 +2867,7 @@ struct blg_handle {
         return P0->d_pw;
     }
     template <int CAP> void launch_padj(const PAStep* d, int n0, int n, int blocks, double* part, int wblocks, int wcap) {
-        const size_t smem = wblocks > 0 ? (size_t)4 * 8 * wcap * sizeof(double) : 0;
+        const size_t smem = wblocks > 0 ? (size_t)4 * (8 * (size_t)wcap + 32 * 33) * sizeof(double) : 0;
         if (smem > 48 * 1024) CK(cudaFuncSetAttribute(padj_parent_kernel<CAP>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         padj_parent_kernel<CAP><<<wblocks + blocks, 128, smem, stream>>>(d + n0, n, d_nk.p, pascal.p, pdim, part, wblocks, wcap);
         CK(cudaGetLastError());
@@ -2938,18 +2939,19 @@ struct blg_handle {
             // a depth is as slow as its longest thread: the patterns with many counts go to the warp path of the same launch
             // (from 16 counts at a depth with few patterns, where nothing else hides the thread path's latency; from 40
             // where the thread path's throughput is what counts)
-            int T = 257;
+            int T = 257, msmin = 8;
             {
                 long long total = 0;
                 for (int u : postorder)
                     if (!children[u].empty() && depth[u] == d) total += pat_of(S, S.Tp[u])->U;
-                T = total <= padj_warp_level ? 16 : padj_warp_big;
+                T = total <= padj_warp_level ? 12 : padj_warp_big;
+                msmin = total <= padj_warp_level ? 0 : 8;
                 if (padj_warp_min > 0) T = padj_warp_min;
                 long long ctotal = 0;
                 for (int u : postorder)
                     if (!children[u].empty() && depth[u] == d && children[u].size() == 2)
                         for (int c : children[u]) if (!children[c].empty()) ctotal += pat_of(S, S.Tp[c])->U;
-                lv.midM = ctotal <= padj_warp_level ? BLG_PB_MID : 0x7fff;
+                lv.midM = ctotal <= padj_warp_level ? BLG_PB_MID : padj_mid_big;
             }
             for (auto it = postorder.rbegin(); it != postorder.rend(); ++it) {
                 const int u = *it;
@@ -2965,27 +2967,30 @@ struct blg_handle {
                 as.k = k; as.node = u; as.U = Pu->U; as.ld = (int)Pu->ld;
                 as.blk0 = lv.ablk; as.nblk = (Pu->U + 127) / 128; as.pblk0 = pblk;
                 lv.ablk += as.nblk; pblk += as.nblk;
-                as.T = T;
+                as.T = T; as.msmin = msmin;
+                as.wblk0 = lv.wblk; as.wpblk0 = pblk;
+                lv.acap = std::max(lv.acap, Pu->xmax + 1);
                 if (Pu->xmax >= T) {
-                    auto bi = Pu->big.find(T);
-                    if (bi == Pu->big.end()) {
+                    const int key = (msmin << 16) | T;
+                    auto bi = lk->big.find(key);
+                    if (bi == lk->big.end()) {
                         std::vector<int> bl;
-                        for (int q = 0; q < Pu->U; ++q) if (Pu->h_cnt[q] >= T) bl.push_back(q);
+                        Pat* Pc0 = pat_of(S, S.Tp[ord[0]]);
+                        Pat* Pc1 = k == 2 ? pat_of(S, S.Tp[ord[1]]) : nullptr;
+                        for (int q = 0; q < Pu->U; ++q) {
+                            const int r = Pu->rep[q];
+                            const int m0 = Pc0->h_cnt[Pc0->fam2pat[r]], m1 = Pc1 ? (int)Pc1->h_cnt[Pc1->fam2pat[r]] : 0;
+                            if (padj_is_big(k, T, msmin, Pu->h_cnt[q], m0, m1)) bl.push_back(q);
+                        }
                         int* dbl = nullptr;
                         CK(cudaMalloc(&dbl, std::max<size_t>(bl.size(), 1) * sizeof(int)));
                         CK(cudaMemcpy(dbl, bl.data(), bl.size() * sizeof(int), cudaMemcpyHostToDevice));
-                        bi = Pu->big.emplace(T, std::make_pair(dbl, (int)bl.size())).first;
+                        bi = lk->big.emplace(key, std::make_pair(dbl, (int)bl.size())).first;
                     }
                     as.big = bi->second.first; as.nbig = bi->second.second;
                     as.nwblk = (as.nbig + 3) / 4;
-                    as.wblk0 = lv.wblk; as.wpblk0 = pblk;
                     lv.wblk += as.nwblk; pblk += as.nwblk;
-                    lv.wcap = std::max(lv.wcap, Pu->xmax + 1);
-                    // (the thread kernel's arrays only have to hold what is left to it)
-                    lv.acap = std::max(lv.acap, T);
-                } else {
-                    as.wblk0 = lv.wblk; as.wpblk0 = pblk;
-                    lv.acap = std::max(lv.acap, Pu->xmax + 1);
+                    if (as.nbig > 0) lv.wcap = std::max(lv.wcap, Pu->xmax + 1);
                 }
                 Slab* su = readable(S, u);
                 as.ell = su->ell; as.scl = su->scl; as.cnt = Pu->d_cnt; as.adj = adj[u]; as.ipow = tabs[u].ipow;
@@ -3378,6 +3383,7 @@ int blg_create(int device, void* stream, blg_handle** out) {
         if (const char* o = getenv("BLG_PADJ_WARP")) h->padj_warp_min = std::max(0, atoi(o));
         if (const char* o = getenv("BLG_PADJ_LEVEL")) h->padj_warp_level = atoll(o);
         if (const char* o = getenv("BLG_PADJ_BIG")) h->padj_warp_big = std::max(1, atoi(o));
+        if (const char* o = getenv("BLG_PB_MIDM")) h->padj_mid_big = std::max(BLG_PB_MID, atoi(o));
         if (const char* w = getenv("BLG_WPB")) { int v = atoi(w); if (v == 1 || v == 2 || v == 4) h->sweep_wpb = v; }
         if (const char* sc = getenv("BLG_SLICE")) h->slice_cap = std::max(8, std::min(224, atoi(sc)));
         // families whose root count reaches this go to the heavy shard; above BLG_FAST_MAXCOUNT+1 the fast shard leaves the

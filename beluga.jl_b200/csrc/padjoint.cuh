@@ -40,9 +40,10 @@ struct PAStep {
     int blk0;                // first block of the step inside its launch
     int pblk0;               // first slot of the step's per-block partial sums
     int nblk;
-    int T;                   // patterns with at least T counts are left to padj_parent_warp_kernel (one warp each)
+    int T;                   // patterns with at least T counts whose children both have at least msmin go to the warp path
     int wblk0, nwblk;        // the step's blocks inside the warp kernel's launch (4 patterns each)
     int wpblk0, nbig;        // first slot of their partial sums; number of such patterns
+    int msmin, pad_;
     const int* big;          // their indices
     PAChild child[2];        // merge order
     const double* ell;       // the node's stored columns, exponents, counts
@@ -66,6 +67,12 @@ struct PBStep {
 };
 
 __device__ __forceinline__ double padj_clamp(double v) { return fmin(v, 1e300); }
+__constant__ double c_rinv[257];      // 1/s, s = 1..256 (filled by the host at the first gradient)
+
+// which patterns of a step the warp path takes (the host builds PAStep::big with the same rule)
+__host__ __device__ __forceinline__ bool padj_is_big(int k, int T, int msmin, int X, int M0, int M1) {
+    return X >= T && (k == 1 || (M0 < M1 ? M0 : M1) >= msmin);
+}
 
 template <class Step>
 __device__ __forceinline__ int padj_find(const Step* __restrict__ steps, int nsteps, int block) {
@@ -119,7 +126,7 @@ __device__ __forceinline__ double padj_warp_sum(double v) {
 // every loop of the thread path (a thread there walks O(M0·M1 + M0² + M1²) dependent steps, which for the heaviest
 // patterns of a tree depth takes longer than everything else at that depth)
 __device__ __forceinline__ void padj_warp_pattern(const PAStep& st, int item, const NodeK* __restrict__ nk, const double* __restrict__ pascal,
-                                                  int pdim, double* __restrict__ Ab, int cap, double (&sc)[2][3]) {
+                                                  int pdim, double* __restrict__ Ab, int cap, double* __restrict__ P, double (&sc)[2][3]) {
     const int lane = threadIdx.x & 31;
     const size_t ld = (size_t)st.ld;
     double* bq[2] = {Ab + cap, Ab + 2 * cap};
@@ -144,7 +151,8 @@ __device__ __forceinline__ void padj_warp_pattern(const PAStep& st, int item, co
             Ab[n] = padj_clamp(scalbn(o * st.ipow[n], -ex));
             Ekb = fma((double)n * o, st.ell[(size_t)n * ld + p], Ekb);
         }
-        Ekb = padj_warp_sum(Ekb) * nk[st.node].inv;
+        const double SAA = padj_warp_sum(Ekb);             // Σ_n n Ā[n] A[n]
+        Ekb = SAA * nk[st.node].inv;
         for (int i = 0; i < st.k; ++i) {
             const PAChild& c = st.child[i];
             const int Mi = M[i];
@@ -171,7 +179,83 @@ __device__ __forceinline__ void padj_warp_pattern(const PAStep& st, int item, co
                 sc[0][2] += Ekb;
             }
         }
-        for (int i = 0; i < st.k; ++i) {
+        const bool two = st.k == 2 && st.child[0].dW == nullptr && st.child[1].dW == nullptr && (M[0] < M[1] ? M[0] : M[1]) <= 31;
+        if (two) {
+            // both b̄ from the rows of the child with fewer counts (padj_merge2_reg explains the recursions): lane s holds
+            // B_S^(t)[s], then R^(t)[s]; the products K(t,s)·B_S^(t)[s] of 32 steps t go to P, whose rows are then summed by
+            // one lane each (no reduction across lanes anywhere)
+            const int L = M[0] >= M[1] ? 0 : 1, S = 1 - L;
+            const int ML = M[L], MS = M[S];
+            const PAChild& cL = st.child[L];
+            const PAChild& cS = st.child[S];
+            const double* bL = bq[L];
+            const double* bS = bq[S];
+            const double eL = L == 0 ? e0 : e1, eS = L == 0 ? e1 : e0;
+            const double EL = eL > 1.0 ? 1.0 : eL;
+            double* outL = (cL.bbar != nullptr && ML > 0) ? cL.bbar + cL.pos[p] : nullptr;
+            double* outS = (cS.bbar != nullptr && MS > 0) ? cS.bbar + cS.pos[p] : nullptr;
+            double* rinv = pws;
+            for (int q = lane; q < cap; q += 32) rinv[q] = c_rinv[q < 256 ? q : 256];
+            __syncwarp();
+            const bool on = lane <= MS;
+            double row = on ? bS[lane] : 0.0;
+            double cb = 0.0, nd = (double)lane;
+            if (on) {
+                double pw = 1.0, base = EL;                    // C(s, s)·E_L^s
+                for (int q = lane; q > 0; q >>= 1) { if (q & 1) pw *= base; base *= base; }
+                cb = pw;
+            }
+            double csL = 0.0, psL = 0.0;
+            for (int t0 = 0; t0 <= ML; t0 += 32) {
+                const int tn = ML + 1 - t0 < 32 ? ML + 1 - t0 : 32;
+                for (int r = 0; r < tn; ++r) {
+                    const int t = t0 + r;
+                    const double K = on ? cb * Ab[t + lane] : 0.0;
+                    P[r * 33 + lane] = K * row;
+                    double up = __shfl_down_sync(0xffffffffu, row, 1);
+                    if (lane == 31) up = 0.0;
+                    row = fma(eS, row, up);
+                    nd += 1.0;
+                    cb *= nd * rinv[t + 1];                    // C(t+1+s, s) = C(t+s, s)·(t+s+1)/(t+1)
+                }
+                __syncwarp();
+                if (lane < tn) {
+                    const int t = t0 + lane;
+                    double acc = 0.0;
+                    for (int q = 0; q <= MS; ++q) acc += P[lane * 33 + q];
+                    acc = padj_clamp(acc);
+                    const double w = (double)t * acc;
+                    csL = fma(w, bL[t], csL);
+                    if (t < ML) psL = fma(w, bL[t + 1], psL);
+                    if (outL) outL[(size_t)t * ld] = acc;
+                }
+                __syncwarp();
+            }
+            double R = 0.0;
+            for (int t = ML; t >= 0; --t) {
+                if (on) cb *= (double)(t + 1) * rinv[t + 1 + lane];   // C(t+s, s) = C(t+1+s, s)·(t+1)/(t+1+s)
+                const double K = on ? cb * Ab[t + lane] : 0.0;
+                double dn = __shfl_up_sync(0xffffffffu, R, 1);
+                if (lane == 0) dn = 0.0;
+                R = on ? fma(K, bL[t], fma(eS, R, dn)) : 0.0;
+            }
+            double csS = 0.0, psS = 0.0;
+            if (on) {
+                const double r = padj_clamp(R);
+                const double w = (double)lane * r;
+                csS = w * bS[lane];
+                if (lane < MS) psS = w * bS[lane + 1];
+                if (outS) outS[(size_t)lane * ld] = r;
+            }
+            const double ccL = nk[cL.id].cc, ccS = nk[cS.id].cc;
+            sc[L][0] += psL / ccL; sc[L][1] += csL / ccL;
+            sc[S][0] += psS / ccS; sc[S][1] += csS / ccS;
+            const double saa = lane == 0 ? SAA : 0.0;          // (per-lane shares: the block reduction adds them up)
+            if (eL < 1.0 && eL > 0.0) sc[L][2] += (saa - csL) / eL;
+            if (eS < 1.0 && eS > 0.0) sc[S][2] += (saa - csS) / eS;
+            __syncwarp();
+        }
+        for (int i = 0; i < (two ? 0 : st.k); ++i) {
             const PAChild& c = st.child[i];
             const int Mi = M[i];
             const double* bi = bq[i];
@@ -262,8 +346,6 @@ __device__ __forceinline__ void padj_warp_pattern(const PAStep& st, int item, co
 // Σ_n n Ā[n] A[n] - cs_i the derivative with respect to e_i: every term of A[n] carries e_i to the power n - (index of b_i)).
 // (K is built along s from C(t+s+1, s+1) = C(t+s, s)·(t+s+1)/(s+1) with the reciprocals from constant memory: no table
 // look-up per term)
-__constant__ double c_rinv[257];      // 1/s, s = 1..256 (filled by the host at the first gradient)
-
 template <int RS>
 __device__ __forceinline__ void padj_merge2_reg(const double* __restrict__ Ab, const double* __restrict__ bL, const double* __restrict__ bS,
                                                 int ML, int MS, double EL, double eS, double* __restrict__ outL, double* __restrict__ outS,
@@ -393,21 +475,25 @@ __global__ void __launch_bounds__(128, BLG_PADJ_MINB) padj_parent_kernel(const P
 #pragma unroll
     for (int i = 0; i < 2; ++i) { sc[i][0] = 0.0; sc[i][1] = 0.0; sc[i][2] = 0.0; }
     int X = (p >= 0 && p < st.U) ? (int)st.cnt[p] : 0;
-    if (X >= st.T) X = 0;              // (the warp path)
     if (wpath) {
         const int item = (vb - st.wblk0) * 4 + (int)(threadIdx.x >> 5);
-        if (item < st.nbig) padj_warp_pattern(st, item, nk, pascal, pdim, blg_smem + (size_t)(threadIdx.x >> 5) * 8 * wcap, wcap, sc);
+        double* wsm = blg_smem + (size_t)(threadIdx.x >> 5) * (8 * (size_t)wcap + 32 * 33);
+        if (item < st.nbig) padj_warp_pattern(st, item, nk, pascal, pdim, wsm, wcap, wsm + 8 * (size_t)wcap, sc);
     }
+    double Ab[CAP], b0[CAP], b1[CAP], Br[CAP], bb[CAP], lc[CAP];
+    int cidx[2] = {p, p}, M[2] = {0, 0};
+    int ex = 0;
     if (X > 0) {
-        double Ab[CAP], b0[CAP], b1[CAP], Br[CAP], bb[CAP], lc[CAP];
-        int cidx[2] = {p, p}, M[2] = {0, 0};
-        int ex = st.scl[p];
+        ex = st.scl[p];
         for (int i = 0; i < st.k; ++i) {
             const PAChild& c = st.child[i];
             if (c.pidx) cidx[i] = c.pidx[p];
             M[i] = c.xcnt ? (int)c.xcnt[p] : (int)c.cnt[cidx[i]];
             if (c.scl) ex -= c.scl[cidx[i]];
         }
+        if (padj_is_big(st.k, st.T, st.msmin, X, M[0], M[1])) X = 0;      // (the warp path has it)
+    }
+    if (X > 0) {
         // Ā[n] = ô_u[n]·2^(-ex)·(1-E_k)^(-n); adjoint of the normalisation
         double Ekb = 0.0;
         for (int n = 0; n <= X; ++n) {
@@ -586,6 +672,7 @@ __global__ void __launch_bounds__(128) padj_child_kernel(const PBStep* __restric
         const int c = st.mid[item];
         const int M = st.cnt[c];
         const int k0 = st.off[c], k1 = st.off[c + 1];
+        if (k1 - k0 <= BLG_PB_HIT && M < st.midM) return;      // (listed for a lower bound: the thread path has it)
         if (k1 - k0 >= 32) {
             for (int t = 0; t <= M; ++t) {
                 const double* row = st.bbar + (size_t)t * ldp;
