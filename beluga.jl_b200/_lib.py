@@ -10,7 +10,7 @@ _lib = None
 
 # every symbol include/beluga_b200.h declares
 SYMBOLS = [
-    "blg_create", "blg_destroy", "blg_last_error", "blg_set_profiles", "blg_set_topology", "blg_set_params",
+    "blg_create", "blg_destroy", "blg_last_error", "blg_set_profiles", "blg_set_profiles_columns", "blg_set_topology", "blg_set_params",
     "blg_rebuild", "blg_logpdf_full", "blg_logpdf_from", "blg_logpdf_root", "blg_logpdf_full_async",
     "blg_logpdf_from_async", "blg_logpdf_root_async", "blg_gradient", "blg_gradient_cr", "blg_comm_unique_id", "blg_comm_init", "blg_comm_size",
     "blg_commit", "blg_revert", "blg_extend", "blg_shrink", "blg_get_column", "blg_get_family_logpdf",
@@ -53,6 +53,7 @@ def lib():
     L.blg_last_error.argtypes = [vp]
     L.blg_last_error.restype = C.c_char_p
     L.blg_set_profiles.argtypes = [vp, i32p, i64p, C.c_int, C.c_int]
+    L.blg_set_profiles_columns.argtypes = [vp, i32p, i64p, C.c_int, C.c_int]
     L.blg_set_topology.argtypes = [vp, C.c_int, i32p, u8p, i32p]
     L.blg_set_params.argtypes = [vp, C.c_int, dp, dp, dp, dp, C.c_double]
     L.blg_rebuild.argtypes = [vp, i32p, C.c_int]

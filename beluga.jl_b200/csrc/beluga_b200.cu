@@ -18,6 +18,7 @@
 #include <dlfcn.h>
 
 #include <algorithm>
+#include <atomic>
 #include <cmath>
 #include <limits>
 #include <cstdint>
@@ -25,10 +26,12 @@
 #include <chrono>
 #include <cstring>
 #include <deque>
+#include <functional>
 #include <map>
 #include <memory>
 #include <stdexcept>
 #include <string>
+#include <thread>
 #include <unordered_map>
 #include <vector>
 
@@ -1281,6 +1284,7 @@ struct Pat {
     std::vector<int> fam2pat;        // host
     std::vector<int> rep;            // a family of each pattern
     std::vector<uint16_t> h_cnt;
+    std::vector<const Pat*> kids;    // the children's patterns these were built from (a link over exactly these needs no check)
     ~Pat() {
         if (d_cnt) cudaFree(d_cnt);
         if (d_fam2pat) cudaFree(d_fam2pat);
@@ -1444,6 +1448,7 @@ struct blg_handle {
     // sweep-kernel plumbing
     int kernel_version = 2;
     bool order_resident = true;
+    double link_ms = 0.0;                // host time spent building links during the current sweep (BLG_PDEBUG)
     bool padj_constants = false;
     int padj_warp_min = 0;               // BLG_PADJ_WARP: fixed count bound of the warp kernel of the pattern adjoint (0: per depth)
     int padj_warp_big = 257;             // BLG_PADJ_BIG: the warp path's count bound at depths with many patterns
@@ -2012,118 +2017,172 @@ struct blg_handle {
     }
     // distinct sub-patterns of every column of the current topology, bottom-up: a leaf's patterns are its distinct counts,
     // a single child hands its patterns up unchanged, otherwise the distinct tuples of the children's patterns
-    void ensure_pats(Shard& S) {
+    // the host side of one node's patterns (no CUDA calls: nodes of one tree level are built on several host threads)
+    std::shared_ptr<Pat> build_pat(const Shard& S, int u) const {
         const int N = S.N;
+        const Col& cu = S.Tp[u];
+        const int k = (int)children[u].size();
+        auto P = std::make_shared<Pat>();
+        const uint16_t* hx = host_counts(S, cu);
+        // entries above the column's bound belong to the heavy family set: pattern -1; so does every entry with such a child
+        const int hm = cu.lmax + 1;
+        std::vector<int> id(N, -1);
+        int U = 0;
+        std::vector<Pat*> cp;
+        if (k == 0) {
+            std::vector<int> tab(cu.xmax + 1, -1);
+            for (int f = 0; f < N; ++f) if (hx[f] < hm) tab[hx[f]] = 0;
+            for (int v = cu.xmax; v >= 0; --v) if (tab[v] == 0) tab[v] = U++;      // descending counts
+            for (int f = 0; f < N; ++f) if (hx[f] < hm) id[f] = tab[hx[f]];
+        } else {
+            for (int c : children[u]) {
+                if (c >= (int)S.Tp.size()) throw std::runtime_error("logpdf: child id beyond the profile columns");
+                cp.push_back(S.pats.at(S.Tp[c].cnt).get());
+            }
+            for (int f = 0; f < N; ++f) {
+                if (hx[f] >= hm) continue;
+                bool ok = true;
+                for (int j = 0; j < k; ++j) ok = ok && cp[j]->fam2pat[f] >= 0;
+                if (ok) id[f] = cp[0]->fam2pat[f];
+            }
+            U = cp[0]->U;
+            for (int j = 1; j < k; ++j) {
+                const std::vector<int>& b = cp[j]->fam2pat;
+                const uint64_t Ub = (uint64_t)cp[j]->U, space = (uint64_t)U * Ub;
+                int next = 0;
+                if (space <= std::max<uint64_t>(2ull * (uint64_t)N, 1ull << 16)) {
+                    std::vector<int> tab((size_t)space, -1);
+                    for (int f = 0; f < N; ++f) {
+                        if (id[f] < 0) continue;
+                        int& t_ = tab[(size_t)((uint64_t)id[f] * Ub + (uint64_t)b[f])];
+                        if (t_ < 0) t_ = next++;
+                        id[f] = t_;
+                    }
+                } else {
+                    // open addressing, linear probing: (key + 1, value) slots, at most half full
+                    size_t cap = 1024;
+                    while (cap < (size_t)N * 2) cap <<= 1;
+                    std::vector<uint64_t> hk(cap, 0);
+                    std::vector<int> hv(cap, 0);
+                    for (int f = 0; f < N; ++f) {
+                        if (id[f] < 0) continue;
+                        const uint64_t key = (uint64_t)id[f] * Ub + (uint64_t)b[f] + 1;
+                        size_t slot = (size_t)((key * 0x9E3779B97F4A7C15ull) >> 20) & (cap - 1);
+                        while (hk[slot] != 0 && hk[slot] != key) slot = (slot + 1) & (cap - 1);
+                        if (hk[slot] == 0) { hk[slot] = key; hv[slot] = next++; }
+                        id[f] = hv[slot];
+                    }
+                }
+                U = next;
+            }
+        }
+        // a family of each pattern, then the patterns in descending order of (own count, children's counts): the 32
+        // patterns of a tile get (nearly) the same loop bounds, and the heaviest tiles start first
+        {   // ids may have gaps (patterns of a child that only heavy entries of this node use): make them dense
+            std::vector<int> dense(std::max(U, 1), -1);
+            int nu = 0;
+            for (int f = 0; f < N; ++f) if (id[f] >= 0 && dense[id[f]] < 0) dense[id[f]] = nu++;
+            for (int f = 0; f < N; ++f) if (id[f] >= 0) id[f] = dense[id[f]];
+            U = nu;
+        }
+        std::vector<int> rep(U, -1);
+        for (int f = 0; f < N; ++f) if (id[f] >= 0 && rep[id[f]] < 0) rep[id[f]] = f;
+        std::vector<int> ord(U);
+        for (int i = 0; i < U; ++i) ord[i] = i;
+        int nvery = 0, nwide = 0;
+        if (k >= 2) {
+            std::vector<uint64_t> key(U);
+            for (int i = 0; i < U; ++i) {
+                const int r = rep[i];
+                int m1 = 0, m2 = 0;                     // largest and second-largest child count
+                int mc[2] = {0, 0};
+                for (int j = 0; j < k; ++j) {
+                    const int mj = cp[j]->h_cnt[cp[j]->fam2pat[r]];
+                    if (j < 2) mc[j] = mj;
+                    if (mj > m1) { m2 = m1; m1 = mj; } else if (mj > m2) m2 = mj;
+                }
+                // class, then (own count, the larger child's count) descending: the 32 patterns of a tile get (nearly)
+                // the same loop bounds AND the same register-tiled side
+                // (polytomies: no wide class — their tiles run on the generic instantiation, anything beyond its register
+                // merges on the general kernel)
+                uint64_t cls = (m2 >= 36 || (k > 2 && m2 >= 20)) ? 3 : m2 >= 20 ? 2 : (mc[0] >= mc[1] ? 1 : 0);
+                if (cls == 3) ++nvery; else if (cls == 2) ++nwide;
+                key[i] = (cls << 60) | ((uint64_t)hx[r] << 32) | ((uint64_t)std::max(mc[0], mc[1]) << 16) | (uint64_t)std::min(mc[0], mc[1]);
+            }
+            // (sorted as (key, index) pairs — the order a stable sort by descending key gives, without its indirection)
+            std::vector<std::pair<uint64_t, int>> kv(U);
+            for (int i = 0; i < U; ++i) kv[i] = {~key[i], i};
+            std::sort(kv.begin(), kv.end());
+            for (int i = 0; i < U; ++i) ord[i] = kv[i].second;
+        }
+        P->nvery = nvery;
+        P->nwide = nwide;
+        P->kids.assign(cp.begin(), cp.end());
+        std::vector<int> newidx(U);
+        for (int i = 0; i < U; ++i) newidx[ord[i]] = i;
+        P->U = U;
+        P->rep.resize(U);
+        P->h_cnt.resize(U);
+        for (int i = 0; i < U; ++i) { P->rep[i] = rep[ord[i]]; P->h_cnt[i] = hx[rep[ord[i]]]; }
+        for (int f = 0; f < N; ++f) if (id[f] >= 0) id[f] = newidx[id[f]];
+        P->fam2pat.swap(id);
+        P->xmax = 0;
+        P->colsum = 0.0;
+        for (int i = 0; i < U; ++i) { P->colsum += (double)P->h_cnt[i] + 1.0; P->xmax = std::max(P->xmax, (int)P->h_cnt[i]); }
+        return P;
+    }
+    void ensure_pats(Shard& S) {
+        // levels: a node is built after its children; single-child nodes share their child's patterns
+        std::vector<int> lev(ncols_model, -1);
+        std::vector<std::vector<int>> bylev, alias;
         for (int u : postorder) {
             require(u < (int)S.Tp.size(), "logpdf: model has more node ids than the profile has columns (call blg_extend)");
-            const Col& cu = S.Tp[u];
-            if (S.pats.count(cu.cnt)) continue;
+            if (S.pats.count(S.Tp[u].cnt)) continue;
             const int k = (int)children[u].size();
-            if (k == 1) {
-                const int c = children[u][0];
+            int lv = 0;
+            for (int c : children[u]) {
                 require(c < (int)S.Tp.size(), "logpdf: child id beyond the profile columns");
-                S.pats[cu.cnt] = S.pats.at(S.Tp[c].cnt);
-                continue;
+                if (lev[c] >= 0) lv = std::max(lv, lev[c] + (k == 1 ? 0 : 1));
             }
-            auto P = std::make_shared<Pat>();
-            const uint16_t* hx = host_counts(S, cu);
-            // entries above the column's bound belong to the heavy family set: pattern -1; so does every entry with such a child
-            const int hm = cu.lmax + 1;
-            std::vector<int> id(N, -1);
-            int U = 0;
-            std::vector<Pat*> cp;
-            if (k == 0) {
-                std::vector<int> tab(cu.xmax + 1, -1);
-                for (int f = 0; f < N; ++f) if (hx[f] < hm) tab[hx[f]] = 0;
-                for (int v = cu.xmax; v >= 0; --v) if (tab[v] == 0) tab[v] = U++;      // descending counts
-                for (int f = 0; f < N; ++f) if (hx[f] < hm) id[f] = tab[hx[f]];
-            } else {
-                for (int c : children[u]) {
-                    require(c < (int)S.Tp.size(), "logpdf: child id beyond the profile columns");
-                    cp.push_back(S.pats.at(S.Tp[c].cnt).get());
+            lev[u] = lv;
+            if ((int)bylev.size() <= lv) { bylev.resize(lv + 1); alias.resize(lv + 1); }
+            (k == 1 ? alias : bylev)[lv].push_back(u);
+        }
+        for (size_t lv = 0; lv < bylev.size(); ++lv) {
+            const std::vector<int>& nodes = bylev[lv];
+            std::vector<std::shared_ptr<Pat>> built(nodes.size());
+            std::vector<std::string> errs(nodes.size());
+            // heaviest nodes first: the threads take them one at a time
+            std::atomic<size_t> next{0};
+            std::vector<size_t> order(nodes.size());
+            for (size_t i = 0; i < order.size(); ++i) order[i] = i;
+            std::stable_sort(order.begin(), order.end(), [&](size_t a, size_t b) { return children[nodes[a]].size() > children[nodes[b]].size(); });
+            auto work = [&]() {
+                for (;;) {
+                    const size_t q = next.fetch_add(1);
+                    if (q >= order.size()) break;
+                    const size_t i = order[q];
+                    try { built[i] = build_pat(S, nodes[i]); } catch (const std::exception& e) { errs[i] = e.what(); }
                 }
-                for (int f = 0; f < N; ++f) {
-                    if (hx[f] >= hm) continue;
-                    bool ok = true;
-                    for (int j = 0; j < k; ++j) ok = ok && cp[j]->fam2pat[f] >= 0;
-                    if (ok) id[f] = cp[0]->fam2pat[f];
-                }
-                U = cp[0]->U;
-                for (int j = 1; j < k; ++j) {
-                    const std::vector<int>& b = cp[j]->fam2pat;
-                    const uint64_t Ub = (uint64_t)cp[j]->U, space = (uint64_t)U * Ub;
-                    int next = 0;
-                    if (space <= std::max<uint64_t>(8ull * (uint64_t)N, 1ull << 16)) {
-                        std::vector<int> tab((size_t)space, -1);
-                        for (int f = 0; f < N; ++f) {
-                            if (id[f] < 0) continue;
-                            int& t_ = tab[(size_t)((uint64_t)id[f] * Ub + (uint64_t)b[f])];
-                            if (t_ < 0) t_ = next++;
-                            id[f] = t_;
-                        }
-                    } else {
-                        std::unordered_map<uint64_t, int> mp;
-                        mp.reserve((size_t)N * 2);
-                        for (int f = 0; f < N; ++f) {
-                            if (id[f] < 0) continue;
-                            auto ins = mp.emplace((uint64_t)id[f] * Ub + (uint64_t)b[f], next);
-                            if (ins.second) ++next;
-                            id[f] = ins.first->second;
-                        }
-                    }
-                    U = next;
-                }
+            };
+            const unsigned nt = (unsigned)std::min<size_t>(std::min<unsigned>(16u, std::max(1u, std::thread::hardware_concurrency())), nodes.size());
+            if (nt <= 1 || S.N < 4096) work();
+            else {
+                std::vector<std::thread> th;
+                for (unsigned t = 0; t < nt; ++t) th.emplace_back(work);
+                for (auto& x : th) x.join();
             }
-            // a family of each pattern, then the patterns in descending order of (own count, children's counts): the 32
-            // patterns of a tile get (nearly) the same loop bounds, and the heaviest tiles start first
-            {   // ids may have gaps (patterns of a child that only heavy entries of this node use): make them dense
-                std::vector<int> dense(std::max(U, 1), -1);
-                int nu = 0;
-                for (int f = 0; f < N; ++f) if (id[f] >= 0 && dense[id[f]] < 0) dense[id[f]] = nu++;
-                for (int f = 0; f < N; ++f) if (id[f] >= 0) id[f] = dense[id[f]];
-                U = nu;
+            for (size_t i = 0; i < nodes.size(); ++i) {
+                if (!errs[i].empty()) throw std::runtime_error(errs[i]);
+                const Col& cu = S.Tp[nodes[i]];
+                if (S.pats.count(cu.cnt)) continue;
+                upload_pat(*built[i]);
+                S.pats[cu.cnt] = built[i];
             }
-            std::vector<int> rep(U, -1);
-            for (int f = 0; f < N; ++f) if (id[f] >= 0 && rep[id[f]] < 0) rep[id[f]] = f;
-            std::vector<int> ord(U);
-            for (int i = 0; i < U; ++i) ord[i] = i;
-            int nvery = 0, nwide = 0;
-            if (k >= 2) {
-                std::vector<uint64_t> key(U);
-                for (int i = 0; i < U; ++i) {
-                    const int r = rep[i];
-                    int m1 = 0, m2 = 0;                     // largest and second-largest child count
-                    int mc[2] = {0, 0};
-                    for (int j = 0; j < k; ++j) {
-                        const int mj = cp[j]->h_cnt[cp[j]->fam2pat[r]];
-                        if (j < 2) mc[j] = mj;
-                        if (mj > m1) { m2 = m1; m1 = mj; } else if (mj > m2) m2 = mj;
-                    }
-                    // class, then (own count, the larger child's count) descending: the 32 patterns of a tile get (nearly)
-                    // the same loop bounds AND the same register-tiled side
-                    // (polytomies: no wide class — their tiles run on the generic instantiation, anything beyond its register
-                    // merges on the general kernel)
-                    uint64_t cls = (m2 >= 36 || (k > 2 && m2 >= 20)) ? 3 : m2 >= 20 ? 2 : (mc[0] >= mc[1] ? 1 : 0);
-                    if (cls == 3) ++nvery; else if (cls == 2) ++nwide;
-                    key[i] = (cls << 60) | ((uint64_t)hx[r] << 32) | ((uint64_t)std::max(mc[0], mc[1]) << 16) | (uint64_t)std::min(mc[0], mc[1]);
-                }
-                std::stable_sort(ord.begin(), ord.end(), [&](int a, int b) { return key[a] > key[b]; });
+            for (int u : alias[lv]) {                       // (postorder inside the level: chains resolve bottom-up)
+                const Col& cu = S.Tp[u];
+                if (!S.pats.count(cu.cnt)) S.pats[cu.cnt] = S.pats.at(S.Tp[children[u][0]].cnt);
             }
-            P->nvery = nvery;
-            P->nwide = nwide;
-            std::vector<int> newidx(U);
-            for (int i = 0; i < U; ++i) newidx[ord[i]] = i;
-            P->U = U;
-            P->rep.resize(U);
-            P->h_cnt.resize(U);
-            for (int i = 0; i < U; ++i) { P->rep[i] = rep[ord[i]]; P->h_cnt[i] = hx[rep[ord[i]]]; }
-            for (int f = 0; f < N; ++f) if (id[f] >= 0) id[f] = newidx[id[f]];
-            P->fam2pat.swap(id);
-            P->xmax = 0;
-            P->colsum = 0.0;
-            for (int i = 0; i < U; ++i) { P->colsum += (double)P->h_cnt[i] + 1.0; P->xmax = std::max(P->xmax, (int)P->h_cnt[i]); }
-            upload_pat(*P);
-            S.pats[cu.cnt] = P;
         }
     }
     // node pattern → child pattern maps for node u with its children in the order `ord`
@@ -2133,6 +2192,10 @@ struct blg_handle {
         for (int c : ord) key.push_back(S.Tp[c].cnt);
         auto it = S.links.find(key);
         if (it != S.links.end()) return it->second.get();
+        struct Clock {
+            double& acc; std::chrono::steady_clock::time_point t0 = std::chrono::steady_clock::now();
+            ~Clock() { acc += std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t0).count(); }
+        } clock{link_ms};
         Pat* Pu = pat_of(S, S.Tp[u]);
         auto L = std::make_shared<Link>();
         for (size_t j = 0; j < ord.size(); ++j) {
@@ -2144,10 +2207,11 @@ struct blg_handle {
             std::vector<int> px(Pu->ld, 0);
             for (int q = 0; q < Pu->U; ++q) px[q] = Pc->fam2pat[Pu->rep[q]];
             for (size_t q = Pu->U; q < Pu->ld; ++q) px[q] = Pu->U > 0 ? px[Pu->U - 1] : 0;
-            // the node's pattern must determine the child's for EVERY family (it does when the patterns were built for
-            // this tree; a different tree over the same columns needs new patterns)
-            for (int f = 0; f < S.N; ++f)
-                if (Pu->fam2pat[f] >= 0 && px[Pu->fam2pat[f]] != Pc->fam2pat[f]) throw std::runtime_error("logpdf: node patterns do not match the topology (call blg_set_profiles again after changing the species tree)");
+            // the node's pattern must determine the child's for EVERY family: it does by construction when the node's
+            // patterns were built from this child's; a different tree over the same columns needs new patterns
+            if (std::find(Pu->kids.begin(), Pu->kids.end(), (const Pat*)Pc) == Pu->kids.end() || Pu->kids.size() != ord.size())
+                for (int f = 0; f < S.N; ++f)
+                    if (Pu->fam2pat[f] >= 0 && px[Pu->fam2pat[f]] != Pc->fam2pat[f]) throw std::runtime_error("logpdf: node patterns do not match the topology (call blg_set_profiles again after changing the species tree)");
             CK(cudaMalloc(&L->d_pidx[j], Pu->ld * sizeof(int)));
             CK(cudaMemcpy(L->d_pidx[j], px.data(), Pu->ld * sizeof(int), cudaMemcpyHostToDevice));
             std::vector<uint16_t> xc(Pu->ld, 0);
@@ -2209,7 +2273,13 @@ struct blg_handle {
     // general == true: everything on the general kernel (parameters outside the table-free forms' range).
     void psweep(const std::vector<int>& nodes, bool general) {
         Shard& S = F;
-        ensure_pats(S);
+        {
+            const auto t0 = std::chrono::steady_clock::now();
+            ensure_pats(S);
+            const double ms = std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t0).count();
+            if (pdebug && ms > 1.0) fprintf(stderr, "[blg ingest] node patterns built in %.1f ms\n", ms);
+            link_ms = 0.0;
+        }
         std::vector<int> level(ncols_model, -1), head(ncols_model, -1);
         std::vector<std::vector<int>> chain(ncols_model);
         int nlev = 0;
@@ -2449,6 +2519,7 @@ struct blg_handle {
                 }
             }
         }
+        if (pdebug && link_ms > 1.0) fprintf(stderr, "[blg ingest] pattern links and tiles built in %.1f ms\n", link_ms);
     }
     void fill_gchild(Shard& S, GChild& gc, int u, int c, Pat* Pc, Slab* sl, const int* pidx) {
         memset(&gc, 0, sizeof(gc));
@@ -3470,37 +3541,60 @@ static void family_order(const int32_t* X, int ncols, std::vector<int>& perm) {
 }
 
 // upload one family set: counts [column][family] (uint16), weights, column tables
-static void upload_shard(blg_handle* h, Shard& S, const int32_t* X, const int64_t* weight, int ncols, const std::vector<char>& isheavy) {
+// runs body(t, lo, hi) over [0, n) in contiguous chunks on up to 16 host threads
+static void host_parallel(size_t n, size_t grain, const std::function<void(unsigned, size_t, size_t)>& body) {
+    unsigned nt = std::min<unsigned>(16u, std::max(1u, std::thread::hardware_concurrency()));
+    nt = (unsigned)std::min<size_t>(nt, std::max<size_t>(1, n / std::max<size_t>(grain, 1)));
+    if (nt <= 1) { body(0u, (size_t)0, n); return; }
+    std::vector<std::thread> th;
+    const size_t chunk = (n + nt - 1) / nt;
+    for (unsigned t = 0; t < nt; ++t) {
+        const size_t lo = std::min(n, (size_t)t * chunk), hi = std::min(n, lo + chunk);
+        th.emplace_back([&body, t, lo, hi]() { body(t, lo, hi); });
+    }
+    for (auto& x : th) x.join();
+}
+
+// X: row-major [pattern][column] (colmajor = false) or column-major [column][pattern]
+static void upload_shard(blg_handle* h, Shard& S, const int32_t* X, bool colmajor, int npatterns, const int64_t* weight, int ncols,
+                         const std::vector<char>& isheavy) {
     S.N = (int)S.perm.size();
     S.ld = ((size_t)S.N + 127) / 128 * 128;
     if (S.N == 0) return;
     const size_t ld = S.ld;
     std::vector<uint16_t> stage((size_t)ncols * ld, 0);
     std::vector<Col> cols(ncols);
-    for (int c = 0; c < ncols; ++c) {
-        int mx = 0;
-        double cs = 0.0;
-        uint16_t* dst = stage.data() + (size_t)c * ld;
-        int fastmax = 0;                 // largest count of this column among the families below the heavy bound
-        for (int f = 0; f < S.N; ++f) {
-            const int32_t v = X[(size_t)S.perm[f] * ncols + c];
-            dst[f] = (uint16_t)v;
-            if (!isheavy[S.perm[f]]) fastmax = std::max(fastmax, (int)v);
-            mx = std::max(mx, (int)v);
-            cs += (double)v + 1.0;
+    const int N = S.N;
+    const int* perm = S.perm.data();
+    const bool ragged = S.ragged;
+    const int heavy_min = h->heavy_min;
+    // one column per task: conversion to 16 bits in device order, the column's bounds and byte count
+    host_parallel((size_t)ncols, 1, [&](unsigned, size_t c0, size_t c1) {
+        for (size_t c = c0; c < c1; ++c) {
+            int mx = 0;
+            double cs = 0.0;
+            uint16_t* dst = stage.data() + c * ld;
+            int fastmax = 0;                 // largest count of this column among the families below the heavy bound
+            for (int f = 0; f < N; ++f) {
+                const int32_t v = colmajor ? X[c * (size_t)npatterns + perm[f]] : X[(size_t)perm[f] * ncols + c];
+                dst[f] = (uint16_t)v;
+                if (!isheavy[perm[f]]) fastmax = std::max(fastmax, (int)v);
+                mx = std::max(mx, (int)v);
+                cs += (double)v + 1.0;
+            }
+            if (!ragged) {
+                // the fast set holds every family, but a heavy family's entries are evaluated there (as node patterns) only up
+                // to the count the other families reach at this column (at least 32): the column's bound — and with it the
+                // range of the table-free merge, whose scalings grow with the bound — stays what the fast families need
+                const int lmax = std::min(heavy_min - 1, std::max(fastmax, 32));
+                cols[c].lmax = lmax;
+                mx = 0;
+                for (int f = 0; f < N; ++f) if ((int)dst[f] <= lmax) mx = std::max(mx, (int)dst[f]);
+            }
+            cols[c].xmax = mx;
+            cols[c].colsum = cs;
         }
-        if (!S.ragged) {
-            // the fast set holds every family, but a heavy family's entries are evaluated there (as node patterns) only up to
-            // the count the other families reach at this column (at least 32): the column's bound — and with it the
-            // range of the table-free merge, whose scalings grow with the bound — stays what the fast families need
-            const int lmax = std::min(h->heavy_min - 1, std::max(fastmax, 32));
-            cols[c].lmax = lmax;
-            mx = 0;
-            for (int f = 0; f < S.N; ++f) if ((int)dst[f] <= lmax) mx = std::max(mx, (int)dst[f]);
-        }
-        cols[c].xmax = mx;
-        cols[c].colsum = cs;
-    }
+    });
     uint16_t* dcnt = nullptr;
     CK(cudaMalloc(&dcnt, stage.size() * sizeof(uint16_t)));
     S.count_allocs.push_back(dcnt);
@@ -3535,8 +3629,9 @@ static void upload_shard(blg_handle* h, Shard& S, const int32_t* X, const int64_
     S.Tp = cols;
 }
 
-int blg_set_profiles(blg_handle* h, const int32_t* X, const int64_t* weight, int ncols, int npatterns) {
+static int set_profiles_impl(blg_handle* h, const int32_t* X, bool colmajor, const int64_t* weight, int ncols, int npatterns) {
     BLG_ENTER(h)
+    const auto t_0 = std::chrono::steady_clock::now();
     h->require(ncols >= 0 && npatterns >= 0, "set_profiles: negative size");
     CK(cudaStreamSynchronize(h->stream));
     h->F.release();
@@ -3551,19 +3646,51 @@ int blg_set_profiles(blg_handle* h, const int32_t* X, const int64_t* weight, int
     if (npatterns == 0) return 0;
     h->require(X && weight && ncols >= 1, "set_profiles: null pointer");
     // split by the family's largest count (its root count, for an extended profile)
-    std::vector<int> rootc(npatterns);
-    for (int f = 0; f < npatterns; ++f) {
-        int mx = 0;
-        const int32_t* x = X + (size_t)f * ncols;
-        for (int c = 0; c < ncols; ++c) {
-            if (x[c] < 0 || x[c] > BLG_MAXCOUNT) throw std::runtime_error("set_profiles: count outside [0, " + std::to_string(BLG_MAXCOUNT) + "]");
-            mx = std::max(mx, (int)x[c]);
-        }
-        rootc[f] = mx;
-        h->F.perm.push_back(f);                                    // the fast set holds EVERY family (its entries below the heavy bound)
-        if (mx >= h->heavy_min) h->H.perm.push_back(f);            // the heavy set: the families with an entry at or above it
+    std::vector<int> rootc(npatterns, 0);
+    std::vector<int> bad(16, 0);
+    if (colmajor) {
+        host_parallel((size_t)npatterns, 1 << 14, [&](unsigned t, size_t f0, size_t f1) {
+            for (int c = 0; c < ncols; ++c) {
+                const int32_t* x = X + (size_t)c * npatterns;
+                for (size_t f = f0; f < f1; ++f) {
+                    if (x[f] < 0 || x[f] > BLG_MAXCOUNT) bad[t] = 1;
+                    rootc[f] = std::max(rootc[f], (int)x[f]);
+                }
+            }
+        });
+    } else {
+        host_parallel((size_t)npatterns, 1 << 14, [&](unsigned t, size_t f0, size_t f1) {
+            for (size_t f = f0; f < f1; ++f) {
+                int mx = 0;
+                const int32_t* x = X + f * ncols;
+                for (int c = 0; c < ncols; ++c) {
+                    if (x[c] < 0 || x[c] > BLG_MAXCOUNT) bad[t] = 1;
+                    mx = std::max(mx, (int)x[c]);
+                }
+                rootc[f] = mx;
+            }
+        });
     }
-    family_order(X, ncols, h->F.perm);
+    for (int b : bad) if (b) throw std::runtime_error("set_profiles: count outside [0, " + std::to_string(BLG_MAXCOUNT) + "]");
+    h->F.perm.resize(npatterns);
+    for (int f = 0; f < npatterns; ++f) {
+        h->F.perm[f] = f;                                          // the fast set holds EVERY family (its entries below the heavy bound)
+        if (rootc[f] >= h->heavy_min) h->H.perm.push_back(f);      // the heavy set: the families with an entry at or above it
+    }
+    const auto t_1 = std::chrono::steady_clock::now();
+    // the k-d family order serves the kernels that give every FAMILY a lane (BLG_DEDUP=0); node patterns have their own
+    // order per node (ensure_pats), the families stay as the caller gave them
+    if (!h->pat_mode) {
+        if (colmajor) {
+            std::vector<int32_t> rows((size_t)npatterns * ncols);
+            for (int c = 0; c < ncols; ++c)
+                for (int f = 0; f < npatterns; ++f) rows[(size_t)f * ncols + c] = X[(size_t)c * npatterns + f];
+            family_order(rows.data(), ncols, h->F.perm);
+        } else {
+            family_order(X, ncols, h->F.perm);
+        }
+    }
+    const auto t_2 = std::chrono::steady_clock::now();
     // heavy shard: heaviest first (the general kernel hands families out one per warp), launch groups by root count
     std::stable_sort(h->H.perm.begin(), h->H.perm.end(), [&](int a, int b) { return rootc[a] > rootc[b]; });
     {
@@ -3579,8 +3706,9 @@ int blg_set_profiles(blg_handle* h, const int32_t* X, const int64_t* weight, int
     }
     std::vector<char> isheavy(npatterns, 0);
     for (int f : h->H.perm) isheavy[f] = 1;
-    upload_shard(h, h->F, X, weight, ncols, isheavy);
-    upload_shard(h, h->H, X, weight, ncols, isheavy);
+    upload_shard(h, h->F, X, colmajor, npatterns, weight, ncols, isheavy);
+    upload_shard(h, h->H, X, colmajor, npatterns, weight, ncols, isheavy);
+    const auto t_3 = std::chrono::steady_clock::now();
     h->loc.assign(npatterns, 0);
     h->hloc.assign(npatterns, -1);
     for (int i = 0; i < h->F.N; ++i) h->loc[h->F.perm[i]] = i;
@@ -3600,7 +3728,18 @@ int blg_set_profiles(blg_handle* h, const int32_t* X, const int64_t* weight, int
         CK(cudaGetLastError());
     }
     CK(cudaStreamSynchronize(h->stream));
+    if (h->pdebug) {
+        auto ms = [](std::chrono::steady_clock::time_point a, std::chrono::steady_clock::time_point b) { return std::chrono::duration<double, std::milli>(b - a).count(); };
+        fprintf(stderr, "[blg set_profiles] %d patterns x %d columns (%s): bounds %.1f ms | family order %.1f ms | staging + upload %.1f ms | total %.1f ms\n",
+                npatterns, ncols, colmajor ? "column-major" : "row-major", ms(t_0, t_1), ms(t_1, t_2), ms(t_2, t_3), ms(t_0, std::chrono::steady_clock::now()));
+    }
     BLG_LEAVE(h)
+}
+int blg_set_profiles(blg_handle* h, const int32_t* X, const int64_t* weight, int ncols, int npatterns) {
+    return set_profiles_impl(h, X, false, weight, ncols, npatterns);
+}
+int blg_set_profiles_columns(blg_handle* h, const int32_t* Xc, const int64_t* weight, int ncols, int npatterns) {
+    return set_profiles_impl(h, Xc, true, weight, ncols, npatterns);
 }
 
 int blg_set_topology(blg_handle* h, int ncols, const int32_t* parent, const uint8_t* kind, const int32_t* child_pos) {

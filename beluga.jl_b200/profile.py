@@ -49,7 +49,11 @@ class PArray:
             self.N = 0
             self.ncols0 = 0
             return
-        X = np.ascontiguousarray(X, dtype=np.int32)
+        X = np.asarray(X)
+        # a column-major matrix (what profile() builds: one contiguous run per node) goes to the library as it is
+        self._colmajor = X.ndim == 2 and X.dtype == np.int32 and X.flags.f_contiguous and not X.flags.c_contiguous
+        if not self._colmajor:
+            X = np.ascontiguousarray(X, dtype=np.int32)
         weights = np.ascontiguousarray(weights, dtype=np.int64)
         assert X.ndim == 2 and weights.shape == (X.shape[0],)
         self.N = X.shape[0]
@@ -73,8 +77,9 @@ class PArray:
         self.world = 1
         if self.distributed:
             self._join_communicator()
-        self._ck(self.L.blg_set_profiles(self.h, X.ctypes.data_as(C.POINTER(C.c_int32)),
-                                         weights.ctypes.data_as(C.POINTER(C.c_int64)), X.shape[1], X.shape[0]))
+        entry = self.L.blg_set_profiles_columns if self._colmajor else self.L.blg_set_profiles
+        self._ck(entry(self.h, X.ctypes.data_as(C.POINTER(C.c_int32)), weights.ctypes.data_as(C.POINTER(C.c_int64)),
+                       X.shape[1], X.shape[0]))
 
     def _join_communicator(self):
         """blg_comm_unique_id on rank 0, broadcast of the 128 bytes over torch.distributed, blg_comm_init everywhere."""
@@ -305,13 +310,16 @@ class PArray:
 # ---- profile construction, src/model.jl:40-49 ---------------------------------------------------------
 def _as_table(df):
     """Accept a pandas DataFrame, a (names, counts) pair or a dict name -> column."""
+    def ints(a):                       # integer tables keep their width (10^6 x 100 counts: no 800 MB int64 copy)
+        a = np.asarray(a)
+        return a if a.dtype.kind in "iu" else a.astype(np.int64)
     if hasattr(df, "columns") and hasattr(df, "to_numpy"):
-        return [str(c) for c in df.columns], np.asarray(df.to_numpy(), dtype=np.int64)
+        return [str(c) for c in df.columns], ints(df.to_numpy())
     if isinstance(df, dict):
         names = list(df.keys())
-        return names, np.stack([np.asarray(df[k], dtype=np.int64) for k in names], axis=1)
+        return names, np.stack([ints(df[k]) for k in names], axis=1)
     names, counts = df
-    return list(names), np.asarray(counts, dtype=np.int64)
+    return list(names), ints(counts)
 
 
 def site_patterns(counts, device=None):
@@ -329,7 +337,7 @@ def site_patterns(counts, device=None):
             device = torch.cuda.current_device() if use else None
         except ImportError:
             use = False
-    if use and int(counts.max(initial=0)) < 2 ** 31:
+    if use and (counts.dtype.itemsize < 4 or counts.dtype == np.int32 or int(counts.max(initial=0)) < 2 ** 31):
         c32 = np.ascontiguousarray(counts, dtype=np.int32)
         rep = np.zeros(N, dtype=np.int32)
         wgt = np.zeros(N, dtype=np.int64)
@@ -339,7 +347,7 @@ def site_patterns(counts, device=None):
         if rc != 0:
             raise _lib.BelugaError(_lib.lib().blg_last_error(None).decode())
         rep = rep[: n.value]
-        return counts[rep], wgt[: n.value].copy()
+        return c32[rep], wgt[: n.value].copy()
     uniq, first, mult = np.unique(counts, axis=0, return_index=True, return_counts=True)
     order = np.argsort(first, kind="stable")
     return uniq[order], mult[order]
@@ -362,13 +370,17 @@ def profile(t, leaves, df, device=None):
         nodes.append(n)
         stack.extend(n.c)
     nn = len(nodes)
-    M = np.zeros((uniq.shape[0], nn), dtype=np.int64)
+    # built one node at a time, every node a contiguous run (column-major storage): the matrix handed back is the
+    # transposed view, and PArray passes it to the library without another copy
+    Mt = np.zeros((nn, uniq.shape[0]), dtype=np.int32)
+    ut = np.ascontiguousarray(uniq.T, dtype=np.int32)
     for n in reversed(nodes):          # reversed pre-order visits children before parents
         if not n.c:
-            M[:, n.i - 1] = uniq[:, col[leaves[n.i]]]
+            Mt[n.i - 1] = ut[col[leaves[n.i]]]
         else:
-            M[:, n.i - 1] = sum(M[:, c.i - 1] for c in n.c)
-    return M, mult.astype(np.int64), int(M.max()) + 1
+            kids = [c.i - 1 for c in n.c]
+            np.add(Mt[kids[0]], Mt[kids[1]], out=Mt[n.i - 1]) if len(kids) == 2 else np.sum(Mt[kids], axis=0, out=Mt[n.i - 1])
+    return Mt.T, mult.astype(np.int64), int(Mt.max()) + 1
 
 
 def DLWGD_(nw, df=None, lam=1.0, mu=1.0, eta=0.9, nt=BRANCH, device=0, distributed=False):

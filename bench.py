@@ -411,7 +411,6 @@ def leaf50_leg(args, local):
     ext = add_random_wgds(model, args.wgds, seed=SEED)
     names, counts = rand_profiles_device(model, args.leaf50_families, seed=SEED, device=local, max_leaf=args.max_count)
     X, w, m = B.profile(t, l, (names, counts))
-    X = np.ascontiguousarray(X, dtype=np.int32)
     fma = algorithmic_fma(model, X)
     data = B.PArray(X, w, device=local)
     for i in ext:
@@ -515,7 +514,6 @@ def main():
     nw, model, ext, t, l, names, counts = build_workload(args, rank, device="cuda:%d" % local)
     torch.cuda.empty_cache()
     X, w, m = B.profile(t, l, (names, counts))
-    X = np.ascontiguousarray(X, dtype=np.int32)
     npat, nfam = X.shape[0], int(w.sum())
     alg_fma = algorithmic_fma(model, X)
     data = B.PArray(X, w, device=local, distributed=True)

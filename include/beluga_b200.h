@@ -55,6 +55,9 @@ const char* blg_last_error(blg_handle* h);
  * (committed L and proposal Lp, profile.jl:14-20).  npatterns == 0 is the mock profile
  * (profile.jl:28,31): every likelihood entry then returns 0. */
 int blg_set_profiles(blg_handle* h, const int32_t* X, const int64_t* weight, int ncols, int npatterns);
+/* the same with X in column-major order (Xc[c * npatterns + f]: one contiguous run per node id — what a column-wise
+ * construction of the extended profile, leaves first, produces; no transposition on either side) */
+int blg_set_profiles_columns(blg_handle* h, const int32_t* Xc, const int64_t* weight, int ncols, int npatterns);
 
 /* --- rand(model, N; condition) (sim.jl:17-27), count level, on the device: families are drawn from the handle's current
  * topology and parameters (no profiles needed) until N are accepted.  condition: 0 none, 1 non-extinct (the reference's
