@@ -3600,7 +3600,6 @@ static void upload_shard(blg_handle* h, Shard& S, const int32_t* X, bool colmajo
     S.count_allocs.push_back(dcnt);
     CK(cudaMemcpyAsync(dcnt, stage.data(), stage.size() * sizeof(uint16_t), cudaMemcpyHostToDevice, h->stream));
     for (int c = 0; c < ncols; ++c) cols[c].cnt = dcnt + (size_t)c * ld;
-    if (!S.ragged) S.h_counts = stage;
     if (S.ragged) {
         // ragged slabs: family f's column starts at off[f] and holds exactly count+1 doubles
         std::vector<uint32_t> ostage((size_t)ncols * ld, 0);
@@ -3625,6 +3624,7 @@ static void upload_shard(blg_handle* h, Shard& S, const int32_t* X, bool colmajo
     CK(cudaMemcpyAsync(S.weight.p, w.data(), ld * sizeof(double), cudaMemcpyHostToDevice, h->stream));
     CK(cudaMemsetAsync(S.fam_ll.p, 0, ld * sizeof(double), h->stream));
     CK(cudaStreamSynchronize(h->stream));       // the staging vectors die here
+    if (!S.ragged) S.h_counts = std::move(stage);   // (kept on the host: the node patterns are built from it)
     S.Tc = cols;
     S.Tp = cols;
 }
@@ -4156,7 +4156,9 @@ int blg_rand_profiles(blg_handle* h, int N, unsigned long long seed, int conditi
 // order of first appearance.  counts: N × T, row-major (one row per family, one column per taxon), host memory.
 // rep_out[k] = index of the first family with pattern k, weight_out[k] = how many families share it, k < *npatterns.
 // Runs on the given device (hash grouping, csrc/ingest.cuh); the host only sorts the representatives.
-int blg_site_patterns(int device, const int32_t* counts, int N, int T, int32_t* rep_out, int64_t* weight_out, int* npatterns) {
+extern "C++" {
+template <class V>
+static int site_patterns_impl(int device, const V* counts, int N, int T, int32_t* rep_out, int64_t* weight_out, int* npatterns) {
     if (!counts || !rep_out || !weight_out || !npatterns || N < 0 || T < 1) return 1;
     try {
         *npatterns = 0;
@@ -4164,7 +4166,7 @@ int blg_site_patterns(int device, const int32_t* counts, int N, int T, int32_t* 
         CK(cudaSetDevice(device));
         unsigned int nslots = 1024;
         while (nslots < 2u * (unsigned int)N) nslots <<= 1;
-        DevBuf<int32_t> d_counts;
+        DevBuf<V> d_counts;
         DevBuf<unsigned int> d_u;           // [slot_rep | slot_min | slot_cnt] (nslots each), fam_slot (N), out_rep, out_cnt (N each), counter
         d_counts.ensure((size_t)N * T);
         d_u.ensure((size_t)3 * nslots + (size_t)3 * N + 16);
@@ -4175,12 +4177,12 @@ int blg_site_patterns(int device, const int32_t* counts, int N, int T, int32_t* 
         unsigned int* out_rep = fam_slot + N;
         unsigned int* out_cnt = out_rep + N;
         unsigned int* counter = out_cnt + N;
-        CK(cudaMemcpy(d_counts.p, counts, (size_t)N * T * sizeof(int32_t), cudaMemcpyHostToDevice));
+        CK(cudaMemcpy(d_counts.p, counts, (size_t)N * T * sizeof(V), cudaMemcpyHostToDevice));
         CK(cudaMemset(slot_rep, 0xff, (size_t)2 * nslots * sizeof(unsigned int)));      // rep and min: 0xffffffff
         CK(cudaMemset(slot_cnt, 0, (size_t)nslots * sizeof(unsigned int)));
         CK(cudaMemset(counter, 0, sizeof(unsigned int)));
         const int nb = (N + 255) / 256;
-        ingest_insert_kernel<<<nb, 256>>>(d_counts.p, N, T, slot_rep, fam_slot, nslots - 1);
+        ingest_insert_kernel<V><<<nb, 256>>>(d_counts.p, N, T, slot_rep, fam_slot, nslots - 1);
         ingest_group_kernel<<<nb, 256>>>(N, fam_slot, slot_min, slot_cnt);
         ingest_compact_kernel<<<(nslots + 255) / 256, 256>>>(nslots, slot_min, slot_cnt, out_rep, out_cnt, counter);
         CK(cudaGetLastError());
@@ -4198,6 +4200,13 @@ int blg_site_patterns(int device, const int32_t* counts, int N, int T, int32_t* 
         *npatterns = (int)U;
     } catch (const std::exception& e) { g_create_error = e.what(); return 2; }
     return 0;
+}
+}  // extern "C++"
+int blg_site_patterns(int device, const int32_t* counts, int N, int T, int32_t* rep_out, int64_t* weight_out, int* npatterns) {
+    return site_patterns_impl<int32_t>(device, counts, N, T, rep_out, weight_out, npatterns);
+}
+int blg_site_patterns_u16(int device, const uint16_t* counts, int N, int T, int32_t* rep_out, int64_t* weight_out, int* npatterns) {
+    return site_patterns_impl<uint16_t>(device, counts, N, T, rep_out, weight_out, npatterns);
 }
 int blg_set_timing(blg_handle* h, int on) {
     if (!h) return 1;

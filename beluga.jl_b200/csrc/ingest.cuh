@@ -14,11 +14,12 @@ __device__ __forceinline__ unsigned long long ing_mix(unsigned long long h) {
     return h;
 }
 // slot_rep[s]: representative family of the group living in slot s (0xffffffff: empty); fam_slot[f]: the slot of family f
-__global__ void __launch_bounds__(256) ingest_insert_kernel(const int32_t* __restrict__ counts, int N, int T, unsigned int* __restrict__ slot_rep,
+template <class V>
+__global__ void __launch_bounds__(256) ingest_insert_kernel(const V* __restrict__ counts, int N, int T, unsigned int* __restrict__ slot_rep,
                                                             unsigned int* __restrict__ fam_slot, unsigned int nslots_mask) {
     const int f = blockIdx.x * blockDim.x + threadIdx.x;
     if (f >= N) return;
-    const int32_t* row = counts + (size_t)f * T;
+    const V* row = counts + (size_t)f * T;
     unsigned long long h = 0x9e3779b97f4a7c15ULL;
     for (int j = 0; j < T; ++j) h = ing_mix(h ^ (unsigned long long)(unsigned int)row[j]) + 0x9e3779b97f4a7c15ULL * (unsigned long long)(j + 1);
     unsigned int s = (unsigned int)(h >> 17) & nslots_mask;
@@ -26,7 +27,7 @@ __global__ void __launch_bounds__(256) ingest_insert_kernel(const int32_t* __res
         unsigned int rep = atomicCAS(&slot_rep[s], 0xffffffffu, (unsigned int)f);
         if (rep == 0xffffffffu) { fam_slot[f] = s; return; }        // claimed an empty slot: f is (for now) the representative
         // occupied: the same pattern?  (the representative's row is immutable input: safe to read at any time)
-        const int32_t* other = counts + (size_t)rep * T;
+        const V* other = counts + (size_t)rep * T;
         bool same = true;
         for (int j = 0; j < T; ++j) if (row[j] != other[j]) { same = false; break; }
         if (same) { fam_slot[f] = s; return; }

@@ -338,16 +338,21 @@ def site_patterns(counts, device=None):
         except ImportError:
             use = False
     if use and (counts.dtype.itemsize < 4 or counts.dtype == np.int32 or int(counts.max(initial=0)) < 2 ** 31):
-        c32 = np.ascontiguousarray(counts, dtype=np.int32)
         rep = np.zeros(N, dtype=np.int32)
         wgt = np.zeros(N, dtype=np.int64)
         n = C.c_int()
-        rc = _lib.lib().blg_site_patterns(int(device), c32.ctypes.data_as(C.POINTER(C.c_int32)), N, c32.shape[1],
-                                          rep.ctypes.data_as(C.POINTER(C.c_int32)), wgt.ctypes.data_as(C.POINTER(C.c_int64)), C.byref(n))
+        if counts.dtype == np.uint16:              # (the device sampler's tables: uploaded as they are)
+            tab = np.ascontiguousarray(counts)
+            rc = _lib.lib().blg_site_patterns_u16(int(device), tab.ctypes.data_as(C.POINTER(C.c_uint16)), N, tab.shape[1],
+                                                  rep.ctypes.data_as(C.POINTER(C.c_int32)), wgt.ctypes.data_as(C.POINTER(C.c_int64)), C.byref(n))
+        else:
+            tab = np.ascontiguousarray(counts, dtype=np.int32)
+            rc = _lib.lib().blg_site_patterns(int(device), tab.ctypes.data_as(C.POINTER(C.c_int32)), N, tab.shape[1],
+                                              rep.ctypes.data_as(C.POINTER(C.c_int32)), wgt.ctypes.data_as(C.POINTER(C.c_int64)), C.byref(n))
         if rc != 0:
             raise _lib.BelugaError(_lib.lib().blg_last_error(None).decode())
         rep = rep[: n.value]
-        return c32[rep], wgt[: n.value].copy()
+        return tab[rep], wgt[: n.value].copy()
     uniq, first, mult = np.unique(counts, axis=0, return_index=True, return_counts=True)
     order = np.argsort(first, kind="stable")
     return uniq[order], mult[order]

@@ -71,6 +71,9 @@ int blg_rand_profiles(blg_handle* h, int N, unsigned long long seed, int conditi
  * table.  rep_out[k] = first family with pattern k, weight_out[k] = its multiplicity (both with room for N entries). */
 int blg_site_patterns(int device, const int32_t* counts, int N, int T, int32_t* rep_out, int64_t* weight_out,
                       int* npatterns);
+/* the same for a table of 16-bit counts (what blg_rand_profiles writes): half the bytes to the device, no widening copy */
+int blg_site_patterns_u16(int device, const uint16_t* counts, int N, int T, int32_t* rep_out, int64_t* weight_out,
+                          int* npatterns);
 
 /* --- model graph: initmodel (model.jl:227-244), addwgd!/addwgt!/removewgd!/reindex!
  * (model.jl:106-183) -----------------------------------------------------------------------------
