@@ -891,6 +891,8 @@ def test_site_patterns_on_device_match_the_host_grouping():
         assert np.array_equal(ud, uniq[order])                # same patterns, in order of first appearance
         assert np.array_equal(wd, mult[order])
         assert wd.sum() == N
+        u16, w16 = site_patterns(counts.astype(np.uint16), device=0)      # the 16-bit entry (blg_site_patterns_u16)
+        assert u16.dtype == np.uint16 and np.array_equal(u16, uniq[order]) and np.array_equal(w16, mult[order])
         if u0 is not None:
             assert np.array_equal(u0, ud) and np.array_equal(w0, wd)
     # and through profile(): extended counts of the compressed table
@@ -902,6 +904,31 @@ def test_site_patterns_on_device_match_the_host_grouping():
     uniq, first, mult = np.unique(counts, axis=0, return_index=True, return_counts=True)
     assert Xd.shape[0] == uniq.shape[0] and wdv.sum() == 60000
     assert np.array_equal(Xd[:, 0], Xd[:, [i - 1 for i in sorted(l)]].sum(axis=1))     # root = Σ leaves
+
+
+def test_column_major_profile_goes_to_the_library_without_a_copy_and_gives_the_same_values(dicots):
+    # profile() builds the extended counts one node at a time and returns the transposed view; PArray hands it to
+    # blg_set_profiles_columns.  The row-major entry (what the Julia glue passes) must give the same numbers.
+    from beluga_b200.model import build_model
+    nw, df = dicots
+    rng = np.random.default_rng(3)
+    names = df[0]
+    counts = rng.integers(0, 6, size=(700, len(names))).astype(np.uint16)
+    counts[:, 0] += 1; counts[:, -1] += 1
+    model, t, l = build_model(nw, 0.7, 0.9, 0.8, B.BRANCH)
+    X, w, m = B.profile(t, l, (names, counts))
+    assert X.dtype == np.int32 and X.flags.f_contiguous and not X.flags.c_contiguous
+    orc = OracleDLWGD(nw, names, counts.astype(np.int64), 0.7, 0.9, 0.8, OBRANCH, threads=4)
+    ow, ox = orc.profile()
+    assert np.array_equal(np.asarray(ox), X) and np.array_equal(np.asarray(ow), w)
+    dcol = B.PArray(X, w, device=0)
+    drow = B.PArray(np.ascontiguousarray(X), w, device=0)
+    assert dcol._colmajor and not drow._colmajor
+    lc, lr = B.logpdf_(model, dcol), B.logpdf_(model, drow)
+    assert lc == lr                                              # same families in the same order: bit-identical
+    assert lc == pytest.approx(orc.logpdf(), rel=1e-10)
+    gc, gr = B.gradient(model, dcol), B.gradient(model, drow)
+    assert np.array_equal(gc, gr)
 
 
 # ---- rand(model, N) on the device (src/sim.jl:17-145 at the count level) ------------------------------------------------
