@@ -1989,11 +1989,28 @@ struct blg_handle {
             }
             if (fan) CK(cudaEventRecord(ev_fork, stream));
             int gi = 0;
+            std::vector<cudaEvent_t> dbg;                    // BLG_PDEBUG: start and end of every class on its stream
+            cudaEvent_t dbg0 = nullptr;
+            if (pdebug && fan) { CK(cudaEventCreate(&dbg0)); CK(cudaEventRecord(dbg0, stream)); }
             for (const auto& g : groups) {
                 if (fan) { CK(cudaStreamWaitEvent(gstreams[gi % 8], ev_fork, 0)); lstream = gstreams[gi % 8]; }
+                if (dbg0) { cudaEvent_t e; CK(cudaEventCreate(&e)); CK(cudaEventRecord(e, lstream)); dbg.push_back(e); }
                 launch_general(L, g.f0, g.f1, g.maxroot, 1, when, gi);
+                if (dbg0) { cudaEvent_t e; CK(cudaEventCreate(&e)); CK(cudaEventRecord(e, lstream)); dbg.push_back(e); }
                 lstream = nullptr;
                 ++gi;
+            }
+            if (dbg0) {
+                for (int q = 0; q < std::min<int>(8, (int)groups.size()); ++q) CK(cudaStreamSynchronize(gstreams[q]));
+                for (size_t q = 0; q < groups.size(); ++q) {
+                    float a = 0.f, b = 0.f;
+                    CK(cudaEventElapsedTime(&a, dbg0, dbg[2 * q]));
+                    CK(cudaEventElapsedTime(&b, dbg0, dbg[2 * q + 1]));
+                    fprintf(stderr, "[blg heavy] class %zu: families %d..%d, root count <= %d: from %.2f ms to %.2f ms after the fork\n", q, groups[q].f0,
+                            groups[q].f1, groups[q].maxroot, a, b);
+                }
+                for (auto e : dbg) cudaEventDestroy(e);
+                cudaEventDestroy(dbg0);
             }
             if (fan) {
                 for (int q = 0; q < std::min<int>(8, (int)groups.size()); ++q) {

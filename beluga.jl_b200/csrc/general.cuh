@@ -140,7 +140,7 @@ __device__ __forceinline__ void g_horner_any(double* col, int M, double psi, dou
 }
 
 // contraction below a WGD in polynomial form: v (= ℓ, in place in `v`) is advanced M times, out[n] = v_n[0].
-__device__ __noinline__ void g_wgd_poly(double* v, double* out, int M, double ahat, double bhat, int lane) {
+__device__ __noinline__ void g_wgd_poly_iter(double* v, double* out, int M, double ahat, double bhat, int lane) {
     if (lane == 0) out[0] = v[0];
     // v[M+1], v[M+2] are read as zero
     if (lane == 0) { v[M + 1] = 0.0; v[M + 2] = 0.0; }
@@ -160,6 +160,44 @@ __device__ __noinline__ void g_wgd_poly(double* v, double* out, int M, double ah
         if (lane == 0) { out[n] = v[0]; v[top + 1] = 0.0; }      // (v_n[M-n+1] = 0 for the next stage)
         __syncwarp();
     }
+}
+
+// The same contraction in closed form.  With S the shift (Sℓ)[i] = ℓ[i+1] the stages above are v_n = (â S + b̂ S²)ⁿ ℓ, so
+//   out[n] = v_n[0] = Σ_k C(n,k) âⁿ⁻ᵏ b̂ᵏ ℓ[n+k],   k = 0 … min(n, M−n):
+// every output is an independent sum — lane L takes n = n0 + L, all lanes walk k together (the reciprocal 1/(k+1) is the
+// same for the warp), no shared-memory stores and no warp barriers between the M stages.  âⁿ is factored out and applied
+// at the end through its exponent (it underflows for n in the hundreds while the sum does not); the running term
+// C(n,k)(b̂/â)ᵏ and the sum are rescaled together by a power of two whenever they grow large.
+__device__ __noinline__ void g_wgd_poly(double* v, double* out, int M, double ahat, double bhat, int lane) {
+    if (!(ahat > 1e-12) || !(bhat >= 0.0) || bhat > 1e3 * ahat) { g_wgd_poly_iter(v, out, M, ahat, bhat, lane); return; }
+    const double ba = bhat / ahat;
+    const double l2a = log2(ahat);
+#pragma unroll 1
+    for (int n0 = 0; n0 <= M; n0 += 32) {
+        const int n = n0 + lane;
+        const int kmax = n <= M ? (n < M - n ? n : M - n) : -1;
+        const int kw = __reduce_max_sync(0xffffffffu, kmax);
+        const double nd = (double)n;
+        double t = 1.0, acc = 0.0;
+        int e = 0;
+#pragma unroll 1
+        for (int k0 = 0; k0 <= kw; k0 += 16) {
+            const int k1 = k0 + 15 < kw ? k0 + 15 : kw;
+#pragma unroll 4
+            for (int k = k0; k <= k1; ++k) {
+                if (k <= kmax) {
+                    acc = fma(t, v[n + k], acc);
+                    t *= (nd - (double)k) * (c_inv[k + 1] * ba);
+                }
+            }
+            if (t > 0x1p+300 || acc > 0x1p+300) { t *= 0x1p-300; acc *= 0x1p-300; e += 300; }
+        }
+        if (n <= M) {
+            const double x = nd * l2a, xi = floor(x);
+            out[n] = scalbn(acc * exp2(x - xi), (int)xi + e);
+        }
+    }
+    __syncwarp();
 }
 
 // table contraction (branch below a WGT; literal table of node.jl:205-218): out[s] = (1-e)^(-s)·Σ_j Wt[j·wdp+s]·in[j]

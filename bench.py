@@ -513,13 +513,24 @@ def main():
 
     nw, model, ext, t, l, names, counts = build_workload(args, rank, device="cuda:%d" % local)
     torch.cuda.empty_cache()
+    torch.cuda.synchronize()
+    t_i0 = time.perf_counter()
     X, w, m = B.profile(t, l, (names, counts))
+    t_i1 = time.perf_counter()
     npat, nfam = X.shape[0], int(w.sum())
     alg_fma = algorithmic_fma(model, X)
+    t_i2 = time.perf_counter()
     data = B.PArray(X, w, device=local, distributed=True)
+    t_i3 = time.perf_counter()
     for i in ext:                 # extend!(data, i) for every inserted WGD (src/profile.jl:108), then set!(data)
         B.extend_(data, i)
     B.set_(data)
+    B.logpdf_(model, data)        # first call: ε/W tables, node patterns, links, slabs
+    t_i4 = time.perf_counter()
+    ingest = {"what": "host wall clock of getting the count table (%d x %d, %s) ready for the first likelihood on rank 0: profile() = site patterns "
+                      "on the device + extended counts; PArray = blg_set_profiles_columns; first logpdf! = extend!/set!, ε/W tables, node "
+                      "patterns, links, slabs, one sweep" % (counts.shape[0], counts.shape[1], counts.dtype),
+              "profile_s": t_i1 - t_i0, "set_profiles_s": t_i3 - t_i2, "first_logpdf_s": t_i4 - t_i3}
     # the CPU baseline gets a uniform sample of THIS pattern set (same pattern mix as the CUDA arm)
     leaf_ids = sorted(l)
     sel = np.random.default_rng(SEED).permutation(X.shape[0])[:20000]
@@ -665,6 +676,7 @@ def main():
                     line[key] = {"error": repr(e)}
             if c5_grad is not None and isinstance(line.get("gradient"), dict):
                 line["gradient"]["C5"] = c5_grad
+        line["ingest"] = ingest
         if strong is not None:
             line["strong_scaling"] = strong
         if world == 1 and args.leaf50_families > 0:
