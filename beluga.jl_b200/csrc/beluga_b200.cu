@@ -1449,6 +1449,7 @@ struct blg_handle {
     int kernel_version = 2;
     bool order_resident = true;
     double link_ms = 0.0;                // host time spent building links during the current sweep (BLG_PDEBUG)
+    bool family_order_always = false;    // BLG_FAMILY_ORDER=1
     bool padj_constants = false;
     int padj_warp_min = 0;               // BLG_PADJ_WARP: fixed count bound of the warp kernel of the pattern adjoint (0: per depth)
     int padj_warp_big = 257;             // BLG_PADJ_BIG: the warp path's count bound at depths with many patterns
@@ -3468,6 +3469,7 @@ int blg_create(int device, void* stream, blg_handle** out) {
         if (const char* o = getenv("BLG_PROF")) h->profile_sweep = atoi(o);
         if (const char* o = getenv("BLG_GRAD")) h->grad_mode = (strcmp(o, "forward") == 0) ? 0 : 1;
         if (const char* o = getenv("BLG_GRAD_PAT")) h->grad_pat = atoi(o) != 0;
+        if (const char* o = getenv("BLG_FAMILY_ORDER")) h->family_order_always = atoi(o) != 0;
         if (const char* o = getenv("BLG_PADJ_WARP")) h->padj_warp_min = std::max(0, atoi(o));
         if (const char* o = getenv("BLG_PADJ_LEVEL")) h->padj_warp_level = atoll(o);
         if (const char* o = getenv("BLG_PADJ_BIG")) h->padj_warp_big = std::max(1, atoi(o));
@@ -3695,9 +3697,10 @@ static int set_profiles_impl(blg_handle* h, const int32_t* X, bool colmajor, con
         if (rootc[f] >= h->heavy_min) h->H.perm.push_back(f);      // the heavy set: the families with an entry at or above it
     }
     const auto t_1 = std::chrono::steady_clock::now();
-    // the k-d family order serves the kernels that give every FAMILY a lane (BLG_DEDUP=0); node patterns have their own
-    // order per node (ensure_pats), the families stay as the caller gave them
-    if (!h->pat_mode) {
+    // the k-d family order serves the kernels that give every FAMILY a lane (BLG_DEDUP=0, the forward-mode gradient of trees
+    // with polytomies, BLG_GRAD_PAT=0: 2.4x faster with it); node patterns have their own order per node (ensure_pats), the
+    // families stay as the caller gave them unless BLG_FAMILY_ORDER=1 asks for the order (0.5-1 s of host time for 10^6 rows)
+    if (!h->pat_mode || h->family_order_always) {
         if (colmajor) {
             std::vector<int32_t> rows((size_t)npatterns * ncols);
             for (int c = 0; c < ncols; ++c)
