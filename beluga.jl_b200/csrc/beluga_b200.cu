@@ -1450,6 +1450,7 @@ struct blg_handle {
     bool order_resident = true;
     double link_ms = 0.0;                // host time spent building links during the current sweep (BLG_PDEBUG)
     bool family_order_always = false;    // BLG_FAMILY_ORDER=1
+    bool pattern_tiebreak = true;        // BLG_PAT_TIEBREAK=0: patterns of the same shape in order of first appearance
     bool padj_constants = false;
     int padj_warp_min = 0;               // BLG_PADJ_WARP: fixed count bound of the warp kernel of the pattern adjoint (0: per depth)
     int padj_warp_big = 257;             // BLG_PADJ_BIG: the warp path's count bound at depths with many patterns
@@ -2127,11 +2128,17 @@ struct blg_handle {
                 if (cls == 3) ++nvery; else if (cls == 2) ++nwide;
                 key[i] = (cls << 60) | ((uint64_t)hx[r] << 32) | ((uint64_t)std::max(mc[0], mc[1]) << 16) | (uint64_t)std::min(mc[0], mc[1]);
             }
-            // (sorted as (key, index) pairs — the order a stable sort by descending key gives, without its indirection)
-            std::vector<std::pair<uint64_t, int>> kv(U);
-            for (int i = 0; i < U; ++i) kv[i] = {~key[i], i};
+            // sorted by descending key; patterns of the same shape by the pattern index of their larger child, so that the
+            // lanes of a tile gather neighbouring columns of that child (whatever order the families came in)
+            std::vector<std::pair<uint64_t, uint64_t>> kv(U);
+            for (int i = 0; i < U; ++i) {
+                const int r = rep[i];
+                const int p0 = cp[0]->fam2pat[r], p1 = cp[1]->fam2pat[r];
+                const int big = pattern_tiebreak ? (cp[0]->h_cnt[p0] >= cp[1]->h_cnt[p1] ? p0 : p1) : 0;
+                kv[i] = {~key[i], ((uint64_t)(uint32_t)big << 32) | (uint32_t)i};
+            }
             std::sort(kv.begin(), kv.end());
-            for (int i = 0; i < U; ++i) ord[i] = kv[i].second;
+            for (int i = 0; i < U; ++i) ord[i] = (int)(kv[i].second & 0xffffffffu);
         }
         P->nvery = nvery;
         P->nwide = nwide;
@@ -3470,6 +3477,7 @@ int blg_create(int device, void* stream, blg_handle** out) {
         if (const char* o = getenv("BLG_GRAD")) h->grad_mode = (strcmp(o, "forward") == 0) ? 0 : 1;
         if (const char* o = getenv("BLG_GRAD_PAT")) h->grad_pat = atoi(o) != 0;
         if (const char* o = getenv("BLG_FAMILY_ORDER")) h->family_order_always = atoi(o) != 0;
+        if (const char* o = getenv("BLG_PAT_TIEBREAK")) h->pattern_tiebreak = atoi(o) != 0;
         if (const char* o = getenv("BLG_PADJ_WARP")) h->padj_warp_min = std::max(0, atoi(o));
         if (const char* o = getenv("BLG_PADJ_LEVEL")) h->padj_warp_level = atoll(o);
         if (const char* o = getenv("BLG_PADJ_BIG")) h->padj_warp_big = std::max(1, atoi(o));
