@@ -1303,7 +1303,7 @@ struct Link {
     int maxneed[2] = {0, 0};             // largest slice need (doubles per lane) over the tiles
     bool cut = false;                    // tiles were cut (binary merges); otherwise the generic instantiation runs
     // the inverse maps (padjoint.cuh, built at the first gradient): per child pattern the node patterns that use it, as a
-    // CSR in ascending node-pattern order, and the child patterns with more than BLG_PB_HIT of them
+    // run of consecutive positions (ascending node-pattern order inside a run), and the child patterns for phase B's warp and block paths
     int* d_inv_off[BLG_MAXK] = {nullptr};
     int* d_inv_idx[BLG_MAXK] = {nullptr};    // node pattern → its place in that order
     int* d_hit[BLG_MAXK] = {nullptr};

@@ -3,13 +3,15 @@
 //
 // The forward sweep stores one column per distinct sub-pattern of every node; many patterns of a node share one pattern
 // of a child.  The adjoint of a child's pattern column is therefore the SUM of what the node's patterns send down:
-//   phase A (padj_parent_kernel, one thread per pattern of the node, every node of a tree depth in one launch):
-//            exactly the per-family step of adjoint.cuh — Ā from ô_u, b_i = W_i ℓ̂_i from the children's pattern columns,
-//            b̄_i from the other child's B rows, the branch scalars ψ̄', c̄ (or Q̄, Ē below a WGD/WGT) and ē_i — but b̄_i of
-//            an internal child is stored per pattern of the NODE instead of being pushed through W_iᵀ;
-//   phase B (padj_child_kernel / padj_child_heavy_kernel, one thread / one block per pattern of the child): sums b̄_i over
-//            the node patterns that use the child pattern (inverse of the link's pattern map, in a fixed order: the
-//            gradient stays bit-reproducible) and applies W_iᵀ once per child pattern: ô_i = W_iᵀ Σ b̄_i.
+//   phase A (padj_parent_kernel, every node of a tree depth in one launch; one thread per pattern of the node, or one warp
+//            per pattern where a depth holds few patterns): Ā from ô_u, b_i = W_i ℓ̂_i from the children's pattern columns,
+//            both b̄_i from one set of rows of the child with fewer counts (padj_merge2_reg), the branch scalars ψ̄', c̄
+//            (or Q̄, Ē below a WGD/WGT) and ē_i — b̄_i of an internal child is stored per pattern of the NODE instead of
+//            being pushed through W_iᵀ;
+//   phase B (padj_child_kernel, every internal child of a tree depth in one launch; one thread, warp or block per pattern of
+//            the child): sums b̄_i over the node patterns that use the child pattern (stored next to each other: the
+//            inverse of the link's pattern map; fixed order: the gradient stays bit-reproducible) and applies W_iᵀ once
+//            per child pattern: ô_i = W_iᵀ Σ b̄_i.
 // Single-child nodes (WGD-type nodes) share their child's patterns one to one: phase A writes ô_i directly.
 //
 // Scaling.  L = Σ_f w_f log L_f and L_f is linear in every node column, so Σ_n ô_u[n] ℓ̂_u[n] = (weight of the families
@@ -17,9 +19,9 @@
 // exponent of their own.  Entries that would leave the double range (ℓ̂_u[n] below 1e-300 of the column's top) are clamped.
 #pragma once
 
-#define BLG_PB_HIT 48                 // child patterns with more node patterns than this, or with at least BLG_PB_MID counts,
-#define BLG_PB_MID 16                 //   are summed by a warp (padj_child_warp_kernel);
-#define BLG_PB_BLOCK 2048             //   with more node patterns than this by a whole block (padj_child_heavy_kernel)
+#define BLG_PB_HIT 48                 // phase B: child patterns with more node patterns than this (or, at depths with few patterns,
+#define BLG_PB_MID 16                 //   with at least BLG_PB_MID counts) are summed by a warp,
+#define BLG_PB_BLOCK 2048             //   with more node patterns than this by a whole block
 
 struct PAChild {
     const double* ell;       // child's stored pattern columns (nullptr: leaf), [n][ld]
