@@ -650,6 +650,41 @@ def test_gradient_c5_shaped_tree_with_stacked_wgds(nt):
         np.testing.assert_allclose(g[ok], dual[ok], rtol=GRTOL, atol=GRTOL * scale)
 
 
+def test_gradient_node_patterns_against_the_per_family_sweep_with_shared_child_patterns(monkeypatch):
+    # one clade with very few distinct sub-patterns below a root with thousands: a child pattern used by more than 2048
+    # node patterns (phase B's block path), others by 49..2048 (warp path) and by a few (thread path); counts up to 45
+    # at the root (the warp-per-pattern path of phase A at this small tree).  The per-family sweep (BLG_GRAD_PAT=0) is
+    # the independent implementation; the oracle pins the log-likelihood.
+    nw = "((A:0.4,B:0.5):0.3,(C:0.6,(D:0.2,E:0.3):0.2):0.25);"
+    rng = np.random.default_rng(77)
+    N = 30000
+    counts = np.zeros((N, 5), dtype=np.int64)
+    counts[:, 0] = (rng.random(N) < 0.9).astype(np.int64)
+    counts[:, 1] = (rng.random(N) < 0.05).astype(np.int64)
+    counts[:, 2:] = rng.integers(0, 16, size=(N, 3))
+    counts[counts[:, :2].sum(axis=1) == 0, 0] = 1             # both root clades non-empty
+    counts[counts[:, 2:].sum(axis=1) == 0, 4] = 1
+    names = list("ABCDE")
+    model, data, orc = pair(nw, (names, counts), 0.8, 1.1, 0.75, B.BRANCH)
+    w = B.addwgd_(model, model[4], 0.1, 0.3); orc.addwgd(4, 0.1, 0.3)
+    B.extend_(data, 4); orc.extend(4)
+    X = np.exp(np.random.default_rng(5).normal(0, 0.3, size=(2, model.ne() + 1))) * np.array([[0.8], [1.1]])
+    model.setrates_(X); orc.setrates(X)
+    g, ll = data.gradient(model)
+    assert ll == pytest.approx(orc.logpdf(), rel=1e-10)
+    monkeypatch.setenv("BLG_GRAD_PAT", "0")
+    model2, data2 = B.DLWGD(nw, (names, counts), 0.8, 1.1, 0.75, B.BRANCH, device=0)
+    B.addwgd_(model2, model2[4], 0.1, 0.3); B.extend_(data2, 4)
+    model2.setrates_(X)
+    g2, ll2 = data2.gradient(model2)
+    monkeypatch.delenv("BLG_GRAD_PAT")
+    assert ll2 == pytest.approx(ll, rel=1e-12)
+    np.testing.assert_allclose(g, g2, rtol=1e-9, atol=1e-11 * np.abs(g2).max())
+    # and twice the same vector, bit for bit (fixed-order sums)
+    g3, _ = data.gradient(model)
+    assert np.array_equal(g, g3)
+
+
 def test_gradient_cr(dicots):
     nw, df = dicots
     model, data, orc = pair(nw, df, 1.0, 0.92, 0.66, B.BRANCH)
