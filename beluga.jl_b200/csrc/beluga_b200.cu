@@ -210,7 +210,37 @@ __device__ __noinline__ double d_powi(double b, int n) {   // b^n, n >= 0, by sq
 // segments (seg[0..nseg]) such that no node depends on another node of its own segment: the host passes either
 // one node per segment (a literal replay of the reference's call order) or the nodes grouped by height above
 // the leaves (set!(d): every level in parallel).  One block; threads of a segment work concurrently.
-__global__ void __launch_bounds__(128) eps_kernel(ModelDev m, const int* __restrict__ list, const int* __restrict__ seg, int nseg) {
+// stage != 0: the topology, the parameters, ε and the two lists are first copied to shared memory (one parallel pass): the
+// levels are a chain of dependent reads, one L2 round trip each if left in global memory (61·n + 4·(nlist + nseg) bytes).
+__global__ void __launch_bounds__(128) eps_kernel(ModelDev mg, const int* __restrict__ glist, const int* __restrict__ gseg, int nseg, int nlist,
+                                                  int stage) {
+    extern __shared__ double esm[];
+    ModelDev m = mg;
+    const int* list = glist;
+    const int* seg = gseg;
+    if (stage) {
+        const int n = mg.n;
+        double* s_t = esm; double* s_lam = s_t + n; double* s_mu = s_lam + n; double* s_q = s_mu + n;
+        double* s_e0 = s_q + n; double* s_e1 = s_e0 + n;
+        int* s_parent = reinterpret_cast<int*>(s_e1 + n);
+        int* s_off = s_parent + n;
+        int* s_idx = s_off + n + 1;
+        int* s_list = s_idx + n;
+        int* s_seg = s_list + nlist;
+        uint8_t* s_kind = reinterpret_cast<uint8_t*>(s_seg + nseg + 1);
+        for (int i = threadIdx.x; i < n; i += blockDim.x) {
+            s_t[i] = mg.t[i]; s_lam[i] = mg.lam[i]; s_mu[i] = mg.mu[i]; s_q[i] = mg.q[i];
+            s_e0[i] = mg.eps0[i]; s_e1[i] = mg.eps1[i];
+            s_parent[i] = mg.parent[i]; s_off[i] = mg.child_off[i]; s_idx[i] = mg.child_idx[i]; s_kind[i] = mg.kind[i];
+        }
+        if (threadIdx.x == 0) s_off[n] = mg.child_off[n];
+        for (int i = threadIdx.x; i < nlist; i += blockDim.x) s_list[i] = glist[i];
+        for (int i = threadIdx.x; i <= nseg; i += blockDim.x) s_seg[i] = gseg[i];
+        m.t = s_t; m.lam = s_lam; m.mu = s_mu; m.q = s_q; m.eps0 = s_e0; m.eps1 = s_e1;
+        m.parent = s_parent; m.child_off = s_off; m.child_idx = s_idx; m.kind = s_kind;
+        list = s_list; seg = s_seg;
+        __syncthreads();
+    }
     for (int sg = 0; sg < nseg; ++sg) {
       for (int li = seg[sg] + (int)threadIdx.x; li < seg[sg + 1]; li += (int)blockDim.x) {
         int n = list[li];
@@ -247,6 +277,8 @@ __global__ void __launch_bounds__(128) eps_kernel(ModelDev m, const int* __restr
       }
       __syncthreads();
     }
+    if (stage)      // (entries the lists did not touch go back as they came)
+        for (int i = threadIdx.x; i < mg.n; i += blockDim.x) { mg.eps0[i] = m.eps0[i]; mg.eps1[i] = m.eps1[i]; }
 }
 
 __device__ __forceinline__ double d_log1mexp(double x) { return x < -0.6931471805599453 ? log1p(-exp(x)) : log(-expm1(x)); }
@@ -1761,7 +1793,12 @@ struct blg_handle {
         } else {
             rootw_valid = false;
         }
-        eps_kernel<<<1, 128, 0, stream>>>(m, d_elist_p, d_seg_p, (int)seg.size() - 1);
+        {
+            const int nseg_ = (int)seg.size() - 1, nlist_ = seg.back();
+            const size_t esm = (size_t)ncols_model * 61 + ((size_t)nlist_ + nseg_ + 4) * 4 + 64;
+            const int stage = esm <= 46 * 1024 ? 1 : 0;
+            eps_kernel<<<1, 128, stage ? esm : 0, stream>>>(m, d_elist_p, d_seg_p, nseg_, nlist_, stage);
+        }
         CK(cudaGetLastError());
         const size_t tsm = std::max(2 * (size_t)maxdim * sizeof(double), (5 * nn + 8) * sizeof(int));
         tables_kernel<<<(unsigned)tlist.size(), 128, tsm, stream>>>(m, d_list_p, (int)tlist.size());
