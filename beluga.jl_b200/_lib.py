@@ -15,7 +15,7 @@ SYMBOLS = [
     "blg_logpdf_from_async", "blg_logpdf_root_async", "blg_gradient", "blg_gradient_cr", "blg_comm_unique_id", "blg_comm_init", "blg_comm_size",
     "blg_commit", "blg_revert", "blg_extend", "blg_shrink", "blg_get_column", "blg_get_family_logpdf",
     "blg_get_eps", "blg_get_W", "blg_ncols", "blg_npatterns", "blg_last_algorithmic", "blg_sync",
-    "blg_set_timing", "blg_last_timing", "blg_family_order", "blg_fp64_peak", "blg_kernel_runs", "blg_pattern_stats", "blg_site_patterns", "blg_site_patterns_u16", "blg_rand_profiles",
+    "blg_set_timing", "blg_last_timing", "blg_family_order", "blg_fp64_peak", "blg_kernel_runs", "blg_pattern_stats", "blg_graph_stats", "blg_site_patterns", "blg_site_patterns_u16", "blg_rand_profiles",
 ]
 
 
@@ -81,6 +81,7 @@ def lib():
     L.blg_last_algorithmic.argtypes = [vp, dp, dp, ip]
     L.blg_kernel_runs.argtypes = [vp, C.POINTER(C.c_uint), C.POINTER(C.c_uint), ip, ip]
     L.blg_pattern_stats.argtypes = [vp, dp, dp, dp]
+    L.blg_graph_stats.argtypes = [vp, C.POINTER(C.c_ulonglong), C.POINTER(C.c_ulonglong)]
     L.blg_rand_profiles.argtypes = [vp, C.c_int, C.c_ulonglong, C.c_int, C.c_int, C.c_int, C.POINTER(C.c_int32), ip, C.POINTER(C.c_uint16), C.POINTER(C.c_longlong)]
     L.blg_site_patterns.argtypes = [C.c_int, C.POINTER(C.c_int32), C.c_int, C.c_int, C.POINTER(C.c_int32), C.POINTER(C.c_int64), ip]
     L.blg_site_patterns_u16.argtypes = [C.c_int, C.POINTER(C.c_uint16), C.c_int, C.c_int, C.POINTER(C.c_int32), C.POINTER(C.c_int64), ip]

@@ -55,6 +55,21 @@ struct CudaError : std::runtime_error { using std::runtime_error::runtime_error;
 
 thread_local std::string g_create_error;
 
+// Every device allocation and release of the library goes through these two: a cached CUDA graph of a likelihood call
+// (blg_handle::logpdf) stays valid only while no pointer it could hold has changed, and nothing may be allocated while a
+// call is being captured (the capture is dropped and the call runs launch by launch instead).
+std::atomic<unsigned long long> g_mem_epoch{0};
+thread_local bool g_capturing = false;
+template <class T> cudaError_t blgMalloc(T** p, size_t bytes) {
+    if (g_capturing) throw std::runtime_error("internal: device allocation inside a graph capture");
+    g_mem_epoch.fetch_add(1, std::memory_order_relaxed);
+    return cudaMalloc((void**)p, bytes);
+}
+inline cudaError_t blgFree(void* p) {
+    g_mem_epoch.fetch_add(1, std::memory_order_relaxed);
+    return cudaFree(p);
+}
+
 // ------------------------------------------------------------------------------------------------
 // NCCL, bound at run time (dlopen): the library owns the communicator of a multi-GPU run (one process per GPU, one
 // handle per process) and every likelihood / gradient entry returns the all-reduced value (src/profile.jl:56-75 is a
@@ -1281,18 +1296,18 @@ template <class T> struct DevBuf {
     DevBuf() = default;
     DevBuf(const DevBuf&) = delete;
     DevBuf& operator=(const DevBuf&) = delete;
-    ~DevBuf() { if (p) cudaFree(p); }           // (also on the exception paths of the entries that use local buffers)
+    ~DevBuf() { if (p) blgFree(p); }           // (also on the exception paths of the entries that use local buffers)
     void ensure(size_t n) {
         if (n <= cap) return;
-        if (p) cudaFree(p);
+        if (p) blgFree(p);
         p = nullptr;
         cap = 0;
         size_t want = std::max<size_t>(n, 16);
-        cudaError_t e = cudaMalloc(&p, want * sizeof(T));
+        cudaError_t e = blgMalloc(&p, want * sizeof(T));
         if (e != cudaSuccess) throw CudaError(std::string("cudaMalloc: ") + cudaGetErrorString(e));
         cap = want;
     }
-    void free_() { if (p) cudaFree(p); p = nullptr; cap = 0; }
+    void free_() { if (p) blgFree(p); p = nullptr; cap = 0; }
 };
 
 // One of the two family sets of a handle.  The FAST shard holds the families whose root count is at most
@@ -1318,9 +1333,9 @@ struct Pat {
     std::vector<uint16_t> h_cnt;
     std::vector<const Pat*> kids;    // the children's patterns these were built from (a link over exactly these needs no check)
     ~Pat() {
-        if (d_cnt) cudaFree(d_cnt);
-        if (d_fam2pat) cudaFree(d_fam2pat);
-        if (d_pw) cudaFree(d_pw);
+        if (d_cnt) blgFree(d_cnt);
+        if (d_fam2pat) blgFree(d_fam2pat);
+        if (d_pw) blgFree(d_pw);
     }
 };
 // pattern of a node → pattern of each child, for one (node column, ordered child columns) combination
@@ -1345,14 +1360,14 @@ struct Link {
     int nmid_many[BLG_MAXK] = {0};
     std::map<int, std::pair<int*, int>> big;   // (msmin, T) → the node patterns of the adjoint's warp path (padj_is_big)
     ~Link() {
-        for (int* q : d_pidx) if (q) cudaFree(q);
-        for (int* q : d_tiles) if (q) cudaFree(q);
-        for (uint16_t* q : d_xcnt) if (q) cudaFree(q);
-        for (int* q : d_inv_off) if (q) cudaFree(q);
-        for (int* q : d_inv_idx) if (q) cudaFree(q);
-        for (int* q : d_hit) if (q) cudaFree(q);
-        for (int* q : d_mid) if (q) cudaFree(q);
-        for (auto& b : big) if (b.second.first) cudaFree(b.second.first);
+        for (int* q : d_pidx) if (q) blgFree(q);
+        for (int* q : d_tiles) if (q) blgFree(q);
+        for (uint16_t* q : d_xcnt) if (q) blgFree(q);
+        for (int* q : d_inv_off) if (q) blgFree(q);
+        for (int* q : d_inv_idx) if (q) blgFree(q);
+        for (int* q : d_hit) if (q) blgFree(q);
+        for (int* q : d_mid) if (q) blgFree(q);
+        for (auto& b : big) if (b.second.first) blgFree(b.second.first);
     }
 };
 
@@ -1378,11 +1393,11 @@ struct Shard {
         Tc.clear();          // the slab deleters push into `pool`: run them while it is still alive
         Tp.clear();
         pool.clear();
-        for (auto* sl : all_slabs) { cudaFree(sl->ell); cudaFree(sl->scl); delete sl; }
+        for (auto* sl : all_slabs) { blgFree(sl->ell); blgFree(sl->scl); delete sl; }
         all_slabs.clear();
-        for (auto* o : off_allocs) cudaFree(o);
+        for (auto* o : off_allocs) blgFree(o);
         off_allocs.clear();
-        for (auto* c : count_allocs) cudaFree(c);
+        for (auto* c : count_allocs) blgFree(c);
         count_allocs.clear();
         N = 0; ld = 0; perm.clear(); classes.clear(); weight_total = 0.0;
         pats.clear(); links.clear(); h_counts.clear(); h_counts.shrink_to_fit();
@@ -1508,10 +1523,40 @@ struct blg_handle {
     cudaEvent_t ev[3] = {nullptr, nullptr, nullptr};
     bool ev_valid = false;
 
+    // CUDA graphs of whole likelihood calls.  A call is described launch by launch on the host (tile lists, links, slabs:
+    // ~10^2 map lookups and 20-40 launches for a 100-taxon tree); the second call in an unchanged state is captured and every
+    // later one is a single cudaGraphLaunch.  "Unchanged" = no device allocation or release anywhere in the library
+    // (g_mem_epoch), no entry that edits the column tables, topology, profiles or table descriptors (state_epoch), and the
+    // same kernel choice.  BLG_GRAPH=0 switches it off.
+    struct CallGraph {
+        cudaGraphExec_t exec = nullptr;
+        int stage = 0;                        // 0: unseen, 1: ran launch by launch in this state, 2: captured, -1: capture failed in this state
+        unsigned long long mem_epoch = 0, state_epoch = 0;
+        bool general = false, timing = false, rootw_ok = false;
+        // what the call leaves behind on the host
+        double bytes = 0.0, prune_bytes = 0.0, pattern_bytes = 0.0, pattern_cols = 0.0, family_cols = 0.0;
+        int launches = 0, rootw_rows = 0;
+        bool root_fused = false, rootw_valid = false;
+    };
+    std::map<std::tuple<int, int, const void*>, CallGraph> call_graphs;
+    unsigned long long state_epoch = 0;
+    bool graph_on = true;
+    unsigned long long graph_replays = 0, graph_captures = 0;
+    void drop_graphs() {
+        for (auto& kv : call_graphs) if (kv.second.exec) cudaGraphExecDestroy(kv.second.exec);
+        call_graphs.clear();
+    }
+    // an event the caller reads back (blg_last_timing): inside a capture it has to become an event-record node
+    void record_timing(cudaEvent_t e) {
+        if (g_capturing) CK(cudaEventRecordWithFlags(e, stream, cudaEventRecordExternal));
+        else CK(cudaEventRecord(e, stream));
+    }
+
     ~blg_handle() {
         cudaSetDevice(device);
         if (stream) cudaStreamSynchronize(stream);
-        for (auto& kv : hpat) cudaFree(kv.second);
+        drop_graphs();
+        for (auto& kv : hpat) blgFree(kv.second);
         F.release();
         H.release();
         F.weight.free_(); F.fam_ll.free_(); H.weight.free_(); H.fam_ll.free_();
@@ -1535,9 +1580,9 @@ struct blg_handle {
         if (own_stream && stream) cudaStreamDestroy(stream);
     }
     static void free_tab(HostTab& tb) {
-        if (tb.Wt) cudaFree(tb.Wt);
-        if (tb.ipow) cudaFree(tb.ipow);
-        for (int i = 0; i < BLG_MAXK; ++i) if (tb.coefD[i]) cudaFree(tb.coefD[i]);
+        if (tb.Wt) blgFree(tb.Wt);
+        if (tb.ipow) blgFree(tb.ipow);
+        for (int i = 0; i < BLG_MAXK; ++i) if (tb.coefD[i]) blgFree(tb.coefD[i]);
         tb = HostTab();
     }
 
@@ -1554,15 +1599,17 @@ struct blg_handle {
         return (size_t)(col.xmax + 1) * S.ld;
     }
     std::shared_ptr<Slab> new_slab(Shard& S, size_t nd) {
+        require(!g_capturing, "internal: slab assignment inside a graph capture");
+        ++state_epoch;                         // (a column changes its slab: pooled slabs come without an allocation)
         Slab* s = nullptr;
         auto it = S.pool.find(nd);
         if (it != S.pool.end() && !it->second.empty()) { s = it->second.back(); it->second.pop_back(); }
         else {
             s = new Slab();
             s->nd = nd;
-            CK(cudaMalloc(&s->ell, nd * sizeof(double)));
-            cudaError_t e = cudaMalloc(&s->scl, S.ld * sizeof(int));
-            if (e != cudaSuccess) { cudaFree(s->ell); delete s; throw CudaError(std::string("cudaMalloc: ") + cudaGetErrorString(e)); }
+            CK(blgMalloc(&s->ell, nd * sizeof(double)));
+            cudaError_t e = blgMalloc(&s->scl, S.ld * sizeof(int));
+            if (e != cudaSuccess) { blgFree(s->ell); delete s; throw CudaError(std::string("cudaMalloc: ") + cudaGetErrorString(e)); }
             S.all_slabs.push_back(s);
         }
         s->pat = pattern_layout(S);
@@ -1677,14 +1724,14 @@ struct blg_handle {
         free_tab(tb);
         tb.wdim = wdim; tb.wdp = round_up(std::max(wdim, 1), 16); tb.nrow = nrow; tb.k = k; tb.xfast = xm;
         for (int c = 0; c < k; ++c) tb.mo[c] = mo[c];
-        if (wdim > 0) CK(cudaMalloc(&tb.Wt, (size_t)wdim * tb.wdp * sizeof(double)));
+        if (wdim > 0) CK(blgMalloc(&tb.Wt, (size_t)wdim * tb.wdp * sizeof(double)));
         if (nrow > 0) {
-            CK(cudaMalloc(&tb.ipow, (size_t)nrow * sizeof(double)));
+            CK(blgMalloc(&tb.ipow, (size_t)nrow * sizeof(double)));
             for (int c = 1; c < k; ++c) {
                 int ci = mo[c];
                 int cx = xmax_of(F, ci);
                 tb.cdp[c] = round_up(cx + 1, BLG_TS);
-                CK(cudaMalloc(&tb.coefD[c], (size_t)nrow * tb.cdp[c] * sizeof(double)));
+                CK(blgMalloc(&tb.coefD[c], (size_t)nrow * tb.cdp[c] * sizeof(double)));
             }
         }
     }
@@ -1738,7 +1785,7 @@ struct blg_handle {
             memset(&nt, 0, sizeof(nt));
             nt.Wt = tb.Wt; nt.wdim = tb.wdim; nt.wdp = tb.wdp; nt.ipow = tb.ipow; nt.nrow = tb.nrow; nt.xfast = tb.xfast;
             for (int c = 0; c < BLG_MAXK; ++c) { nt.coefD[c] = tb.coefD[c]; nt.cdp[c] = tb.cdp[c]; nt.mo[c] = tb.mo[c]; }
-            if (memcmp(&tab_stage[i], &nt, sizeof(nt)) != 0) { tab_stage[i] = nt; tab_dirty = true; }
+            if (memcmp(&tab_stage[i], &nt, sizeof(nt)) != 0) { tab_stage[i] = nt; tab_dirty = true; ++state_epoch; }
             tb.built = true;
             maxdim = std::max(maxdim, tb.wdim);
         }
@@ -1947,7 +1994,7 @@ struct blg_handle {
         std::vector<int> v(std::max(H.N, 1), -1);
         for (int i = 0; i < H.N; ++i) v[i] = P->fam2pat[H2F[i]];
         int* d = nullptr;
-        CK(cudaMalloc(&d, v.size() * sizeof(int)));
+        CK(blgMalloc(&d, v.size() * sizeof(int)));
         CK(cudaMemcpy(d, v.data(), v.size() * sizeof(int), cudaMemcpyHostToDevice));
         hpat[key] = d;
         return d;
@@ -2068,7 +2115,7 @@ struct blg_handle {
         P.ld = std::max<size_t>(((size_t)P.U + 31) / 32 * 32, 32);
         std::vector<uint16_t> st(P.ld, P.h_cnt.empty() ? 0 : P.h_cnt.back());
         std::copy(P.h_cnt.begin(), P.h_cnt.end(), st.begin());
-        CK(cudaMalloc(&P.d_cnt, P.ld * sizeof(uint16_t)));
+        CK(blgMalloc(&P.d_cnt, P.ld * sizeof(uint16_t)));
         CK(cudaMemcpy(P.d_cnt, st.data(), P.ld * sizeof(uint16_t), cudaMemcpyHostToDevice));
     }
     // distinct sub-patterns of every column of the current topology, bottom-up: a leaf's patterns are its distinct counts,
@@ -2274,11 +2321,11 @@ struct blg_handle {
             if (std::find(Pu->kids.begin(), Pu->kids.end(), (const Pat*)Pc) == Pu->kids.end() || Pu->kids.size() != ord.size())
                 for (int f = 0; f < S.N; ++f)
                     if (Pu->fam2pat[f] >= 0 && px[Pu->fam2pat[f]] != Pc->fam2pat[f]) throw std::runtime_error("logpdf: node patterns do not match the topology (call blg_set_profiles again after changing the species tree)");
-            CK(cudaMalloc(&L->d_pidx[j], Pu->ld * sizeof(int)));
+            CK(blgMalloc(&L->d_pidx[j], Pu->ld * sizeof(int)));
             CK(cudaMemcpy(L->d_pidx[j], px.data(), Pu->ld * sizeof(int), cudaMemcpyHostToDevice));
             std::vector<uint16_t> xc(Pu->ld, 0);
             for (size_t q = 0; q < Pu->ld; ++q) xc[q] = px[q] < Pc->U ? Pc->h_cnt[px[q]] : 0;     // (a node without light patterns: U = 0)
-            CK(cudaMalloc(&L->d_xcnt[j], Pu->ld * sizeof(uint16_t)));
+            CK(blgMalloc(&L->d_xcnt[j], Pu->ld * sizeof(uint16_t)));
             CK(cudaMemcpy(L->d_xcnt[j], xc.data(), Pu->ld * sizeof(uint16_t), cudaMemcpyHostToDevice));
         }
         // ---- cut the tiles -------------------------------------------------------------------------------------------
@@ -2308,7 +2355,7 @@ struct blg_handle {
                 tb.push_back(hi);
                 L->ntiles[w] = (int)tb.size() - 1;
                 L->maxneed[w] = need;
-                CK(cudaMalloc(&L->d_tiles[w], tb.size() * sizeof(int)));
+                CK(blgMalloc(&L->d_tiles[w], tb.size() * sizeof(int)));
                 CK(cudaMemcpy(L->d_tiles[w], tb.data(), tb.size() * sizeof(int), cudaMemcpyHostToDevice));
             }
             if (pdebug) fprintf(stderr, "[blg link] node %d U %d x %d: tiles %d (need %d) | wide tiles %d (need %d)\n", u, Pu->U, Pu->xmax,
@@ -2652,12 +2699,12 @@ struct blg_handle {
         auto& v = gpool[bytes];
         if (!v.empty()) { void* p = v.back(); v.pop_back(); return p; }
         void* p = nullptr;
-        CK(cudaMalloc(&p, bytes));
+        CK(blgMalloc(&p, bytes));
         return p;
     }
     void gfree(void* p, size_t bytes) { bytes = (bytes + 255) / 256 * 256; gpool[bytes].push_back(p); }
     void gpool_release() {
-        for (auto& kv : gpool) for (void* p : kv.second) cudaFree(p);
+        for (auto& kv : gpool) for (void* p : kv.second) blgFree(p);
         gpool.clear();
     }
     int nonwgdchild_h(int i) const { while (kind[i] == BLG_WGD || kind[i] == BLG_WGT || kind[i] == BLG_WGDAFTER) i = children[i][0]; return i; }
@@ -2971,19 +3018,19 @@ struct blg_handle {
         mid.insert(mid.end(), mid2.begin(), mid2.end());
         lk->nmid[j] = (int)mid.size();
         if (!mid.empty()) {
-            CK(cudaMalloc(&lk->d_mid[j], mid.size() * sizeof(int)));
+            CK(blgMalloc(&lk->d_mid[j], mid.size() * sizeof(int)));
             CK(cudaMemcpy(lk->d_mid[j], mid.data(), mid.size() * sizeof(int), cudaMemcpyHostToDevice));
         }
-        CK(cudaMalloc(&lk->d_inv_off[j], (size_t)(Pc->U + 1) * sizeof(int)));
+        CK(blgMalloc(&lk->d_inv_off[j], (size_t)(Pc->U + 1) * sizeof(int)));
         CK(cudaMemcpy(lk->d_inv_off[j], off.data(), (size_t)(Pc->U + 1) * sizeof(int), cudaMemcpyHostToDevice));
         // (uploaded as the inverse permutation: where phase A puts a node pattern's b̄)
         std::vector<int> pos(std::max(Pu->U, 1), 0);
         for (int k = 0; k < Pu->U; ++k) pos[idx[k]] = k;
-        CK(cudaMalloc(&lk->d_inv_idx[j], pos.size() * sizeof(int)));
+        CK(blgMalloc(&lk->d_inv_idx[j], pos.size() * sizeof(int)));
         CK(cudaMemcpy(lk->d_inv_idx[j], pos.data(), pos.size() * sizeof(int), cudaMemcpyHostToDevice));
         lk->nhit[j] = (int)hit.size();
         if (!hit.empty()) {
-            CK(cudaMalloc(&lk->d_hit[j], hit.size() * sizeof(int)));
+            CK(blgMalloc(&lk->d_hit[j], hit.size() * sizeof(int)));
             CK(cudaMemcpy(lk->d_hit[j], hit.data(), hit.size() * sizeof(int), cudaMemcpyHostToDevice));
         }
         (void)S;
@@ -2995,7 +3042,7 @@ struct blg_handle {
         CK(cudaMemcpyAsync(w.data(), S.weight.p, (size_t)S.N * sizeof(double), cudaMemcpyDeviceToHost, stream));
         CK(cudaStreamSynchronize(stream));
         for (int f = 0; f < S.N; ++f) if (P0->fam2pat[f] >= 0) pw[P0->fam2pat[f]] += w[f];
-        CK(cudaMalloc(&P0->d_pw, P0->ld * sizeof(double)));
+        CK(blgMalloc(&P0->d_pw, P0->ld * sizeof(double)));
         CK(cudaMemcpy(P0->d_pw, pw.data(), P0->ld * sizeof(double), cudaMemcpyHostToDevice));
         return P0->d_pw;
     }
@@ -3116,7 +3163,7 @@ struct blg_handle {
                             if (padj_is_big(k, T, msmin, Pu->h_cnt[q], m0, m1)) bl.push_back(q);
                         }
                         int* dbl = nullptr;
-                        CK(cudaMalloc(&dbl, std::max<size_t>(bl.size(), 1) * sizeof(int)));
+                        CK(blgMalloc(&dbl, std::max<size_t>(bl.size(), 1) * sizeof(int)));
                         CK(cudaMemcpy(dbl, bl.data(), bl.size() * sizeof(int), cudaMemcpyHostToDevice));
                         bi = lk->big.emplace(key, std::make_pair(dbl, (int)bl.size())).first;
                     }
@@ -3364,7 +3411,7 @@ struct blg_handle {
                 ensure_pats(F);
                 Pat* P0 = pat_of(F, F.Tp[0]);
                 if (!P0->d_fam2pat) {
-                    CK(cudaMalloc(&P0->d_fam2pat, F.ld * sizeof(int)));
+                    CK(blgMalloc(&P0->d_fam2pat, F.ld * sizeof(int)));
                     CK(cudaMemcpy(P0->d_fam2pat, P0->fam2pat.data(), (size_t)F.N * sizeof(int), cudaMemcpyHostToDevice));
                 }
                 root_pattern_kernel<<<bF, 256, 0, stream>>>(s->ell, s->scl, P0->d_cnt, P0->d_fam2pat, rootw.p, F.weight.p, F.fam_ll.p, partial.p, F.N,
@@ -3409,18 +3456,82 @@ struct blg_handle {
     void logpdf(int mode, int node, double* d_out, bool force_general = false) {
         // mode 0 full, 1 from node, 2 root only
         require(have_topology, "logpdf: no topology");
-        last_bytes = 0.0;
-        last_launches = 0;
-        last_pattern_bytes = last_pattern_cols = last_family_cols = 0.0;
-        root_fused = false;
         if (Ntot == 0) {                                                                  // profile.jl:56
+            last_bytes = 0.0;
+            last_launches = 0;
+            last_pattern_bytes = last_pattern_cols = last_family_cols = 0.0;
+            root_fused = false;
             CK(cudaMemsetAsync(d_out, 0, sizeof(double), stream));
             CK(cudaMemsetAsync(result.p + 8, 0, sizeof(double), stream));
             allreduce_sum(d_out, 1);             // (an empty shard still takes part in the sum)
             return;
         }
         require(have_params && tabs_valid, "logpdf: ε/W tables are stale (call blg_rebuild)");
-        if (timing) { for (auto& e : ev) if (!e) CK(cudaEventCreate(&e)); CK(cudaEventRecord(ev[0], stream)); }
+        if (timing) for (auto& e : ev) if (!e) CK(cudaEventCreate(&e));
+        const bool general = force_general || kernel_version == 1 || flag_cache == 0;
+        const bool graphable = graph_on && !pdebug && pat_mode && H.N == 0 && F.N > 0 && !profile_sweep;
+        CallGraph* E = nullptr;
+        if (graphable) {
+            if (call_graphs.size() > 1024) drop_graphs();
+            E = &call_graphs[std::make_tuple(mode, node, (const void*)d_out)];
+            const bool rootw_ok = rootw_valid && rootw_rows == root_rows();
+            const bool match = E->stage != 0 && E->mem_epoch == g_mem_epoch.load() && E->state_epoch == state_epoch &&
+                               E->general == general && E->timing == timing && E->rootw_ok == rootw_ok;
+            if (!match) {
+                if (E->exec) { cudaGraphExecDestroy(E->exec); E->exec = nullptr; }
+                E->stage = 0;
+            }
+            if (E->stage == 1) {                 // second call in this state: capture it
+                cudaGraph_t g = nullptr;
+                bool ok = cudaStreamBeginCapture(stream, cudaStreamCaptureModeRelaxed) == cudaSuccess;
+                if (ok) {
+                    g_capturing = true;
+                    try { logpdf_launches(mode, node, d_out, general); } catch (const std::exception&) { ok = false; }
+                    g_capturing = false;
+                    if (cudaStreamEndCapture(stream, &g) != cudaSuccess) ok = false;
+                    ok = ok && g != nullptr && E->mem_epoch == g_mem_epoch.load() && E->state_epoch == state_epoch;
+                    if (ok && cudaGraphInstantiate(&E->exec, g, 0) != cudaSuccess) { ok = false; E->exec = nullptr; }
+                    if (g) cudaGraphDestroy(g);
+                }
+                (void)cudaGetLastError();
+                if (ok) {
+                    E->stage = 2;
+                    E->bytes = last_bytes; E->prune_bytes = last_prune_bytes; E->pattern_bytes = last_pattern_bytes;
+                    E->pattern_cols = last_pattern_cols; E->family_cols = last_family_cols; E->launches = last_launches;
+                    E->root_fused = root_fused; E->rootw_valid = rootw_valid; E->rootw_rows = rootw_rows;
+                    ++graph_captures;
+                } else {
+                    E->stage = -1;               // this state does not capture: launch by launch until it changes
+                }
+            }
+            if (E->stage == 2) {
+                last_bytes = E->bytes; last_prune_bytes = E->prune_bytes; last_pattern_bytes = E->pattern_bytes;
+                last_pattern_cols = E->pattern_cols; last_family_cols = E->family_cols; last_launches = E->launches;
+                root_fused = E->root_fused; rootw_valid = E->rootw_valid; rootw_rows = E->rootw_rows;
+                CK(cudaGraphLaunch(E->exec, stream));
+                ++graph_replays;
+                allreduce_sum(d_out, 1);
+                if (timing) { CK(cudaEventRecord(ev[2], stream)); ev_valid = true; }
+                return;
+            }
+        }
+        logpdf_launches(mode, node, d_out, general);
+        if (E && E->stage == 0) {                // (epochs AFTER the call: its first run allocates slabs, patterns and links)
+            E->stage = 1;
+            E->mem_epoch = g_mem_epoch.load(); E->state_epoch = state_epoch;
+            E->general = general; E->timing = timing;
+            E->rootw_ok = rootw_valid && rootw_rows == root_rows();     // (what the next call in this state starts from)
+        }
+        allreduce_sum(d_out, 1);                 // Σ over the ranks' shards, on the same stream (8 bytes over NVLink)
+        if (timing) { CK(cudaEventRecord(ev[2], stream)); ev_valid = true; }
+    }
+    // the launches of one likelihood call up to the rank's own scalar in d_out (everything a graph of the call holds)
+    void logpdf_launches(int mode, int node, double* d_out, bool general) {
+        last_bytes = 0.0;
+        last_launches = 0;
+        last_pattern_bytes = last_pattern_cols = last_family_cols = 0.0;
+        root_fused = false;
+        if (timing) record_timing(ev[0]);
         require(pat_mode || H.N == 0, "families at or above the heavy bound need the node-pattern evaluation (BLG_DEDUP=0 and the gradient do not support them)");
         if (H.N > 0) ensure_pats(F);
         for (Shard* S : {&F, &H}) {
@@ -3438,7 +3549,7 @@ struct blg_handle {
             }
             if (nodes.empty()) continue;
             if (S == &H) general_sweep(H, nodes, 0, false);     // (the fast set's accounting already covers every family)
-            else if (pat_mode) psweep(nodes, force_general || kernel_version == 1 || flag_cache == 0);
+            else if (pat_mode) psweep(nodes, general);
             else if (kernel_version == 1) general_sweep(F, nodes, 0, true);
             else {
                 // the table-free kernel, and right behind it the general one, which only works when the device-side
@@ -3447,11 +3558,9 @@ struct blg_handle {
                 general_sweep(F, nodes, 1, false);
             }
         }
-        if (timing) CK(cudaEventRecord(ev[1], stream));
+        if (timing) record_timing(ev[1]);
         last_prune_bytes = last_bytes;
         root_reduce(d_out);
-        allreduce_sum(d_out, 1);                 // Σ over the ranks' shards, on the same stream (8 bytes over NVLink)
-        if (timing) { CK(cudaEventRecord(ev[2], stream)); ev_valid = true; }
     }
     // the pattern path runs OPTIMISTICALLY on the table-free kernel: the kernels leave at once when the device-side range
     // flag of the last ε/W build says no, and the root kernel hands the flag back next to the result.
@@ -3524,6 +3633,7 @@ int blg_create(int device, void* stream, blg_handle** out) {
         // families whose root count reaches this go to the heavy shard; above BLG_FAST_MAXCOUNT+1 the fast shard leaves the
         // table-free kernel's range (general kernel on SoA slabs) but stays inside the table-based gradient kernels' (<= 256)
         if (const char* pd = getenv("BLG_PDEBUG")) h->pdebug = atoi(pd);
+        if (const char* gr = getenv("BLG_GRAPH")) h->graph_on = atoi(gr) != 0;
         if (const char* fn = getenv("BLG_FAN")) h->fan_classes = atoi(fn) != 0;
         if (const char* sd = getenv("BLG_SIDE")) h->side_min = atoi(sd);
         if (const char* dd = getenv("BLG_DEDUP")) h->pat_mode = h->pat_default = atoi(dd) != 0;
@@ -3660,7 +3770,7 @@ static void upload_shard(blg_handle* h, Shard& S, const int32_t* X, bool colmajo
         }
     });
     uint16_t* dcnt = nullptr;
-    CK(cudaMalloc(&dcnt, stage.size() * sizeof(uint16_t)));
+    CK(blgMalloc(&dcnt, stage.size() * sizeof(uint16_t)));
     S.count_allocs.push_back(dcnt);
     CK(cudaMemcpyAsync(dcnt, stage.data(), stage.size() * sizeof(uint16_t), cudaMemcpyHostToDevice, h->stream));
     for (int c = 0; c < ncols; ++c) cols[c].cnt = dcnt + (size_t)c * ld;
@@ -3675,7 +3785,7 @@ static void upload_shard(blg_handle* h, Shard& S, const int32_t* X, bool colmajo
             for (int f = 0; f < S.N; ++f) { dst[f] = run; run += (uint32_t)src[f] + 1u; }
         }
         uint32_t* doff = nullptr;
-        CK(cudaMalloc(&doff, ostage.size() * sizeof(uint32_t)));
+        CK(blgMalloc(&doff, ostage.size() * sizeof(uint32_t)));
         S.off_allocs.push_back(doff);
         CK(cudaMemcpy(doff, ostage.data(), ostage.size() * sizeof(uint32_t), cudaMemcpyHostToDevice));
         for (int c = 0; c < ncols; ++c) cols[c].off = doff + (size_t)c * ld;
@@ -3698,6 +3808,8 @@ static int set_profiles_impl(blg_handle* h, const int32_t* X, bool colmajor, con
     const auto t_0 = std::chrono::steady_clock::now();
     h->require(ncols >= 0 && npatterns >= 0, "set_profiles: negative size");
     CK(cudaStreamSynchronize(h->stream));
+    h->drop_graphs();
+    ++h->state_epoch;
     h->F.release();
     h->H.release();
     h->F.ragged = false;
@@ -3779,7 +3891,7 @@ static int set_profiles_impl(blg_handle* h, const int32_t* X, bool colmajor, con
     for (int i = 0; i < h->F.N; ++i) h->loc[h->F.perm[i]] = i;
     h->H2F.assign(h->H.N, 0);
     for (int i = 0; i < h->H.N; ++i) { h->hloc[h->H.perm[i]] = i; h->H2F[i] = h->loc[h->H.perm[i]]; }
-    for (auto& kv : h->hpat) cudaFree(kv.second);
+    for (auto& kv : h->hpat) blgFree(kv.second);
     h->hpat.clear();
     // Pascal triangle for the merge tables of the gradient kernels (fast shard bounds only)
     int gmax = 0;
@@ -3810,6 +3922,8 @@ int blg_set_profiles_columns(blg_handle* h, const int32_t* Xc, const int64_t* we
 int blg_set_topology(blg_handle* h, int ncols, const int32_t* parent, const uint8_t* kind, const int32_t* child_pos) {
     BLG_ENTER(h)
     h->require(ncols >= 1 && parent && kind && child_pos, "set_topology: bad arguments");
+    h->drop_graphs();
+    ++h->state_epoch;
     h->ncols_model = ncols;
     h->parent.assign(ncols, -1);
     h->kind.assign(kind, kind + ncols);
@@ -3918,14 +4032,18 @@ static void gradient_allreduce(blg_handle* h, double* g, int P) {
 int blg_gradient(blg_handle* h, double* g, int len, double* logpdf_out) {
     BLG_ENTER(h)
     h->require(g != nullptr, "gradient: null output");
+    ++h->state_epoch;                    // (the gradient may switch the fast set between node patterns and family columns)
     h->gradient(g, len, logpdf_out, false);
+    ++h->state_epoch;
     gradient_allreduce(h, g, len);
     BLG_LEAVE(h)
 }
 int blg_gradient_cr(blg_handle* h, double* g2, double* logpdf_out) {
     BLG_ENTER(h)
     h->require(g2 != nullptr, "gradient_cr: null output");
+    ++h->state_epoch;
     h->gradient(g2, 2, logpdf_out, true);
+    ++h->state_epoch;
     gradient_allreduce(h, g2, 2);
     BLG_LEAVE(h)
 }
@@ -3945,6 +4063,7 @@ int blg_comm_init(blg_handle* h, int nranks, int rank, const uint8_t* id128) {
     BLG_ENTER(h)
     h->require(id128 != nullptr && nranks >= 1 && rank >= 0 && rank < nranks, "comm_init: bad arguments");
     h->require(h->comm == nullptr, "comm_init: this handle already has a communicator");
+    ++h->state_epoch;
     if (!g_nccl.load()) throw std::runtime_error("NCCL not available (" + g_nccl.why + "); set BLG_NCCL_LIB");
     NcclApi::UniqueId id;
     memcpy(id.internal, id128, 128);
@@ -3957,18 +4076,21 @@ int blg_comm_size(blg_handle* h) { return h ? h->comm_size : -1; }
 
 int blg_commit(blg_handle* h) {
     BLG_ENTER(h)
+    ++h->state_epoch;
     h->F.Tc = h->F.Tp;
     h->H.Tc = h->H.Tp;
     BLG_LEAVE(h)
 }
 int blg_revert(blg_handle* h) {
     BLG_ENTER(h)
+    ++h->state_epoch;
     h->F.Tp = h->F.Tc;
     h->H.Tp = h->H.Tc;
     BLG_LEAVE(h)
 }
 int blg_extend(blg_handle* h, int i) {
     BLG_ENTER(h)
+    ++h->state_epoch;
     if (h->Ntot == 0) return 0;
     for (Shard* S : {&h->F, &h->H}) {
         if (S->N == 0) continue;
@@ -3982,6 +4104,7 @@ int blg_extend(blg_handle* h, int i) {
 }
 int blg_shrink(blg_handle* h, int i) {
     BLG_ENTER(h)
+    ++h->state_epoch;
     if (h->Ntot == 0) return 0;
     for (Shard* S : {&h->F, &h->H}) {
         if (S->N == 0) continue;
@@ -4117,6 +4240,12 @@ int blg_kernel_runs(blg_handle* h, unsigned int* sweep_runs, unsigned int* gener
 // what the last likelihood call did on the fast family set: bytes of pattern columns actually written + read, node steps ×
 // distinct patterns evaluated, node steps × families they stand for (diagnostic; the algorithmic figure of
 // blg_last_algorithmic stays SURVEY §8(d)'s per-family definition)
+int blg_graph_stats(blg_handle* h, unsigned long long* captures, unsigned long long* replays) {
+    if (!h) return 1;
+    if (captures) *captures = h->graph_captures;
+    if (replays) *replays = h->graph_replays;
+    return 0;
+}
 int blg_pattern_stats(blg_handle* h, double* bytes_moved, double* pattern_columns, double* family_columns) {
     if (!h) return 1;
     if (bytes_moved) *bytes_moved = h->last_pattern_bytes;

@@ -288,6 +288,12 @@ class PArray:
         self.L.blg_pattern_stats(self.h, C.byref(a), C.byref(b), C.byref(c))
         return a.value, b.value, c.value
 
+    def graph_stats(self):
+        """-> (captures, replays): likelihood calls captured as CUDA graphs / replayed from one (diagnostic)."""
+        a, b = C.c_ulonglong(), C.c_ulonglong()
+        self.L.blg_graph_stats(self.h, C.byref(a), C.byref(b))
+        return a.value, b.value
+
     def set_timing(self, on=True):
         self._ck(self.L.blg_set_timing(self.h, 1 if on else 0))
 

@@ -79,17 +79,51 @@ def build_workload(args, rank, device=None, families=None):
 
 
 class ClockSampler(threading.Thread):
-    """nvidia-smi clocks / throttle reasons sampled while the timed region runs."""
+    """SM clocks / throttle reasons sampled while the timed region runs: NVML in-process (nvidia_ml_py — the same counters
+    nvidia-smi prints; no fork of this process, no second NVML client per sample), `nvidia-smi` itself as the fallback.
+    With several ranks only rank 0 samples: eight nvidia-smi clients polling the driver stall the other ranks' launches."""
 
     Q = "clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
 
-    def __init__(self, index):
+    def __init__(self, index, enabled=True):
         super().__init__(daemon=True)
         self.index = index
+        self.enabled = enabled
         self.stop_ = threading.Event()
         self.rows = []
+        self.source = None
+
+    def _nvml_handle(self):
+        import pynvml
+        pynvml.nvmlInit()
+        # LOCAL_RANK counts the visible devices: translate through CUDA_VISIBLE_DEVICES when it lists indices
+        vis = os.environ.get("CUDA_VISIBLE_DEVICES", "")
+        idx = self.index
+        ids = [v.strip() for v in vis.split(",") if v.strip()]
+        if ids and all(v.isdigit() for v in ids) and self.index < len(ids):
+            idx = int(ids[self.index])
+        return pynvml, pynvml.nvmlDeviceGetHandleByIndex(idx)
 
     def run(self):
+        if not self.enabled:
+            return
+        try:
+            nv, h = self._nvml_handle()
+            self.source = "nvml"
+            bits = [nv.nvmlClocksEventReasonHwSlowdown, nv.nvmlClocksEventReasonHwThermalSlowdown,
+                    nv.nvmlClocksEventReasonSwThermalSlowdown, nv.nvmlClocksEventReasonSwPowerCap]
+            mx = nv.nvmlDeviceGetMaxClockInfo(h, nv.NVML_CLOCK_SM)
+            while not self.stop_.is_set():
+                try:
+                    sm = nv.nvmlDeviceGetClockInfo(h, nv.NVML_CLOCK_SM)
+                    r = nv.nvmlDeviceGetCurrentClocksEventReasons(h)
+                    self.rows.append([str(sm), str(mx)] + ["Active" if (r & b) else "Not Active" for b in bits])
+                except Exception:
+                    pass
+                self.stop_.wait(0.05)
+            return
+        except Exception:
+            self.source = "nvidia-smi"
         while not self.stop_.is_set():
             try:
                 o = subprocess.run(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.Q, "--format=csv,noheader,nounits"],
@@ -108,7 +142,7 @@ class ClockSampler(threading.Thread):
         names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
         reasons = [n for k, n in enumerate(names) if any(len(r) > 2 + k and r[2 + k].lower().startswith("active") for r in self.rows)]
         return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
-                "reasons": reasons, "samples": len(self.rows)}
+                "reasons": reasons, "samples": len(self.rows), "source": self.source}
 
 
 def sample_pattern_rows(args, device=None, nsample=20000):
@@ -555,7 +589,7 @@ def main():
     def step_resident():
         data._ck(data.L.blg_logpdf_full_async(data.h, ptr))      # (sweep, root, and the library's own all-reduce of the scalar)
 
-    sampler = ClockSampler(local)          # samples clocks from the warm-up through both timed regions
+    sampler = ClockSampler(local, enabled=(rank == 0))     # samples clocks from the warm-up through both timed regions
     sampler.start()
     for _ in range(args.warmup):
         step_resident()

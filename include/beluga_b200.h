@@ -160,6 +160,10 @@ int blg_kernel_runs(blg_handle* h, unsigned int* sweep_runs, unsigned int* gener
 /* diagnostic: node patterns (families are deduplicated per node by the counts below it, csrc/pattern.cuh) — bytes of
  * pattern columns the last likelihood call wrote + read, node steps × distinct patterns evaluated, node steps × families */
 int blg_pattern_stats(blg_handle* h, double* bytes_moved, double* pattern_columns, double* family_columns);
+/* diagnostic: likelihood calls captured as CUDA graphs so far / replayed from a captured graph.  The second call in an
+ * unchanged state (same entry, same output pointer; no allocation, commit/revert/extend/shrink, topology, profile or table
+ * descriptor change in between) is captured, later ones are one cudaGraphLaunch (+ the all-reduce).  BLG_GRAPH=0 disables it. */
+int blg_graph_stats(blg_handle* h, unsigned long long* captures, unsigned long long* replays);
 int blg_sync(blg_handle* h);
 /* measurement: when on, every likelihood call records CUDA events on the handle's stream around its
  * pruning launches and around its root/reduction launches; blg_last_timing waits for them and returns

@@ -1030,3 +1030,62 @@ def test_wide_tree_many_nodes_per_level():
     assert close(B.logpdf_(model, data), orc.logpdf(), RTOL)
     moved, pattern_cols, family_cols = data.pattern_stats()
     assert pattern_cols < 0.5 * family_cols
+
+
+def test_repeated_calls_replay_a_captured_graph_and_stay_on_the_oracle(dicots, monkeypatch):
+    """The second likelihood call in an unchanged device state is captured as a CUDA graph and later ones replay it
+    (blg_graph_stats).  Replays must be bit-identical to the launch-by-launch call, follow parameter updates (the tables
+    are rewritten in place), and every state change (update!/set!/rev!/extend!) must drop back to fresh launches."""
+    nw, df = dicots
+    model, data, orc = pair(nw, df, 1.0, 0.92, 0.66, B.NODE)
+    want = orc.logpdf()
+    vals = [B.logpdf_(model, data) for _ in range(5)]
+    assert all(v == vals[0] for v in vals), vals
+    assert close(vals[0], want)
+    cap, rep = data.graph_stats()
+    assert cap >= 1 and rep >= 3, (cap, rep)
+    # new rates, same state: the same graph, new value
+    rng = np.random.default_rng(3)
+    for _ in range(3):
+        X = model.getrates() * np.exp(rng.normal(0, 0.05, size=model.getrates().shape))
+        model.setrates_(X); orc.setrates(X)
+        assert close(B.logpdf_(model, data), orc.logpdf())
+    cap2, rep2 = data.graph_stats()
+    assert cap2 == cap and rep2 >= rep + 3, (cap, rep, cap2, rep2)
+    # the same handle with graphs switched off gives the same bits
+    monkeypatch.setenv("BLG_GRAPH", "0")
+    model0, data0 = B.DLWGD(nw, df, 1.0, 0.92, 0.66, B.NODE, device=0)
+    monkeypatch.delenv("BLG_GRAPH")
+    model0.setrates_(model.getrates())
+    assert B.logpdf_(model0, data0) == B.logpdf_(model, data)
+    assert data0.graph_stats() == (0, 0)
+    # proposals: partial paths, reject, accept, jump — replayed graphs must never serve a changed state
+    B.set_(data); orc.set()
+    for node, lam_, mu_, accept in ((5, 2.5, 0.3, False), (5, 0.7, 0.8, True), (12, 0.4, 0.5, True), (5, 1.1, 0.9, False)):
+        old = (model[node]["λ"], model[node]["μ"])
+        B.update_(model[node], λ=lam_, μ=mu_); orc.update(node, lam=lam_, mu=mu_)
+        for _ in range(3):                            # (the third call of the same proposal is a replay)
+            assert close(B.logpdf_(model[node], data), orc.logpdf_from(node))
+        if accept:
+            B.set_(data); orc.set()
+        else:
+            B.update_(model[node], λ=old[0], μ=old[1]); orc.update(node, lam=old[0], mu=old[1])
+            B.rev_(data); orc.rev()
+        for _ in range(3):
+            assert close(B.logpdfroot(model[1], data), orc.logpdfroot())
+    w = B.addwgd_(model, model[6], 0.01, 0.25); ow = orc.addwgd(6, 0.01, 0.25)
+    B.extend_(data, 6); orc.extend(6)
+    for _ in range(3):
+        assert close(B.logpdf_(model[6], data), orc.logpdf_from(6))
+    B.set_(data); orc.set()
+    for _ in range(4):
+        assert close(B.logpdf_(model, data), orc.logpdf())
+    # timed calls (event-record nodes inside the graph) report sane phase times
+    data.set_timing(True)
+    for _ in range(4):
+        v = B.logpdf_(model, data)
+    pm, rm = data.last_timing()
+    data.set_timing(False)
+    assert close(v, orc.logpdf())
+    assert 0.0 < pm < 50.0 and 0.0 < rm < 50.0, (pm, rm)
+    assert data.graph_stats()[0] > cap2
