@@ -183,3 +183,79 @@ def test_shard_range_partitions():
                 assert a[1] == b[0]
             sizes = [hi - lo for lo, hi in cuts]
             assert max(sizes) - min(sizes) <= 1
+
+
+def _split_top(s):
+    """Split at top-level commas (brace/paren aware)."""
+    out, depth, cur = [], 0, ""
+    for ch in s:
+        if ch in "({[":
+            depth += 1
+        elif ch in ")}]":
+            depth -= 1
+        if ch == "," and depth == 0:
+            out.append(cur.strip()); cur = ""
+        else:
+            cur += ch
+    if cur.strip():
+        out.append(cur.strip())
+    return out
+
+
+def test_julia_glue_and_python_mirror_bind_the_header_as_declared():
+    """No `julia` in this image: the glue (julia/BelugaB200.jl) cannot run here, so its ccalls are checked statically
+    against include/beluga_b200.h — symbol declared, argument count, and the C type class of every argument — and the
+    ctypes argtypes of the Python mirror get the same count check."""
+    header = open(os.path.join(ROOT, "include", "beluga_b200.h")).read()
+    header = re.sub(r"/\*.*?\*/", "", header, flags=re.S)
+    decl = {}
+    for m in re.finditer(r"\b(?:const\s+char\s*\*|int)\s+(blg_[a-z_A-Z0-9]+)\s*\(([^;]*?)\)\s*;", header, flags=re.S):
+        args = [a for a in _split_top(" ".join(m.group(2).split())) if a and a != "void"]
+        decl[m.group(1)] = args
+    assert len(decl) == len(_lib.SYMBOLS), sorted(set(_lib.SYMBOLS) ^ set(decl))
+
+    def c_class(a):
+        a = a.replace("const ", "")
+        if "**" in a:
+            return "pp"
+        if "*" in a:
+            return "p"
+        return "f" if a.split()[0] == "double" else "i"
+
+    def jl_class(t):
+        t = t.strip()
+        if t.startswith("Ptr{Ptr{"):
+            return "pp"
+        if t.startswith("Ptr{") or t == "Cstring":
+            return "p"
+        return "f" if t in ("Float64", "Cdouble") else "i"
+
+    jl = open(os.path.join(ROOT, "julia", "BelugaB200.jl")).read()
+    jl = "\n".join(line.split("#")[0] if not line.lstrip().startswith("#") else "" for line in jl.splitlines())
+    seen = set()
+    for m in re.finditer(r"ccall\(\(:(blg_[a-z_0-9]+),\s*LIBBLG\),\s*(\w+),\s*\(", jl):
+        name = m.group(1)
+        assert name in decl, "julia glue calls an undeclared symbol: " + name
+        # the argument-type tuple: balanced parentheses from the match's end
+        i, depth = m.end(), 1
+        while depth:
+            depth += {"(": 1, ")": -1}.get(jl[i], 0)
+            i += 1
+        types = [t for t in _split_top(jl[m.end():i - 1]) if t]
+        want = decl[name]
+        assert len(types) == len(want), (name, types, want)
+        assert [jl_class(t) for t in types] == [c_class(a) for a in want], (name, types, want)
+        seen.add(name)
+    # every entry the reference's methods map to (INTEGRATION.md §1) is bound by the glue
+    for name in ("blg_create", "blg_destroy", "blg_set_profiles", "blg_set_topology", "blg_set_params", "blg_rebuild",
+                 "blg_logpdf_full", "blg_logpdf_from", "blg_logpdf_root", "blg_gradient", "blg_gradient_cr", "blg_commit",
+                 "blg_revert", "blg_extend", "blg_shrink", "blg_comm_unique_id", "blg_comm_init", "blg_last_error"):
+        assert name in seen, name
+    # Python mirror: argtypes of every symbol it declares have the header's length
+    import __graft_entry__
+    __graft_entry__.build()
+    L = _lib.lib()
+    for name, want in decl.items():
+        at = getattr(L, name).argtypes
+        if at is not None:
+            assert len(at) == len(want), (name, at, want)
