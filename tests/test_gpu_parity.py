@@ -1039,19 +1039,21 @@ def test_repeated_calls_replay_a_captured_graph_and_stay_on_the_oracle(dicots, m
     nw, df = dicots
     model, data, orc = pair(nw, df, 1.0, 0.92, 0.66, B.NODE)
     want = orc.logpdf()
-    vals = [B.logpdf_(model, data) for _ in range(5)]
+    vals = [B.logpdf_(model, data) for _ in range(6)]
     assert all(v == vals[0] for v in vals), vals
     assert close(vals[0], want)
     cap, rep = data.graph_stats()
     assert cap >= 1 and rep >= 3, (cap, rep)
     # new rates, same state: the same graph, new value
     rng = np.random.default_rng(3)
-    for _ in range(3):
+    for _ in range(5):
         X = model.getrates() * np.exp(rng.normal(0, 0.05, size=model.getrates().shape))
         model.setrates_(X); orc.setrates(X)
         assert close(B.logpdf_(model, data), orc.logpdf())
     cap2, rep2 = data.graph_stats()
-    assert cap2 == cap and rep2 >= rep + 3, (cap, rep, cap2, rep2)
+    # (the allocation epoch is process-wide: another handle released by the garbage collector in between costs one
+    # launch-by-launch call and one re-capture, no more)
+    assert cap2 <= cap + 1 and rep2 >= rep + 3, (cap, rep, cap2, rep2)
     # the same handle with graphs switched off gives the same bits
     monkeypatch.setenv("BLG_GRAPH", "0")
     model0, data0 = B.DLWGD(nw, df, 1.0, 0.92, 0.66, B.NODE, device=0)
